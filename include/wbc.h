@@ -1,0 +1,176 @@
+/* wbc.h — C ABI of the batched whole-body controller (libwbc_b200.so).
+ *
+ * Drop-in boundary for the per-control-step path of vincekurtz/quadruped_drake.
+ * Every entry point replaces a block of pydrake calls made by the reference
+ * controllers; the citation after each declaration is the reference code it
+ * stands in for (paths relative to the reference tree).
+ *
+ * Conventions
+ *   - plain C, no exceptions; every function returns an int status, 0 = WBC_OK;
+ *     wbc_last_error() gives the text for the last non-zero return on a handle;
+ *   - all arithmetic is FP64; arrays are instance-major (row i = instance i);
+ *   - q  = [qw qx qy qz  px py pz  theta(12)]            (19)  Drake position order
+ *     v  = [omega_W(3)  pdot_W(3)  thetadot(12)]         (18)  Drake velocity order
+ *     joint/velocity order inside theta is given by wbc_model.v_index;
+ *   - traj[54] follows lcm_types/trunk_state_t.lcm:10-35 field order:
+ *       base p, pd, pdd, rpy, rpyd, rpydd (18),
+ *       foot p   LF RF LH RH (12), foot pd (12), foot pdd (12);
+ *     contact[4] = planned stance flags LF RF LH RH (trunk_state_t.lcm:38-41,
+ *     planners/simple.py:67);
+ *   - tau[12] is in actuator (URDF <transmission>) order, like the vector the
+ *     reference writes to its `quad_torques` port (basic_controller.py:320);
+ *   - metrics[4] = [V, err, res, Vdot] (basic_controller.py:271-283);
+ *   - per-instance failures go to status[i] (bit mask below), never abort the batch
+ *     (the reference asserts instead: inverse_dynamics_controller.py:224);
+ *   - "device" entry points take device pointers and a cudaStream_t passed as void*;
+ *     "_host" entry points take host pointers and do the copies themselves.
+ *   - one handle per device; calls on one handle must be serialised by the caller.
+ */
+#ifndef WBC_B200_H
+#define WBC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WBC_NQ 19
+#define WBC_NV 18
+#define WBC_NU 12
+#define WBC_NLEG 4
+#define WBC_NBODY 13      /* floating base + 4 x (hip/abduct, thigh, shank) after welding */
+#define WBC_NTRAJ 54
+#define WBC_NMETRIC 4
+
+/* return codes */
+#define WBC_OK 0
+#define WBC_ERR_ARG 1
+#define WBC_ERR_CUDA 2
+#define WBC_ERR_NOMEM 3
+
+/* per-instance status bits */
+#define WBC_ST_OK 0
+#define WBC_ST_MAXITER 1       /* active-set iteration cap reached                       */
+#define WBC_ST_INFEASIBLE 2    /* QP constraints inconsistent                            */
+#define WBC_ST_RANKDEF 4       /* equality constraints rank deficient (e.g. singular leg) */
+#define WBC_ST_GIMBAL 8        /* |cos(pitch)| < 1e-6: rpy rates undefined   */
+#define WBC_ST_NOTPD 16        /* reduced Hessian not positive definite                   */
+#define WBC_ST_BADQUAT 32      /* zero / non-finite quaternion                            */
+
+/* controller kinds: reference controllers/__init__.py:1-5 */
+#define WBC_CTRL_ID 0          /* controllers/inverse_dynamics_controller.py */
+#define WBC_CTRL_CLF 1         /* controllers/clf_controller.py              */
+#define WBC_CTRL_PC 2          /* controllers/pc_controller.py               */
+
+/* Flattened robot: what Drake's Parser + MultibodyPlant::Finalize hold after
+ * simulate.py:37-64. Body 0 = floating base, body 1+3*leg+j = link j of leg
+ * (legs in foot order LF RF LH RH, basic_controller.py:67-70). Welded links are
+ * already merged into their parent. Joint k = 3*leg+j connects body k+1 to its
+ * parent (base for j = 0, body k otherwise); all joint frames are unrotated
+ * (every moving-joint rpy is 0 in both reference URDFs). */
+typedef struct wbc_model {
+  double mass[WBC_NBODY];
+  double com[WBC_NBODY][3];          /* CoM in the body frame                                  */
+  double inertia_com[WBC_NBODY][6];  /* about the CoM, body axes: xx yy zz xy xz yz            */
+  double joint_xyz[WBC_NU][3];       /* joint origin in the parent body frame                  */
+  double joint_axis[WBC_NU][3];      /* unit axis (same in parent and child frame)             */
+  double foot_xyz[WBC_NLEG][3];      /* foot frame origin in the shank frame                   */
+  double effort[WBC_NU];             /* URDF effort limit of joint k                           */
+  double gravity[3];                 /* world gravity vector, (0,0,-9.81)                      */
+  int32_t v_index[WBC_NU];           /* index of joint k in Drake's v (6..17); q index = +1    */
+  int32_t act_index[WBC_NU];         /* actuator (output tau) index of joint k                 */
+} wbc_model;
+
+/* Gains and weights: the literals inside each reference ControlLaw. */
+typedef struct wbc_params {
+  /* ID  (inverse_dynamics_controller.py:116-128) */
+  double id_kp_body_p, id_kd_body_p, id_kp_body_rpy, id_kd_body_rpy;
+  double id_kp_foot, id_kd_foot, id_w_body, id_w_foot;
+  /* CLF (clf_controller.py:65-78) */
+  double clf_q_body_p, clf_q_body_pd, clf_q_body_rpy, clf_q_body_rpyd;
+  double clf_q_foot_p, clf_q_foot_pd, clf_r, clf_w_delta;
+  /* PC  (pc_controller.py:63-76) */
+  double pc_kp_body_p, pc_kd_body_p, pc_kp_body_rpy, pc_kd_body_rpy;
+  double pc_kp_foot, pc_kd_foot, pc_w_body, pc_w_foot;
+  /* shared (inverse_dynamics_controller.py:19,94) */
+  double mu;                 /* friction coefficient, 0.7                      */
+  double contact_damping;    /* Kd of the no-slip constraint, 100              */
+  /* declared tie-break: + reg_f/2 |f|^2 + reg_tau/2 |tau|^2
+   * + reg_vd/2 |vd|^2 added to the reference cost so the optimum is unique.     */
+  double reg_f, reg_tau, reg_vd;
+  int32_t torque_limits;     /* 0 = reference QP; 1 = add |tau_k| <= effort_k  */
+  int32_t max_iter;          /* active-set iteration cap                       */
+} wbc_params;
+
+typedef struct wbc_handle wbc_handle;
+
+/* Optional per-step buffers beyond tau/metrics/status; any pointer may be NULL. */
+typedef struct wbc_io {
+  const double* q;        /* [N][19] */
+  const double* v;        /* [N][18] */
+  const double* traj;     /* [N][54] */
+  const uint8_t* contact; /* [N][4]  */
+  double* tau;            /* [N][12] */
+  double* metrics;        /* [N][4]  */
+  int32_t* status;        /* [N]     */
+  double* vd;             /* [N][18] QP accelerations, Drake velocity order (optional)  */
+  double* f;              /* [N][12] contact forces LF RF LH RH, 0 for swing (optional) */
+  double* qp_info;        /* [N][4]  objective, max primal violation, delta, #iters (optional) */
+} wbc_io;
+
+/* Fill *p with the reference's constants. */
+int wbc_default_params(wbc_params* p);
+
+/* BasicController.__init__ (basic_controller.py:21-77): create the plant context
+ * equivalent — uploads the model tables and gains to `device`. */
+int wbc_create(const wbc_model* model, const wbc_params* params, int device, wbc_handle** out);
+int wbc_destroy(wbc_handle* h);
+const char* wbc_last_error(const wbc_handle* h);
+
+/* BasicController.CalcDynamics (basic_controller.py:101-115),
+ * CalcFramePositionQuantities x4 (:173-196) on device buffers. Outputs (any may be NULL):
+ *   M [N][18][18], Cv [N][18], taug [N][18] (= -CalcGravityGeneralizedForces, :112),
+ *   Jfeet [N][4][3][18], Jdv [N][4][3], pfeet [N][4][3]; all in Drake velocity order. */
+int wbc_dynamics(wbc_handle* h, int64_t n, const double* q, const double* v,
+                 double* M, double* Cv, double* taug, double* Jfeet, double* Jdv,
+                 double* pfeet, void* stream);
+
+/* BasicController.CalcCoriolisMatrix (basic_controller.py:117-132) and
+ * CalcFrameJacobianDot x4 (:198-220): C [N][18][18] with C v = Cv, Jd [N][4][3][18]. */
+int wbc_coriolis(wbc_handle* h, int64_t n, const double* q, const double* v,
+                 double* C, double* Jd, void* stream);
+
+/* One control step for n instances: DoSetControlTorques -> ControlLaw
+ * (basic_controller.py:286-320; inverse_dynamics_controller.py:103-234;
+ * clf_controller.py:48-234; pc_controller.py:43-255). Device pointers. */
+int wbc_step(wbc_handle* h, int kind, int64_t n, const wbc_io* io, void* stream);
+int wbc_step_id(wbc_handle* h, int64_t n, const double* q, const double* v, const double* traj,
+                const uint8_t* contact, double* tau, double* metrics, int32_t* status, void* stream);
+int wbc_step_clf(wbc_handle* h, int64_t n, const double* q, const double* v, const double* traj,
+                 const uint8_t* contact, double* tau, double* metrics, int32_t* status, void* stream);
+int wbc_step_pc(wbc_handle* h, int64_t n, const double* q, const double* v, const double* traj,
+                const uint8_t* contact, double* tau, double* metrics, int32_t* status, void* stream);
+
+/* Same step with HOST buffers (what the Python LeafSystem shim calls): copies the
+ * inputs to the device, runs wbc_step, copies tau/metrics/status (and any optional
+ * outputs that are non-NULL) back, and synchronises. */
+int wbc_step_host(wbc_handle* h, int kind, int64_t n, const wbc_io* host_io);
+
+/* Device-side timing helper for benchmarks: runs `reps` back-to-back wbc_step
+ * launches on `stream` and returns the mean device time per launch (CUDA events
+ * recorded on that same stream). */
+int wbc_time_step(wbc_handle* h, int kind, int64_t n, const wbc_io* io, int reps, void* stream,
+                  double* ms_per_launch);
+
+/* Measured-peak helper: FP64 FMA throughput of this device in TFLOP/s (a register
+ * resident DFMA loop over all SMs), used as the FP64 roofline denominator. */
+int wbc_measure_fp64_peak(int device, double* tflops);
+
+/* Number of kernel launches issued through this handle since creation. */
+int64_t wbc_launch_count(const wbc_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WBC_B200_H */
