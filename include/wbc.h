@@ -29,6 +29,7 @@
 #ifndef WBC_B200_H
 #define WBC_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -156,6 +157,14 @@ int wbc_step_pc(wbc_handle* h, int64_t n, const double* q, const double* v, cons
  * inputs to the device, runs wbc_step, copies tau/metrics/status (and any optional
  * outputs that are non-NULL) back, and synchronises. */
 int wbc_step_host(wbc_handle* h, int kind, int64_t n, const wbc_io* host_io);
+
+/* Host-buffer version of wbc_dynamics (allocates device scratch per call; a test/debug entry). */
+int wbc_dynamics_host(wbc_handle* h, int64_t n, const double* q, const double* v,
+                      double* M, double* Cv, double* taug, double* Jfeet, double* Jdv, double* pfeet);
+
+/* Pinned (page-locked) host memory for wbc_step_host buffers. */
+void* wbc_host_alloc(size_t bytes);
+void wbc_host_free(void* p);
 
 /* Device-side timing helper for benchmarks: runs `reps` back-to-back wbc_step
  * launches on `stream` and returns the mean device time per launch (CUDA events

@@ -116,6 +116,20 @@ def _eq_solve(P, q, A, b, G, h, W):
     return sol[:n], sol[n:n + me], sol[n + me:]
 
 
+def _independent(A, G, W):
+    """Greedy subset of W whose rows, together with A, are linearly independent."""
+    keep = []
+    base = A
+    rank = np.linalg.matrix_rank(base) if base.shape[0] else 0
+    for i in W:
+        cand = np.vstack([base, G[i:i + 1]])
+        r = np.linalg.matrix_rank(cand, tol=1e-9 * max(1.0, np.abs(cand).max()))
+        if r > rank:
+            keep.append(i)
+            base, rank = cand, r
+    return keep
+
+
 def solve_qp(P, q, A, b, G, h, feas_tol=1e-9, max_polish=100):
     P, q = np.asarray(P, float), np.asarray(q, float)
     n = P.shape[0]
@@ -124,17 +138,25 @@ def solve_qp(P, q, A, b, G, h, feas_tol=1e-9, max_polish=100):
     G = np.zeros((0, n)) if G is None else np.asarray(G, float).reshape(-1, n)
     h = np.zeros(0) if h is None else np.asarray(h, float).ravel()
     mi = G.shape[0]
-    x, nu, s, lam, it = _ipm(P, q, A, b, G, h)
-    status = "optimal"
+    x, nu, s, lam, it = _ipm(P, q, A, b, G, h, max_iter=80, tol=1e-12)
+    status = "ipm"                      # interior-point answer kept unless the polish certifies a vertex
+    if mi == 0:
+        return QPResult(x, nu, lam, [], it, "optimal")
     W = [i for i in range(mi) if lam[i] > s[i]]
-    gscale = np.maximum(1.0, np.abs(G).sum(axis=1)) if mi else np.zeros(0)
+    gscale = np.maximum(1.0, np.abs(G).sum(axis=1))
+    seen = set()
     for _ in range(max_polish):
+        W = _independent(A, G, W)
+        key = tuple(W)
+        if key in seen:
+            break                       # cycling on a degenerate vertex
+        seen.add(key)
         xw, nuw, lw = _eq_solve(P, q, A, b, G, h, W)
-        viol = (G @ xw - h) / gscale if mi else np.zeros(0)
+        viol = (G @ xw - h) / gscale
         if len(W):
             viol[W] = 0.0
-        worst = int(np.argmax(viol)) if mi else -1
-        if mi and viol[worst] > feas_tol:
+        worst = int(np.argmax(viol))
+        if viol[worst] > feas_tol:
             W = sorted(W + [worst])
             continue
         if len(W) and lw.min() < -1e-9 * max(1.0, np.abs(lw).max()):
@@ -144,7 +166,6 @@ def solve_qp(P, q, A, b, G, h, feas_tol=1e-9, max_polish=100):
         lam = np.zeros(mi)
         if len(W):
             lam[W] = np.maximum(lw, 0.0)
+        status = "optimal"
         break
-    else:
-        status = "polish_failed"
     return QPResult(x, nu, lam, W, it, status)

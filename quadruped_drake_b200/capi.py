@@ -1,0 +1,128 @@
+"""ctypes binding of include/wbc.h (libwbc_b200.so). No torch types cross this boundary.
+
+The library is built in-tree by `__graft_entry__.build()` (nvcc, sm_100a). There is no CPU
+fallback: if the shared library is missing or no CUDA device is usable, loading raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+from .model import WbcModelStruct
+
+LIB_PATH = Path(__file__).resolve().parent / "csrc" / "libwbc_b200.so"
+
+WBC_CTRL_ID, WBC_CTRL_CLF, WBC_CTRL_PC = 0, 1, 2
+KINDS = {"id": WBC_CTRL_ID, "clf": WBC_CTRL_CLF, "pc": WBC_CTRL_PC}
+ST_MAXITER, ST_INFEASIBLE, ST_RANKDEF, ST_GIMBAL, ST_NOTPD, ST_BADQUAT = 1, 2, 4, 8, 16, 32
+
+_PARAM_DOUBLES = [
+    "id_kp_body_p", "id_kd_body_p", "id_kp_body_rpy", "id_kd_body_rpy", "id_kp_foot", "id_kd_foot", "id_w_body", "id_w_foot",
+    "clf_q_body_p", "clf_q_body_pd", "clf_q_body_rpy", "clf_q_body_rpyd", "clf_q_foot_p", "clf_q_foot_pd", "clf_r", "clf_w_delta",
+    "pc_kp_body_p", "pc_kd_body_p", "pc_kp_body_rpy", "pc_kd_body_rpy", "pc_kp_foot", "pc_kd_foot", "pc_w_body", "pc_w_foot",
+    "mu", "contact_damping", "reg_f", "reg_tau", "reg_vd",
+]
+
+
+class WbcParams(C.Structure):
+    """ctypes mirror of `wbc_params`."""
+    _fields_ = [(n, C.c_double) for n in _PARAM_DOUBLES] + [("torque_limits", C.c_int32), ("max_iter", C.c_int32)]
+
+
+# Reference constants; kept here so the struct can be filled without the library.
+DEFAULT_PARAMS = dict(
+    id_kp_body_p=500.0, id_kd_body_p=50.0, id_kp_body_rpy=500.0, id_kd_body_rpy=50.0,
+    id_kp_foot=100.0, id_kd_foot=20.0, id_w_body=10.0, id_w_foot=1.0,
+    clf_q_body_p=5000.0, clf_q_body_pd=200.0, clf_q_body_rpy=5000.0, clf_q_body_rpyd=200.0,
+    clf_q_foot_p=200.0, clf_q_foot_pd=20.0, clf_r=1.0, clf_w_delta=1000.0,
+    pc_kp_body_p=100.0, pc_kd_body_p=10.0, pc_kp_body_rpy=100.0, pc_kd_body_rpy=10.0,
+    pc_kp_foot=200.0, pc_kd_foot=20.0, pc_w_body=10.0, pc_w_foot=1.0,
+    mu=0.7, contact_damping=100.0, reg_f=1e-6, reg_tau=0.0, reg_vd=0.0, torque_limits=0, max_iter=200,
+)
+
+
+def make_params(**overrides) -> WbcParams:
+    vals = dict(DEFAULT_PARAMS)
+    unknown = set(overrides) - set(vals)
+    if unknown:
+        raise KeyError(f"unknown controller parameters: {sorted(unknown)}")
+    vals.update(overrides)
+    p = WbcParams()
+    for k, v in vals.items():
+        setattr(p, k, int(v) if k in ("torque_limits", "max_iter") else float(v))
+    return p
+
+
+class WbcIO(C.Structure):
+    """ctypes mirror of `wbc_io`; pointers are raw addresses (host or device)."""
+    _fields_ = [("q", C.c_void_p), ("v", C.c_void_p), ("traj", C.c_void_p), ("contact", C.c_void_p),
+                ("tau", C.c_void_p), ("metrics", C.c_void_p), ("status", C.c_void_p),
+                ("vd", C.c_void_p), ("f", C.c_void_p), ("qp_info", C.c_void_p)]
+
+
+def np_ptr(a: np.ndarray):
+    return C.c_void_p(a.ctypes.data)
+
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """Load libwbc_b200.so and declare every symbol of include/wbc.h. Raises if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise RuntimeError(f"{LIB_PATH} is not built - run `python -c 'import __graft_entry__ as g; g.build()'`. "
+                           "There is no CPU fallback for the controller path.")
+    lib = C.CDLL(str(LIB_PATH))
+    H = C.c_void_p
+    i64, i32, dp = C.c_int64, C.c_int, C.c_void_p
+    lib.wbc_default_params.argtypes = [C.POINTER(WbcParams)]
+    lib.wbc_create.argtypes = [C.POINTER(WbcModelStruct), C.POINTER(WbcParams), i32, C.POINTER(H)]
+    lib.wbc_destroy.argtypes = [H]
+    lib.wbc_last_error.argtypes = [H]
+    lib.wbc_last_error.restype = C.c_char_p
+    lib.wbc_dynamics.argtypes = [H, i64, dp, dp, dp, dp, dp, dp, dp, dp, dp]
+    lib.wbc_coriolis.argtypes = [H, i64, dp, dp, dp, dp, dp]
+    lib.wbc_step.argtypes = [H, i32, i64, C.POINTER(WbcIO), dp]
+    for name in ("wbc_step_id", "wbc_step_clf", "wbc_step_pc"):
+        getattr(lib, name).argtypes = [H, i64, dp, dp, dp, dp, dp, dp, dp, dp]
+    lib.wbc_step_host.argtypes = [H, i32, i64, C.POINTER(WbcIO)]
+    lib.wbc_time_step.argtypes = [H, i32, i64, C.POINTER(WbcIO), i32, dp, C.POINTER(C.c_double)]
+    lib.wbc_measure_fp64_peak.argtypes = [i32, C.POINTER(C.c_double)]
+    lib.wbc_dynamics_host.argtypes = [H, i64] + [dp] * 8
+    lib.wbc_dynamics_host.restype = C.c_int
+    lib.wbc_host_alloc.argtypes = [C.c_size_t]
+    lib.wbc_host_alloc.restype = C.c_void_p
+    lib.wbc_host_free.argtypes = [C.c_void_p]
+    lib.wbc_host_free.restype = None
+    lib.wbc_launch_count.argtypes = [H]
+    lib.wbc_launch_count.restype = C.c_int64
+    for name in ("wbc_default_params", "wbc_create", "wbc_destroy", "wbc_dynamics", "wbc_coriolis", "wbc_step",
+                 "wbc_step_id", "wbc_step_clf", "wbc_step_pc", "wbc_step_host", "wbc_time_step", "wbc_measure_fp64_peak"):
+        getattr(lib, name).restype = C.c_int
+    _lib = lib
+    return lib
+
+
+EXPORTED_SYMBOLS = ["wbc_default_params", "wbc_create", "wbc_destroy", "wbc_last_error", "wbc_dynamics", "wbc_coriolis",
+                    "wbc_step", "wbc_step_id", "wbc_step_clf", "wbc_step_pc", "wbc_step_host", "wbc_time_step",
+                    "wbc_measure_fp64_peak", "wbc_launch_count", "wbc_dynamics_host", "wbc_host_alloc", "wbc_host_free"]
+
+
+def pinned_empty(shape, dtype=np.float64) -> np.ndarray:
+    """NumPy array over page-locked host memory (wbc_host_alloc); freed when the array is collected."""
+    lib = load_library()
+    dtype = np.dtype(dtype)
+    nbytes = int(np.prod(shape)) * dtype.itemsize
+    ptr = lib.wbc_host_alloc(max(nbytes, 1))
+    if not ptr:
+        raise MemoryError("wbc_host_alloc failed")
+    buf = (C.c_char * max(nbytes, 1)).from_address(ptr)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    import weakref
+    weakref.finalize(buf, lib.wbc_host_free, ptr)
+    return arr

@@ -1,0 +1,329 @@
+"""Host-side mirror of the reference controller interface, on top of the C ABI.
+
+`BatchedController` is the pydrake-free batch entry:
+
+    step(kind, q[N,19], v[N,18], traj[N,54], contact[N,4]) -> tau[N,12], metrics[N,4], status[N]
+
+on NumPy arrays (host buffers; copies happen inside `wbc_step_host`) or torch CUDA tensors
+(device pointers, launched on torch's current stream).
+
+`IDController`, `CLFController`, `PCController` keep the reference constructor
+`(plant, dt, use_lcm=False)` and port layout (reference controllers/basic_controller.py:21-77,
+inverse_dynamics_controller.py:10-23): in0 "quad_state" (37), in1 "trunk_input" (abstract dict,
+reference planners/simple.py:45-85), out0 "quad_torques" (12), out1 "output_metrics" (4). With
+pydrake importable they are real LeafSystems; without it they expose the same callbacks
+(`DoSetControlTorques`, `SetLoggingOutputs`, `ControlLaw`) over minimal port stand-ins.
+Solver failure raises AssertionError exactly where the reference asserts
+(inverse_dynamics_controller.py:224); the batch entry reports it in `status` instead.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .capi import KINDS, WbcIO, make_params, np_ptr
+from .model import NQ, NTRAJ, NU, NV, RobotModel, load_robot
+
+FEET = ["lf", "rf", "lh", "rh"]
+
+
+def dict_to_traj(d):
+    """Reference trunk dict (planners/simple.py:45-85) -> (traj[54], contact[4]) in the wbc.h layout."""
+    t = np.zeros(NTRAJ)
+    for k, key in enumerate(["p_body", "pd_body", "pdd_body", "rpy_body", "rpyd_body", "rpydd_body"]):
+        t[3 * k:3 * k + 3] = np.asarray(d[key], float).ravel()
+    for i, f in enumerate(FEET):
+        t[18 + 3 * i:21 + 3 * i] = np.asarray(d["p_" + f], float).ravel()
+        t[30 + 3 * i:33 + 3 * i] = np.asarray(d["pd_" + f], float).ravel()
+        t[42 + 3 * i:45 + 3 * i] = np.asarray(d["pdd_" + f], float).ravel()
+    return t, np.array([1 if c else 0 for c in d["contact_states"]], dtype=np.uint8)
+
+
+def _is_torch(x):
+    return type(x).__module__.startswith("torch")
+
+
+class StepOutput:
+    __slots__ = ("tau", "metrics", "status", "vd", "f", "qp_info")
+
+    def __init__(self, tau, metrics, status, vd=None, f=None, qp_info=None):
+        self.tau, self.metrics, self.status, self.vd, self.f, self.qp_info = tau, metrics, status, vd, f, qp_info
+
+    def __iter__(self):
+        return iter((self.tau, self.metrics, self.status))
+
+
+class BatchedController:
+    """One handle of libwbc_b200.so on one device."""
+
+    def __init__(self, robot="mini_cheetah", device=0, dof_order="depth_first", **params):
+        self.lib = capi.load_library()
+        self.model = robot if isinstance(robot, RobotModel) else load_robot(robot, dof_order=dof_order)
+        self.params = make_params(**params)
+        self.device = int(device)
+        self._h = C.c_void_p()
+        ms = self.model.as_struct()
+        rc = self.lib.wbc_create(C.byref(ms), C.byref(self.params), self.device, C.byref(self._h))
+        if rc != 0:
+            msg = self.lib.wbc_last_error(self._h).decode() if self._h else "allocation failed"
+            if self._h:
+                self.lib.wbc_destroy(self._h)
+                self._h = C.c_void_p()
+            raise RuntimeError(f"wbc_create failed ({rc}): {msg}")
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.wbc_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise RuntimeError(f"{what} failed ({rc}): {self.lib.wbc_last_error(self._h).decode()}")
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.wbc_launch_count(self._h))
+
+    # ------------------------------------------------------------------ batch step
+    def step(self, kind, q, v, traj, contact, debug=False) -> StepOutput:
+        k = KINDS[kind] if isinstance(kind, str) else int(kind)
+        if _is_torch(q):
+            return self._step_torch(k, q, v, traj, contact, debug)
+        q = np.ascontiguousarray(q, dtype=np.float64).reshape(-1, NQ)
+        n = q.shape[0]
+        v = np.ascontiguousarray(v, dtype=np.float64).reshape(n, NV)
+        traj = np.ascontiguousarray(traj, dtype=np.float64).reshape(n, NTRAJ)
+        contact = np.ascontiguousarray(np.asarray(contact) != 0, dtype=np.uint8).reshape(n, 4)
+        tau, met, st = np.empty((n, NU)), np.empty((n, 4)), np.empty(n, dtype=np.int32)
+        vd = np.empty((n, NV)) if debug else None
+        f = np.empty((n, 4, 3)) if debug else None
+        qi = np.empty((n, 4)) if debug else None
+        io = WbcIO(np_ptr(q), np_ptr(v), np_ptr(traj), np_ptr(contact), np_ptr(tau), np_ptr(met), np_ptr(st),
+                   np_ptr(vd) if debug else None, np_ptr(f) if debug else None, np_ptr(qi) if debug else None)
+        self._check(self.lib.wbc_step_host(self._h, k, n, C.byref(io)), "wbc_step_host")
+        return StepOutput(tau, met, st, vd, f, qi)
+
+    def _step_torch(self, k, q, v, traj, contact, debug):
+        import torch
+        n = q.shape[0]
+        for t, w, dt in ((q, NQ, torch.float64), (v, NV, torch.float64), (traj, NTRAJ, torch.float64), (contact, 4, torch.uint8)):
+            if not (t.is_cuda and t.is_contiguous() and t.dtype == dt and t.shape == (n, w)):
+                raise ValueError("device inputs must be contiguous CUDA tensors: q f64[N,19], v f64[N,18], traj f64[N,54], contact u8[N,4]")
+        dev = q.device
+        tau = torch.empty((n, NU), dtype=torch.float64, device=dev)
+        met = torch.empty((n, 4), dtype=torch.float64, device=dev)
+        st = torch.empty((n,), dtype=torch.int32, device=dev)
+        vd = torch.empty((n, NV), dtype=torch.float64, device=dev) if debug else None
+        f = torch.empty((n, 4, 3), dtype=torch.float64, device=dev) if debug else None
+        qi = torch.empty((n, 4), dtype=torch.float64, device=dev) if debug else None
+        io = self.make_io(q, v, traj, contact, tau, met, st, vd, f, qi)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        self._check(self.lib.wbc_step(self._h, k, n, C.byref(io), C.c_void_p(stream)), "wbc_step")
+        return StepOutput(tau, met, st, vd, f, qi)
+
+    @staticmethod
+    def make_io(q, v, traj, contact, tau, met, st, vd=None, f=None, qi=None) -> WbcIO:
+        p = lambda t: None if t is None else C.c_void_p(t.data_ptr())  # noqa: E731
+        return WbcIO(p(q), p(v), p(traj), p(contact), p(tau), p(met), p(st), p(vd), p(f), p(qi))
+
+    def time_step(self, kind, io: WbcIO, n: int, reps: int, stream=0) -> float:
+        """Mean device milliseconds per launch over `reps` back-to-back launches (CUDA events on `stream`)."""
+        k = KINDS[kind] if isinstance(kind, str) else int(kind)
+        ms = C.c_double()
+        self._check(self.lib.wbc_time_step(self._h, k, n, C.byref(io), reps, C.c_void_p(stream), C.byref(ms)), "wbc_time_step")
+        return ms.value
+
+    # ------------------------------------------------------------------ dynamics parity entry
+    def dynamics(self, q, v):
+        """CalcDynamics + CalcFramePositionQuantities x4 (basic_controller.py:101-115,173-196) for a batch
+        of host states -> dict(M, Cv, tau_g, J_feet, Jdv_feet, p_feet) in Drake velocity order."""
+        q = np.ascontiguousarray(q, dtype=np.float64).reshape(-1, NQ)
+        n = q.shape[0]
+        v = np.ascontiguousarray(v, dtype=np.float64).reshape(n, NV)
+        out = dict(M=np.empty((n, NV, NV)), Cv=np.empty((n, NV)), tau_g=np.empty((n, NV)),
+                   J_feet=np.empty((n, 4, 3, NV)), Jdv_feet=np.empty((n, 4, 3)), p_feet=np.empty((n, 4, 3)))
+        fn = self.lib.wbc_dynamics_host
+        fn.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 8
+        fn.restype = C.c_int
+        self._check(fn(self._h, n, np_ptr(q), np_ptr(v), np_ptr(out["M"]), np_ptr(out["Cv"]), np_ptr(out["tau_g"]),
+                       np_ptr(out["J_feet"]), np_ptr(out["Jdv_feet"]), np_ptr(out["p_feet"])), "wbc_dynamics_host")
+        return out
+
+    def fk(self, q, v):
+        """Foot positions and velocities (for synth.generate)."""
+        d = self.dynamics(q, v)
+        return d["p_feet"], np.einsum("nkij,nj->nki", d["J_feet"], np.asarray(v, float).reshape(len(d["M"]), NV))
+
+
+def measure_fp64_peak(device=0) -> float:
+    lib = capi.load_library()
+    t = C.c_double()
+    rc = lib.wbc_measure_fp64_peak(int(device), C.byref(t))
+    if rc != 0:
+        raise RuntimeError(f"wbc_measure_fp64_peak failed ({rc})")
+    return t.value
+
+
+# ----------------------------------------------------------------------- LeafSystem mirror
+try:  # pragma: no cover - pydrake is not in the build image
+    from pydrake.all import AbstractValue, BasicVector, LeafSystem
+    _HAVE_DRAKE = True
+except Exception:  # noqa: BLE001
+    _HAVE_DRAKE = False
+
+    class BasicVector:
+        def __init__(self, n):
+            self._v = np.zeros(int(n))
+
+        def SetFromVector(self, v):
+            self._v[:] = np.asarray(v, float).ravel()
+
+        def get_value(self):
+            return self._v
+
+        def size(self):
+            return self._v.size
+
+    class AbstractValue:
+        def __init__(self, v):
+            self._v = v
+
+        @staticmethod
+        def Make(v):
+            return AbstractValue(v)
+
+        def get_value(self):
+            return self._v
+
+    class _Port:
+        def __init__(self, name, index, model_value, calc=None):
+            self.name, self.index, self.model_value, self.calc = name, index, model_value, calc
+
+        def get_name(self):
+            return self.name
+
+        def get_index(self):
+            return self.index
+
+    class Context:
+        """Stand-in for a Drake context: holds the fixed input-port values."""
+        def __init__(self):
+            self.inputs = {}
+
+        def FixValue(self, index, value):
+            self.inputs[index] = value
+
+    class LeafSystem:
+        def __init__(self):
+            self._in, self._out = [], []
+
+        def DeclareVectorInputPort(self, name, model):
+            self._in.append(_Port(name, len(self._in), model))
+            return self._in[-1]
+
+        def DeclareAbstractInputPort(self, name, model):
+            self._in.append(_Port(name, len(self._in), model))
+            return self._in[-1]
+
+        def DeclareVectorOutputPort(self, name, model, calc):
+            self._out.append(_Port(name, len(self._out), model, calc))
+            return self._out[-1]
+
+        def get_input_port(self, i):
+            return self._in[i]
+
+        def get_output_port(self, i):
+            return self._out[i]
+
+        def GetInputPort(self, name):
+            return next(p for p in self._in if p.name == name)
+
+        def GetOutputPort(self, name):
+            return next(p for p in self._out if p.name == name)
+
+        def CreateDefaultContext(self):
+            return Context()
+
+        def EvalVectorInput(self, context, i):
+            b = BasicVector(len(context.inputs[i]))
+            b.SetFromVector(context.inputs[i])
+            return b
+
+        def EvalAbstractInput(self, context, i):
+            return AbstractValue(context.inputs[i])
+
+        def EvalOutput(self, context, i):
+            port = self._out[i]
+            out = BasicVector(port.model_value.size())
+            port.calc(context, out)
+            return out.get_value().copy()
+
+
+class _QPController(LeafSystem):
+    KIND = "id"
+
+    def __init__(self, plant, dt, use_lcm=False, device=0, dof_order="depth_first", **params):
+        LeafSystem.__init__(self)
+        if use_lcm:
+            raise NotImplementedError("the LCM bridge (basic_controller.py:291-317) is outside the accelerated path")
+        self.dt = dt
+        self.plant = plant
+        robot = plant if isinstance(plant, (str, RobotModel)) else getattr(plant, "wbc_robot", "mini_cheetah")
+        self.batched = BatchedController(robot, device=device, dof_order=dof_order, **params)
+        self.DeclareVectorInputPort("quad_state", BasicVector(NQ + NV))
+        self.DeclareVectorOutputPort("quad_torques", BasicVector(NU), self.DoSetControlTorques)
+        self.V = self.err = self.res = self.Vdot = 0.0
+        self.DeclareVectorOutputPort("output_metrics", BasicVector(4), self.SetLoggingOutputs)
+        self.DeclareAbstractInputPort("trunk_input", AbstractValue.Make({}))
+        self.last_status = 0
+
+    def SetLoggingOutputs(self, context, output):
+        output.SetFromVector(np.asarray([self.V, self.err, self.res, self.Vdot]))
+
+    def DoSetControlTorques(self, context, output):
+        state = np.asarray(self.EvalVectorInput(context, 0).get_value(), float)
+        q, v = state[:NQ], state[-NV:]
+        output.SetFromVector(self.ControlLaw(context, q, v))
+
+    def ControlLaw(self, context, q, v):
+        trunk = self.EvalAbstractInput(context, 1).get_value()
+        traj, contact = dict_to_traj(trunk)
+        out = self.batched.step(self.KIND, q[None], v[None], traj[None], contact[None])
+        self.last_status = int(out.status[0])
+        assert self.last_status & (capi.ST_INFEASIBLE | capi.ST_MAXITER | capi.ST_RANKDEF | capi.ST_NOTPD) == 0, \
+            f"QP solve failed (status {self.last_status})"   # reference: assert result.is_success()
+        m = out.metrics[0]
+        self._log(m)
+        return out.tau[0].copy()
+
+    def _log(self, m):
+        self.err, self.res = float(m[1]), float(m[2])
+
+
+class IDController(_QPController):
+    """Drop-in for reference controllers/inverse_dynamics_controller.py:IDController."""
+    KIND = "id"
+
+
+class CLFController(_QPController):
+    """Drop-in for reference controllers/clf_controller.py:CLFController."""
+    KIND = "clf"
+
+    def _log(self, m):
+        self.V, self.err, self.Vdot = float(m[0]), float(m[1]), float(m[3])
+
+
+class PCController(_QPController):
+    """Drop-in for reference controllers/pc_controller.py:PCController."""
+    KIND = "pc"
+
+    def _log(self, m):
+        self.V, self.err, self.Vdot = float(m[0]), float(m[1]), float(m[3])

@@ -1,0 +1,351 @@
+// wbc_api.cu — C ABI (include/wbc.h) and kernel launches of the batched whole-body controller.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+
+#include "wbc_device.cuh"
+
+namespace {
+
+constexpr int WARPS = 4;  // instances (warps) per CTA
+
+struct DevConst { wbc_model md; wbc_params pr; };
+
+struct SmemLayout {
+  DevConst dc;
+  wbc::WarpSmem w[WARPS];
+};
+
+__device__ __forceinline__ const DevConst& stage_consts(SmemLayout* sm, const DevConst* g) {
+  // model + gains into shared memory once per CTA (lane-divergent table lookups stay on chip)
+  const int nwords = sizeof(DevConst) / 4;
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(g);
+  uint32_t* dst = reinterpret_cast<uint32_t*>(&sm->dc);
+  for (int i = threadIdx.x; i < nwords; i += blockDim.x) dst[i] = src[i];
+  __syncthreads();
+  return sm->dc;
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(WARPS * 32) wbc_step_kernel(const DevConst* __restrict__ gdc, wbc::StepArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SmemLayout* sm = reinterpret_cast<SmemLayout*>(smem_raw);
+  const DevConst& dc = stage_consts(sm, gdc);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long inst = (long long)blockIdx.x * WARPS + warp;
+  if (inst < a.n) wbc::step_instance<KIND>(sm->w[warp], dc.md, dc.pr, a, inst, lane);
+}
+
+__global__ void __launch_bounds__(WARPS * 32) wbc_dynamics_kernel(const DevConst* __restrict__ gdc, const double* q,
+                                                                   const double* v, wbc::DynOut o, long long n) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SmemLayout* sm = reinterpret_cast<SmemLayout*>(smem_raw);
+  const DevConst& dc = stage_consts(sm, gdc);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long inst = (long long)blockIdx.x * WARPS + warp;
+  if (inst < n) wbc::dynamics_instance(sm->w[warp], dc.md, q, v, o, inst, lane);
+}
+
+// Register-resident DFMA loop: 8 independent chains per thread, 2 flop per FMA.
+__global__ void fp64_peak_kernel(double* out, int iters) {
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double m = 1.0000001, c = 1e-9;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+}  // namespace
+
+struct wbc_handle {
+  int device = 0;
+  DevConst* d_const = nullptr;
+  wbc_params params;
+  std::string err;
+  int64_t launches = 0;
+  cudaStream_t stream = nullptr;       // used by the host entry points
+  // device staging for wbc_step_host
+  int64_t cap = 0;
+  double *d_q = nullptr, *d_v = nullptr, *d_traj = nullptr, *d_tau = nullptr, *d_metrics = nullptr, *d_vd = nullptr,
+         *d_f = nullptr, *d_info = nullptr;
+  uint8_t* d_contact = nullptr;
+  int32_t* d_status = nullptr;
+};
+
+#define WBC_CUDA(h, call)                                                                       \
+  do {                                                                                          \
+    cudaError_t e_ = (call);                                                                    \
+    if (e_ != cudaSuccess) {                                                                    \
+      (h)->err = std::string(#call) + ": " + cudaGetErrorString(e_);                            \
+      return WBC_ERR_CUDA;                                                                      \
+    }                                                                                           \
+  } while (0)
+
+static int fail_arg(wbc_handle* h, const char* msg) {
+  if (h) h->err = msg;
+  return WBC_ERR_ARG;
+}
+
+extern "C" int wbc_default_params(wbc_params* p) {
+  if (!p) return WBC_ERR_ARG;
+  memset(p, 0, sizeof(*p));
+  p->id_kp_body_p = 500; p->id_kd_body_p = 50; p->id_kp_body_rpy = 500; p->id_kd_body_rpy = 50;
+  p->id_kp_foot = 100; p->id_kd_foot = 20; p->id_w_body = 10; p->id_w_foot = 1;
+  p->clf_q_body_p = 5000; p->clf_q_body_pd = 200; p->clf_q_body_rpy = 5000; p->clf_q_body_rpyd = 200;
+  p->clf_q_foot_p = 200; p->clf_q_foot_pd = 20; p->clf_r = 1; p->clf_w_delta = 1000;
+  p->pc_kp_body_p = 100; p->pc_kd_body_p = 10; p->pc_kp_body_rpy = 100; p->pc_kd_body_rpy = 10;
+  p->pc_kp_foot = 200; p->pc_kd_foot = 20; p->pc_w_body = 10; p->pc_w_foot = 1;
+  p->mu = 0.7; p->contact_damping = 100; p->reg_f = 1e-6; p->reg_tau = 0; p->reg_vd = 0;
+  p->torque_limits = 0; p->max_iter = 200;
+  return WBC_OK;
+}
+
+static int set_smem_attr(wbc_handle* h) {
+  const int bytes = (int)sizeof(SmemLayout);
+  WBC_CUDA(h, cudaFuncSetAttribute(wbc_step_kernel<WBC_CTRL_ID>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  WBC_CUDA(h, cudaFuncSetAttribute(wbc_step_kernel<WBC_CTRL_CLF>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  WBC_CUDA(h, cudaFuncSetAttribute(wbc_step_kernel<WBC_CTRL_PC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  WBC_CUDA(h, cudaFuncSetAttribute(wbc_dynamics_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  return WBC_OK;
+}
+
+extern "C" int wbc_create(const wbc_model* model, const wbc_params* params, int device, wbc_handle** out) {
+  if (!model || !out) return WBC_ERR_ARG;
+  *out = nullptr;
+  wbc_handle* h = new (std::nothrow) wbc_handle();
+  if (!h) return WBC_ERR_NOMEM;
+  h->device = device;
+  if (params) h->params = *params; else wbc_default_params(&h->params);
+  int rc = WBC_OK;
+  auto bail = [&](int code) { *out = h; return code; };  // hand the handle back so wbc_last_error works
+  if (h->params.reg_vd != 0.0) { h->err = "reg_vd is not supported yet (must be 0)"; return bail(WBC_ERR_ARG); }
+  if (!(h->params.reg_f > 0.0)) { h->err = "reg_f must be > 0 (tie-break that makes the QP strictly convex)"; return bail(WBC_ERR_ARG); }
+  for (int k = 0; k < WBC_NU; ++k) {
+    if (model->v_index[k] < 6 || model->v_index[k] >= WBC_NV || model->act_index[k] < 0 || model->act_index[k] >= WBC_NU) {
+      h->err = "wbc_model: v_index/act_index out of range"; return bail(WBC_ERR_ARG);
+    }
+  }
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) { h->err = std::string("cudaSetDevice: ") + cudaGetErrorString(e); return bail(WBC_ERR_CUDA); }
+  DevConst hc;
+  hc.md = *model; hc.pr = h->params;
+  e = cudaMalloc(&h->d_const, sizeof(DevConst));
+  if (e != cudaSuccess) { h->err = std::string("cudaMalloc: ") + cudaGetErrorString(e); return bail(WBC_ERR_CUDA); }
+  e = cudaMemcpy(h->d_const, &hc, sizeof(DevConst), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { h->err = std::string("cudaMemcpy: ") + cudaGetErrorString(e); return bail(WBC_ERR_CUDA); }
+  e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) { h->err = std::string("cudaStreamCreate: ") + cudaGetErrorString(e); return bail(WBC_ERR_CUDA); }
+  rc = set_smem_attr(h);
+  *out = h;
+  return rc;
+}
+
+static void free_staging(wbc_handle* h) {
+  cudaFree(h->d_q); cudaFree(h->d_v); cudaFree(h->d_traj); cudaFree(h->d_tau); cudaFree(h->d_metrics);
+  cudaFree(h->d_vd); cudaFree(h->d_f); cudaFree(h->d_info); cudaFree(h->d_contact); cudaFree(h->d_status);
+  h->d_q = h->d_v = h->d_traj = h->d_tau = h->d_metrics = h->d_vd = h->d_f = h->d_info = nullptr;
+  h->d_contact = nullptr; h->d_status = nullptr; h->cap = 0;
+}
+
+extern "C" int wbc_destroy(wbc_handle* h) {
+  if (!h) return WBC_OK;
+  cudaSetDevice(h->device);
+  free_staging(h);
+  if (h->d_const) cudaFree(h->d_const);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return WBC_OK;
+}
+
+extern "C" const char* wbc_last_error(const wbc_handle* h) { return h ? h->err.c_str() : "null handle"; }
+extern "C" int64_t wbc_launch_count(const wbc_handle* h) { return h ? h->launches : 0; }
+
+extern "C" int wbc_dynamics(wbc_handle* h, int64_t n, const double* q, const double* v, double* M, double* Cv,
+                            double* taug, double* Jfeet, double* Jdv, double* pfeet, void* stream) {
+  if (!h) return WBC_ERR_ARG;
+  if (n < 0 || (n > 0 && (!q || !v))) return fail_arg(h, "wbc_dynamics: null input");
+  if (n == 0) return WBC_OK;
+  WBC_CUDA(h, cudaSetDevice(h->device));
+  wbc::DynOut o{M, Cv, taug, Jfeet, Jdv, pfeet};
+  const unsigned grid = (unsigned)((n + WARPS - 1) / WARPS);
+  wbc_dynamics_kernel<<<grid, WARPS * 32, sizeof(SmemLayout), (cudaStream_t)stream>>>(h->d_const, q, v, o, n);
+  h->launches++;
+  WBC_CUDA(h, cudaGetLastError());
+  return WBC_OK;
+}
+
+extern "C" int wbc_coriolis(wbc_handle* h, int64_t, const double*, const double*, double*, double*, void*) {
+  return fail_arg(h, "wbc_coriolis: not implemented in this build");
+}
+
+extern "C" int wbc_step(wbc_handle* h, int kind, int64_t n, const wbc_io* io, void* stream) {
+  if (!h) return WBC_ERR_ARG;
+  if (!io || n < 0) return fail_arg(h, "wbc_step: bad arguments");
+  if (n == 0) return WBC_OK;
+  if (!io->q || !io->v || !io->traj || !io->contact || !io->tau || !io->metrics || !io->status)
+    return fail_arg(h, "wbc_step: q, v, traj, contact, tau, metrics and status are required");
+  WBC_CUDA(h, cudaSetDevice(h->device));
+  wbc::StepArgs a{io->q, io->v, io->traj, io->contact, io->tau, io->metrics, io->status, io->vd, io->f, io->qp_info,
+                  (long long)n, kind};
+  const unsigned grid = (unsigned)((n + WARPS - 1) / WARPS);
+  const size_t sm = sizeof(SmemLayout);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (kind) {
+    case WBC_CTRL_ID: wbc_step_kernel<WBC_CTRL_ID><<<grid, WARPS * 32, sm, st>>>(h->d_const, a); break;
+    case WBC_CTRL_CLF: return fail_arg(h, "wbc_step: CLF controller not implemented in this build");
+    case WBC_CTRL_PC: return fail_arg(h, "wbc_step: PC controller not implemented in this build");
+    default: return fail_arg(h, "wbc_step: unknown controller kind");
+  }
+  h->launches++;
+  WBC_CUDA(h, cudaGetLastError());
+  return WBC_OK;
+}
+
+#define WBC_STEP_WRAPPER(name, kind)                                                                               \
+  extern "C" int name(wbc_handle* h, int64_t n, const double* q, const double* v, const double* traj,              \
+                      const uint8_t* contact, double* tau, double* metrics, int32_t* status, void* stream) {       \
+    wbc_io io{q, v, traj, contact, tau, metrics, status, nullptr, nullptr, nullptr};                               \
+    return wbc_step(h, kind, n, &io, stream);                                                                      \
+  }
+WBC_STEP_WRAPPER(wbc_step_id, WBC_CTRL_ID)
+WBC_STEP_WRAPPER(wbc_step_clf, WBC_CTRL_CLF)
+WBC_STEP_WRAPPER(wbc_step_pc, WBC_CTRL_PC)
+
+static int ensure_staging(wbc_handle* h, int64_t n) {
+  if (n <= h->cap) return WBC_OK;
+  free_staging(h);
+  WBC_CUDA(h, cudaMalloc(&h->d_q, n * WBC_NQ * sizeof(double)));
+  WBC_CUDA(h, cudaMalloc(&h->d_v, n * WBC_NV * sizeof(double)));
+  WBC_CUDA(h, cudaMalloc(&h->d_traj, n * WBC_NTRAJ * sizeof(double)));
+  WBC_CUDA(h, cudaMalloc(&h->d_contact, n * 4));
+  WBC_CUDA(h, cudaMalloc(&h->d_tau, n * WBC_NU * sizeof(double)));
+  WBC_CUDA(h, cudaMalloc(&h->d_metrics, n * WBC_NMETRIC * sizeof(double)));
+  WBC_CUDA(h, cudaMalloc(&h->d_status, n * sizeof(int32_t)));
+  WBC_CUDA(h, cudaMalloc(&h->d_vd, n * WBC_NV * sizeof(double)));
+  WBC_CUDA(h, cudaMalloc(&h->d_f, n * 12 * sizeof(double)));
+  WBC_CUDA(h, cudaMalloc(&h->d_info, n * 4 * sizeof(double)));
+  h->cap = n;
+  return WBC_OK;
+}
+
+extern "C" int wbc_step_host(wbc_handle* h, int kind, int64_t n, const wbc_io* io) {
+  if (!h) return WBC_ERR_ARG;
+  if (!io || n < 0) return fail_arg(h, "wbc_step_host: bad arguments");
+  if (n == 0) return WBC_OK;
+  if (!io->q || !io->v || !io->traj || !io->contact || !io->tau || !io->metrics || !io->status)
+    return fail_arg(h, "wbc_step_host: q, v, traj, contact, tau, metrics and status are required");
+  WBC_CUDA(h, cudaSetDevice(h->device));
+  int rc = ensure_staging(h, n);
+  if (rc) return rc;
+  cudaStream_t st = h->stream;
+  WBC_CUDA(h, cudaMemcpyAsync(h->d_q, io->q, n * WBC_NQ * sizeof(double), cudaMemcpyHostToDevice, st));
+  WBC_CUDA(h, cudaMemcpyAsync(h->d_v, io->v, n * WBC_NV * sizeof(double), cudaMemcpyHostToDevice, st));
+  WBC_CUDA(h, cudaMemcpyAsync(h->d_traj, io->traj, n * WBC_NTRAJ * sizeof(double), cudaMemcpyHostToDevice, st));
+  WBC_CUDA(h, cudaMemcpyAsync(h->d_contact, io->contact, n * 4, cudaMemcpyHostToDevice, st));
+  wbc_io dio{h->d_q, h->d_v, h->d_traj, h->d_contact, h->d_tau, h->d_metrics, h->d_status,
+             io->vd ? h->d_vd : nullptr, io->f ? h->d_f : nullptr, io->qp_info ? h->d_info : nullptr};
+  rc = wbc_step(h, kind, n, &dio, st);
+  if (rc) return rc;
+  WBC_CUDA(h, cudaMemcpyAsync(io->tau, h->d_tau, n * WBC_NU * sizeof(double), cudaMemcpyDeviceToHost, st));
+  WBC_CUDA(h, cudaMemcpyAsync(io->metrics, h->d_metrics, n * WBC_NMETRIC * sizeof(double), cudaMemcpyDeviceToHost, st));
+  WBC_CUDA(h, cudaMemcpyAsync(io->status, h->d_status, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  if (io->vd) WBC_CUDA(h, cudaMemcpyAsync(io->vd, h->d_vd, n * WBC_NV * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (io->f) WBC_CUDA(h, cudaMemcpyAsync(io->f, h->d_f, n * 12 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (io->qp_info) WBC_CUDA(h, cudaMemcpyAsync(io->qp_info, h->d_info, n * 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  WBC_CUDA(h, cudaStreamSynchronize(st));
+  return WBC_OK;
+}
+
+extern "C" int wbc_dynamics_host(wbc_handle* h, int64_t n, const double* q, const double* v, double* M, double* Cv,
+                                 double* taug, double* Jfeet, double* Jdv, double* pfeet) {
+  if (!h) return WBC_ERR_ARG;
+  if (n <= 0) return n == 0 ? WBC_OK : fail_arg(h, "wbc_dynamics_host: n < 0");
+  WBC_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  double *dq, *dv, *dM = nullptr, *dCv = nullptr, *dtg = nullptr, *dJ = nullptr, *dJdv = nullptr, *dp = nullptr;
+  WBC_CUDA(h, cudaMalloc(&dq, n * WBC_NQ * 8)); WBC_CUDA(h, cudaMalloc(&dv, n * WBC_NV * 8));
+  if (M) WBC_CUDA(h, cudaMalloc(&dM, n * 324 * 8));
+  if (Cv) WBC_CUDA(h, cudaMalloc(&dCv, n * 18 * 8));
+  if (taug) WBC_CUDA(h, cudaMalloc(&dtg, n * 18 * 8));
+  if (Jfeet) WBC_CUDA(h, cudaMalloc(&dJ, n * 216 * 8));
+  if (Jdv) WBC_CUDA(h, cudaMalloc(&dJdv, n * 12 * 8));
+  if (pfeet) WBC_CUDA(h, cudaMalloc(&dp, n * 12 * 8));
+  WBC_CUDA(h, cudaMemcpyAsync(dq, q, n * WBC_NQ * 8, cudaMemcpyHostToDevice, st));
+  WBC_CUDA(h, cudaMemcpyAsync(dv, v, n * WBC_NV * 8, cudaMemcpyHostToDevice, st));
+  int rc = wbc_dynamics(h, n, dq, dv, dM, dCv, dtg, dJ, dJdv, dp, st);
+  if (rc == WBC_OK) {
+    if (M) WBC_CUDA(h, cudaMemcpyAsync(M, dM, n * 324 * 8, cudaMemcpyDeviceToHost, st));
+    if (Cv) WBC_CUDA(h, cudaMemcpyAsync(Cv, dCv, n * 18 * 8, cudaMemcpyDeviceToHost, st));
+    if (taug) WBC_CUDA(h, cudaMemcpyAsync(taug, dtg, n * 18 * 8, cudaMemcpyDeviceToHost, st));
+    if (Jfeet) WBC_CUDA(h, cudaMemcpyAsync(Jfeet, dJ, n * 216 * 8, cudaMemcpyDeviceToHost, st));
+    if (Jdv) WBC_CUDA(h, cudaMemcpyAsync(Jdv, dJdv, n * 12 * 8, cudaMemcpyDeviceToHost, st));
+    if (pfeet) WBC_CUDA(h, cudaMemcpyAsync(pfeet, dp, n * 12 * 8, cudaMemcpyDeviceToHost, st));
+    WBC_CUDA(h, cudaStreamSynchronize(st));
+  }
+  cudaFree(dq); cudaFree(dv); cudaFree(dM); cudaFree(dCv); cudaFree(dtg); cudaFree(dJ); cudaFree(dJdv); cudaFree(dp);
+  return rc;
+}
+
+extern "C" int wbc_time_step(wbc_handle* h, int kind, int64_t n, const wbc_io* io, int reps, void* stream,
+                             double* ms_per_launch) {
+  if (!h) return WBC_ERR_ARG;
+  if (!ms_per_launch || reps <= 0) return fail_arg(h, "wbc_time_step: bad arguments");
+  WBC_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaEvent_t e0, e1;
+  WBC_CUDA(h, cudaEventCreate(&e0));
+  WBC_CUDA(h, cudaEventCreate(&e1));
+  WBC_CUDA(h, cudaEventRecord(e0, st));
+  for (int r = 0; r < reps; ++r) {
+    int rc = wbc_step(h, kind, n, io, stream);
+    if (rc) { cudaEventDestroy(e0); cudaEventDestroy(e1); return rc; }
+  }
+  WBC_CUDA(h, cudaEventRecord(e1, st));
+  WBC_CUDA(h, cudaEventSynchronize(e1));
+  float ms = 0.f;
+  WBC_CUDA(h, cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  *ms_per_launch = (double)ms / reps;
+  return WBC_OK;
+}
+
+extern "C" void* wbc_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaMallocHost(&p, bytes) != cudaSuccess) return nullptr;
+  return p;
+}
+extern "C" void wbc_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+extern "C" int wbc_measure_fp64_peak(int device, double* tflops) {
+  if (!tflops) return WBC_ERR_ARG;
+  if (cudaSetDevice(device) != cudaSuccess) return WBC_ERR_CUDA;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return WBC_ERR_CUDA;
+  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 15;
+  double* out = nullptr;
+  if (cudaMalloc(&out, (size_t)blocks * threads * sizeof(double)) != cudaSuccess) return WBC_ERR_CUDA;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  fp64_peak_kernel<<<blocks, threads>>>(out, 1024);  // warm-up
+  double best = 0.0;
+  for (int rep = 0; rep < 5; ++rep) {
+    cudaEventRecord(e0);
+    fp64_peak_kernel<<<blocks, threads>>>(out, iters);
+    cudaEventRecord(e1);
+    if (cudaEventSynchronize(e1) != cudaSuccess) { cudaFree(out); return WBC_ERR_CUDA; }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double fl = 2.0 * 8.0 * (double)iters * blocks * threads;
+    const double tf = fl / (ms * 1e-3) / 1e12;
+    if (tf > best) best = tf;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(out);
+  *tflops = best;
+  return WBC_OK;
+}

@@ -1,0 +1,924 @@
+// wbc_device.cuh — per-warp whole-body controller step (sm_100a, FP64 on the CUDA cores).
+//
+// One warp owns one robot instance from load to store; nothing but the 860 B/step of
+// algorithmic I/O touches HBM. Phases:
+//   1. dynamics   composite spatial inertias about the base origin, world axes
+//                 (replaces basic_controller.py:101-115 CalcDynamics and :173-196 foot queries)
+//   2. equalities [A|b] of the tau-eliminated QP, one column per lane, in shared memory
+//   3. Gauss-Jordan with column pivoting -> z = z0 + Z w  (12 or 13 free variables)
+//   4. reduced rows Y = [a_b; f / swing-task; tau; extra] as affine maps of w
+//   5. reduced Hessian / gradient, Cholesky, J = L^-T
+//   6. Goldfarb-Idnani dual active set on w (exact optimum; replaces OsqpSolver().Solve,
+//      inverse_dynamics_controller.py:223)
+//   7. tau / metrics / status
+//
+// The file is plain CUDA C++ restricted to warp-synchronous primitives so that
+// tests/emu/ can compile it for the host with a lock-step warp emulator.
+#pragma once
+#include <stdint.h>
+#include <math.h>
+#include "wbc.h"
+
+#ifndef WBC_DEV
+#define WBC_DEV __device__ __forceinline__
+#endif
+#ifndef WBC_FULL
+#define WBC_FULL 0xffffffffu
+#endif
+
+namespace wbc {
+
+constexpr int NF = 13;      // reduced dimension (12 free variables for ID/PC, 13 for CLF; padded to 13)
+constexpr int YS = 14;      // row stride of Y: 13 coefficients + constant
+constexpr int YROWS = 32;   // 0-5 a_b | 6-17 leg rows (f of a stance leg / task accel of a swing leg) | 18-29 tau | 30,31 extra
+constexpr int AR = 18;      // max equality rows
+constexpr int AC = 32;      // columns of [A|b]: lane c owns column c, lane 31 the right-hand side
+
+struct StepArgs {
+  const double* q; const double* v; const double* traj; const uint8_t* contact;
+  double* tau; double* metrics; int32_t* status; double* vd; double* f; double* qp_info;
+  long long n; int kind;
+};
+
+// Per-warp shared memory. Everything a step needs between load and store lives here.
+struct WarpSmem {
+  // ---- inputs
+  double q[WBC_NQ], v[WBC_NV], traj[WBC_NTRAJ];
+  // ---- dynamics block (internal joint order k = 3*leg + j)
+  double Mb[18][6];      // Mb[c][r] = M[r][c] for r < 6 (base rows of the mass matrix, column major)
+  double Mleg[4][6];     // per-leg 3x3 block, upper triangle (0,0)(0,1)(0,2)(1,1)(1,2)(2,2)
+  double hb[6], hj[12];  // bias: C v + tau_g (controller sign)
+  double rho[4][3];      // foot position relative to the base origin, world axes
+  double L[4][3][3];     // leg block of the foot Jacobian: L[leg][row][joint]
+  double Jdv[4][3], vf[4][3];
+  double task[16];       // 0-5 desired base accel [omega_dot; p_ddot], 6.. scratch
+  // ---- equality system and its reduction
+  double A[AR][AC];
+  int rowof[AC];         // pivot row of variable c, -1 if free
+  int pc[AR];
+  // ---- reduced problem
+  double Y[YROWS][YS];
+  double cw[YROWS], ct[YROWS];   // cost weight / target of each Y row: 1/2 cw (y - ct)^2
+  double glin[NF];               // extra linear cost term on w
+  double H[NF][NF];              // reduced Hessian -> Cholesky factor (lower)
+  double g[NF];
+  // ---- Goldfarb-Idnani state
+  double J[NF][NF], R[NF][NF];
+  double d[NF], z[NF], r[NF], x[NF], u[NF], npv[NF], y[YROWS];
+  int act[NF];
+  int fcol[NF];          // free (non-pivot) columns of A in increasing order
+};
+
+// ------------------------------------------------------------------ small vector helpers
+struct V3 { double x, y, z; };
+WBC_DEV V3 mk(double x, double y, double z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
+WBC_DEV V3 operator+(V3 a, V3 b) { return mk(a.x + b.x, a.y + b.y, a.z + b.z); }
+WBC_DEV V3 operator-(V3 a, V3 b) { return mk(a.x - b.x, a.y - b.y, a.z - b.z); }
+WBC_DEV V3 operator*(double s, V3 a) { return mk(s * a.x, s * a.y, s * a.z); }
+WBC_DEV V3 cross(V3 a, V3 b) { return mk(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+WBC_DEV double dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+WBC_DEV double comp(V3 a, int i) { return i == 0 ? a.x : (i == 1 ? a.y : a.z); }
+struct M3 { V3 c0, c1, c2; };  // columns
+WBC_DEV V3 mul(const M3& R, V3 a) { return a.x * R.c0 + a.y * R.c1 + a.z * R.c2; }
+struct S6 { double xx, yy, zz, xy, xz, yz; };  // symmetric 3x3
+WBC_DEV V3 mul(const S6& I, V3 a) {
+  return mk(I.xx * a.x + I.xy * a.y + I.xz * a.z, I.xy * a.x + I.yy * a.y + I.yz * a.z, I.xz * a.x + I.yz * a.y + I.zz * a.z);
+}
+WBC_DEV V3 ld3(const double* p) { return mk(p[0], p[1], p[2]); }
+
+template <typename T> WBC_DEV T shfl(T v, int src) { return __shfl_sync(WBC_FULL, v, src); }
+WBC_DEV double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(WBC_FULL, v, o);
+  return v;
+}
+WBC_DEV double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(WBC_FULL, v, o));
+  return v;
+}
+// argmin with index; ties -> lowest index
+WBC_DEV void warp_argmin(double& v, int& idx) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    double ov = __shfl_xor_sync(WBC_FULL, v, o);
+    int oi = __shfl_xor_sync(WBC_FULL, idx, o);
+    if (ov < v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+  }
+}
+
+// Spatial inertia about the base origin P, world axes: mass, first moment h = m c, rotational part.
+struct SpI { double m; V3 h; S6 I; };
+// World-frame spatial inertia of a link with body-frame CoM `com`, inertia about CoM `Ic`,
+// pose (R, rho) relative to P.
+WBC_DEV SpI link_inertia(double m, V3 com, const double* ic, const M3& R, V3 rho) {
+  SpI s; s.m = m;
+  V3 c = rho + mul(R, com);
+  s.h = m * c;
+  // R Ic R^T
+  S6 Ic; Ic.xx = ic[0]; Ic.yy = ic[1]; Ic.zz = ic[2]; Ic.xy = ic[3]; Ic.xz = ic[4]; Ic.yz = ic[5];
+  // T = R * Ic (columns of T = R * columns of Ic)
+  V3 t0 = mul(R, mk(Ic.xx, Ic.xy, Ic.xz)), t1 = mul(R, mk(Ic.xy, Ic.yy, Ic.yz)), t2 = mul(R, mk(Ic.xz, Ic.yz, Ic.zz));
+  // (T R^T)_{ab} = sum_k T_{ak} R_{bk};  R_{bk} = component b of column k
+  auto e = [&](int a, int b) {
+    return comp(t0, a) * comp(R.c0, b) + comp(t1, a) * comp(R.c1, b) + comp(t2, a) * comp(R.c2, b);
+  };
+  double cc = dot(c, c);
+  s.I.xx = e(0, 0) + m * (cc - c.x * c.x); s.I.yy = e(1, 1) + m * (cc - c.y * c.y); s.I.zz = e(2, 2) + m * (cc - c.z * c.z);
+  s.I.xy = e(0, 1) - m * c.x * c.y; s.I.xz = e(0, 2) - m * c.x * c.z; s.I.yz = e(1, 2) - m * c.y * c.z;
+  return s;
+}
+// momentum-like product I * [w; u] -> (n, f)
+WBC_DEV void spi_mul(const SpI& s, V3 w, V3 u, V3& n, V3& f) {
+  n = mul(s.I, w) + cross(s.h, u);
+  f = s.m * u - cross(s.h, w);
+}
+WBC_DEV SpI spi_add(const SpI& a, const SpI& b) {
+  SpI s; s.m = a.m + b.m; s.h = a.h + b.h;
+  s.I.xx = a.I.xx + b.I.xx; s.I.yy = a.I.yy + b.I.yy; s.I.zz = a.I.zz + b.I.zz;
+  s.I.xy = a.I.xy + b.I.xy; s.I.xz = a.I.xz + b.I.xz; s.I.yz = a.I.yz + b.I.yz;
+  return s;
+}
+#define WBC_SPI_SHFL(OP, s, arg, W)                                                                          \
+  {                                                                                                          \
+    SpI t_;                                                                                                  \
+    t_.m = OP(WBC_FULL, s.m, arg, W); t_.h.x = OP(WBC_FULL, s.h.x, arg, W); t_.h.y = OP(WBC_FULL, s.h.y, arg, W); \
+    t_.h.z = OP(WBC_FULL, s.h.z, arg, W); t_.I.xx = OP(WBC_FULL, s.I.xx, arg, W); t_.I.yy = OP(WBC_FULL, s.I.yy, arg, W); \
+    t_.I.zz = OP(WBC_FULL, s.I.zz, arg, W); t_.I.xy = OP(WBC_FULL, s.I.xy, arg, W); t_.I.xz = OP(WBC_FULL, s.I.xz, arg, W); \
+    t_.I.yz = OP(WBC_FULL, s.I.yz, arg, W); tmp_spi = t_;                                                    \
+  }
+#define WBC_V3_SHFL(OP, a, arg, W) mk(OP(WBC_FULL, (a).x, arg, W), OP(WBC_FULL, (a).y, arg, W), OP(WBC_FULL, (a).z, arg, W))
+
+WBC_DEV int sym3(int i, int j) {  // upper-triangle index of a 3x3 symmetric block, i <= j
+  return i == 0 ? j : (i == 1 ? 2 + j : 5);
+}
+
+// Output selector for the dynamics parity entry.
+struct DynOut { double* M; double* Cv; double* taug; double* Jfeet; double* Jdv; double* pfeet; };
+
+// ------------------------------------------------------------------------------ phase 1
+// Fills the dynamics block of `s` for the state in s.q / s.v. GRAV: fold gravity into the bias
+// (hb/hj = Cv + tau_g) as the step kernels need; otherwise hb/hj = Cv only and, if taug != nullptr,
+// the controller-sign gravity term is written there (internal order, 18 doubles in shared memory).
+template <bool GRAV>
+WBC_DEV void dynamics_phase(WarpSmem& s, const wbc_model& md, int lane, int& status, double* taug_sm) {
+  const int leg = lane >> 3, j = lane & 7;
+  const bool link = j < 3;
+  const int jl = link ? j : 2;
+  // base rotation from the (normalised) quaternion
+  double qw = s.q[0], qx = s.q[1], qy = s.q[2], qz = s.q[3];
+  double nn = qw * qw + qx * qx + qy * qy + qz * qz;
+  if (!(nn > 1e-300) || !(nn < 1e300)) { status |= WBC_ST_BADQUAT; nn = 1.0; qw = 1.0; qx = qy = qz = 0.0; }
+  double inv = 1.0 / sqrt(nn);
+  qw *= inv; qx *= inv; qy *= inv; qz *= inv;
+  M3 R0;
+  R0.c0 = mk(1 - 2 * (qy * qy + qz * qz), 2 * (qx * qy + qw * qz), 2 * (qx * qz - qw * qy));
+  R0.c1 = mk(2 * (qx * qy - qw * qz), 1 - 2 * (qx * qx + qz * qz), 2 * (qy * qz + qw * qx));
+  R0.c2 = mk(2 * (qx * qz + qw * qy), 2 * (qy * qz - qw * qx), 1 - 2 * (qx * qx + qy * qy));
+  const V3 wb = ld3(&s.v[0]), vb = ld3(&s.v[3]);
+  const V3 grav = ld3(md.gravity);
+  V3 aw0 = mk(0, 0, 0);
+  V3 av0 = mk(0, 0, 0) - cross(wb, vb);
+  if (GRAV) av0 = av0 - grav;
+
+  // ---- leg chain (every lane of a leg group walks the whole chain; lane j keeps link j)
+  M3 R = R0; V3 rho = mk(0, 0, 0);
+  V3 vw = wb, vv = vb, aw = aw0, av = av0;
+  V3 ax[3], org[3];
+  M3 Rm = R0; V3 rhom = rho, vwm = vw, vvm = vv, awm = aw, avm = av;
+#pragma unroll
+  for (int jj = 0; jj < 3; ++jj) {
+    const int k = 3 * leg + jj;
+    rho = rho + mul(R, ld3(md.joint_xyz[k]));
+    const V3 la = ld3(md.joint_axis[k]);
+    const V3 a = mul(R, la);
+    const int vi = md.v_index[k];
+    const double th = s.q[vi + 1], thd = s.v[vi];
+    double sn, cs; sincos(th, &sn, &cs);
+    // R <- R * Rot(la, th):  Rot e_m = cs e_m + sn (la x e_m) + (1-cs) la (la . e_m)
+    const double oc = 1.0 - cs;
+    V3 r0 = mk(cs + oc * la.x * la.x, sn * la.z + oc * la.y * la.x, -sn * la.y + oc * la.z * la.x);
+    V3 r1 = mk(-sn * la.z + oc * la.x * la.y, cs + oc * la.y * la.y, sn * la.x + oc * la.z * la.y);
+    V3 r2 = mk(sn * la.y + oc * la.x * la.z, -sn * la.x + oc * la.y * la.z, cs + oc * la.z * la.z);
+    M3 Rn; Rn.c0 = mul(R, r0); Rn.c1 = mul(R, r1); Rn.c2 = mul(R, r2);
+    R = Rn;
+    const V3 b = cross(rho, a);            // S = [a; rho x a]
+    // acc += (vel x S) thd ; vel += S thd
+    aw = aw + thd * cross(vw, a);
+    av = av + thd * (cross(vw, b) + cross(vv, a));
+    vw = vw + thd * a; vv = vv + thd * b;
+    ax[jj] = a; org[jj] = rho;
+    if (jj == jl) { Rm = R; rhom = rho; vwm = vw; vvm = vv; awm = aw; avm = av; }
+  }
+  // ---- own link: spatial inertia about P and inertial force
+  const int bi = 1 + 3 * leg + jl;
+  SpI Il = link_inertia(md.mass[bi], ld3(md.com[bi]), md.inertia_com[bi], Rm, rhom);
+  V3 pn, pf, fn, ff;
+  spi_mul(Il, vwm, vvm, pn, pf);
+  spi_mul(Il, awm, avm, fn, ff);
+  fn = fn + cross(vwm, pn) + cross(vvm, pf);
+  ff = ff + cross(vwm, pf);
+  if (!link) {
+    Il.m = 0; Il.h = mk(0, 0, 0); Il.I.xx = Il.I.yy = Il.I.zz = Il.I.xy = Il.I.xz = Il.I.yz = 0;
+    fn = mk(0, 0, 0); ff = mk(0, 0, 0);
+  }
+  // composite over the sub-chain: lane j gets links j..2 (lanes 3..7 hold zeros)
+  SpI Ic = Il, tmp_spi;
+  V3 fcn = fn, fcf = ff;
+  WBC_SPI_SHFL(__shfl_down_sync, Il, 1, 8); Ic = spi_add(Ic, tmp_spi);
+  WBC_SPI_SHFL(__shfl_down_sync, Il, 2, 8); Ic = spi_add(Ic, tmp_spi);
+  fcn = fcn + WBC_V3_SHFL(__shfl_down_sync, fn, 1, 8) + WBC_V3_SHFL(__shfl_down_sync, fn, 2, 8);
+  fcf = fcf + WBC_V3_SHFL(__shfl_down_sync, ff, 1, 8) + WBC_V3_SHFL(__shfl_down_sync, ff, 2, 8);
+  // ---- mass-matrix columns of joint (leg, j)
+  const V3 a = ax[jl], b = cross(org[jl], ax[jl]);
+  V3 Fn, Ff;
+  spi_mul(Ic, a, b, Fn, Ff);
+  if (link) {
+    const int c = 6 + 3 * leg + j;
+    s.Mb[c][0] = Fn.x; s.Mb[c][1] = Fn.y; s.Mb[c][2] = Fn.z; s.Mb[c][3] = Ff.x; s.Mb[c][4] = Ff.y; s.Mb[c][5] = Ff.z;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+      if (i <= j) s.Mleg[leg][sym3(i, j)] = dot(ax[i], Fn) + dot(cross(org[i], ax[i]), Ff);
+    s.hj[3 * leg + j] = dot(a, fcn) + dot(b, fcf);
+    if (!GRAV && taug_sm) {
+      // controller-sign gravity term: -S . [h x g ; m g]
+      taug_sm[6 + 3 * leg + j] = -(dot(a, cross(Ic.h, grav)) + Ic.m * dot(b, grav));
+    }
+  }
+  // ---- totals: leg composites sit in lanes j == 0; butterfly over the four legs, then add the base body
+  SpI It = Ic; V3 ftn = fcn, ftf = fcf;
+  if (j != 0) { It.m = 0; It.h = mk(0, 0, 0); It.I.xx = It.I.yy = It.I.zz = It.I.xy = It.I.xz = It.I.yz = 0; ftn = mk(0, 0, 0); ftf = mk(0, 0, 0); }
+#pragma unroll
+  for (int o = 8; o <= 16; o <<= 1) {
+    SpI cur = It;
+    WBC_SPI_SHFL(__shfl_xor_sync, cur, o, 32); It = spi_add(It, tmp_spi);
+    V3 tn = WBC_V3_SHFL(__shfl_xor_sync, ftn, o, 32), tf = WBC_V3_SHFL(__shfl_xor_sync, ftf, o, 32);
+    ftn = ftn + tn; ftf = ftf + tf;
+  }
+  // broadcast from lane 0 (lanes with j != 0 hold partial garbage-free zeros + others)
+  {
+    SpI cur = It;
+    WBC_SPI_SHFL(__shfl_sync, cur, 0, 32); It = tmp_spi;
+    ftn = WBC_V3_SHFL(__shfl_sync, ftn, 0, 32); ftf = WBC_V3_SHFL(__shfl_sync, ftf, 0, 32);
+  }
+  {
+    SpI Ib = link_inertia(md.mass[0], ld3(md.com[0]), md.inertia_com[0], R0, mk(0, 0, 0));
+    V3 bn, bf, gn, gf;
+    spi_mul(Ib, wb, vb, bn, bf);
+    spi_mul(Ib, aw0, av0, gn, gf);
+    gn = gn + cross(wb, bn) + cross(vb, bf);
+    gf = gf + cross(wb, bf);
+    It = spi_add(It, Ib); ftn = ftn + gn; ftf = ftf + gf;
+  }
+  if (lane < 6) {
+    // column c of [[I, skew(h)], [-skew(h), m 1]]
+    const int c = lane;
+    double col[6];
+    if (c < 3) {
+      V3 e = mk(c == 0, c == 1, c == 2);
+      V3 top = mul(It.I, e), bot = mk(0, 0, 0) - cross(It.h, e);
+      col[0] = top.x; col[1] = top.y; col[2] = top.z; col[3] = bot.x; col[4] = bot.y; col[5] = bot.z;
+    } else {
+      V3 e = mk(c == 3, c == 4, c == 5);
+      V3 top = cross(It.h, e), bot = It.m * e;
+      col[0] = top.x; col[1] = top.y; col[2] = top.z; col[3] = bot.x; col[4] = bot.y; col[5] = bot.z;
+    }
+#pragma unroll
+    for (int r = 0; r < 6; ++r) s.Mb[c][r] = col[r];
+    s.hb[c] = c < 3 ? comp(ftn, c) : comp(ftf, c - 3);
+    if (!GRAV && taug_sm) {
+      V3 tg = cross(It.h, grav);
+      taug_sm[c] = c < 3 ? -comp(tg, c) : -It.m * comp(grav, c - 3);
+    }
+  }
+  // ---- foot point (shank = last link of the chain; every lane of the leg has it)
+  const V3 rf = rho + mul(R, ld3(md.foot_xyz[leg]));
+  const V3 vfoot = vv + cross(vw, rf);
+  V3 jdv = av + cross(aw, rf) + cross(vw, vfoot);
+  if (GRAV) jdv = jdv + grav;
+  if (link) {
+    const V3 Lc = cross(ax[j], rf - org[j]);
+    s.L[leg][0][j] = Lc.x; s.L[leg][1][j] = Lc.y; s.L[leg][2][j] = Lc.z;
+    s.rho[leg][j] = comp(rf, j);
+    s.Jdv[leg][j] = comp(jdv, j);
+    s.vf[leg][j] = comp(vfoot, j);
+  }
+  // base rotation for the task-space block: stash R0 in task[7..15]
+  if (lane == 0) {
+    s.task[7] = R0.c0.x; s.task[8] = R0.c0.y; s.task[9] = R0.c0.z;
+    s.task[10] = R0.c1.x; s.task[11] = R0.c1.y; s.task[12] = R0.c1.z;
+    s.task[13] = R0.c2.x; s.task[14] = R0.c2.y; s.task[15] = R0.c2.z;
+  }
+  __syncwarp();
+}
+
+// --------------------------------------------------------------------------- task space
+// RollPitchYaw(R) and the rate map N (inverse_dynamics_controller.py:163-166).
+struct BodyTask { double rpy[3], rpyd[3]; double N[3][3]; };
+WBC_DEV void body_task(const WarpSmem& s, int lane, int& status, BodyTask& t) {
+  const double r00 = s.task[7], r10 = s.task[8], r20 = s.task[9], r21 = s.task[12], r22 = s.task[15];
+  const double cp = sqrt(r00 * r00 + r10 * r10);
+  // spread the three atan2 over three lanes
+  const int m = lane % 3;
+  double num = m == 0 ? r21 : (m == 1 ? -r20 : r10);
+  double den = m == 0 ? r22 : (m == 1 ? cp : r00);
+  double ang = atan2(num, den);
+  t.rpy[0] = shfl(ang, 0); t.rpy[1] = shfl(ang, 1); t.rpy[2] = shfl(ang, 2);
+  double cy, sy;
+  if (cp < 1e-6) { status |= WBC_ST_GIMBAL; cy = 1.0; sy = 0.0; }
+  else { cy = r00 / cp; sy = r10 / cp; }
+  const double sp = -r20;
+  t.N[0][0] = cy * cp; t.N[0][1] = -sy; t.N[0][2] = 0.0;
+  t.N[1][0] = sy * cp; t.N[1][1] = cy;  t.N[1][2] = 0.0;
+  t.N[2][0] = -sp;     t.N[2][1] = 0.0; t.N[2][2] = 1.0;
+  // rpyd = N^-1 omega
+  const double wx = s.v[0], wy = s.v[1], wz = s.v[2];
+  const double icp = cp < 1e-6 ? 0.0 : 1.0 / cp;
+  t.rpyd[0] = (cy * wx + sy * wy) * icp;
+  t.rpyd[1] = -sy * wx + cy * wy;
+  t.rpyd[2] = wz + sp * t.rpyd[0];
+}
+
+// ------------------------------------------------------------------------------ phase 2+3
+// skew(r)[i][c] with skew(r) = [[0,-rz,ry],[rz,0,-rx],[-ry,rx,0]]
+WBC_DEV double skew_ent(V3 r, int i, int c) {
+  if (i == c) return 0.0;
+  const double m = comp(r, 3 - i - c);
+  return ((i + 1) % 3 == c) ? -m : m;
+}
+WBC_DEV int stance_slot(unsigned cmask, int k) {  // index of foot k among the stance feet, -1 if swing
+  return ((cmask >> k) & 1) ? __popc(cmask & ((1u << k) - 1)) : -1;
+}
+WBC_DEV int stance_foot(unsigned cmask, int slot) {  // foot index of the slot-th stance foot
+  int k = 0, cnt = 0;
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) { if ((cmask >> kk) & 1) { if (cnt == slot) k = kk; ++cnt; } }
+  return k;
+}
+
+// Column `lane` of the tau-eliminated equality system [A|b] (SURVEY Appendix C.1 with
+// tau = M_j vd + h_j - J_c,j' f substituted):
+//   rows 0-5          M_b vd - sum_c Jb_c' f_c = -h_b          (base rows of AddDynamicsConstraint)
+//   rows 6+3s..8+3s   J_c vd = -Jdv_c - Kd J_c v               (AddContactConstraint)
+// variables: 0-5 base accel, 6-17 joint accel, 18.. contact forces (3 per stance foot), then extras.
+WBC_DEV void build_equalities(WarpSmem& s, int lane, unsigned cmask, int nc, double kd) {
+  const int c = lane;
+#pragma unroll
+  for (int r = 0; r < AR; ++r) s.A[r][c] = 0.0;
+  if (c < 18) {
+#pragma unroll
+    for (int r = 0; r < 6; ++r) s.A[r][c] = s.Mb[c][r];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int sl = stance_slot(cmask, k);
+      if (sl < 0) continue;
+      const V3 rh = ld3(s.rho[k]);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        double val = 0.0;
+        if (c < 3) val = -skew_ent(rh, i, c);
+        else if (c < 6) val = (c - 3 == i) ? 1.0 : 0.0;
+        else if ((c - 6) / 3 == k) val = s.L[k][i][(c - 6) % 3];
+        s.A[6 + 3 * sl + i][c] = val;
+      }
+    }
+  } else if (c < 18 + 3 * nc) {
+    const int sl = (c - 18) / 3, i = (c - 18) % 3;
+    const V3 rh = ld3(s.rho[stance_foot(cmask, sl)]);
+    // -Jb' e_i = -[skew(rho)[:, i]; e_i]
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      s.A[r][c] = -skew_ent(rh, r, i);
+      s.A[3 + r][c] = r == i ? -1.0 : 0.0;
+    }
+  } else if (c == 31) {
+#pragma unroll
+    for (int r = 0; r < 6; ++r) s.A[r][c] = -s.hb[r];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int sl = stance_slot(cmask, k);
+      if (sl < 0) continue;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) s.A[6 + 3 * sl + i][c] = -s.Jdv[k][i] - kd * s.vf[k][i];
+    }
+  }
+  s.rowof[c] = -1;
+  __syncwarp();
+}
+
+// Gauss-Jordan, one pivot per row, pivot column = largest remaining entry of that row.
+// Returns the bit mask of pivot columns.
+WBC_DEV unsigned gauss_jordan(WarpSmem& s, int lane, int m, int n, int& status) {
+  unsigned used = 0;
+  for (int r = 0; r < m; ++r) {
+    const double arc0 = s.A[r][lane];
+    const double av = (lane < n) ? fabs(arc0) : -1.0;
+    const double scale = warp_max(av);
+    double cand = (lane < n && !((used >> lane) & 1)) ? -av : 1.0;  // argmin of -|a|
+    int idx = lane;
+    warp_argmin(cand, idx);
+    if (!(-cand > 1e-11 * fmax(1.0, scale))) {
+      status |= WBC_ST_RANKDEF;
+      if (lane == 0) s.pc[r] = -1;
+      continue;
+    }
+    const int pcol = idx;
+    const double piv = shfl(arc0, pcol);
+    const double arc = arc0 / piv;
+    s.A[r][lane] = (lane == pcol) ? 1.0 : arc;
+    if (lane != pcol) {
+      for (int i = 0; i < m; ++i) {
+        if (i == r) continue;
+        const double f = s.A[i][pcol];
+        s.A[i][lane] = fma(-f, arc, s.A[i][lane]);
+      }
+    }
+    __syncwarp();
+    if (lane == pcol) {
+      for (int i = 0; i < m; ++i) if (i != r) s.A[i][lane] = 0.0;
+      s.rowof[lane] = r;
+    }
+    if (lane == 0) s.pc[r] = pcol;
+    used |= 1u << pcol;
+    __syncwarp();
+  }
+  return used;
+}
+
+// Entry (var, column `lane`) of Z (free lanes) or of z0 (lane 31).
+WBC_DEV double zent(const WarpSmem& s, int lane, int var) {
+  const int r = s.rowof[var];
+  if (lane == 31) return r >= 0 ? s.A[r][31] : 0.0;
+  return r >= 0 ? -s.A[r][lane] : (var == lane ? 1.0 : 0.0);
+}
+
+// ------------------------------------------------------------------------------ phase 5
+WBC_DEV void tri_pair(int e, int& i, int& k) {  // e in [0,91): lower-triangle pair i >= k of a 13x13
+  int ii = 0;
+  while ((ii + 1) * (ii + 2) / 2 <= e) ++ii;
+  i = ii; k = e - ii * (ii + 1) / 2;
+}
+
+// H = sum_r cw_r Y_r' Y_r (+ identity on padded dims), g = sum_r cw_r Y_r (y0_r - ct_r) + glin
+WBC_DEV void reduced_hessian(WarpSmem& s, int lane, int nf, int nrows) {
+  for (int e = lane; e < NF * (NF + 1) / 2; e += 32) {
+    int i, k; tri_pair(e, i, k);
+    double acc = 0.0;
+    for (int r = 0; r < nrows; ++r) acc = fma(s.cw[r] * s.Y[r][i], s.Y[r][k], acc);
+    if (i >= nf) acc = (i == k) ? 1.0 : 0.0;
+    s.H[i][k] = acc;
+  }
+  if (lane < NF) {
+    double acc = (lane < nf) ? s.glin[lane] : 0.0;
+    for (int r = 0; r < nrows; ++r) acc = fma(s.cw[r] * s.Y[r][lane], s.Y[r][NF] - s.ct[r], acc);
+    s.g[lane] = (lane < nf) ? acc : 0.0;
+  }
+  __syncwarp();
+}
+
+// In-place Cholesky (lower) of s.H, then J = L^-T (J J' = H^-1) and the unconstrained minimiser x.
+WBC_DEV void factor_and_start(WarpSmem& s, int lane, int& status) {
+  for (int j = 0; j < NF; ++j) {
+    const double dj = s.H[j][j];
+    if (!(dj > 1e-300)) { status |= WBC_ST_NOTPD; }
+    const double inv = 1.0 / sqrt(dj > 1e-300 ? dj : 1.0);
+    __syncwarp();
+    if (lane < NF && lane >= j) s.H[lane][j] *= inv;
+    __syncwarp();
+    for (int e = lane; e < NF * (NF + 1) / 2; e += 32) {
+      int i, k; tri_pair(e, i, k);
+      if (k > j) s.H[i][k] = fma(-s.H[i][j], s.H[k][j], s.H[i][k]);
+    }
+    __syncwarp();
+  }
+  // column `lane` of X = L^-1 is row `lane` of J = X'
+  if (lane < NF) {
+    double xcol[NF];
+#pragma unroll
+    for (int i = 0; i < NF; ++i) {
+      double acc = (i == lane) ? 1.0 : 0.0;
+#pragma unroll
+      for (int mm = 0; mm < NF; ++mm)
+        if (mm < i) acc = fma(-s.H[i][mm], xcol[mm], acc);
+      xcol[i] = acc / s.H[i][i];
+    }
+#pragma unroll
+    for (int i = 0; i < NF; ++i) s.J[lane][i] = (i >= lane) ? xcol[i] : 0.0;
+  }
+  __syncwarp();
+  // x = -J J' g
+  if (lane < NF) {
+    double t = 0.0;
+    for (int i = 0; i < NF; ++i) t = fma(s.J[i][lane], s.g[i], t);
+    s.d[lane] = t;
+  }
+  __syncwarp();
+  if (lane < NF) {
+    double t = 0.0;
+    for (int k = 0; k < NF; ++k) t = fma(s.J[lane][k], s.d[k], t);
+    s.x[lane] = -t;
+  }
+  __syncwarp();
+}
+
+// ------------------------------------------------------------------------------ phase 6
+// Inequality i is  ca*y[ra] + cb*y[rb] <= bound  with y = Y w + y0.
+struct Ineq { int ra, rb; double ca, cb, bound; };
+struct IneqSet {
+  unsigned cmask; int nc; double mu; int nfric; int nextra; int ntl; const double* effort; const int* dummy;
+  double extra_bound[2];
+};
+WBC_DEV Ineq get_ineq(const IneqSet& S, int i) {
+  Ineq q; q.ra = q.rb = 0; q.ca = q.cb = 0.0; q.bound = 0.0;
+  if (i < S.nfric) {
+    // friction pyramid of the (i/4)-th stance foot (inverse_dynamics_controller.py:66-86)
+    int sl = i >> 2, t = i & 3, k = 0, cnt = 0;
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) { if ((S.cmask >> kk) & 1) { if (cnt == sl) k = kk; ++cnt; } }
+    q.ra = 6 + 3 * k + (t >> 1); q.ca = (t & 1) ? -1.0 : 1.0;
+    q.rb = 6 + 3 * k + 2; q.cb = -S.mu; q.bound = 0.0;
+  } else if (i < S.nfric + S.nextra) {
+    const int e = i - S.nfric;
+    q.ra = 30 + e; q.ca = 1.0; q.bound = S.extra_bound[e];
+  } else {
+    const int e = i - S.nfric - S.nextra;   // torque limits: +-tau_k <= effort_k
+    const int k = e % 12;
+    q.ra = 18 + k; q.ca = e < 12 ? 1.0 : -1.0; q.bound = S.effort[k];
+  }
+  return q;
+}
+
+// Goldfarb-Idnani dual active-set method on  min 1/2 w'Hw + g'w  s.t. the IneqSet.
+// On entry s.J, s.x hold L^-T and the unconstrained minimiser. Returns iterations; multipliers in s.u.
+WBC_DEV int gi_solve(WarpSmem& s, int lane, const IneqSet& S, int max_iter, int& status, int& q_out, double& minslack) {
+  const int mi = S.nfric + S.nextra + S.ntl;
+  int q = 0, iters = 0;
+  unsigned long long activemask = 0ull;
+  minslack = 0.0;
+  for (;;) {
+    // y = Y x + y0
+    {
+      double acc = s.Y[lane][NF];
+#pragma unroll
+      for (int k = 0; k < NF; ++k) acc = fma(s.Y[lane][k], s.x[k], acc);
+      s.y[lane] = acc;
+    }
+    __syncwarp();
+    double worst = 0.0; int widx = -1;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int i = lane + 32 * h;
+      if (i < mi && !((activemask >> i) & 1ull)) {
+        const Ineq c = get_ineq(S, i);
+        const double ta = c.ca * s.y[c.ra], tb = c.cb * s.y[c.rb];
+        const double sl = c.bound - ta - tb;
+        const double tol = 1e-10 * (1.0 + fabs(c.bound) + fabs(ta) + fabs(tb));
+        if (sl < -tol && sl < worst) { worst = sl; widx = i; }
+      }
+    }
+    int pidx = widx < 0 ? 1 << 20 : widx;
+    warp_argmin(worst, pidx);
+    minslack = worst;
+    if (!(worst < 0.0)) break;
+    const int p = pidx;
+    const Ineq cp = get_ineq(S, p);
+    if (lane < NF) s.npv[lane] = -(cp.ca * s.Y[cp.ra][lane] + cp.cb * s.Y[cp.rb][lane]);
+    double up = 0.0;
+    __syncwarp();
+    bool fail = false;
+    for (;;) {
+      if (++iters > max_iter) { status |= WBC_ST_MAXITER; fail = true; break; }
+      // d = J' n
+      if (lane < NF) {
+        double acc = 0.0;
+#pragma unroll
+        for (int i = 0; i < NF; ++i) acc = fma(s.J[i][lane], s.npv[i], acc);
+        s.d[lane] = acc;
+      }
+      __syncwarp();
+      // z = J[:, q:] d[q:],  zn = |d[q:]|^2,  dd = |d|^2,  sp = slack of p
+      double zi = 0.0;
+      if (lane < NF) {
+        for (int k = q; k < NF; ++k) zi = fma(s.J[lane][k], s.d[k], zi);
+        s.z[lane] = zi;
+      }
+      const double dl = lane < NF ? s.d[lane] : 0.0;
+      const double zn = warp_sum(lane >= q ? dl * dl : 0.0);
+      const double dd = warp_sum(dl * dl);
+      const double sp = cp.bound - cp.ca * s.y[cp.ra] - cp.cb * s.y[cp.rb];  // s.y is kept current below
+      // r = R^-1 d[:q]  (back substitution; lane k owns r_k)
+      double rk = dl;
+      for (int jj = q - 1; jj >= 0; --jj) {
+        const double rj = shfl(rk, jj) / s.R[jj][jj];
+        if (lane == jj) rk = rj;
+        else if (lane < jj) rk = fma(-s.R[lane][jj], rj, rk);
+      }
+      // step lengths
+      double t1 = (lane < q && rk > 0.0) ? s.u[lane] / rk : INFINITY;
+      int l = lane;
+      warp_argmin(t1, l);
+      const double t2 = (zn > 1e-14 * fmax(dd, 1e-300)) ? -sp / zn : INFINITY;
+      const double t = fmin(t1, t2);
+      if (!(t < INFINITY)) { status |= WBC_ST_INFEASIBLE; fail = true; break; }
+      const bool dual_only = !(t2 < INFINITY);
+      if (lane < q) s.u[lane] -= t * rk;
+      up += t;
+      if (!dual_only) {
+        if (lane < NF) s.x[lane] = fma(t, zi, s.x[lane]);
+        __syncwarp();
+        // refresh y (the slack of p and, later, of everyone)
+        double acc = s.Y[lane][NF];
+#pragma unroll
+        for (int k = 0; k < NF; ++k) acc = fma(s.Y[lane][k], s.x[k], acc);
+        __syncwarp();
+        s.y[lane] = acc;
+      }
+      __syncwarp();
+      if (!dual_only && t == t2) {
+        // ---- full step: add p. Householder on d[q:] -> (alpha, 0, ..), J[:, q:] <- J[:, q:] (I - 2 v v'/v'v)
+        const double nrm = sqrt(zn);
+        const double dq = s.d[q];
+        const double alpha = dq > 0.0 ? -nrm : nrm;
+        if (q < NF - 1) {
+          const double vv = 2.0 * (zn - dq * alpha);   // |v|^2 with v = d[q:] - alpha e_q
+          if (lane < NF && vv > 0.0) {
+            double dt = 0.0;
+            for (int k = q; k < NF; ++k) dt = fma(s.J[lane][k], (k == q ? dq - alpha : s.d[k]), dt);
+            const double sc = 2.0 * dt / vv;
+            for (int k = q; k < NF; ++k) s.J[lane][k] = fma(-sc, (k == q ? dq - alpha : s.d[k]), s.J[lane][k]);
+          }
+          if (lane < q) s.R[lane][q] = s.d[lane];
+          if (lane == q) s.R[q][q] = alpha;
+        } else {
+          if (lane < q) s.R[lane][q] = s.d[lane];
+          if (lane == q) s.R[q][q] = dq;
+        }
+        if (lane == q) { s.u[q] = up; s.act[q] = p; }
+        activemask |= 1ull << p;
+        ++q;
+        __syncwarp();
+        break;
+      }
+      // ---- drop the blocking constraint l (position in the active list)
+      {
+        const int dropped = s.act[l];
+        __syncwarp();
+        activemask &= ~(1ull << dropped);
+        // shift R columns, u, act left from l
+        if (lane < NF) {
+          for (int jj = l; jj < q - 1; ++jj) s.R[lane][jj] = s.R[lane][jj + 1];
+          s.R[lane][q - 1] = 0.0;
+        }
+        double un = 0.0; int an = 0;
+        if (lane >= l && lane < q - 1) { un = s.u[lane + 1]; an = s.act[lane + 1]; }
+        __syncwarp();
+        if (lane >= l && lane < q - 1) { s.u[lane] = un; s.act[lane] = an; }
+        __syncwarp();
+        // Givens rotations restoring the triangle; same rotations on the columns of J
+        for (int k = l; k < q - 1; ++k) {
+          const double a = s.R[k][k], b = s.R[k + 1][k];
+          const double rr = sqrt(a * a + b * b);
+          __syncwarp();
+          if (rr > 0.0) {
+            const double c = a / rr, sn = b / rr;
+            if (lane < NF) {
+              const double r0 = s.R[k][lane], r1 = s.R[k + 1][lane];
+              s.R[k][lane] = c * r0 + sn * r1; s.R[k + 1][lane] = -sn * r0 + c * r1;
+              const double j0 = s.J[lane][k], j1 = s.J[lane][k + 1];
+              s.J[lane][k] = c * j0 + sn * j1; s.J[lane][k + 1] = -sn * j0 + c * j1;
+            }
+          }
+          __syncwarp();
+        }
+        --q;
+      }
+    }
+    if (fail) break;
+  }
+  q_out = q;
+  return iters;
+}
+
+
+// ------------------------------------------------------------------------------ phase 4
+// Coefficients of the functional  sum_v rho_v z_v  in the reduced variables (free lanes) or its
+// value at z0 (lane 31) are accumulated by the caller with zent(); this stores one result.
+WBC_DEV void put_y(WarpSmem& s, int row, int ycol, double val) { if (ycol >= 0) s.Y[row][ycol] = val; }
+
+// Rows 0-29 of Y for all three controllers: a_b, per-leg rows (contact force of a stance leg,
+// task acceleration J_s vd of a swing leg), joint torques tau = M_j vd + h_j - L' f.
+WBC_DEV void build_common_rows(WarpSmem& s, int lane, int ycol, unsigned cmask) {
+  double zb[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) { zb[i] = zent(s, lane, i); put_y(s, i, ycol, zb[i]); }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int sl = stance_slot(cmask, k);
+    double zl[3], zf[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      zl[i] = zent(s, lane, 6 + 3 * k + i);
+      zf[i] = sl >= 0 ? zent(s, lane, 18 + 3 * sl + i) : 0.0;
+    }
+    const V3 rh = ld3(s.rho[k]);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      double val;
+      if (sl >= 0) val = zf[i];
+      else {
+        // row i of J_k = [-skew(rho) | 1 | L_k]
+        val = zb[3 + i];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) val = fma(-skew_ent(rh, i, c), zb[c], val);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) val = fma(s.L[k][i][c], zl[c], val);
+      }
+      put_y(s, 6 + 3 * k + i, ycol, val);
+    }
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const int kk = 3 * k + j;
+      double val = (lane == 31) ? s.hj[kk] : 0.0;
+#pragma unroll
+      for (int r = 0; r < 6; ++r) val = fma(s.Mb[6 + kk][r], zb[r], val);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) val = fma(s.Mleg[k][sym3(i < j ? i : j, i < j ? j : i)], zl[i], val);
+      if (sl >= 0) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) val = fma(-s.L[k][i][j], zf[i], val);
+      }
+      put_y(s, 18 + kk, ycol, val);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------ the step
+// One control step of instance `inst` (DoSetControlTorques -> ControlLaw,
+// basic_controller.py:286-320). KIND selects the cost / extra rows.
+template <int KIND>
+WBC_DEV void step_instance(WarpSmem& s, const wbc_model& md, const wbc_params& pr, const StepArgs& a,
+                           long long inst, int lane) {
+  int status = 0;
+  // ---- phase 0: coalesced loads into shared memory
+  for (int i = lane; i < WBC_NQ; i += 32) s.q[i] = a.q[inst * WBC_NQ + i];
+  for (int i = lane; i < WBC_NV; i += 32) s.v[i] = a.v[inst * WBC_NV + i];
+  for (int i = lane; i < WBC_NTRAJ; i += 32) s.traj[i] = a.traj[inst * WBC_NTRAJ + i];
+  unsigned cmask = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) cmask |= (a.contact[inst * 4 + k] ? 1u : 0u) << k;
+  const int nc = __popc(cmask);
+  __syncwarp();
+  // ---- phase 1
+  dynamics_phase<true>(s, md, lane, status, nullptr);
+  BodyTask bt;
+  body_task(s, lane, status, bt);
+  // ---- phases 2,3
+  const int ndelta = (KIND == WBC_CTRL_CLF) ? 1 : 0;
+  const int n = 18 + 3 * nc + ndelta, m = 6 + 3 * nc;
+  build_equalities(s, lane, cmask, nc, pr.contact_damping);
+  const unsigned used = gauss_jordan(s, lane, m, n, status);
+  const unsigned freemask = ~used & ((n >= 32) ? 0xffffffffu : ((1u << n) - 1u));
+  const int nf = __popc(freemask);
+  const bool isfree = (freemask >> lane) & 1u;
+  const int widx = __popc(freemask & ((1u << lane) - 1u));
+  const int ycol = lane == 31 ? NF : (isfree ? widx : -1);
+  bool ok = nf <= NF;
+  if (ok) {
+    if (isfree) s.fcol[widx] = lane;
+    // ---- phase 4
+    for (int e = lane; e < YROWS * YS; e += 32) (&s.Y[0][0])[e] = 0.0;
+    s.cw[lane] = 0.0; s.ct[lane] = 0.0;
+    if (lane < NF) s.glin[lane] = 0.0;
+    __syncwarp();
+    build_common_rows(s, lane, ycol, cmask);
+    // ---- costs
+    const double* tr = s.traj;
+    double err = 0.0;
+    if (KIND == WBC_CTRL_ID) {
+      // inverse_dynamics_controller.py:187-197 task-space PD
+      double rdd[3], add[3];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        rdd[i] = tr[15 + i] - pr.id_kp_body_rpy * (bt.rpy[i] - tr[9 + i]) - pr.id_kd_body_rpy * (bt.rpyd[i] - tr[12 + i]);
+        add[i] = tr[6 + i] - pr.id_kp_body_p * (s.q[4 + i] - tr[i]) - pr.id_kd_body_p * (s.v[3 + i] - tr[3 + i]);
+        err += (bt.rpy[i] - tr[9 + i]) * (bt.rpy[i] - tr[9 + i]) + (s.q[4 + i] - tr[i]) * (s.q[4 + i] - tr[i]);
+      }
+      if (lane < 3) { s.cw[lane] = pr.id_w_body; s.ct[lane] = bt.N[lane][0] * rdd[0] + bt.N[lane][1] * rdd[1] + bt.N[lane][2] * rdd[2]; }
+      else if (lane < 6) { s.cw[lane] = pr.id_w_body; s.ct[lane] = add[lane - 3]; }
+      else if (lane < 18) {
+        const int k = (lane - 6) / 3, i = (lane - 6) % 3;
+        if ((cmask >> k) & 1) { s.cw[lane] = pr.reg_f; s.ct[lane] = 0.0; }
+        else {
+          const double pfoot = s.q[4 + i] + s.rho[k][i];
+          const double as = tr[42 + 3 * k + i] - pr.id_kp_foot * (pfoot - tr[18 + 3 * k + i]) - pr.id_kd_foot * (s.vf[k][i] - tr[30 + 3 * k + i]);
+          s.cw[lane] = pr.id_w_foot; s.ct[lane] = as - s.Jdv[k][i];
+        }
+      } else if (lane < 30) { s.cw[lane] = pr.reg_tau; s.ct[lane] = 0.0; }
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (!((cmask >> k) & 1)) {
+#pragma unroll
+          for (int i = 0; i < 3; ++i) { const double e = s.q[4 + i] + s.rho[k][i] - tr[18 + 3 * k + i]; err += e * e; }
+        }
+    }
+    __syncwarp();
+    // ---- phase 5
+    reduced_hessian(s, lane, nf, 30);
+    factor_and_start(s, lane, status);
+    // ---- phase 6
+    IneqSet S;
+    S.cmask = cmask; S.nc = nc; S.mu = pr.mu; S.nfric = 4 * nc; S.nextra = 0; S.ntl = pr.torque_limits ? 24 : 0;
+    S.effort = md.effort; S.dummy = nullptr; S.extra_bound[0] = S.extra_bound[1] = 0.0;
+    int qact = 0; double minslack = 0.0;
+    int iters = 0;
+    if (!(status & WBC_ST_NOTPD)) iters = gi_solve(s, lane, S, pr.max_iter, status, qact, minslack);
+    // ---- phase 7: y = Y x + y0 is current in s.y
+    const double res = minslack < 0.0 ? -minslack : 0.0;
+    if (lane < 12) {
+      a.tau[inst * WBC_NU + md.act_index[lane]] = s.y[18 + lane];
+      if (a.f) a.f[inst * 12 + lane] = ((cmask >> (lane / 3)) & 1) ? s.y[6 + lane] : 0.0;
+    }
+    if (a.vd) {
+      if (lane < 18) {
+        const int r = s.rowof[lane];
+        double val;
+        if (r >= 0) {
+          val = s.A[r][31];
+          for (int w = 0; w < nf; ++w) val = fma(-s.A[r][s.fcol[w]], s.x[w], val);
+        } else val = s.x[widx];
+        const int dst = lane < 6 ? lane : md.v_index[lane - 6];
+        a.vd[inst * WBC_NV + dst] = val;
+      }
+    }
+    // reference objective 1/2 x'P0x + q0'x (constants dropped, E.5b): rows with a reference cost
+    double obj = 0.0;
+    if (lane < 18) {
+      const bool refrow = lane < 6 || !((cmask >> ((lane - 6) / 3)) & 1);
+      if (refrow) { const double yy = s.y[lane], t = s.ct[lane], w = s.cw[lane]; obj = 0.5 * w * yy * yy - w * t * yy; }
+    }
+    obj = warp_sum(obj);
+    if (lane == 0) {
+      double* mt = a.metrics + inst * WBC_NMETRIC;
+      mt[0] = 0.0; mt[1] = err; mt[2] = res; mt[3] = 0.0;
+      if (a.qp_info) { double* qi = a.qp_info + inst * 4; qi[0] = obj; qi[1] = res; qi[2] = 0.0; qi[3] = (double)iters; }
+    }
+  } else {
+    status |= WBC_ST_RANKDEF;
+    if (lane < 12) { a.tau[inst * WBC_NU + lane] = 0.0; if (a.f) a.f[inst * 12 + lane] = 0.0; }
+    if (a.vd && lane < 18) a.vd[inst * WBC_NV + lane] = 0.0;
+    if (lane < 4) a.metrics[inst * WBC_NMETRIC + lane] = 0.0;
+    if (a.qp_info && lane < 4) a.qp_info[inst * 4 + lane] = 0.0;
+  }
+  if (lane == 0) a.status[inst] = status;
+  __syncwarp();
+}
+
+// ---------------------------------------------------------------- dynamics parity entry
+// CalcDynamics + CalcFramePositionQuantities x4 for instance `inst`, written in Drake order.
+WBC_DEV void dynamics_instance(WarpSmem& s, const wbc_model& md, const double* q, const double* v, const DynOut& o,
+                               long long inst, int lane) {
+  int status = 0;
+  for (int i = lane; i < WBC_NQ; i += 32) s.q[i] = q[inst * WBC_NQ + i];
+  for (int i = lane; i < WBC_NV; i += 32) s.v[i] = v[inst * WBC_NV + i];
+  __syncwarp();
+  double* taug = &s.A[0][0];  // scratch: 18 doubles
+  dynamics_phase<false>(s, md, lane, status, taug);
+  // internal -> Drake index
+  auto didx = [&](int c) { return c < 6 ? c : md.v_index[c - 6]; };
+  if (o.M) {
+    double* M = o.M + inst * 324;
+    for (int e = lane; e < 324; e += 32) {
+      const int r = e / 18, c = e % 18;
+      double val;
+      if (r < 6) val = s.Mb[c][r];
+      else if (c < 6) val = s.Mb[r][c];
+      else if ((r - 6) / 3 == (c - 6) / 3) { const int i = (r - 6) % 3, j = (c - 6) % 3; val = s.Mleg[(r - 6) / 3][sym3(i < j ? i : j, i < j ? j : i)]; }
+      else val = 0.0;
+      M[didx(r) * 18 + didx(c)] = val;
+    }
+  }
+  if (lane < 18) {
+    const double cv = lane < 6 ? s.hb[lane] : s.hj[lane - 6];
+    if (o.Cv) o.Cv[inst * 18 + didx(lane)] = cv;
+    if (o.taug) o.taug[inst * 18 + didx(lane)] = taug[lane];
+  }
+  if (o.Jfeet) {
+    double* J = o.Jfeet + inst * 216;
+    for (int e = lane; e < 216; e += 32) {
+      const int k = e / 54, i = (e % 54) / 18, c = e % 18;
+      const V3 rh = ld3(s.rho[k]);
+      double val = 0.0;
+      if (c < 3) val = -skew_ent(rh, i, c);
+      else if (c < 6) val = (c - 3 == i) ? 1.0 : 0.0;
+      else if ((c - 6) / 3 == k) val = s.L[k][i][(c - 6) % 3];
+      J[k * 54 + i * 18 + didx(c)] = val;
+    }
+  }
+  if (lane < 12) {
+    if (o.Jdv) o.Jdv[inst * 12 + lane] = s.Jdv[lane / 3][lane % 3];
+    if (o.pfeet) o.pfeet[inst * 12 + lane] = s.q[4 + lane % 3] + s.rho[lane / 3][lane % 3];
+  }
+  __syncwarp();
+}
+
+}  // namespace wbc

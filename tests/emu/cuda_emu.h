@@ -1,0 +1,47 @@
+// Lock-step warp emulator: lets csrc/wbc_device.cuh be compiled for the host so the per-warp
+// algorithm can be debugged without a GPU. TEST INFRASTRUCTURE ONLY - never part of the product
+// library. Each lane is an OS thread; every warp collective is a pair of barriers.
+#pragma once
+#ifndef _GNU_SOURCE
+#define _GNU_SOURCE
+#endif
+#include <math.h>
+#include <pthread.h>
+#include <stdint.h>
+#include <string.h>
+
+struct EmuWarp {
+  pthread_barrier_t bar;
+  uint64_t slots[32];
+};
+extern thread_local int emu_lane;
+extern thread_local EmuWarp* emu_warp;
+
+static inline void emu_sync() { pthread_barrier_wait(&emu_warp->bar); }
+template <typename T> static inline T emu_exchange(T v, int src) {
+  static_assert(sizeof(T) <= 8, "shuffle payload");
+  uint64_t raw = 0;
+  memcpy(&raw, &v, sizeof(T));
+  emu_warp->slots[emu_lane] = raw;
+  emu_sync();
+  uint64_t got = emu_warp->slots[src & 31];
+  emu_sync();
+  T out;
+  memcpy(&out, &got, sizeof(T));
+  return out;
+}
+template <typename T> static inline T __shfl_sync(unsigned, T v, int src, int width = 32) {
+  const int base = emu_lane & ~(width - 1);
+  return emu_exchange(v, base | (src & (width - 1)));
+}
+template <typename T> static inline T __shfl_down_sync(unsigned, T v, int delta, int width = 32) {
+  const int pos = emu_lane & (width - 1);
+  return emu_exchange(v, pos + delta < width ? emu_lane + delta : emu_lane);
+}
+template <typename T> static inline T __shfl_xor_sync(unsigned, T v, int mask, int width = 32) {
+  (void)width;
+  return emu_exchange(v, emu_lane ^ mask);
+}
+static inline void __syncwarp(unsigned = 0xffffffffu) { emu_sync(); }
+static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+#define WBC_DEV static inline

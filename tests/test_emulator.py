@@ -1,0 +1,63 @@
+"""The exact device source (csrc/wbc_device.cuh) compiled for the host with the lock-step warp emulator
+(tests/emu) against the oracle. Exercises the kernel's algorithm on CPU; the product path never uses it."""
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import controllers as oc
+
+GOLD = Path(__file__).parent / "golden"
+
+
+@pytest.fixture(scope="module")
+def emu(built):
+    lib = C.CDLL(str(Path(__file__).parent / "emu" / "libwbc_emu.so"))
+    lib.emu_dynamics.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 8
+    lib.emu_step.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_void_p]
+    return lib
+
+
+def run_step(emu, robot, kind, g, **params):
+    from quadruped_drake_b200 import load_robot
+    from quadruped_drake_b200.capi import KINDS, WbcIO, make_params, np_ptr
+    ms, pr = load_robot(robot).as_struct(), make_params(**params)
+    q, v, traj, contact = (np.ascontiguousarray(g[k]) for k in ("q", "v", "traj", "contact"))
+    n = len(q)
+    tau, met, st = np.zeros((n, 12)), np.zeros((n, 4)), np.zeros(n, np.int32)
+    vd, f, qi = np.zeros((n, 18)), np.zeros((n, 4, 3)), np.zeros((n, 4))
+    io = WbcIO(np_ptr(q), np_ptr(v), np_ptr(traj), np_ptr(contact), np_ptr(tau), np_ptr(met), np_ptr(st), np_ptr(vd), np_ptr(f), np_ptr(qi))
+    assert emu.emu_step(C.byref(ms), C.byref(pr), KINDS[kind], n, C.byref(io)) == 0
+    return tau, met, st, vd, f, qi
+
+
+@pytest.mark.parametrize("case", ["cfg2_mini_cheetah_stand", "cfg3_anymal_trot", "mixed_mini_cheetah"])
+def test_emulated_dynamics_match_golden(emu, case):
+    from quadruped_drake_b200 import load_robot
+    from quadruped_drake_b200.capi import np_ptr
+    g = np.load(GOLD / f"{case}.npz")
+    robot = "anymal_b" if "anymal" in case else "mini_cheetah"
+    ms = load_robot(robot).as_struct()
+    q, v = np.ascontiguousarray(g["q"]), np.ascontiguousarray(g["v"])
+    n = len(q)
+    M, Cv, tg = np.zeros((n, 18, 18)), np.zeros((n, 18)), np.zeros((n, 18))
+    J, Jdv, pf = np.zeros((n, 4, 3, 18)), np.zeros((n, 4, 3)), np.zeros((n, 4, 3))
+    emu.emu_dynamics(C.byref(ms), n, np_ptr(q), np_ptr(v), np_ptr(M), np_ptr(Cv), np_ptr(tg), np_ptr(J), np_ptr(Jdv), np_ptr(pf))
+    for name, got in (("M", M), ("Cv", Cv), ("tau_g", tg), ("J_feet", J), ("Jdv_feet", Jdv), ("p_feet", pf)):
+        ref = g[name]
+        scale = np.abs(ref).reshape(n, -1).max(axis=1).reshape((n,) + (1,) * (ref.ndim - 1))
+        assert (np.abs(got - ref) / np.maximum(scale, 1e-3)).max() < 1e-9, name     # 1e-9 relative (north star)
+
+
+@pytest.mark.parametrize("case", ["cfg2_mini_cheetah_stand", "cfg3_anymal_trot", "cfg4_mini_cheetah_walk", "mixed_mini_cheetah"])
+def test_emulated_id_step_matches_golden(emu, case):
+    g = np.load(GOLD / f"{case}.npz")
+    robot = "anymal_b" if "anymal" in case else "mini_cheetah"
+    tau, met, st, vd, f, qi = run_step(emu, robot, "id", g)
+    assert (st == 0).all()
+    assert np.abs(tau - g["id_tau"]).max() < 1e-5          # north star: 1e-5 on QP torques
+    assert np.abs(vd - g["id_vd"]).max() < 1e-6
+    assert np.abs(f - g["id_f"]).max() < 1e-5
+    assert np.abs(qi[:, 0] - g["id_objective"]).max() < 1e-6 * max(1.0, np.abs(g["id_objective"]).max())
+    assert np.abs(met[:, 1] - g["id_metrics"][:, 1]).max() < 1e-12
