@@ -40,6 +40,8 @@ def kkt_residuals(P, q, A, b, G, h, x, nu, lam):
 
 def _solve_sym(K, rhs):
     """Solve K y = rhs for a (possibly singular) symmetric KKT matrix, refined in long double."""
+    if not (np.all(np.isfinite(K)) and np.all(np.isfinite(rhs))):
+        raise np.linalg.LinAlgError("non-finite KKT system")
     try:
         y = np.linalg.solve(K, rhs)
         if not np.all(np.isfinite(y)):
@@ -57,52 +59,70 @@ def _solve_sym(K, rhs):
 
 
 def _ipm(P, q, A, b, G, h, max_iter=60, tol=1e-10):
+    """Mehrotra predictor-corrector. Keeps the best iterate seen (smallest residual + gap) so that pushing the
+    tolerance to round-off level can never return a worse or non-finite point."""
     n, me, mi = P.shape[0], A.shape[0], G.shape[0]
     x, nu = np.zeros(n), np.zeros(me)
     s, lam = np.ones(mi), np.ones(mi)
     if mi:
         s = np.maximum(h - G @ x, 1.0)
+    best, best_score = (x, nu, s, lam), np.inf
     it = 0
-    for it in range(1, max_iter + 1):
-        rd = P @ x + q + (A.T @ nu if me else 0) + (G.T @ lam if mi else 0)
-        re = A @ x - b if me else np.zeros(0)
-        ri = G @ x + s - h if mi else np.zeros(0)
-        mu = float(lam @ s) / mi if mi else 0.0
-        if max(np.abs(rd).max(), np.abs(re).max() if me else 0, np.abs(ri).max() if mi else 0) < tol and mu < tol:
-            break
-        d = lam / s if mi else np.zeros(0)
-        H = P + (G.T * d) @ G if mi else P
-        K = np.block([[H, A.T], [A, np.zeros((me, me))]]) if me else H
+    with np.errstate(all="ignore"):
+        for it in range(1, max_iter + 1):
+            rd = P @ x + q + (A.T @ nu if me else 0) + (G.T @ lam if mi else 0)
+            re = A @ x - b if me else np.zeros(0)
+            ri = G @ x + s - h if mi else np.zeros(0)
+            mu = float(lam @ s) / mi if mi else 0.0
+            score = max(np.abs(rd).max(), np.abs(re).max() if me else 0, np.abs(ri).max() if mi else 0, mu)
+            if not np.isfinite(score):
+                break
+            if score < best_score:
+                best, best_score = (x, nu, s, lam), score
+            if score < tol:
+                break
+            d = lam / s if mi else np.zeros(0)
+            H = P + (G.T * d) @ G if mi else P
+            K = np.block([[H, A.T], [A, np.zeros((me, me))]]) if me else H
+            if not np.all(np.isfinite(K)):
+                break
 
-        def step(rc):
-            # rc: complementarity residual target (lam*s + ... )
-            r1 = -rd + (G.T @ ((rc - lam * ri) / s) if mi else 0)  # eliminate ds, dlam
-            rhs = np.hstack([r1, -re]) if me else r1
-            sol = _solve_sym(K, rhs)
-            dx, dnu = sol[:n], sol[n:]
-            if mi:
-                ds = -ri - G @ dx
-                dlam = -(rc + lam * ds) / s
-            else:
-                ds, dlam = np.zeros(0), np.zeros(0)
-            return dx, dnu, ds, dlam
+            def step(rc):
+                r1 = -rd + (G.T @ ((rc - lam * ri) / s) if mi else 0)  # eliminate ds, dlam
+                rhs = np.hstack([r1, -re]) if me else r1
+                sol = _solve_sym(K, rhs)
+                dx, dnu = sol[:n], sol[n:]
+                if mi:
+                    ds = -ri - G @ dx
+                    dlam = -(rc + lam * ds) / s
+                else:
+                    ds, dlam = np.zeros(0), np.zeros(0)
+                return dx, dnu, ds, dlam
 
-        def maxstep(z, dz):
-            neg = dz < 0
-            return min(1.0, float((-z[neg] / dz[neg]).min())) if neg.any() else 1.0
+            def maxstep(z, dz):
+                neg = dz < 0
+                return min(1.0, float((-z[neg] / dz[neg]).min())) if neg.any() else 1.0
 
-        if mi:
-            dx, dnu, ds, dlam = step(lam * s)
-            a = min(maxstep(s, ds), maxstep(lam, dlam))
-            mu_aff = float((lam + a * dlam) @ (s + a * ds)) / mi
-            sigma = (mu_aff / mu) ** 3 if mu > 0 else 0.0
-            dx, dnu, ds, dlam = step(lam * s + ds * dlam - sigma * mu)
-            a = 0.99 * min(maxstep(s, ds), maxstep(lam, dlam))
-            a = min(a, 1.0)
-            x, nu, s, lam = x + a * dx, nu + a * dnu, s + a * ds, lam + a * dlam
-        else:
-            dx, dnu, _, _ = step(np.zeros(0))
-            x, nu = x + dx, nu + dnu
+            try:
+                if mi:
+                    dx, dnu, ds, dlam = step(lam * s)
+                    a = min(maxstep(s, ds), maxstep(lam, dlam))
+                    mu_aff = float((lam + a * dlam) @ (s + a * ds)) / mi
+                    sigma = (mu_aff / mu) ** 3 if mu > 0 else 0.0
+                    dx, dnu, ds, dlam = step(lam * s + ds * dlam - sigma * mu)
+                    a = min(0.99 * min(maxstep(s, ds), maxstep(lam, dlam)), 1.0)
+                    xn, nun, sn, lamn = x + a * dx, nu + a * dnu, s + a * ds, lam + a * dlam
+                else:
+                    dx, dnu, _, _ = step(np.zeros(0))
+                    xn, nun, sn, lamn = x + dx, nu + dnu, s, lam
+            except np.linalg.LinAlgError:
+                break
+            if not (np.all(np.isfinite(xn)) and np.all(np.isfinite(lamn)) and np.all(np.isfinite(sn))):
+                break
+            if mi and (sn.min() <= 0 or lamn.min() <= 0):
+                break
+            x, nu, s, lam = xn, nun, sn, lamn
+    x, nu, s, lam = best
     return x, nu, s, lam, it
 
 

@@ -1,0 +1,174 @@
+"""Parity tests proper: the CUDA path, called through the C ABI, against the oracle's golden vectors and,
+at the benchmark's full sizes, through size-independent properties (KKT conditions of the reference QP)."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+GOLD = Path(__file__).parent / "golden"
+CASES = ["cfg2_mini_cheetah_stand", "cfg3_anymal_trot", "cfg4_mini_cheetah_walk", "mixed_mini_cheetah"]
+
+
+def robot_of(case):
+    return "anymal_b" if "anymal" in case else "mini_cheetah"
+
+
+@pytest.fixture(scope="module")
+def ctl_cache(built):
+    from quadruped_drake_b200.controller import BatchedController
+    cache = {}
+
+    def get(robot, **params):
+        key = (robot, tuple(sorted(params.items())))
+        if key not in cache:
+            cache[key] = BatchedController(robot, device=0, **params)
+        return cache[key]
+    yield get
+    for c in cache.values():
+        c.close()
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_dynamics_match_golden(ctl_cache, case):
+    """M, Cv, tau_g, J, Jdot v, p within 1e-9 relative (BASELINE.json north star)."""
+    g = np.load(GOLD / f"{case}.npz")
+    d = ctl_cache(robot_of(case)).dynamics(g["q"], g["v"])
+    n = len(g["q"])
+    for name in ("M", "Cv", "tau_g", "J_feet", "Jdv_feet", "p_feet"):
+        ref, got = g[name], d[name]
+        scale = np.abs(ref).reshape(n, -1).max(axis=1).reshape((n,) + (1,) * (ref.ndim - 1))
+        assert (np.abs(got - ref) / np.maximum(scale, 1e-3)).max() < 1e-9, name
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_id_step_matches_golden(ctl_cache, case):
+    """tau within 1e-5 of the exact optimum of the reference QP (+ declared tie-break); vd, f, objective too."""
+    g = np.load(GOLD / f"{case}.npz")
+    out = ctl_cache(robot_of(case)).step("id", g["q"], g["v"], g["traj"], g["contact"], debug=True)
+    assert (out.status == 0).all()
+    assert np.abs(out.tau - g["id_tau"]).max() < 1e-5
+    assert np.abs(out.vd - g["id_vd"]).max() < 1e-6
+    assert np.abs(out.f - g["id_f"]).max() < 1e-5
+    assert np.abs(out.qp_info[:, 0] - g["id_objective"]).max() < 1e-6 * max(1.0, np.abs(g["id_objective"]).max())
+    assert np.abs(out.metrics[:, 1] - g["id_metrics"][:, 1]).max() < 1e-12
+
+
+def test_named_wrapper_and_torch_device_path(ctl_cache):
+    """wbc_step_id on device pointers (torch only carries the memory and the stream) equals the host entry."""
+    import ctypes as C
+    import torch
+    g = np.load(GOLD / "mixed_mini_cheetah.npz")
+    ctl = ctl_cache("mini_cheetah")
+    host = ctl.step("id", g["q"], g["v"], g["traj"], g["contact"])
+    dev = torch.device("cuda:0")
+    tq, tv, tt = (torch.from_numpy(np.ascontiguousarray(g[k])).to(dev) for k in ("q", "v", "traj"))
+    tc = torch.from_numpy(np.ascontiguousarray(g["contact"])).to(dev)
+    out = ctl.step("id", tq, tv, tt, tc)
+    torch.cuda.synchronize()
+    assert np.array_equal(out.tau.cpu().numpy(), host.tau)            # bit-identical: same kernel, same inputs
+    n = len(g["q"])
+    tau = torch.empty((n, 12), dtype=torch.float64, device=dev)
+    met = torch.empty((n, 4), dtype=torch.float64, device=dev)
+    st = torch.empty((n,), dtype=torch.int32, device=dev)
+    p = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+    rc = ctl.lib.wbc_step_id(ctl._h, n, p(tq), p(tv), p(tt), p(tc), p(tau), p(met), p(st), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    assert rc == 0 and np.array_equal(tau.cpu().numpy(), host.tau)
+
+
+def kkt_properties(ctl, q, v, traj, contact, out, mu=0.7, kd=100.0):
+    """Residuals of the *reference* constraints evaluated with the GPU's own dynamics."""
+    d = ctl.dynamics(q, v)
+    B = ctl.model.actuation_matrix()
+    n = len(q)
+    c = contact.astype(bool)
+    f = out.f * c[:, :, None]
+    lhs = np.einsum("nij,nj->ni", d["M"], out.vd) + d["Cv"] + d["tau_g"]
+    rhs = out.tau @ B.T + np.einsum("nkij,nki->nj", d["J_feet"], f)
+    dyn = np.abs(lhs - rhs).max(axis=1)
+    acc = np.einsum("nkij,nj->nki", d["J_feet"], out.vd) + d["Jdv_feet"] + kd * np.einsum("nkij,nj->nki", d["J_feet"], v)
+    con = np.abs(acc * c[:, :, None]).reshape(n, -1).max(axis=1)
+    fr = np.maximum(np.abs(f[:, :, 0]) - mu * f[:, :, 2], np.abs(f[:, :, 1]) - mu * f[:, :, 2]).max(axis=1)
+    return dyn, con, fr
+
+
+@pytest.mark.parametrize("robot,pattern,n,seed", [("mini_cheetah", "stand", 4096, 20260119), ("anymal_b", "trot", 16384, 20260120),
+                                                   ("mini_cheetah", "mixed", 8192, 5)])
+def test_full_size_properties(ctl_cache, robot, pattern, n, seed):
+    """BASELINE configs 2 and 3 at full size: every instance solves, and the solution satisfies the reference's
+    dynamics / contact / friction constraints to 1e-7 (absolute, on O(1..100) quantities)."""
+    from quadruped_drake_b200.synth import generate
+    ctl = ctl_cache(robot)
+    q, v, traj, contact = generate(ctl.model, n, seed, pattern, ctl.fk)
+    out = ctl.step("id", q, v, traj, contact, debug=True)
+    assert (out.status == 0).all(), np.unique(out.status, return_counts=True)
+    dyn, con, fr = kkt_properties(ctl, q, v, traj, contact, out)
+    assert dyn.max() < 1e-7 and con.max() < 1e-7 and fr.max() < 1e-7
+    # determinism / idempotence: same inputs, same bits
+    again = ctl.step("id", q, v, traj, contact)
+    assert np.array_equal(again.tau, out.tau)
+    # swing feet carry no force, flight instances have tau = M_j vd + h_j only
+    assert np.all(out.f[contact == 0] == 0)
+
+
+def test_instance_independence_and_ragged_sizes(ctl_cache):
+    """Results do not depend on batch size or position in the batch (N = 1, 3, 5, 127 incl. partial CTAs)."""
+    from quadruped_drake_b200.synth import generate
+    ctl = ctl_cache("mini_cheetah")
+    q, v, traj, contact = generate(ctl.model, 127, 77, "mixed", ctl.fk)
+    full = ctl.step("id", q, v, traj, contact).tau
+    for n in (1, 3, 5):
+        assert np.array_equal(ctl.step("id", q[:n], v[:n], traj[:n], contact[:n]).tau, full[:n])
+    perm = np.random.default_rng(0).permutation(127)
+    assert np.array_equal(ctl.step("id", q[perm], v[perm], traj[perm], contact[perm]).tau, full[perm])
+    empty = ctl.step("id", q[:0], v[:0], traj[:0], contact[:0])
+    assert empty.tau.shape == (0, 12)
+
+
+def test_status_flags(ctl_cache):
+    """Per-instance failure reporting instead of the reference's assert: bad quaternion, gimbal lock."""
+    from quadruped_drake_b200 import capi
+    from quadruped_drake_b200.synth import generate
+    ctl = ctl_cache("mini_cheetah")
+    q, v, traj, contact = generate(ctl.model, 8, 3, "stand", ctl.fk)
+    q[1, 0:4] = 0.0                                             # zero quaternion
+    q[2, 0:4] = [np.cos(np.pi / 4), 0.0, np.sin(np.pi / 4), 0.0]  # pitch = +90 deg
+    out = ctl.step("id", q, v, traj, contact)
+    assert out.status[1] & capi.ST_BADQUAT
+    assert out.status[2] & capi.ST_GIMBAL
+    assert (out.status[[0, 3, 4, 5, 6, 7]] == 0).all()
+    assert np.isfinite(out.tau[[0, 3, 4, 5, 6, 7]]).all()
+
+
+def test_torque_limits_option(ctl_cache):
+    """BASELINE config 3: optional |tau| <= URDF effort box (not in the reference QP)."""
+    from quadruped_drake_b200.synth import generate
+    ctl = ctl_cache("mini_cheetah", torque_limits=1)
+    free = ctl_cache("mini_cheetah")
+    q, v, traj, contact = generate(ctl.model, 2048, 21, "walk", ctl.fk)
+    lim = ctl.model.effort[np.argsort(ctl.model.act_index)]
+    a, b = ctl.step("id", q, v, traj, contact), free.step("id", q, v, traj, contact)
+    okay = a.status == 0
+    assert okay.mean() > 0.9
+    assert (np.abs(a.tau[okay]) <= lim + 1e-7).all()
+    inside = okay & (np.abs(b.tau) < lim - 1e-3).all(axis=1)
+    assert inside.any() and np.abs(a.tau[inside] - b.tau[inside]).max() < 1e-6   # inactive box changes nothing
+
+
+def test_leafsystem_mirror_standing(built):
+    """Config 1: the reference port layout for one instance (simulate.py:106-139 wiring, SimpleStanding input)."""
+    from oracle import controllers as oc
+    from quadruped_drake_b200.controller import IDController
+    ctl = IDController("mini_cheetah", 5e-3)
+    assert [ctl.get_input_port(i).get_name() for i in (0, 1)] == ["quad_state", "trunk_input"]
+    assert [ctl.get_output_port(i).get_name() for i in (0, 1)] == ["quad_torques", "output_metrics"]
+    q0 = np.array([1, 0, 0, 0, 0, 0, 0.3] + [0, -0.8, 1.6] * 4, float)
+    ctx = ctl.CreateDefaultContext()
+    ctx.FixValue(0, np.hstack([q0, np.zeros(18)]))
+    ctx.FixValue(1, oc.standing_dict())
+    tau = ctl.EvalOutput(ctx, 0)
+    ref = oc.IDController("mini_cheetah").control_law(q0, np.zeros(18), oc.standing_dict())
+    assert np.abs(tau - ref.tau).max() < 1e-5
+    met = ctl.EvalOutput(ctx, 1)
+    assert abs(met[1] - ref.metrics[1]) < 1e-12
