@@ -177,8 +177,8 @@ def run_gpu(args):
     from quadruped_drake_b200.synth import generate
 
     ctl = BatchedController(ROBOT, device=local)
-    n = BATCH
-    q, v, traj, contact = generate(ctl.model, n, SEED + 1000 * rank, PATTERN, ctl.fk)   # each rank its own shard
+    n = args.batch
+    q, v, traj, contact = generate(ctl.model, n, SEED + 1000 * rank, args.pattern, ctl.fk)   # each rank its own shard
     tq, tv, tt = (torch.from_numpy(x).to(dev) for x in (q, v, traj))
     tc = torch.from_numpy(contact).to(dev)
     tau = torch.empty((n, 12), dtype=torch.float64, device=dev)
@@ -272,7 +272,7 @@ def run_gpu(args):
         "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": total_ms / args.steps, "p50_ms_per_step": float(np.median(per)), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "robot": ROBOT, "controller": "ID", "contact_pattern": PATTERN,
+        "config": {"workload": WORKLOAD, "robot": ROBOT, "controller": "ID", "contact_pattern": args.pattern,
                    "instances_per_step_per_gpu": n, "l2": "flushed between timed launches (256 MB memset outside the event pair)",
                    "mean_active_set_iterations": iters, "tie_break_reg_f": 1e-6},
         "e2e": {"value": world * n * args.steps / e2e_s, "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
@@ -286,8 +286,10 @@ def run_gpu(args):
                           "the kernel's null-space + active-set method executes far fewer (DESIGN.md)",
                           "peak_source": "DFMA loop measured in this run (wbc_measure_fp64_peak)"},
     }
-    if world == 1:
-        line["cpu_baseline"] = cpu_port_throughput(q, v, traj, contact)
+    if n != BATCH or args.pattern != PATTERN:
+        line["config"]["workload"] = f"EXPERIMENT (not the BASELINE config): {ROBOT} ID-QP, {n} instances/launch, pattern {args.pattern}"
+    if world == 1 and not args.no_cpu:
+        line["cpu_baseline"] = cpu_port_throughput(q[:4096], v[:4096], traj[:4096], contact[:4096])
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -299,6 +301,9 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH, help="instances per launch per GPU (default: the BASELINE config, 4096)")
+    ap.add_argument("--pattern", default=PATTERN, choices=["stand", "trot", "walk", "mixed"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (experiments only)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -11,8 +11,11 @@
 namespace {
 
 constexpr int WARPS = 4;  // instances (warps) per CTA
+#ifndef WBC_MIN_CTAS
+#define WBC_MIN_CTAS 4
+#endif
 
-struct DevConst { wbc_model md; wbc_params pr; };
+struct DevConst { wbc_model md; wbc_params pr; wbc::Derived dv; };
 
 struct SmemLayout {
   DevConst dc;
@@ -30,13 +33,13 @@ __device__ __forceinline__ const DevConst& stage_consts(SmemLayout* sm, const De
 }
 
 template <int KIND>
-__global__ void __launch_bounds__(WARPS * 32) wbc_step_kernel(const DevConst* __restrict__ gdc, wbc::StepArgs a) {
+__global__ void __launch_bounds__(WARPS * 32, WBC_MIN_CTAS) wbc_step_kernel(const DevConst* __restrict__ gdc, wbc::StepArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SmemLayout* sm = reinterpret_cast<SmemLayout*>(smem_raw);
   const DevConst& dc = stage_consts(sm, gdc);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long inst = (long long)blockIdx.x * WARPS + warp;
-  if (inst < a.n) wbc::step_instance<KIND>(sm->w[warp], dc.md, dc.pr, a, inst, lane);
+  if (inst < a.n) wbc::step_instance<KIND>(sm->w[warp], dc.md, dc.pr, dc.dv, a, inst, lane);
 }
 
 __global__ void __launch_bounds__(WARPS * 32) wbc_dynamics_kernel(const DevConst* __restrict__ gdc, const double* q,
@@ -134,6 +137,7 @@ extern "C" int wbc_create(const wbc_model* model, const wbc_params* params, int 
   if (e != cudaSuccess) { h->err = std::string("cudaSetDevice: ") + cudaGetErrorString(e); return bail(WBC_ERR_CUDA); }
   DevConst hc;
   hc.md = *model; hc.pr = h->params;
+  wbc::derive_constants(h->params, hc.dv);
   e = cudaMalloc(&h->d_const, sizeof(DevConst));
   if (e != cudaSuccess) { h->err = std::string("cudaMalloc: ") + cudaGetErrorString(e); return bail(WBC_ERR_CUDA); }
   e = cudaMemcpy(h->d_const, &hc, sizeof(DevConst), cudaMemcpyHostToDevice);
@@ -197,7 +201,7 @@ extern "C" int wbc_step(wbc_handle* h, int kind, int64_t n, const wbc_io* io, vo
   cudaStream_t st = (cudaStream_t)stream;
   switch (kind) {
     case WBC_CTRL_ID: wbc_step_kernel<WBC_CTRL_ID><<<grid, WARPS * 32, sm, st>>>(h->d_const, a); break;
-    case WBC_CTRL_CLF: return fail_arg(h, "wbc_step: CLF controller not implemented in this build");
+    case WBC_CTRL_CLF: wbc_step_kernel<WBC_CTRL_CLF><<<grid, WARPS * 32, sm, st>>>(h->d_const, a); break;
     case WBC_CTRL_PC: return fail_arg(h, "wbc_step: PC controller not implemented in this build");
     default: return fail_arg(h, "wbc_step: unknown controller kind");
   }

@@ -34,39 +34,76 @@ constexpr int YROWS = 32;   // 0-5 a_b | 6-17 leg rows (f of a stance leg / task
 constexpr int AR = 18;      // max equality rows
 constexpr int AC = 32;      // columns of [A|b]: lane c owns column c, lane 31 the right-hand side
 
+// Host-precomputed constants (wbc_create): per-channel CARE solution of the double integrator and the
+// decay rate gamma of clf_controller.py:170-188 (closed form).
+struct Derived {
+  double clf_p[3][3];     // channel type (0 rpy, 1 base position, 2 swing foot) x (p11, p12, p22)
+  double clf_gamma[2];    // [no swing foot, at least one swing foot]
+};
+
+// Host side (wbc_create and the test emulator).
+// Scalar double-integrator CARE (clf_controller.py:170-187 with block-diagonal Q, R = r I):
+// p12 = sqrt(qp r), p22 = sqrt(r (qd + 2 p12)), p11 = p12 p22 / r; gamma = lambda_min(Q) / lambda_max(P) (:188).
+inline void derive_constants(const wbc_params& p, wbc::Derived& d) {
+  const double qp[3] = {p.clf_q_body_rpy, p.clf_q_body_p, p.clf_q_foot_p};
+  const double qd[3] = {p.clf_q_body_rpyd, p.clf_q_body_pd, p.clf_q_foot_pd};
+  double lmax[3];
+  for (int t = 0; t < 3; ++t) {
+    const double r = p.clf_r;
+    const double p12 = sqrt(qp[t] * r), p22 = sqrt(r * (qd[t] + 2.0 * p12)), p11 = p12 * p22 / r;
+    d.clf_p[t][0] = p11; d.clf_p[t][1] = p12; d.clf_p[t][2] = p22;
+    lmax[t] = 0.5 * (p11 + p22) + sqrt(0.25 * (p11 - p22) * (p11 - p22) + p12 * p12);
+  }
+  auto mn = [](double a, double b) { return a < b ? a : b; };
+  auto mx = [](double a, double b) { return a > b ? a : b; };
+  const double qmin_body = mn(mn(qp[0], qd[0]), mn(qp[1], qd[1]));
+  const double qmin_all = mn(qmin_body, mn(qp[2], qd[2]));
+  d.clf_gamma[0] = qmin_body / mx(lmax[0], lmax[1]);
+  d.clf_gamma[1] = qmin_all / mx(mx(lmax[0], lmax[1]), lmax[2]);
+}
+
+
 struct StepArgs {
   const double* q; const double* v; const double* traj; const uint8_t* contact;
   double* tau; double* metrics; int32_t* status; double* vd; double* f; double* qp_info;
   long long n; int kind;
 };
 
-// Per-warp shared memory. Everything a step needs between load and store lives here.
+// Per-warp shared memory. Everything a step needs between load and store lives here (12.6 KB).
+// The inputs + dynamics block is dead once the reduced problem (Y, cw, ct) is built, so the reduced
+// Hessian / Goldfarb-Idnani workspace overlays it.
 struct WarpSmem {
-  // ---- inputs
-  double q[WBC_NQ], v[WBC_NV], traj[WBC_NTRAJ];
-  // ---- dynamics block (internal joint order k = 3*leg + j)
-  double Mb[18][6];      // Mb[c][r] = M[r][c] for r < 6 (base rows of the mass matrix, column major)
-  double Mleg[4][6];     // per-leg 3x3 block, upper triangle (0,0)(0,1)(0,2)(1,1)(1,2)(2,2)
-  double hb[6], hj[12];  // bias: C v + tau_g (controller sign)
-  double rho[4][3];      // foot position relative to the base origin, world axes
-  double L[4][3][3];     // leg block of the foot Jacobian: L[leg][row][joint]
-  double Jdv[4][3], vf[4][3];
-  double task[16];       // 0-5 desired base accel [omega_dot; p_ddot], 6.. scratch
+  union {
+    struct {
+      // ---- inputs
+      double q[WBC_NQ], v[WBC_NV], traj[WBC_NTRAJ];
+      // ---- dynamics block (internal joint order k = 3*leg + j)
+      double Mb[18][6];      // Mb[c][r] = M[r][c] for r < 6 (base rows of the mass matrix, column major)
+      double Mleg[4][6];     // per-leg 3x3 block, upper triangle (0,0)(0,1)(0,2)(1,1)(1,2)(2,2)
+      double hb[6], hj[12];  // bias: C v + tau_g (controller sign)
+      double rho[4][3];      // foot position relative to the base origin, world axes
+      double L[4][3][3];     // leg block of the foot Jacobian: L[leg][row][joint]
+      double Jdv[4][3], vf[4][3];
+      double task[16];       // 7-15: base rotation matrix (column major)
+    };
+    struct {
+      // ---- reduced Hessian -> Cholesky factor -> J = L^-T (in place), then Goldfarb-Idnani state
+      union { double H[NF][NF]; double J[NF][NF]; };
+      double g[NF];
+      double R[NF][NF];
+      double d[NF], r[NF], x[NF], u[NF], npv[NF], y[YROWS];
+      int act[NF];
+    };
+  };
   // ---- equality system and its reduction
   double A[AR][AC];
   int rowof[AC];         // pivot row of variable c, -1 if free
   int pc[AR];
+  int fcol[NF];          // free (non-pivot) columns of A in increasing order
   // ---- reduced problem
   double Y[YROWS][YS];
   double cw[YROWS], ct[YROWS];   // cost weight / target of each Y row: 1/2 cw (y - ct)^2
   double glin[NF];               // extra linear cost term on w
-  double H[NF][NF];              // reduced Hessian -> Cholesky factor (lower)
-  double g[NF];
-  // ---- Goldfarb-Idnani state
-  double J[NF][NF], R[NF][NF];
-  double d[NF], z[NF], r[NF], x[NF], u[NF], npv[NF], y[YROWS];
-  int act[NF];
-  int fcol[NF];          // free (non-pivot) columns of A in increasing order
 };
 
 // ------------------------------------------------------------------ small vector helpers
@@ -406,38 +443,46 @@ WBC_DEV void build_equalities(WarpSmem& s, int lane, unsigned cmask, int nc, dou
   __syncwarp();
 }
 
+// Max over the warp of a non-negative double, with the owning lane: the lane index rides in the 5 lowest
+// mantissa bits (IEEE order of non-negative doubles = integer order), so one 64-bit butterfly does both.
+WBC_DEV double warp_argmax_nonneg(double v, int lane, int& idx) {
+  unsigned long long key = ((unsigned long long)__double_as_longlong(v) & ~31ull) | (unsigned long long)(31 - lane);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long other = __shfl_xor_sync(WBC_FULL, key, o);
+    key = other > key ? other : key;
+  }
+  idx = 31 - (int)(key & 31ull);
+  return __longlong_as_double((long long)(key & ~31ull));
+}
+
 // Gauss-Jordan, one pivot per row, pivot column = largest remaining entry of that row.
-// Returns the bit mask of pivot columns.
+// Finished pivot columns are left stale (never read again). Returns the bit mask of pivot columns.
 WBC_DEV unsigned gauss_jordan(WarpSmem& s, int lane, int m, int n, int& status) {
   unsigned used = 0;
   for (int r = 0; r < m; ++r) {
     const double arc0 = s.A[r][lane];
-    const double av = (lane < n) ? fabs(arc0) : -1.0;
-    const double scale = warp_max(av);
-    double cand = (lane < n && !((used >> lane) & 1)) ? -av : 1.0;  // argmin of -|a|
-    int idx = lane;
-    warp_argmin(cand, idx);
-    if (!(-cand > 1e-11 * fmax(1.0, scale))) {
+    const bool eligible = lane < n && !((used >> lane) & 1);
+    int pcol;
+    const double best = warp_argmax_nonneg(eligible ? fabs(arc0) : 0.0, lane, pcol);
+    if (!(best > 1e-9)) {            // rows are O(0.01..10) (kg, kg m, lever arms): anything below is round-off
       status |= WBC_ST_RANKDEF;
       if (lane == 0) s.pc[r] = -1;
       continue;
     }
-    const int pcol = idx;
     const double piv = shfl(arc0, pcol);
     const double arc = arc0 / piv;
-    s.A[r][lane] = (lane == pcol) ? 1.0 : arc;
     if (lane != pcol) {
+      // row r itself is updated with factor A[r][pcol] = piv: arc0 - piv*arc = 0, so overwrite it afterwards
+#pragma unroll 6
       for (int i = 0; i < m; ++i) {
-        if (i == r) continue;
         const double f = s.A[i][pcol];
         s.A[i][lane] = fma(-f, arc, s.A[i][lane]);
       }
+      s.A[r][lane] = arc;
     }
     __syncwarp();
-    if (lane == pcol) {
-      for (int i = 0; i < m; ++i) if (i != r) s.A[i][lane] = 0.0;
-      s.rowof[lane] = r;
-    }
+    if (lane == pcol) s.rowof[lane] = r;
     if (lane == 0) s.pc[r] = pcol;
     used |= 1u << pcol;
     __syncwarp();
@@ -453,16 +498,28 @@ WBC_DEV double zent(const WarpSmem& s, int lane, int var) {
 }
 
 // ------------------------------------------------------------------------------ phase 5
-WBC_DEV void tri_pair(int e, int& i, int& k) {  // e in [0,91): lower-triangle pair i >= k of a 13x13
-  int ii = 0;
-  while ((ii + 1) * (ii + 2) / 2 <= e) ++ii;
-  i = ii; k = e - ii * (ii + 1) / 2;
+// Lower-triangle pairs (i >= k) of a 13x13 owned by a lane: entries e = lane, lane+32, lane+64 of the 91.
+struct TriPairs { int i[3], k[3]; };
+WBC_DEV TriPairs tri_pairs(int lane) {
+  TriPairs t;
+#pragma unroll
+  for (int h = 0; h < 3; ++h) {
+    const int e = lane + 32 * h;
+    int ii = 0;
+#pragma unroll
+    for (int c = 1; c < NF; ++c) ii += (c * (c + 1) / 2 <= e) ? 1 : 0;
+    t.i[h] = e < NF * (NF + 1) / 2 ? ii : -1;
+    t.k[h] = e - ii * (ii + 1) / 2;
+  }
+  return t;
 }
 
 // H = sum_r cw_r Y_r' Y_r (+ identity on padded dims), g = sum_r cw_r Y_r (y0_r - ct_r) + glin
-WBC_DEV void reduced_hessian(WarpSmem& s, int lane, int nf, int nrows) {
-  for (int e = lane; e < NF * (NF + 1) / 2; e += 32) {
-    int i, k; tri_pair(e, i, k);
+WBC_DEV void reduced_hessian(WarpSmem& s, int lane, int nf, int nrows, const TriPairs& tp) {
+#pragma unroll
+  for (int h = 0; h < 3; ++h) {
+    const int i = tp.i[h], k = tp.k[h];
+    if (i < 0) continue;
     double acc = 0.0;
     for (int r = 0; r < nrows; ++r) acc = fma(s.cw[r] * s.Y[r][i], s.Y[r][k], acc);
     if (i >= nf) acc = (i == k) ? 1.0 : 0.0;
@@ -477,7 +534,7 @@ WBC_DEV void reduced_hessian(WarpSmem& s, int lane, int nf, int nrows) {
 }
 
 // In-place Cholesky (lower) of s.H, then J = L^-T (J J' = H^-1) and the unconstrained minimiser x.
-WBC_DEV void factor_and_start(WarpSmem& s, int lane, int& status) {
+WBC_DEV void factor_and_start(WarpSmem& s, int lane, int& status, const TriPairs& tp) {
   for (int j = 0; j < NF; ++j) {
     const double dj = s.H[j][j];
     if (!(dj > 1e-300)) { status |= WBC_ST_NOTPD; }
@@ -485,9 +542,10 @@ WBC_DEV void factor_and_start(WarpSmem& s, int lane, int& status) {
     __syncwarp();
     if (lane < NF && lane >= j) s.H[lane][j] *= inv;
     __syncwarp();
-    for (int e = lane; e < NF * (NF + 1) / 2; e += 32) {
-      int i, k; tri_pair(e, i, k);
-      if (k > j) s.H[i][k] = fma(-s.H[i][j], s.H[k][j], s.H[i][k]);
+#pragma unroll
+    for (int h = 0; h < 3; ++h) {
+      const int i = tp.i[h], k = tp.k[h];
+      if (i >= 0 && k > j) s.H[i][k] = fma(-s.H[i][j], s.H[k][j], s.H[i][k]);
     }
     __syncwarp();
   }
@@ -502,8 +560,11 @@ WBC_DEV void factor_and_start(WarpSmem& s, int lane, int& status) {
         if (mm < i) acc = fma(-s.H[i][mm], xcol[mm], acc);
       xcol[i] = acc / s.H[i][i];
     }
+    __syncwarp();            // every lane is done reading L before J overwrites it
 #pragma unroll
     for (int i = 0; i < NF; ++i) s.J[lane][i] = (i >= lane) ? xcol[i] : 0.0;
+  } else {
+    __syncwarp();
   }
   __syncwarp();
   // x = -J J' g
@@ -555,15 +616,14 @@ WBC_DEV int gi_solve(WarpSmem& s, int lane, const IneqSet& S, int max_iter, int&
   int q = 0, iters = 0;
   unsigned long long activemask = 0ull;
   minslack = 0.0;
-  for (;;) {
-    // y = Y x + y0
-    {
-      double acc = s.Y[lane][NF];
+  {  // y = Y x + y0 (kept current after every primal step)
+    double acc = s.Y[lane][NF];
 #pragma unroll
-      for (int k = 0; k < NF; ++k) acc = fma(s.Y[lane][k], s.x[k], acc);
-      s.y[lane] = acc;
-    }
-    __syncwarp();
+    for (int k = 0; k < NF; ++k) acc = fma(s.Y[lane][k], s.x[k], acc);
+    s.y[lane] = acc;
+  }
+  __syncwarp();
+  for (;;) {
     double worst = 0.0; int widx = -1;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -586,6 +646,7 @@ WBC_DEV int gi_solve(WarpSmem& s, int lane, const IneqSet& S, int max_iter, int&
     double up = 0.0;
     __syncwarp();
     bool fail = false;
+    double dd = -1.0;   // |J'n|^2 = n'H^-1 n: invariant under the orthogonal column updates of J
     for (;;) {
       if (++iters > max_iter) { status |= WBC_ST_MAXITER; fail = true; break; }
       // d = J' n
@@ -600,16 +661,15 @@ WBC_DEV int gi_solve(WarpSmem& s, int lane, const IneqSet& S, int max_iter, int&
       double zi = 0.0;
       if (lane < NF) {
         for (int k = q; k < NF; ++k) zi = fma(s.J[lane][k], s.d[k], zi);
-        s.z[lane] = zi;
       }
       const double dl = lane < NF ? s.d[lane] : 0.0;
       const double zn = warp_sum(lane >= q ? dl * dl : 0.0);
-      const double dd = warp_sum(dl * dl);
+      if (dd < 0.0) dd = (q == 0) ? zn : warp_sum(dl * dl);
       const double sp = cp.bound - cp.ca * s.y[cp.ra] - cp.cb * s.y[cp.rb];  // s.y is kept current below
       // r = R^-1 d[:q]  (back substitution; lane k owns r_k)
       double rk = dl;
       for (int jj = q - 1; jj >= 0; --jj) {
-        const double rj = shfl(rk, jj) / s.R[jj][jj];
+        const double rj = shfl(rk, jj) * s.r[jj];          // s.r[jj] = 1 / R[jj][jj]
         if (lane == jj) rk = rj;
         else if (lane < jj) rk = fma(-s.R[lane][jj], rj, rk);
       }
@@ -648,10 +708,10 @@ WBC_DEV int gi_solve(WarpSmem& s, int lane, const IneqSet& S, int max_iter, int&
             for (int k = q; k < NF; ++k) s.J[lane][k] = fma(-sc, (k == q ? dq - alpha : s.d[k]), s.J[lane][k]);
           }
           if (lane < q) s.R[lane][q] = s.d[lane];
-          if (lane == q) s.R[q][q] = alpha;
+          if (lane == q) { s.R[q][q] = alpha; s.r[q] = 1.0 / alpha; }
         } else {
           if (lane < q) s.R[lane][q] = s.d[lane];
-          if (lane == q) s.R[q][q] = dq;
+          if (lane == q) { s.R[q][q] = dq; s.r[q] = 1.0 / dq; }
         }
         if (lane == q) { s.u[q] = up; s.act[q] = p; }
         activemask |= 1ull << p;
@@ -684,6 +744,7 @@ WBC_DEV int gi_solve(WarpSmem& s, int lane, const IneqSet& S, int max_iter, int&
             if (lane < NF) {
               const double r0 = s.R[k][lane], r1 = s.R[k + 1][lane];
               s.R[k][lane] = c * r0 + sn * r1; s.R[k + 1][lane] = -sn * r0 + c * r1;
+              if (lane == k) s.r[k] = 1.0 / (c * r0 + sn * r1);
               const double j0 = s.J[lane][k], j1 = s.J[lane][k + 1];
               s.J[lane][k] = c * j0 + sn * j1; s.J[lane][k + 1] = -sn * j0 + c * j1;
             }
@@ -756,7 +817,7 @@ WBC_DEV void build_common_rows(WarpSmem& s, int lane, int ycol, unsigned cmask) 
 // One control step of instance `inst` (DoSetControlTorques -> ControlLaw,
 // basic_controller.py:286-320). KIND selects the cost / extra rows.
 template <int KIND>
-WBC_DEV void step_instance(WarpSmem& s, const wbc_model& md, const wbc_params& pr, const StepArgs& a,
+WBC_DEV void step_instance(WarpSmem& s, const wbc_model& md, const wbc_params& pr, const Derived& dv, const StepArgs& a,
                            long long inst, int lane) {
   int status = 0;
   // ---- phase 0: coalesced loads into shared memory
@@ -794,6 +855,8 @@ WBC_DEV void step_instance(WarpSmem& s, const wbc_model& md, const wbc_params& p
     // ---- costs
     const double* tr = s.traj;
     double err = 0.0;
+    int nextra = 0;
+    double extra_bound = 0.0, Vl = 0.0, PFl = 0.0, csum = 0.0;
     if (KIND == WBC_CTRL_ID) {
       // inverse_dynamics_controller.py:187-197 task-space PD
       double rdd[3], add[3];
@@ -821,14 +884,64 @@ WBC_DEV void step_instance(WarpSmem& s, const wbc_model& md, const wbc_params& p
           for (int i = 0; i < 3; ++i) { const double e = s.q[4 + i] + s.rho[k][i] - tr[18 + 3 * k + i]; err += e * e; }
         }
     }
+    if (KIND == WBC_CTRL_CLF) {
+      // clf_controller.py:137-209. Lane r < 18 owns task row r (base rows 0-5, swing-foot rows 6-17).
+      double xt = 0.0, xdt = 0.0, xddn = 0.0, jdv = 0.0, kap = 0.0;
+      bool taskrow = false;
+      int type = 0;
+      if (lane < 3) {
+        taskrow = true; type = 0;
+        xt = bt.rpy[lane] - tr[9 + lane];
+        xdt = s.v[lane] - (bt.N[lane][0] * tr[12] + bt.N[lane][1] * tr[13] + bt.N[lane][2] * tr[14]);
+        xddn = bt.N[lane][0] * tr[15] + bt.N[lane][1] * tr[16] + bt.N[lane][2] * tr[17];
+      } else if (lane < 6) {
+        const int i = lane - 3;
+        taskrow = true; type = 1;
+        xt = s.q[4 + i] - tr[i]; xdt = s.v[3 + i] - tr[3 + i]; xddn = tr[6 + i];
+      } else if (lane < 18) {
+        const int k = (lane - 6) / 3, i = (lane - 6) % 3;
+        if (!((cmask >> k) & 1)) {
+          taskrow = true; type = 2;
+          xt = s.q[4 + i] + s.rho[k][i] - tr[18 + 3 * k + i]; xdt = s.vf[k][i] - tr[30 + 3 * k + i]; xddn = tr[42 + 3 * k + i];
+          jdv = s.Jdv[k][i];
+        } else { s.cw[lane] = pr.reg_f; s.ct[lane] = 0.0; }
+      } else if (lane < 30) { s.cw[lane] = pr.reg_tau; s.ct[lane] = 0.0; }
+      if (taskrow) {
+        const double p11 = dv.clf_p[type][0], p12 = dv.clf_p[type][1], p22 = dv.clf_p[type][2];
+        kap = p12 * xt + p22 * xdt;                      // (G' P eta)_r
+        // 1/2 (y + Jdv - xdd_des)^2 + 2 kap y  ==  1/2 (y - t)^2 + const,  t = xdd_des - Jdv - 2 kap
+        s.cw[lane] = 1.0;
+        s.ct[lane] = xddn - kap / pr.clf_r - jdv - 2.0 * kap;
+        Vl = p11 * xt * xt + 2.0 * p12 * xt * xdt + p22 * xdt * xdt;
+        PFl = (p11 * xt + p12 * xdt) * xdt;
+        csum = kap * (jdv - xddn);
+        err = xt * xt;
+      }
+      s.y[lane] = kap;                                   // scratch: kappa per task row (0 elsewhere)
+      Vl = warp_sum(Vl); PFl = warp_sum(PFl); csum = warp_sum(csum); err = warp_sum(err);
+      __syncwarp();
+      // extra rows: 30 = 2 kappa' J vd - delta  (Vdot constraint, :27-45), 31 = delta
+      const int cdel = 18 + 3 * nc;                      // delta's column: never a pivot (all-zero column of A)
+      if (ycol >= 0) {
+        double acc = 0.0;
+        for (int r = 0; r < 18; ++r) acc = fma(2.0 * s.y[r], s.Y[r][ycol], acc);
+        const double isdel = (lane == cdel) ? 1.0 : 0.0;
+        s.Y[30][ycol] = acc - isdel;
+        s.Y[31][ycol] = isdel;
+      }
+      if (lane == 31) { s.cw[31] = 2.0 * pr.clf_w_delta; s.ct[31] = 0.0; }   // AddCost(w delta'delta) -> Q = 2w
+      nextra = 1;
+      extra_bound = -dv.clf_gamma[nc < 4 ? 1 : 0] * Vl - 2.0 * PFl - 2.0 * csum;
+    }
     __syncwarp();
     // ---- phase 5
-    reduced_hessian(s, lane, nf, 30);
-    factor_and_start(s, lane, status);
+    const TriPairs tp = tri_pairs(lane);
+    reduced_hessian(s, lane, nf, KIND == WBC_CTRL_ID ? 30 : 32, tp);
+    factor_and_start(s, lane, status, tp);
     // ---- phase 6
     IneqSet S;
-    S.cmask = cmask; S.nc = nc; S.mu = pr.mu; S.nfric = 4 * nc; S.nextra = 0; S.ntl = pr.torque_limits ? 24 : 0;
-    S.effort = md.effort; S.dummy = nullptr; S.extra_bound[0] = S.extra_bound[1] = 0.0;
+    S.cmask = cmask; S.nc = nc; S.mu = pr.mu; S.nfric = 4 * nc; S.nextra = nextra; S.ntl = pr.torque_limits ? 24 : 0;
+    S.effort = md.effort; S.dummy = nullptr; S.extra_bound[0] = extra_bound; S.extra_bound[1] = 0.0;
     int qact = 0; double minslack = 0.0;
     int iters = 0;
     if (!(status & WBC_ST_NOTPD)) iters = gi_solve(s, lane, S, pr.max_iter, status, qact, minslack);
@@ -852,15 +965,21 @@ WBC_DEV void step_instance(WarpSmem& s, const wbc_model& md, const wbc_params& p
     }
     // reference objective 1/2 x'P0x + q0'x (constants dropped, E.5b): rows with a reference cost
     double obj = 0.0;
-    if (lane < 18) {
-      const bool refrow = lane < 6 || !((cmask >> ((lane - 6) / 3)) & 1);
+    {
+      const bool refrow = lane < 6 || (lane < 18 && !((cmask >> ((lane - 6) / 3)) & 1)) || (KIND == WBC_CTRL_CLF && lane == 31);
       if (refrow) { const double yy = s.y[lane], t = s.ct[lane], w = s.cw[lane]; obj = 0.5 * w * yy * yy - w * t * yy; }
     }
     obj = warp_sum(obj);
     if (lane == 0) {
       double* mt = a.metrics + inst * WBC_NMETRIC;
-      mt[0] = 0.0; mt[1] = err; mt[2] = res; mt[3] = 0.0;
-      if (a.qp_info) { double* qi = a.qp_info + inst * 4; qi[0] = obj; qi[1] = res; qi[2] = 0.0; qi[3] = (double)iters; }
+      double delta = 0.0;
+      if (KIND == WBC_CTRL_ID) { mt[0] = 0.0; mt[1] = err; mt[2] = res; mt[3] = 0.0; }
+      if (KIND == WBC_CTRL_CLF) {
+        // V, err, (res unused by the reference CLF), Vdot = 2 eta'PF eta + 2 eta'PG (J vd + Jdv - xdd_nom)  (:230-232)
+        delta = s.y[31];
+        mt[0] = Vl; mt[1] = err; mt[2] = res; mt[3] = 2.0 * PFl + s.y[30] + delta + 2.0 * csum;
+      }
+      if (a.qp_info) { double* qi = a.qp_info + inst * 4; qi[0] = obj; qi[1] = res; qi[2] = delta; qi[3] = (double)iters; }
     }
   } else {
     status |= WBC_ST_RANKDEF;

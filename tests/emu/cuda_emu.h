@@ -43,5 +43,7 @@ template <typename T> static inline T __shfl_xor_sync(unsigned, T v, int mask, i
   return emu_exchange(v, emu_lane ^ mask);
 }
 static inline void __syncwarp(unsigned = 0xffffffffu) { emu_sync(); }
+static inline long long __double_as_longlong(double v) { long long r; memcpy(&r, &v, 8); return r; }
+static inline double __longlong_as_double(long long v) { double r; memcpy(&r, &v, 8); return r; }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 #define WBC_DEV static inline

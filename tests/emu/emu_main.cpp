@@ -9,7 +9,7 @@ thread_local EmuWarp* emu_warp;
 
 namespace {
 struct Job {
-  EmuWarp* warp; int lane; wbc::WarpSmem* sm; const wbc_model* md; const wbc_params* pr;
+  EmuWarp* warp; int lane; wbc::WarpSmem* sm; const wbc_model* md; const wbc_params* pr; wbc::Derived dv;
   wbc::StepArgs args; wbc::DynOut dyn; const double* q; const double* v; long long n; int mode;
 };
 void* lane_main(void* p) {
@@ -18,7 +18,8 @@ void* lane_main(void* p) {
   emu_warp = j->warp;
   for (long long i = 0; i < j->n; ++i) {
     if (j->mode == 0) {
-      if (j->args.kind == WBC_CTRL_ID) wbc::step_instance<WBC_CTRL_ID>(*j->sm, *j->md, *j->pr, j->args, i, j->lane);
+      if (j->args.kind == WBC_CTRL_ID) wbc::step_instance<WBC_CTRL_ID>(*j->sm, *j->md, *j->pr, j->dv, j->args, i, j->lane);
+      if (j->args.kind == WBC_CTRL_CLF) wbc::step_instance<WBC_CTRL_CLF>(*j->sm, *j->md, *j->pr, j->dv, j->args, i, j->lane);
     } else {
       wbc::dynamics_instance(*j->sm, *j->md, j->q, j->v, j->dyn, i, j->lane);
     }
@@ -45,6 +46,7 @@ int run(Job proto) {
 
 extern "C" int emu_step(const wbc_model* md, const wbc_params* pr, int kind, long long n, const wbc_io* io) {
   Job j{};
+  wbc::derive_constants(*pr, j.dv);
   j.md = md; j.pr = pr; j.n = n; j.mode = 0;
   j.args.q = io->q; j.args.v = io->v; j.args.traj = io->traj; j.args.contact = io->contact;
   j.args.tau = io->tau; j.args.metrics = io->metrics; j.args.status = io->status;
