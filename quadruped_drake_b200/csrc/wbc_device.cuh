@@ -474,10 +474,12 @@ WBC_DEV unsigned gauss_jordan(WarpSmem& s, int lane, int m, int n, int& status) 
     const double arc = arc0 / piv;
     if (lane != pcol) {
       // row r itself is updated with factor A[r][pcol] = piv: arc0 - piv*arc = 0, so overwrite it afterwards
-#pragma unroll 6
-      for (int i = 0; i < m; ++i) {
-        const double f = s.A[i][pcol];
-        s.A[i][lane] = fma(-f, arc, s.A[i][lane]);
+#pragma unroll
+      for (int i = 0; i < AR; ++i) {
+        if (i < m) {
+          const double f = s.A[i][pcol];
+          s.A[i][lane] = fma(-f, arc, s.A[i][lane]);
+        }
       }
       s.A[r][lane] = arc;
     }
@@ -609,10 +611,29 @@ WBC_DEV Ineq get_ineq(const IneqSet& S, int i) {
   return q;
 }
 
+// Min over the warp of a non-negative double with a 6-bit payload (lowest mantissa bits), one butterfly.
+WBC_DEV double warp_argmin_nonneg(double v, int payload, int& out) {
+  unsigned long long key = ((unsigned long long)__double_as_longlong(v) & ~63ull) | (unsigned long long)payload;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long other = __shfl_xor_sync(WBC_FULL, key, o);
+    key = other < key ? other : key;
+  }
+  out = (int)(key & 63ull);
+  return __longlong_as_double((long long)(key & ~63ull));
+}
+
 // Goldfarb-Idnani dual active-set method on  min 1/2 w'Hw + g'w  s.t. the IneqSet.
 // On entry s.J, s.x hold L^-T and the unconstrained minimiser. Returns iterations; multipliers in s.u.
+// All loops over the reduced dimension are fixed-length and branch-free: lanes >= NF compute on a clamped
+// row (results discarded), entries left of the active count q are masked to zero instead of skipped.
 WBC_DEV int gi_solve(WarpSmem& s, int lane, const IneqSet& S, int max_iter, int& status, int& q_out, double& minslack) {
   const int mi = S.nfric + S.nextra + S.ntl;
+  const int li = lane < NF ? lane : NF - 1;     // clamped row for loads
+  const bool row = lane < NF;
+  // the (up to) two inequalities this lane watches, hoisted out of the loop
+  Ineq c0 = get_ineq(S, lane < mi ? lane : 0), c1 = get_ineq(S, lane + 32 < mi ? lane + 32 : 0);
+  const bool have0 = lane < mi, have1 = lane + 32 < mi;
   int q = 0, iters = 0;
   unsigned long long activemask = 0ull;
   minslack = 0.0;
@@ -624,59 +645,64 @@ WBC_DEV int gi_solve(WarpSmem& s, int lane, const IneqSet& S, int max_iter, int&
   }
   __syncwarp();
   for (;;) {
-    double worst = 0.0; int widx = -1;
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int i = lane + 32 * h;
-      if (i < mi && !((activemask >> i) & 1ull)) {
-        const Ineq c = get_ineq(S, i);
-        const double ta = c.ca * s.y[c.ra], tb = c.cb * s.y[c.rb];
-        const double sl = c.bound - ta - tb;
-        const double tol = 1e-10 * (1.0 + fabs(c.bound) + fabs(ta) + fabs(tb));
-        if (sl < -tol && sl < worst) { worst = sl; widx = i; }
-      }
+    // most violated inequality: largest (-slack) beyond tolerance
+    double viol = 0.0; int who = 0;
+    if (have0 && !((activemask >> lane) & 1ull)) {
+      const double ta = c0.ca * s.y[c0.ra], tb = c0.cb * s.y[c0.rb];
+      const double sl = c0.bound - ta - tb;
+      if (sl < -1e-10 * (1.0 + fabs(c0.bound) + fabs(ta) + fabs(tb))) { viol = -sl; who = lane; }
     }
-    int pidx = widx < 0 ? 1 << 20 : widx;
-    warp_argmin(worst, pidx);
-    minslack = worst;
-    if (!(worst < 0.0)) break;
-    const int p = pidx;
+    if (have1 && !((activemask >> (lane + 32)) & 1ull)) {
+      const double ta = c1.ca * s.y[c1.ra], tb = c1.cb * s.y[c1.rb];
+      const double sl = c1.bound - ta - tb;
+      if (sl < -1e-10 * (1.0 + fabs(c1.bound) + fabs(ta) + fabs(tb)) && -sl > viol) { viol = -sl; who = lane + 32; }
+    }
+    int p;
+    {  // arg-max of a non-negative double: complement trick on the min butterfly is not order preserving, so
+       // run a max butterfly with the payload in the low bits
+      unsigned long long key = ((unsigned long long)__double_as_longlong(viol) & ~63ull) | (unsigned long long)who;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(WBC_FULL, key, o);
+        key = other > key ? other : key;
+      }
+      p = (int)(key & 63ull);
+      viol = __longlong_as_double((long long)(key & ~63ull));
+    }
+    minslack = -viol;
+    if (!(viol > 0.0)) break;
     const Ineq cp = get_ineq(S, p);
-    if (lane < NF) s.npv[lane] = -(cp.ca * s.Y[cp.ra][lane] + cp.cb * s.Y[cp.rb][lane]);
+    if (row) s.npv[lane] = -(cp.ca * s.Y[cp.ra][lane] + cp.cb * s.Y[cp.rb][lane]);
     double up = 0.0;
     __syncwarp();
     bool fail = false;
     double dd = -1.0;   // |J'n|^2 = n'H^-1 n: invariant under the orthogonal column updates of J
     for (;;) {
       if (++iters > max_iter) { status |= WBC_ST_MAXITER; fail = true; break; }
-      // d = J' n
-      if (lane < NF) {
-        double acc = 0.0;
+      // d = J' n ; s.d keeps d, s.npv is untouched
+      double dl = 0.0;
 #pragma unroll
-        for (int i = 0; i < NF; ++i) acc = fma(s.J[i][lane], s.npv[i], acc);
-        s.d[lane] = acc;
-      }
-      __syncwarp();
-      // z = J[:, q:] d[q:],  zn = |d[q:]|^2,  dd = |d|^2,  sp = slack of p
-      double zi = 0.0;
-      if (lane < NF) {
-        for (int k = q; k < NF; ++k) zi = fma(s.J[lane][k], s.d[k], zi);
-      }
-      const double dl = lane < NF ? s.d[lane] : 0.0;
-      const double zn = warp_sum(lane >= q ? dl * dl : 0.0);
+      for (int i = 0; i < NF; ++i) dl = fma(s.J[i][li], s.npv[i], dl);
+      if (!row) dl = 0.0;
+      if (row) s.d[lane] = dl;
+      const double dm = lane >= q ? dl : 0.0;           // d masked to the free part
+      const double zn = warp_sum(dm * dm);
       if (dd < 0.0) dd = (q == 0) ? zn : warp_sum(dl * dl);
-      const double sp = cp.bound - cp.ca * s.y[cp.ra] - cp.cb * s.y[cp.rb];  // s.y is kept current below
+      __syncwarp();
+      // z = J[:, q:] d[q:]
+      double zi = 0.0;
+#pragma unroll
+      for (int k = 0; k < NF; ++k) zi = fma(s.J[li][k], (k >= q ? s.d[k] : 0.0), zi);
+      const double sp = cp.bound - cp.ca * s.y[cp.ra] - cp.cb * s.y[cp.rb];
       // r = R^-1 d[:q]  (back substitution; lane k owns r_k)
       double rk = dl;
       for (int jj = q - 1; jj >= 0; --jj) {
         const double rj = shfl(rk, jj) * s.r[jj];          // s.r[jj] = 1 / R[jj][jj]
-        if (lane == jj) rk = rj;
-        else if (lane < jj) rk = fma(-s.R[lane][jj], rj, rk);
+        rk = (lane == jj) ? rj : ((lane < jj) ? fma(-s.R[li][jj], rj, rk) : rk);
       }
       // step lengths
-      double t1 = (lane < q && rk > 0.0) ? s.u[lane] / rk : INFINITY;
-      int l = lane;
-      warp_argmin(t1, l);
+      int l;
+      const double t1 = warp_argmin_nonneg((lane < q && rk > 0.0) ? fmax(s.u[li] / rk, 0.0) : INFINITY, lane, l);
       const double t2 = (zn > 1e-14 * fmax(dd, 1e-300)) ? -sp / zn : INFINITY;
       const double t = fmin(t1, t2);
       if (!(t < INFINITY)) { status |= WBC_ST_INFEASIBLE; fail = true; break; }
@@ -684,36 +710,40 @@ WBC_DEV int gi_solve(WarpSmem& s, int lane, const IneqSet& S, int max_iter, int&
       if (lane < q) s.u[lane] -= t * rk;
       up += t;
       if (!dual_only) {
-        if (lane < NF) s.x[lane] = fma(t, zi, s.x[lane]);
+        if (row) s.x[lane] = fma(t, zi, s.x[lane]);
         __syncwarp();
-        // refresh y (the slack of p and, later, of everyone)
         double acc = s.Y[lane][NF];
 #pragma unroll
         for (int k = 0; k < NF; ++k) acc = fma(s.Y[lane][k], s.x[k], acc);
-        __syncwarp();
         s.y[lane] = acc;
       }
       __syncwarp();
-      if (!dual_only && t == t2) {
+      if (!dual_only && t2 <= t1) {
         // ---- full step: add p. Householder on d[q:] -> (alpha, 0, ..), J[:, q:] <- J[:, q:] (I - 2 v v'/v'v)
         const double nrm = sqrt(zn);
         const double dq = s.d[q];
         const double alpha = dq > 0.0 ? -nrm : nrm;
+        double rqq = dq;
         if (q < NF - 1) {
           const double vv = 2.0 * (zn - dq * alpha);   // |v|^2 with v = d[q:] - alpha e_q
-          if (lane < NF && vv > 0.0) {
+          if (vv > 0.0) {
+            double vk[NF];
             double dt = 0.0;
-            for (int k = q; k < NF; ++k) dt = fma(s.J[lane][k], (k == q ? dq - alpha : s.d[k]), dt);
+#pragma unroll
+            for (int k = 0; k < NF; ++k) {
+              vk[k] = k > q ? s.d[k] : (k == q ? dq - alpha : 0.0);
+              dt = fma(s.J[li][k], vk[k], dt);
+            }
             const double sc = 2.0 * dt / vv;
-            for (int k = q; k < NF; ++k) s.J[lane][k] = fma(-sc, (k == q ? dq - alpha : s.d[k]), s.J[lane][k]);
+            if (row) {
+#pragma unroll
+              for (int k = 0; k < NF; ++k) s.J[lane][k] = fma(-sc, vk[k], s.J[lane][k]);
+            }
           }
-          if (lane < q) s.R[lane][q] = s.d[lane];
-          if (lane == q) { s.R[q][q] = alpha; s.r[q] = 1.0 / alpha; }
-        } else {
-          if (lane < q) s.R[lane][q] = s.d[lane];
-          if (lane == q) { s.R[q][q] = dq; s.r[q] = 1.0 / dq; }
+          rqq = alpha;
         }
-        if (lane == q) { s.u[q] = up; s.act[q] = p; }
+        if (lane < q) s.R[lane][q] = dl;
+        if (lane == q) { s.R[q][q] = rqq; s.r[q] = 1.0 / rqq; s.u[q] = up; s.act[q] = p; }
         activemask |= 1ull << p;
         ++q;
         __syncwarp();
@@ -725,7 +755,7 @@ WBC_DEV int gi_solve(WarpSmem& s, int lane, const IneqSet& S, int max_iter, int&
         __syncwarp();
         activemask &= ~(1ull << dropped);
         // shift R columns, u, act left from l
-        if (lane < NF) {
+        if (row) {
           for (int jj = l; jj < q - 1; ++jj) s.R[lane][jj] = s.R[lane][jj + 1];
           s.R[lane][q - 1] = 0.0;
         }
@@ -741,7 +771,7 @@ WBC_DEV int gi_solve(WarpSmem& s, int lane, const IneqSet& S, int max_iter, int&
           __syncwarp();
           if (rr > 0.0) {
             const double c = a / rr, sn = b / rr;
-            if (lane < NF) {
+            if (row) {
               const double r0 = s.R[k][lane], r1 = s.R[k + 1][lane];
               s.R[k][lane] = c * r0 + sn * r1; s.R[k + 1][lane] = -sn * r0 + c * r1;
               if (lane == k) s.r[k] = 1.0 / (c * r0 + sn * r1);
@@ -759,7 +789,6 @@ WBC_DEV int gi_solve(WarpSmem& s, int lane, const IneqSet& S, int max_iter, int&
   q_out = q;
   return iters;
 }
-
 
 // ------------------------------------------------------------------------------ phase 4
 // Coefficients of the functional  sum_v rho_v z_v  in the reduced variables (free lanes) or its
