@@ -522,8 +522,13 @@ WBC_DEV void reduced_hessian(WarpSmem& s, int lane, int nf, int nrows, const Tri
   for (int h = 0; h < 3; ++h) {
     const int i = tp.i[h], k = tp.k[h];
     if (i < 0) continue;
-    double acc = 0.0;
-    for (int r = 0; r < nrows; ++r) acc = fma(s.cw[r] * s.Y[r][i], s.Y[r][k], acc);
+    double acc = 0.0, acc1 = 0.0;
+#pragma unroll 4
+    for (int r = 0; r < nrows; r += 2) {
+      acc = fma(s.cw[r] * s.Y[r][i], s.Y[r][k], acc);
+      acc1 = fma(s.cw[r + 1] * s.Y[r + 1][i], s.Y[r + 1][k], acc1);
+    }
+    acc += acc1;
     if (i >= nf) acc = (i == k) ? 1.0 : 0.0;
     s.H[i][k] = acc;
   }
@@ -680,19 +685,28 @@ WBC_DEV int gi_solve(WarpSmem& s, int lane, const IneqSet& S, int max_iter, int&
     for (;;) {
       if (++iters > max_iter) { status |= WBC_ST_MAXITER; fail = true; break; }
       // d = J' n ; s.d keeps d, s.npv is untouched
-      double dl = 0.0;
+      double dl = 0.0, dl1 = 0.0, dl2 = 0.0;
 #pragma unroll
-      for (int i = 0; i < NF; ++i) dl = fma(s.J[i][li], s.npv[i], dl);
-      if (!row) dl = 0.0;
+      for (int i = 0; i < NF; i += 3) {
+        dl = fma(s.J[i][li], s.npv[i], dl);
+        if (i + 1 < NF) dl1 = fma(s.J[i + 1][li], s.npv[i + 1], dl1);
+        if (i + 2 < NF) dl2 = fma(s.J[i + 2][li], s.npv[i + 2], dl2);
+      }
+      dl = row ? dl + (dl1 + dl2) : 0.0;
       if (row) s.d[lane] = dl;
       const double dm = lane >= q ? dl : 0.0;           // d masked to the free part
       const double zn = warp_sum(dm * dm);
       if (dd < 0.0) dd = (q == 0) ? zn : warp_sum(dl * dl);
       __syncwarp();
       // z = J[:, q:] d[q:]
-      double zi = 0.0;
+      double zi = 0.0, zi1 = 0.0, zi2 = 0.0;
 #pragma unroll
-      for (int k = 0; k < NF; ++k) zi = fma(s.J[li][k], (k >= q ? s.d[k] : 0.0), zi);
+      for (int k = 0; k < NF; k += 3) {
+        zi = fma(s.J[li][k], (k >= q ? s.d[k] : 0.0), zi);
+        if (k + 1 < NF) zi1 = fma(s.J[li][k + 1], (k + 1 >= q ? s.d[k + 1] : 0.0), zi1);
+        if (k + 2 < NF) zi2 = fma(s.J[li][k + 2], (k + 2 >= q ? s.d[k + 2] : 0.0), zi2);
+      }
+      zi += zi1 + zi2;
       const double sp = cp.bound - cp.ca * s.y[cp.ra] - cp.cb * s.y[cp.rb];
       // r = R^-1 d[:q]  (back substitution; lane k owns r_k)
       double rk = dl;
@@ -712,10 +726,14 @@ WBC_DEV int gi_solve(WarpSmem& s, int lane, const IneqSet& S, int max_iter, int&
       if (!dual_only) {
         if (row) s.x[lane] = fma(t, zi, s.x[lane]);
         __syncwarp();
-        double acc = s.Y[lane][NF];
+        double acc = s.Y[lane][NF], acc1 = 0.0, acc2 = 0.0;
 #pragma unroll
-        for (int k = 0; k < NF; ++k) acc = fma(s.Y[lane][k], s.x[k], acc);
-        s.y[lane] = acc;
+        for (int k = 0; k < NF; k += 3) {
+          acc = fma(s.Y[lane][k], s.x[k], acc);
+          if (k + 1 < NF) acc1 = fma(s.Y[lane][k + 1], s.x[k + 1], acc1);
+          if (k + 2 < NF) acc2 = fma(s.Y[lane][k + 2], s.x[k + 2], acc2);
+        }
+        s.y[lane] = acc + (acc1 + acc2);
       }
       __syncwarp();
       if (!dual_only && t2 <= t1) {
@@ -728,13 +746,13 @@ WBC_DEV int gi_solve(WarpSmem& s, int lane, const IneqSet& S, int max_iter, int&
           const double vv = 2.0 * (zn - dq * alpha);   // |v|^2 with v = d[q:] - alpha e_q
           if (vv > 0.0) {
             double vk[NF];
-            double dt = 0.0;
+            double dt = 0.0, dt1 = 0.0;
 #pragma unroll
             for (int k = 0; k < NF; ++k) {
               vk[k] = k > q ? s.d[k] : (k == q ? dq - alpha : 0.0);
-              dt = fma(s.J[li][k], vk[k], dt);
+              if (k & 1) dt1 = fma(s.J[li][k], vk[k], dt1); else dt = fma(s.J[li][k], vk[k], dt);
             }
-            const double sc = 2.0 * dt / vv;
+            const double sc = 2.0 * (dt + dt1) / vv;
             if (row) {
 #pragma unroll
               for (int k = 0; k < NF; ++k) s.J[lane][k] = fma(-sc, vk[k], s.J[lane][k]);
