@@ -126,20 +126,30 @@ def host_inputs(n, seed):
 
 
 def run_reference(args):
+    """Reference arm: the CPU restatement of the reference path (C twin of the oracle when built, else the numpy
+    oracle) on all host cores, same config / metric / unit; rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sys.path.insert(0, str(ROOT / "tests"))
-    from conftest import oracle_fk
-    from oracle.dynamics import Plant
+    import __graft_entry__ as g
+    g.build_oracle()
     from quadruped_drake_b200 import load_robot
     from quadruped_drake_b200.synth import generate
     model = load_robot(ROBOT)
-    n = 64 * (os.cpu_count() or 1)
-    q, v, traj, contact = generate(model, n, SEED, PATTERN, oracle_fk(Plant(ROBOT)))
+    cport = (ROOT / "oracle" / "_build" / "liboracle_c.so").exists()
+    if cport:
+        from oracle.cport import fk as cfk
+        n, fkc = BATCH, cfk(ROBOT)
+    else:
+        sys.path.insert(0, str(ROOT / "tests"))
+        from conftest import oracle_fk
+        from oracle.dynamics import Plant
+        n, fkc = 64 * (os.cpu_count() or 1), oracle_fk(Plant(ROBOT))
+    q, v, traj, contact = generate(model, n, SEED, PATTERN, fkc)
     vals = []
+    per_step = max(2.0, min(20.0, 120.0 / (args.warmup + args.steps)))
     for s in range(args.warmup + args.steps):
-        r = cpu_port_throughput(q, v, traj, contact, budget_s=max(2.0, 60.0 / (args.warmup + args.steps)))
+        r = cpu_port_throughput(q, v, traj, contact, budget_s=per_step)
         if s >= args.warmup:
             vals.append(r)
     val = float(np.mean([r["value"] for r in vals]))
@@ -148,8 +158,10 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "steps/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * BATCH / val, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "robot": ROBOT, "controller": "ID", "instances_per_step": BATCH,
-                       "note": "CPU restatement of the reference path (pydrake + OSQP are not installable here); each step is a bounded sample"},
+            "config": {"workload": WORKLOAD, "robot": ROBOT, "controller": "ID", "contact_pattern": PATTERN,
+                       "instances_per_step": BATCH,
+                       "note": "CPU restatement of the reference path on all host cores (pydrake + OSQP are not installable "
+                               "here, DESIGN.md 5); each step is a bounded sample of the 4096-instance batch"},
             "cpu_baseline": base,
             "e2e": {"value": val, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))

@@ -54,6 +54,33 @@ def test_id_step_matches_golden(ctl_cache, case):
     assert np.abs(out.metrics[:, 1] - g["id_metrics"][:, 1]).max() < 1e-12
 
 
+@pytest.mark.parametrize("case", CASES)
+def test_clf_step_matches_golden(ctl_cache, case):
+    """CLF-QP (clf_controller.py:48-234): the kernel's closed-form CARE constants against the oracle's numerical CARE."""
+    g = np.load(GOLD / f"{case}.npz")
+    out = ctl_cache(robot_of(case)).step("clf", g["q"], g["v"], g["traj"], g["contact"], debug=True)
+    assert (out.status == 0).all()
+    assert np.abs(out.tau - g["clf_tau"]).max() < 1e-5
+    assert np.abs(out.vd - g["clf_vd"]).max() < 1e-6
+    assert np.abs(out.f - g["clf_f"]).max() < 1e-5
+    m, ref = out.metrics, g["clf_metrics"]
+    scale = np.maximum(1.0, np.abs(ref))
+    assert (np.abs(m[:, [0, 1, 3]] - ref[:, [0, 1, 3]]) / scale[:, [0, 1, 3]]).max() < 1e-8      # V, err, Vdot
+    assert np.abs(out.qp_info[:, 0] - g["clf_objective"]).max() < 1e-6 * max(1.0, np.abs(g["clf_objective"]).max())
+
+
+def test_clf_full_size_config4(ctl_cache):
+    """BASELINE config 4 (CLF-QP, 65536 instances, walk contact patterns): all solve; reference constraints hold."""
+    from quadruped_drake_b200.synth import generate
+    ctl = ctl_cache("mini_cheetah")
+    q, v, traj, contact = generate(ctl.model, 65536, 20260121, "walk", ctl.fk)
+    out = ctl.step("clf", q, v, traj, contact, debug=True)
+    assert (out.status == 0).all(), np.unique(out.status, return_counts=True)
+    dyn, con, fr = kkt_properties(ctl, q, v, traj, contact, out)
+    assert dyn.max() < 1e-7 and con.max() < 1e-7 and fr.max() < 1e-7
+    assert (out.qp_info[:, 2] > -1e-9).all()          # delta >= 0 is never optimal to violate: cost w*delta^2, row -delta
+
+
 def test_named_wrapper_and_torch_device_path(ctl_cache):
     """wbc_step_id on device pointers (torch only carries the memory and the stream) equals the host entry."""
     import ctypes as C
@@ -77,7 +104,7 @@ def test_named_wrapper_and_torch_device_path(ctl_cache):
     assert rc == 0 and np.array_equal(tau.cpu().numpy(), host.tau)
 
 
-def kkt_properties(ctl, q, v, traj, contact, out, mu=0.7, kd=100.0):
+def kkt_properties(ctl, q, v, traj, contact, out, mu=0.7, kd=100.0):  # noqa: E302
     """Residuals of the *reference* constraints evaluated with the GPU's own dynamics."""
     d = ctl.dynamics(q, v)
     B = ctl.model.actuation_matrix()
