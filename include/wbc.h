@@ -58,6 +58,7 @@ extern "C" {
 #define WBC_ST_GIMBAL 8        /* |cos(pitch)| < 1e-6: rpy rates undefined   */
 #define WBC_ST_NOTPD 16        /* reduced Hessian not positive definite                   */
 #define WBC_ST_BADQUAT 32      /* zero / non-finite quaternion                            */
+#define WBC_ST_UNSUPPORTED 64  /* PC controller with no stance foot (the reference raises too) */
 
 /* controller kinds: reference controllers/__init__.py:1-5 */
 #define WBC_CTRL_ID 0          /* controllers/inverse_dynamics_controller.py */
@@ -141,6 +142,8 @@ int wbc_dynamics(wbc_handle* h, int64_t n, const double* q, const double* v,
  * CalcFrameJacobianDot x4 (:198-220): C [N][18][18] with C v = Cv, Jd [N][4][3][18]. */
 int wbc_coriolis(wbc_handle* h, int64_t n, const double* q, const double* v,
                  double* C, double* Jd, void* stream);
+
+int wbc_coriolis_host(wbc_handle* h, int64_t n, const double* q, const double* v, double* C, double* Jd);
 
 /* One control step for n instances: DoSetControlTorques -> ControlLaw
  * (basic_controller.py:286-320; inverse_dynamics_controller.py:103-234;

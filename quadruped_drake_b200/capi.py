@@ -16,7 +16,7 @@ LIB_PATH = Path(__file__).resolve().parent / "csrc" / "libwbc_b200.so"
 
 WBC_CTRL_ID, WBC_CTRL_CLF, WBC_CTRL_PC = 0, 1, 2
 KINDS = {"id": WBC_CTRL_ID, "clf": WBC_CTRL_CLF, "pc": WBC_CTRL_PC}
-ST_MAXITER, ST_INFEASIBLE, ST_RANKDEF, ST_GIMBAL, ST_NOTPD, ST_BADQUAT = 1, 2, 4, 8, 16, 32
+ST_MAXITER, ST_INFEASIBLE, ST_RANKDEF, ST_GIMBAL, ST_NOTPD, ST_BADQUAT, ST_UNSUPPORTED = 1, 2, 4, 8, 16, 32, 64
 
 _PARAM_DOUBLES = [
     "id_kp_body_p", "id_kd_body_p", "id_kp_body_rpy", "id_kd_body_rpy", "id_kp_foot", "id_kd_foot", "id_w_body", "id_w_foot",
@@ -87,6 +87,8 @@ def load_library() -> C.CDLL:
     lib.wbc_last_error.restype = C.c_char_p
     lib.wbc_dynamics.argtypes = [H, i64, dp, dp, dp, dp, dp, dp, dp, dp, dp]
     lib.wbc_coriolis.argtypes = [H, i64, dp, dp, dp, dp, dp]
+    lib.wbc_coriolis_host.argtypes = [H, i64, dp, dp, dp, dp]
+    lib.wbc_coriolis_host.restype = C.c_int
     lib.wbc_step.argtypes = [H, i32, i64, C.POINTER(WbcIO), dp]
     for name in ("wbc_step_id", "wbc_step_clf", "wbc_step_pc"):
         getattr(lib, name).argtypes = [H, i64, dp, dp, dp, dp, dp, dp, dp, dp]
@@ -110,7 +112,7 @@ def load_library() -> C.CDLL:
 
 EXPORTED_SYMBOLS = ["wbc_default_params", "wbc_create", "wbc_destroy", "wbc_last_error", "wbc_dynamics", "wbc_coriolis",
                     "wbc_step", "wbc_step_id", "wbc_step_clf", "wbc_step_pc", "wbc_step_host", "wbc_time_step",
-                    "wbc_measure_fp64_peak", "wbc_launch_count", "wbc_dynamics_host", "wbc_host_alloc", "wbc_host_free"]
+                    "wbc_measure_fp64_peak", "wbc_launch_count", "wbc_dynamics_host", "wbc_coriolis_host", "wbc_host_alloc", "wbc_host_free"]
 
 
 def pinned_empty(shape, dtype=np.float64) -> np.ndarray:

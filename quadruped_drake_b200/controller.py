@@ -157,6 +157,15 @@ class BatchedController:
                        np_ptr(out["J_feet"]), np_ptr(out["Jdv_feet"]), np_ptr(out["p_feet"])), "wbc_dynamics_host")
         return out
 
+    def coriolis(self, q, v):
+        """CalcCoriolisMatrix + CalcFrameJacobianDot x4 (basic_controller.py:117-132,198-220) -> C[n,18,18], Jd[n,4,3,18]."""
+        q = np.ascontiguousarray(q, dtype=np.float64).reshape(-1, NQ)
+        n = q.shape[0]
+        v = np.ascontiguousarray(v, dtype=np.float64).reshape(n, NV)
+        Cm, Jd = np.empty((n, NV, NV)), np.empty((n, 4, 3, NV))
+        self._check(self.lib.wbc_coriolis_host(self._h, n, np_ptr(q), np_ptr(v), np_ptr(Cm), np_ptr(Jd)), "wbc_coriolis_host")
+        return Cm, Jd
+
     def fk(self, q, v):
         """Foot positions and velocities (for synth.generate)."""
         d = self.dynamics(q, v)

@@ -22,7 +22,14 @@ struct SmemLayout {
   wbc::WarpSmem w[WARPS];
 };
 
-__device__ __forceinline__ const DevConst& stage_consts(SmemLayout* sm, const DevConst* g) {
+struct SmemLayoutPC {       // PC controller / Coriolis entry: extra operational-space workspace per warp
+  DevConst dc;
+  wbc::WarpSmem w[WARPS];
+  wbc::PcSmem pc[WARPS];
+};
+
+template <typename L>
+__device__ __forceinline__ const DevConst& stage_consts(L* sm, const DevConst* g) {
   // model + gains into shared memory once per CTA (lane-divergent table lookups stay on chip)
   const int nwords = sizeof(DevConst) / 4;
   const uint32_t* src = reinterpret_cast<const uint32_t*>(g);
@@ -40,6 +47,25 @@ __global__ void __launch_bounds__(WARPS * 32, WBC_MIN_CTAS) wbc_step_kernel(cons
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long inst = (long long)blockIdx.x * WARPS + warp;
   if (inst < a.n) wbc::step_instance<KIND>(sm->w[warp], dc.md, dc.pr, dc.dv, a, inst, lane);
+}
+
+__global__ void __launch_bounds__(WARPS * 32, 3) wbc_step_pc_kernel(const DevConst* __restrict__ gdc, wbc::StepArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SmemLayoutPC* sm = reinterpret_cast<SmemLayoutPC*>(smem_raw);
+  const DevConst& dc = stage_consts(sm, gdc);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long inst = (long long)blockIdx.x * WARPS + warp;
+  if (inst < a.n) wbc::step_instance<WBC_CTRL_PC>(sm->w[warp], dc.md, dc.pr, dc.dv, a, inst, lane, &sm->pc[warp]);
+}
+
+__global__ void __launch_bounds__(WARPS * 32, 3) wbc_coriolis_kernel(const DevConst* __restrict__ gdc, const double* q,
+                                                                     const double* v, double* Cout, double* Jdout, long long n) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SmemLayoutPC* sm = reinterpret_cast<SmemLayoutPC*>(smem_raw);
+  const DevConst& dc = stage_consts(sm, gdc);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long inst = (long long)blockIdx.x * WARPS + warp;
+  if (inst < n) wbc::coriolis_instance(sm->w[warp], sm->pc[warp], dc.md, q, v, Cout, Jdout, inst, lane);
 }
 
 __global__ void __launch_bounds__(WARPS * 32) wbc_dynamics_kernel(const DevConst* __restrict__ gdc, const double* q,
@@ -112,7 +138,8 @@ static int set_smem_attr(wbc_handle* h) {
   const int bytes = (int)sizeof(SmemLayout);
   WBC_CUDA(h, cudaFuncSetAttribute(wbc_step_kernel<WBC_CTRL_ID>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   WBC_CUDA(h, cudaFuncSetAttribute(wbc_step_kernel<WBC_CTRL_CLF>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-  WBC_CUDA(h, cudaFuncSetAttribute(wbc_step_kernel<WBC_CTRL_PC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  WBC_CUDA(h, cudaFuncSetAttribute(wbc_step_pc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemLayoutPC)));
+  WBC_CUDA(h, cudaFuncSetAttribute(wbc_coriolis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemLayoutPC)));
   WBC_CUDA(h, cudaFuncSetAttribute(wbc_dynamics_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   return WBC_OK;
 }
@@ -183,8 +210,37 @@ extern "C" int wbc_dynamics(wbc_handle* h, int64_t n, const double* q, const dou
   return WBC_OK;
 }
 
-extern "C" int wbc_coriolis(wbc_handle* h, int64_t, const double*, const double*, double*, double*, void*) {
-  return fail_arg(h, "wbc_coriolis: not implemented in this build");
+extern "C" int wbc_coriolis(wbc_handle* h, int64_t n, const double* q, const double* v, double* Cm, double* Jd, void* stream) {
+  if (!h) return WBC_ERR_ARG;
+  if (n < 0 || (n > 0 && (!q || !v))) return fail_arg(h, "wbc_coriolis: null input");
+  if (n == 0) return WBC_OK;
+  WBC_CUDA(h, cudaSetDevice(h->device));
+  const unsigned grid = (unsigned)((n + WARPS - 1) / WARPS);
+  wbc_coriolis_kernel<<<grid, WARPS * 32, sizeof(SmemLayoutPC), (cudaStream_t)stream>>>(h->d_const, q, v, Cm, Jd, n);
+  h->launches++;
+  WBC_CUDA(h, cudaGetLastError());
+  return WBC_OK;
+}
+
+extern "C" int wbc_coriolis_host(wbc_handle* h, int64_t n, const double* q, const double* v, double* Cm, double* Jd) {
+  if (!h) return WBC_ERR_ARG;
+  if (n <= 0) return n == 0 ? WBC_OK : fail_arg(h, "wbc_coriolis_host: n < 0");
+  WBC_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  double *dq, *dv, *dC = nullptr, *dJ = nullptr;
+  WBC_CUDA(h, cudaMalloc(&dq, n * WBC_NQ * 8)); WBC_CUDA(h, cudaMalloc(&dv, n * WBC_NV * 8));
+  if (Cm) WBC_CUDA(h, cudaMalloc(&dC, n * 324 * 8));
+  if (Jd) WBC_CUDA(h, cudaMalloc(&dJ, n * 216 * 8));
+  WBC_CUDA(h, cudaMemcpyAsync(dq, q, n * WBC_NQ * 8, cudaMemcpyHostToDevice, st));
+  WBC_CUDA(h, cudaMemcpyAsync(dv, v, n * WBC_NV * 8, cudaMemcpyHostToDevice, st));
+  int rc = wbc_coriolis(h, n, dq, dv, dC, dJ, st);
+  if (rc == WBC_OK) {
+    if (Cm) WBC_CUDA(h, cudaMemcpyAsync(Cm, dC, n * 324 * 8, cudaMemcpyDeviceToHost, st));
+    if (Jd) WBC_CUDA(h, cudaMemcpyAsync(Jd, dJ, n * 216 * 8, cudaMemcpyDeviceToHost, st));
+    WBC_CUDA(h, cudaStreamSynchronize(st));
+  }
+  cudaFree(dq); cudaFree(dv); cudaFree(dC); cudaFree(dJ);
+  return rc;
 }
 
 extern "C" int wbc_step(wbc_handle* h, int kind, int64_t n, const wbc_io* io, void* stream) {
@@ -202,7 +258,7 @@ extern "C" int wbc_step(wbc_handle* h, int kind, int64_t n, const wbc_io* io, vo
   switch (kind) {
     case WBC_CTRL_ID: wbc_step_kernel<WBC_CTRL_ID><<<grid, WARPS * 32, sm, st>>>(h->d_const, a); break;
     case WBC_CTRL_CLF: wbc_step_kernel<WBC_CTRL_CLF><<<grid, WARPS * 32, sm, st>>>(h->d_const, a); break;
-    case WBC_CTRL_PC: return fail_arg(h, "wbc_step: PC controller not implemented in this build");
+    case WBC_CTRL_PC: wbc_step_pc_kernel<<<grid, WARPS * 32, sizeof(SmemLayoutPC), st>>>(h->d_const, a); break;
     default: return fail_arg(h, "wbc_step: unknown controller kind");
   }
   h->launches++;

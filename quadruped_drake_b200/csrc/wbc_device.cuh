@@ -84,6 +84,7 @@ struct WarpSmem {
       double rho[4][3];      // foot position relative to the base origin, world axes
       double L[4][3][3];     // leg block of the foot Jacobian: L[leg][row][joint]
       double Jdv[4][3], vf[4][3];
+      double Ld[4][3][3];    // time derivative of L (PC only): Ld[leg][row][joint]
       double task[16];       // 7-15: base rotation matrix (column major)
     };
     struct {
@@ -194,11 +195,19 @@ WBC_DEV int sym3(int i, int j) {  // upper-triangle index of a 3x3 symmetric blo
 struct DynOut { double* M; double* Cv; double* taug; double* Jfeet; double* Jdv; double* pfeet; };
 
 // ------------------------------------------------------------------------------ phase 1
-// Fills the dynamics block of `s` for the state in s.q / s.v. GRAV: fold gravity into the bias
-// (hb/hj = Cv + tau_g) as the step kernels need; otherwise hb/hj = Cv only and, if taug != nullptr,
-// the controller-sign gravity term is written there (internal order, 18 doubles in shared memory).
-template <bool GRAV>
-WBC_DEV void dynamics_phase(WarpSmem& s, const wbc_model& md, int lane, int& status, double* taug_sm) {
+// Modes of dynamics_phase
+constexpr int DYN_STEP = 0;    // step kernels: gravity folded into the bias (hb/hj = Cv + tau_g)
+constexpr int DYN_PARITY = 1;  // wbc_dynamics: hb/hj = Cv only, tau_g (controller sign) to taug_sm[18] (internal order)
+constexpr int DYN_BIAS = 2;    // bias only: b = C(q, vel) vel for the velocity `vel_int` (internal order) -> bias_out[18]
+constexpr int DYN_STEP_JD = 3; // DYN_STEP plus the Jdot leg blocks Ld (PC controller)
+
+// Fills the dynamics block of `s` for the state in s.q / s.v (see the modes above).
+template <int MODE>
+WBC_DEV void dynamics_phase(WarpSmem& s, const wbc_model& md, int lane, int& status, double* taug_sm,
+                            const double* vel_int = nullptr, double* bias_out = nullptr) {
+  constexpr bool GRAV = (MODE == DYN_STEP || MODE == DYN_STEP_JD);
+  constexpr bool BIAS_ONLY = (MODE == DYN_BIAS);
+  constexpr bool WITH_JD = (MODE == DYN_STEP_JD);
   const int leg = lane >> 3, j = lane & 7;
   const bool link = j < 3;
   const int jl = link ? j : 2;
@@ -212,7 +221,7 @@ WBC_DEV void dynamics_phase(WarpSmem& s, const wbc_model& md, int lane, int& sta
   R0.c0 = mk(1 - 2 * (qy * qy + qz * qz), 2 * (qx * qy + qw * qz), 2 * (qx * qz - qw * qy));
   R0.c1 = mk(2 * (qx * qy - qw * qz), 1 - 2 * (qx * qx + qz * qz), 2 * (qy * qz + qw * qx));
   R0.c2 = mk(2 * (qx * qz + qw * qy), 2 * (qy * qz - qw * qx), 1 - 2 * (qx * qx + qy * qy));
-  const V3 wb = ld3(&s.v[0]), vb = ld3(&s.v[3]);
+  const V3 wb = BIAS_ONLY ? ld3(&vel_int[0]) : ld3(&s.v[0]), vb = BIAS_ONLY ? ld3(&vel_int[3]) : ld3(&s.v[3]);
   const V3 grav = ld3(md.gravity);
   V3 aw0 = mk(0, 0, 0);
   V3 av0 = mk(0, 0, 0) - cross(wb, vb);
@@ -222,6 +231,7 @@ WBC_DEV void dynamics_phase(WarpSmem& s, const wbc_model& md, int lane, int& sta
   M3 R = R0; V3 rho = mk(0, 0, 0);
   V3 vw = wb, vv = vb, aw = aw0, av = av0;
   V3 ax[3], org[3];
+  V3 wpar = wb, vorg = vb;      // (WITH_JD) angular velocity of joint j's parent and velocity of its origin
   M3 Rm = R0; V3 rhom = rho, vwm = vw, vvm = vv, awm = aw, avm = av;
 #pragma unroll
   for (int jj = 0; jj < 3; ++jj) {
@@ -230,7 +240,7 @@ WBC_DEV void dynamics_phase(WarpSmem& s, const wbc_model& md, int lane, int& sta
     const V3 la = ld3(md.joint_axis[k]);
     const V3 a = mul(R, la);
     const int vi = md.v_index[k];
-    const double th = s.q[vi + 1], thd = s.v[vi];
+    const double th = s.q[vi + 1], thd = BIAS_ONLY ? vel_int[6 + k] : s.v[vi];
     double sn, cs; sincos(th, &sn, &cs);
     // R <- R * Rot(la, th):  Rot e_m = cs e_m + sn (la x e_m) + (1-cs) la (la . e_m)
     const double oc = 1.0 - cs;
@@ -240,6 +250,7 @@ WBC_DEV void dynamics_phase(WarpSmem& s, const wbc_model& md, int lane, int& sta
     M3 Rn; Rn.c0 = mul(R, r0); Rn.c1 = mul(R, r1); Rn.c2 = mul(R, r2);
     R = Rn;
     const V3 b = cross(rho, a);            // S = [a; rho x a]
+    if (WITH_JD && jj == jl) { wpar = vw; vorg = vv + cross(vw, rho); }
     // acc += (vel x S) thd ; vel += S thd
     aw = aw + thd * cross(vw, a);
     av = av + thd * (cross(vw, b) + cross(vv, a));
@@ -270,7 +281,8 @@ WBC_DEV void dynamics_phase(WarpSmem& s, const wbc_model& md, int lane, int& sta
   const V3 a = ax[jl], b = cross(org[jl], ax[jl]);
   V3 Fn, Ff;
   spi_mul(Ic, a, b, Fn, Ff);
-  if (link) {
+  if (link && BIAS_ONLY) bias_out[6 + 3 * leg + j] = dot(a, fcn) + dot(b, fcf);
+  if (link && !BIAS_ONLY) {
     const int c = 6 + 3 * leg + j;
     s.Mb[c][0] = Fn.x; s.Mb[c][1] = Fn.y; s.Mb[c][2] = Fn.z; s.Mb[c][3] = Ff.x; s.Mb[c][4] = Ff.y; s.Mb[c][5] = Ff.z;
 #pragma unroll
@@ -307,7 +319,8 @@ WBC_DEV void dynamics_phase(WarpSmem& s, const wbc_model& md, int lane, int& sta
     gf = gf + cross(wb, bf);
     It = spi_add(It, Ib); ftn = ftn + gn; ftf = ftf + gf;
   }
-  if (lane < 6) {
+  if (lane < 6 && BIAS_ONLY) bias_out[lane] = lane < 3 ? comp(ftn, lane) : comp(ftf, lane - 3);
+  if (lane < 6 && !BIAS_ONLY) {
     // column c of [[I, skew(h)], [-skew(h), m 1]]
     const int c = lane;
     double col[6];
@@ -333,7 +346,12 @@ WBC_DEV void dynamics_phase(WarpSmem& s, const wbc_model& md, int lane, int& sta
   const V3 vfoot = vv + cross(vw, rf);
   V3 jdv = av + cross(aw, rf) + cross(vw, vfoot);
   if (GRAV) jdv = jdv + grav;
-  if (link) {
+  if (link && WITH_JD) {
+    // d/dt of column j of L: (omega_parent x a_j) x (p_f - o_j) + a_j x (pdot_f - odot_j)   
+    const V3 Ldc = cross(cross(wpar, ax[j]), rf - org[j]) + cross(ax[j], vfoot - vorg);
+    s.Ld[leg][0][j] = Ldc.x; s.Ld[leg][1][j] = Ldc.y; s.Ld[leg][2][j] = Ldc.z;
+  }
+  if (link && !BIAS_ONLY) {
     const V3 Lc = cross(ax[j], rf - org[j]);
     s.L[leg][0][j] = Lc.x; s.L[leg][1][j] = Lc.y; s.L[leg][2][j] = Lc.z;
     s.rho[leg][j] = comp(rf, j);
@@ -341,7 +359,7 @@ WBC_DEV void dynamics_phase(WarpSmem& s, const wbc_model& md, int lane, int& sta
     s.vf[leg][j] = comp(vfoot, j);
   }
   // base rotation for the task-space block: stash R0 in task[7..15]
-  if (lane == 0) {
+  if (lane == 0 && !BIAS_ONLY) {
     s.task[7] = R0.c0.x; s.task[8] = R0.c0.y; s.task[9] = R0.c0.z;
     s.task[10] = R0.c1.x; s.task[11] = R0.c1.y; s.task[12] = R0.c1.z;
     s.task[13] = R0.c2.x; s.task[14] = R0.c2.y; s.task[15] = R0.c2.z;
@@ -860,12 +878,266 @@ WBC_DEV void build_common_rows(WarpSmem& s, int lane, int ycol, unsigned cmask) 
   }
 }
 
+// ------------------------------------------------------------------------------ PC controller
+// pc_controller.py:43-255 / mptc_controller.py:30-57 in the reduced formulation of DESIGN.md 7:
+//   X = M^-1 J',  Lambda = (J X)^-1,  s1 = Lambda xd~,  w = v - X s1,
+//   g0 = X'(b(v) - C w) - xdd_nom + Jdot w,          (C w by polarisation of the bias b)
+//   cost 1/2 |W^1/2 (Lambda (J vd + g0) + Kp x~ + Kd xd~)|^2,   passivity row  s1'(J vd + g0) + xd~'Kp x~ <= 0.
+struct PcSmem {
+  double Lam[16][16];                        // J M^-1 J' -> its Cholesky factor -> Lambda
+  double s1[16], g0[16], kx[16], xt[16], xdt[16], wt[16];
+  double vi[18], w[18], vw[18];              // v (internal order), w, v + w
+  double bv[18], bvw[18], bw[18];            // bias at v, v + w, w
+  double Sb[6][6];                           // Schur complement of the leg blocks in M -> its Cholesky factor
+  double Dinv[4][6];                         // inverses of the 3x3 leg blocks (symmetric, sym3 indexing)
+  int rowidx[16];                            // task row r -> row of Y
+  double kpxx;                               // xd~' Kp x~
+};
+
+WBC_DEV double sym3get(const double* d, int i, int j) { return d[sym3(i < j ? i : j, i < j ? j : i)]; }
+
+// Task-space errors of row `lane` (shared by CLF and PC): base rpy / position rows 0-5, swing-foot rows.
+struct TaskRow { bool on; int type, foot, comp; double xt, xdt, xddn, jdv; };
+WBC_DEV TaskRow task_row(const WarpSmem& s, const BodyTask& bt, int row, int foot, int comp) {
+  const double* tr = s.traj;
+  TaskRow t; t.on = true; t.foot = foot; t.comp = comp; t.jdv = 0.0;
+  if (row < 3) {
+    t.type = 0;
+    t.xt = bt.rpy[row] - tr[9 + row];
+    t.xdt = s.v[row] - (bt.N[row][0] * tr[12] + bt.N[row][1] * tr[13] + bt.N[row][2] * tr[14]);
+    t.xddn = bt.N[row][0] * tr[15] + bt.N[row][1] * tr[16] + bt.N[row][2] * tr[17];
+  } else if (row < 6) {
+    const int i = row - 3;
+    t.type = 1; t.xt = s.q[4 + i] - tr[i]; t.xdt = s.v[3 + i] - tr[3 + i]; t.xddn = tr[6 + i];
+  } else {
+    t.type = 2;
+    t.xt = s.q[4 + comp] + s.rho[foot][comp] - tr[18 + 3 * foot + comp];
+    t.xdt = s.vf[foot][comp] - tr[30 + 3 * foot + comp];
+    t.xddn = tr[42 + 3 * foot + comp];
+    t.jdv = s.Jdv[foot][comp];
+  }
+  return t;
+}
+
+WBC_DEV int swing_foot(unsigned cmask, int slot) { return stance_foot(~cmask & 15u, slot); }
+
+WBC_DEV void pc_precompute(WarpSmem& s, PcSmem& pc, const wbc_model& md, const wbc_params& pr, const BodyTask& bt,
+                           int lane, unsigned cmask, int m, int& status, double& Vout, double& errout) {
+  double (*X)[16] = reinterpret_cast<double (*)[16]>(&s.A[0][0]);       // 18 x 16, dead before build_equalities
+  double (*T)[16] = X + 18;                                              // 16 x 16 scratch (L^-1)
+  const bool on = lane < m;
+  const int slot = lane >= 6 ? (lane - 6) / 3 : 0, ri = lane >= 6 ? (lane - 6) % 3 : 0;
+  const int rk = (on && lane >= 6) ? swing_foot(cmask, slot) : -1;
+  TaskRow t; t.on = false; t.xt = t.xdt = t.xddn = 0.0;
+  double kp = 0.0, kd = 0.0, wt = 0.0;
+  if (on) {
+    t = task_row(s, bt, lane, rk < 0 ? 0 : rk, ri);
+    kp = t.type == 0 ? pr.pc_kp_body_rpy : (t.type == 1 ? pr.pc_kp_body_p : pr.pc_kp_foot);
+    kd = t.type == 0 ? pr.pc_kd_body_rpy : (t.type == 1 ? pr.pc_kd_body_p : pr.pc_kd_foot);
+    wt = t.type == 2 ? pr.pc_w_foot : pr.pc_w_body;
+  }
+  if (lane < 16) {
+    pc.xt[lane] = t.xt; pc.xdt[lane] = t.xdt; pc.wt[lane] = wt; pc.kx[lane] = kp * t.xt + kd * t.xdt;
+    pc.rowidx[lane] = lane < 6 ? lane : (rk >= 0 ? 6 + 3 * rk + ri : 0);
+  }
+  if (lane < 18) pc.vi[lane] = lane < 6 ? s.v[lane] : s.v[md.v_index[lane - 6]];
+  const double kpxx = warp_sum(t.xdt * kp * t.xt);
+  Vout = 0.5 * warp_sum(kp * t.xt * t.xt);
+  errout = warp_sum(t.xt * t.xt);
+  if (lane == 0) pc.kpxx = kpxx;
+  // ---- inverses of the leg blocks (closed form, SPD 3x3)
+  if (lane < 4) {
+    const double* d = s.Mleg[lane];
+    const double a = d[0], b = d[1], c = d[2], e = d[3], f = d[4], g = d[5];     // [[a b c],[b e f],[c f g]]
+    const double c00 = e * g - f * f, c01 = c * f - b * g, c02 = b * f - c * e;
+    const double det = a * c00 + b * c01 + c * c02, id = 1.0 / det;
+    pc.Dinv[lane][0] = c00 * id; pc.Dinv[lane][1] = c01 * id; pc.Dinv[lane][2] = c02 * id;
+    pc.Dinv[lane][3] = (a * g - c * c) * id; pc.Dinv[lane][4] = (b * c - a * f) * id; pc.Dinv[lane][5] = (a * e - b * b) * id;
+  }
+  __syncwarp();
+  // ---- Schur complement S = Mbb - sum_k Mbk Dk^-1 Mkb, entry (i, j) by lane 6 i + j (lanes 0-31 cover 32 of 36; rest below)
+  for (int e = lane; e < 36; e += 32) {
+    const int i = e / 6, j = e % 6;
+    double acc = s.Mb[j][i];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) acc = fma(-s.Mb[6 + 3 * k + a][i] * sym3get(pc.Dinv[k], a, b), s.Mb[6 + 3 * k + b][j], acc);
+    pc.Sb[i][j] = acc;
+  }
+  __syncwarp();
+  for (int j = 0; j < 6; ++j) {                     // Cholesky of Sb (lower), lanes = rows
+    const double dj = pc.Sb[j][j];
+    if (!(dj > 1e-300)) status |= WBC_ST_NOTPD;
+    const double inv = 1.0 / sqrt(dj > 1e-300 ? dj : 1.0);
+    __syncwarp();
+    if (lane < 6 && lane >= j) pc.Sb[lane][j] *= inv;
+    __syncwarp();
+    if (lane < 6 && lane > j)
+      for (int k = j + 1; k <= lane; ++k) pc.Sb[lane][k] = fma(-pc.Sb[lane][j], pc.Sb[k][j], pc.Sb[lane][k]);
+    __syncwarp();
+  }
+  // ---- X = M^-1 J' : lane r solves for task row r
+  if (on) {
+    double cb[6], cl[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int i = 0; i < 6; ++i) cb[i] = 0.0;
+    if (lane < 6) {
+#pragma unroll
+      for (int i = 0; i < 6; ++i) cb[i] = (i == lane) ? 1.0 : 0.0;
+    } else {
+      const V3 rh = ld3(s.rho[rk]);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) { cb[i] = -skew_ent(rh, ri, i); cb[3 + i] = (i == ri) ? 1.0 : 0.0; cl[i] = s.L[rk][ri][i]; }
+      double tl[3];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) tl[a] = sym3get(pc.Dinv[rk], a, 0) * cl[0] + sym3get(pc.Dinv[rk], a, 1) * cl[1] + sym3get(pc.Dinv[rk], a, 2) * cl[2];
+#pragma unroll
+      for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int a = 0; a < 3; ++a) cb[i] = fma(-s.Mb[6 + 3 * rk + a][i], tl[a], cb[i]);
+    }
+    double xb[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {                   // L y = cb
+      double acc = cb[i];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) if (k < i) acc = fma(-pc.Sb[i][k], xb[k], acc);
+      xb[i] = acc / pc.Sb[i][i];
+    }
+#pragma unroll
+    for (int i = 5; i >= 0; --i) {                  // L' x = y
+      double acc = xb[i];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) if (k > i) acc = fma(-pc.Sb[k][i], xb[k], acc);
+      xb[i] = acc / pc.Sb[i][i];
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) X[i][lane] = xb[i];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      double c3[3];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        double acc = (k == rk) ? cl[a] : 0.0;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) acc = fma(-s.Mb[6 + 3 * k + a][i], xb[i], acc);
+        c3[a] = acc;
+      }
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+        X[6 + 3 * k + a][lane] = sym3get(pc.Dinv[k], a, 0) * c3[0] + sym3get(pc.Dinv[k], a, 1) * c3[1] + sym3get(pc.Dinv[k], a, 2) * c3[2];
+    }
+  }
+  __syncwarp();
+  // ---- J M^-1 J' (row r by lane r)
+  if (on) {
+    const V3 rh = rk >= 0 ? ld3(s.rho[rk]) : mk(0, 0, 0);
+    for (int c = 0; c < m; ++c) {
+      double val;
+      if (lane < 6) val = X[lane][c];
+      else {
+        val = X[3 + ri][c];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) val = fma(-skew_ent(rh, ri, i), X[i][c], val);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) val = fma(s.L[rk][ri][a], X[6 + 3 * rk + a][c], val);
+      }
+      pc.Lam[lane][c] = val;
+    }
+  }
+  __syncwarp();
+  // ---- Lambda = (J M^-1 J')^-1 via Cholesky (lanes = rows), T = L^-1 (lane = column), Lambda = T'T
+  for (int j = 0; j < m; ++j) {
+    const double dj = pc.Lam[j][j];
+    if (!(dj > 1e-300)) status |= WBC_ST_RANKDEF;   // J rank deficient (singular swing leg), pc_controller.py:160 would fail too
+    const double inv = 1.0 / sqrt(dj > 1e-300 ? dj : 1.0);
+    __syncwarp();
+    if (on && lane >= j) pc.Lam[lane][j] *= inv;
+    __syncwarp();
+    if (on && lane > j)
+      for (int k = j + 1; k <= lane; ++k) pc.Lam[lane][k] = fma(-pc.Lam[lane][j], pc.Lam[k][j], pc.Lam[lane][k]);
+    __syncwarp();
+  }
+  if (on) {
+    for (int i = 0; i < m; ++i) {
+      double acc = (i == lane) ? 1.0 : 0.0;
+      for (int k = lane; k < i; ++k) acc = fma(-pc.Lam[i][k], T[k][lane], acc);
+      T[i][lane] = (i >= lane) ? acc / pc.Lam[i][i] : 0.0;
+    }
+  }
+  __syncwarp();
+  if (on) {
+    for (int c = 0; c < m; ++c) {
+      double acc = 0.0;
+      for (int k = (lane > c ? lane : c); k < m; ++k) acc = fma(T[k][lane], T[k][c], acc);
+      pc.Lam[lane][c] = acc;                        // every lane writes its own row; reads are from T only
+    }
+  }
+  __syncwarp();
+  // ---- s1 = Lambda xd~,  w = v - X s1
+  double s1 = 0.0;
+  if (on) for (int c = 0; c < m; ++c) s1 = fma(pc.Lam[lane][c], pc.xdt[c], s1);
+  if (lane < 16) pc.s1[lane] = s1;
+  Vout += 0.5 * warp_sum(t.xdt * s1);
+  __syncwarp();
+  if (lane < 18) {
+    double acc = pc.vi[lane];
+    for (int c = 0; c < m; ++c) acc = fma(-X[lane][c], pc.s1[c], acc);
+    pc.w[lane] = acc; pc.vw[lane] = pc.vi[lane] + acc;
+  }
+  __syncwarp();
+  // ---- C w by polarisation: C w = 1/2 (b(v + w) - b(v) - b(w))          (CalcCoriolisMatrix, basic_controller.py:117-132)
+  int st2 = 0;
+  dynamics_phase<DYN_BIAS>(s, md, lane, st2, nullptr, pc.vi, pc.bv);
+  dynamics_phase<DYN_BIAS>(s, md, lane, st2, nullptr, pc.vw, pc.bvw);
+  dynamics_phase<DYN_BIAS>(s, md, lane, st2, nullptr, pc.w, pc.bw);
+  // ---- g0 = X'(b(v) - C w) - xdd_nom + Jdot w
+  if (on) {
+    double acc = -t.xddn;
+    for (int i = 0; i < 18; ++i) acc = fma(X[i][lane], 1.5 * pc.bv[i] - 0.5 * pc.bvw[i] + 0.5 * pc.bw[i], acc);
+    if (rk >= 0) {
+      // Jdot row: [-skew(pdot_f - pdot_b) | 0 | Ld]   (CalcFrameJacobianDot, basic_controller.py:198-220)
+      const V3 dv = mk(s.vf[rk][0] - s.v[3], s.vf[rk][1] - s.v[4], s.vf[rk][2] - s.v[5]);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) acc = fma(-skew_ent(dv, ri, i), pc.w[i], acc);
+#pragma unroll
+      for (int a = 0; a < 3; ++a) acc = fma(s.Ld[rk][ri][a], pc.w[6 + 3 * rk + a], acc);
+    }
+    pc.g0[lane] = acc;
+  }
+  __syncwarp();
+}
+
+// Replaces the task rows of Y by the weighted task-force rows and adds the passivity row 30 (column `ycol` per lane).
+WBC_DEV void pc_rows(WarpSmem& s, const PcSmem& pc, int lane, int ycol, int m) {
+  if (ycol < 0) return;
+  double yt[15];
+#pragma unroll
+  for (int r = 0; r < 15; ++r) yt[r] = (r < m) ? s.Y[pc.rowidx[r]][ycol] + (lane == 31 ? pc.g0[r] : 0.0) : 0.0;
+  double row30 = (lane == 31) ? pc.kpxx : 0.0;
+#pragma unroll
+  for (int r = 0; r < 15; ++r) if (r < m) row30 = fma(pc.s1[r], yt[r], row30);
+  s.Y[30][ycol] = row30;
+#pragma unroll
+  for (int r = 0; r < 15; ++r) {
+    if (r < m) {
+      double acc = (lane == 31) ? pc.kx[r] : 0.0;
+#pragma unroll
+      for (int c = 0; c < 15; ++c) if (c < m) acc = fma(pc.Lam[r][c], yt[c], acc);
+      s.Y[pc.rowidx[r]][ycol] = sqrt(pc.wt[r]) * acc;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------ the step
 // One control step of instance `inst` (DoSetControlTorques -> ControlLaw,
 // basic_controller.py:286-320). KIND selects the cost / extra rows.
 template <int KIND>
 WBC_DEV void step_instance(WarpSmem& s, const wbc_model& md, const wbc_params& pr, const Derived& dv, const StepArgs& a,
-                           long long inst, int lane) {
+                           long long inst, int lane, PcSmem* pcs = nullptr) {
   int status = 0;
   // ---- phase 0: coalesced loads into shared memory
   for (int i = lane; i < WBC_NQ; i += 32) s.q[i] = a.q[inst * WBC_NQ + i];
@@ -877,9 +1149,17 @@ WBC_DEV void step_instance(WarpSmem& s, const wbc_model& md, const wbc_params& p
   const int nc = __popc(cmask);
   __syncwarp();
   // ---- phase 1
-  dynamics_phase<true>(s, md, lane, status, nullptr);
+  dynamics_phase<(KIND == WBC_CTRL_PC) ? DYN_STEP_JD : DYN_STEP>(s, md, lane, status, nullptr);
   BodyTask bt;
   body_task(s, lane, status, bt);
+  // ---- PC: operational-space quantities (uses the A region as scratch, so it runs before the equalities are built)
+  const int mtask = 6 + 3 * (4 - nc);
+  double Vpc = 0.0, errpc = 0.0;
+  bool pc_ok = true;
+  if (KIND == WBC_CTRL_PC) {
+    if (nc == 0) { status |= WBC_ST_UNSUPPORTED; pc_ok = false; }   // reference PC raises on full flight
+    else pc_precompute(s, *pcs, md, pr, bt, lane, cmask, mtask, status, Vpc, errpc);
+  }
   // ---- phases 2,3
   const int ndelta = (KIND == WBC_CTRL_CLF) ? 1 : 0;
   const int n = 18 + 3 * nc + ndelta, m = 6 + 3 * nc;
@@ -890,7 +1170,7 @@ WBC_DEV void step_instance(WarpSmem& s, const wbc_model& md, const wbc_params& p
   const bool isfree = (freemask >> lane) & 1u;
   const int widx = __popc(freemask & ((1u << lane) - 1u));
   const int ycol = lane == 31 ? NF : (isfree ? widx : -1);
-  bool ok = nf <= NF;
+  bool ok = nf <= NF && pc_ok;
   if (ok) {
     if (isfree) s.fcol[widx] = lane;
     // ---- phase 4
@@ -980,6 +1260,14 @@ WBC_DEV void step_instance(WarpSmem& s, const wbc_model& md, const wbc_params& p
       nextra = 1;
       extra_bound = -dv.clf_gamma[nc < 4 ? 1 : 0] * Vl - 2.0 * PFl - 2.0 * csum;
     }
+    if (KIND == WBC_CTRL_PC) {
+      pc_rows(s, *pcs, lane, ycol, mtask);
+      if (lane < 6 || (lane < 18 && !((cmask >> ((lane - 6) / 3)) & 1))) { s.cw[lane] = 1.0; s.ct[lane] = 0.0; }
+      else if (lane < 18) { s.cw[lane] = pr.reg_f; s.ct[lane] = 0.0; }
+      else if (lane < 30) { s.cw[lane] = pr.reg_tau; s.ct[lane] = 0.0; }
+      nextra = 1; extra_bound = 0.0;
+      err = errpc;
+    }
     __syncwarp();
     // ---- phase 5
     const TriPairs tp = tri_pairs(lane);
@@ -1026,10 +1314,14 @@ WBC_DEV void step_instance(WarpSmem& s, const wbc_model& md, const wbc_params& p
         delta = s.y[31];
         mt[0] = Vl; mt[1] = err; mt[2] = res; mt[3] = 2.0 * PFl + s.y[30] + delta + 2.0 * csum;
       }
+      if (KIND == WBC_CTRL_PC) {
+        // V = 1/2 xd~'Lambda xd~ + 1/2 x~'Kp x~, Vdot = value of the passivity row  (pc_controller.py:244-253)
+        mt[0] = Vpc; mt[1] = err; mt[2] = res; mt[3] = s.y[30];
+      }
       if (a.qp_info) { double* qi = a.qp_info + inst * 4; qi[0] = obj; qi[1] = res; qi[2] = delta; qi[3] = (double)iters; }
     }
   } else {
-    status |= WBC_ST_RANKDEF;
+    if (pc_ok) status |= WBC_ST_RANKDEF;
     if (lane < 12) { a.tau[inst * WBC_NU + lane] = 0.0; if (a.f) a.f[inst * 12 + lane] = 0.0; }
     if (a.vd && lane < 18) a.vd[inst * WBC_NV + lane] = 0.0;
     if (lane < 4) a.metrics[inst * WBC_NMETRIC + lane] = 0.0;
@@ -1048,7 +1340,7 @@ WBC_DEV void dynamics_instance(WarpSmem& s, const wbc_model& md, const double* q
   for (int i = lane; i < WBC_NV; i += 32) s.v[i] = v[inst * WBC_NV + i];
   __syncwarp();
   double* taug = &s.A[0][0];  // scratch: 18 doubles
-  dynamics_phase<false>(s, md, lane, status, taug);
+  dynamics_phase<DYN_PARITY>(s, md, lane, status, taug);
   // internal -> Drake index
   auto didx = [&](int c) { return c < 6 ? c : md.v_index[c - 6]; };
   if (o.M) {
@@ -1083,6 +1375,44 @@ WBC_DEV void dynamics_instance(WarpSmem& s, const wbc_model& md, const double* q
   if (lane < 12) {
     if (o.Jdv) o.Jdv[inst * 12 + lane] = s.Jdv[lane / 3][lane % 3];
     if (o.pfeet) o.pfeet[inst * 12 + lane] = s.q[4 + lane % 3] + s.rho[lane / 3][lane % 3];
+  }
+  __syncwarp();
+}
+
+// ---------------------------------------------------------------- Coriolis parity entry
+// CalcCoriolisMatrix (basic_controller.py:117-132): C = 1/2 d(Cv)/dv, exact by polarisation since Cv is a homogeneous
+// quadratic form in v: C e_j = 1/2 (b(v + e_j) - b(v) - b(e_j)). CalcFrameJacobianDot x4 (:198-220): analytic Jdot.
+WBC_DEV void coriolis_instance(WarpSmem& s, PcSmem& pc, const wbc_model& md, const double* q, const double* v, double* Cout,
+                               double* Jdout, long long inst, int lane) {
+  int status = 0;
+  for (int i = lane; i < WBC_NQ; i += 32) s.q[i] = q[inst * WBC_NQ + i];
+  for (int i = lane; i < WBC_NV; i += 32) s.v[i] = v[inst * WBC_NV + i];
+  __syncwarp();
+  dynamics_phase<DYN_STEP_JD>(s, md, lane, status, nullptr);
+  auto didx = [&](int c) { return c < 6 ? c : md.v_index[c - 6]; };
+  if (lane < 18) pc.vi[lane] = lane < 6 ? s.v[lane] : s.v[md.v_index[lane - 6]];
+  __syncwarp();
+  dynamics_phase<DYN_BIAS>(s, md, lane, status, nullptr, pc.vi, pc.bv);
+  if (Cout) {
+    for (int j = 0; j < 18; ++j) {
+      if (lane < 18) { pc.w[lane] = (lane == j) ? 1.0 : 0.0; pc.vw[lane] = pc.vi[lane] + ((lane == j) ? 1.0 : 0.0); }
+      __syncwarp();
+      dynamics_phase<DYN_BIAS>(s, md, lane, status, nullptr, pc.vw, pc.bvw);
+      dynamics_phase<DYN_BIAS>(s, md, lane, status, nullptr, pc.w, pc.bw);
+      if (lane < 18) Cout[inst * 324 + didx(lane) * 18 + didx(j)] = 0.5 * (pc.bvw[lane] - pc.bv[lane] - pc.bw[lane]);
+      __syncwarp();
+    }
+  }
+  if (Jdout) {
+    double* J = Jdout + inst * 216;
+    for (int e = lane; e < 216; e += 32) {
+      const int k = e / 54, i = (e % 54) / 18, c = e % 18;
+      const V3 dv = mk(s.vf[k][0] - s.v[3], s.vf[k][1] - s.v[4], s.vf[k][2] - s.v[5]);
+      double val = 0.0;
+      if (c < 3) val = -skew_ent(dv, i, c);
+      else if (c >= 6 && (c - 6) / 3 == k) val = s.Ld[k][i][(c - 6) % 3];
+      J[k * 54 + i * 18 + didx(c)] = val;
+    }
   }
   __syncwarp();
 }

@@ -9,7 +9,7 @@ thread_local EmuWarp* emu_warp;
 
 namespace {
 struct Job {
-  EmuWarp* warp; int lane; wbc::WarpSmem* sm; const wbc_model* md; const wbc_params* pr; wbc::Derived dv;
+  EmuWarp* warp; int lane; wbc::WarpSmem* sm; wbc::PcSmem* pcs; double* Cout; double* Jdout; const wbc_model* md; const wbc_params* pr; wbc::Derived dv;
   wbc::StepArgs args; wbc::DynOut dyn; const double* q; const double* v; long long n; int mode;
 };
 void* lane_main(void* p) {
@@ -19,9 +19,12 @@ void* lane_main(void* p) {
   for (long long i = 0; i < j->n; ++i) {
     if (j->mode == 0) {
       if (j->args.kind == WBC_CTRL_ID) wbc::step_instance<WBC_CTRL_ID>(*j->sm, *j->md, *j->pr, j->dv, j->args, i, j->lane);
+      if (j->args.kind == WBC_CTRL_PC) wbc::step_instance<WBC_CTRL_PC>(*j->sm, *j->md, *j->pr, j->dv, j->args, i, j->lane, j->pcs);
       if (j->args.kind == WBC_CTRL_CLF) wbc::step_instance<WBC_CTRL_CLF>(*j->sm, *j->md, *j->pr, j->dv, j->args, i, j->lane);
-    } else {
+    } else if (j->mode == 1) {
       wbc::dynamics_instance(*j->sm, *j->md, j->q, j->v, j->dyn, i, j->lane);
+    } else {
+      wbc::coriolis_instance(*j->sm, *j->pcs, *j->md, j->q, j->v, j->Cout, j->Jdout, i, j->lane);
     }
   }
   return nullptr;
@@ -31,15 +34,18 @@ int run(Job proto) {
   pthread_barrier_init(&warp.bar, nullptr, 32);
   wbc::WarpSmem* sm = new wbc::WarpSmem();
   memset(sm, 0, sizeof(*sm));
+  wbc::PcSmem* pcs = new wbc::PcSmem();
+  memset(pcs, 0, sizeof(*pcs));
   std::vector<Job> jobs(32, proto);
   std::vector<pthread_t> th(32);
   for (int l = 0; l < 32; ++l) {
-    jobs[l].warp = &warp; jobs[l].lane = l; jobs[l].sm = sm;
+    jobs[l].warp = &warp; jobs[l].lane = l; jobs[l].sm = sm; jobs[l].pcs = pcs;
     pthread_create(&th[l], nullptr, lane_main, &jobs[l]);
   }
   for (int l = 0; l < 32; ++l) pthread_join(th[l], nullptr);
   pthread_barrier_destroy(&warp.bar);
   delete sm;
+  delete pcs;
   return 0;
 }
 }  // namespace
@@ -58,6 +64,11 @@ extern "C" int emu_dynamics(const wbc_model* md, long long n, const double* q, c
   Job j{};
   j.md = md; j.n = n; j.mode = 1; j.q = q; j.v = v;
   j.dyn.M = M; j.dyn.Cv = Cv; j.dyn.taug = taug; j.dyn.Jfeet = Jfeet; j.dyn.Jdv = Jdv; j.dyn.pfeet = pfeet;
+  return run(j);
+}
+extern "C" int emu_coriolis(const wbc_model* md, long long n, const double* q, const double* v, double* Cm, double* Jd) {
+  Job j{};
+  j.md = md; j.n = n; j.mode = 2; j.q = q; j.v = v; j.Cout = Cm; j.Jdout = Jd;
   return run(j);
 }
 extern "C" int emu_smem_bytes() { return (int)sizeof(wbc::WarpSmem); }

@@ -61,3 +61,39 @@ def test_emulated_id_step_matches_golden(emu, case):
     assert np.abs(f - g["id_f"]).max() < 1e-5
     assert np.abs(qi[:, 0] - g["id_objective"]).max() < 1e-6 * max(1.0, np.abs(g["id_objective"]).max())
     assert np.abs(met[:, 1] - g["id_metrics"][:, 1]).max() < 1e-12
+
+
+@pytest.mark.parametrize("kind", ["clf", "pc"])
+@pytest.mark.parametrize("case", ["cfg3_anymal_trot", "cfg4_mini_cheetah_walk"])
+def test_emulated_clf_pc_steps_match_golden(emu, case, kind):
+    g = np.load(GOLD / f"{case}.npz")
+    robot = "anymal_b" if "anymal" in case else "mini_cheetah"
+    tau, met, st, vd, f, qi = run_step(emu, robot, kind, g)
+    ok = g[f"{kind}_ok"]
+    assert (st[ok] == 0).all()
+    if kind == "pc":
+        assert (st[~ok] == 64).all()                        # full flight: WBC_ST_UNSUPPORTED (the reference raises)
+    assert np.abs(tau - g[f"{kind}_tau"])[ok].max() < 1e-5
+    assert np.abs(vd - g[f"{kind}_vd"])[ok].max() < 1e-6
+    assert np.abs(f - g[f"{kind}_f"])[ok].max() < 1e-5
+    ref = g[f"{kind}_metrics"][ok]
+    assert (np.abs(met[ok] - ref)[:, [0, 1, 3]] / np.maximum(1.0, np.abs(ref[:, [0, 1, 3]]))).max() < 1e-8
+
+
+def test_emulated_coriolis_matches_oracle(emu):
+    from oracle.dynamics import Plant
+    from quadruped_drake_b200 import load_robot
+    from quadruped_drake_b200.capi import np_ptr
+    emu.emu_coriolis.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 4
+    g = np.load(GOLD / "mixed_mini_cheetah.npz")
+    P, ms = Plant("mini_cheetah"), load_robot("mini_cheetah").as_struct()
+    n = 3
+    q, v = np.ascontiguousarray(g["q"][:n]), np.ascontiguousarray(g["v"][:n])
+    Cm, Jd = np.zeros((n, 18, 18)), np.zeros((n, 4, 3, 18))
+    emu.emu_coriolis(C.byref(ms), n, np_ptr(q), np_ptr(v), np_ptr(Cm), np_ptr(Jd))
+    for i in range(n):
+        Co = P.coriolis_matrix(q[i], v[i])
+        assert np.abs(Cm[i] - Co).max() < 1e-9 * np.abs(Co).max()
+        assert np.abs(Cm[i] @ v[i] - g["Cv"][i]).max() < 1e-9 * max(1.0, np.abs(g["Cv"][i]).max())
+        for k, fr in enumerate(P.foot_frames):
+            assert np.abs(Jd[i, k] - P.frame_jacobian_dot(q[i], v[i], fr)).max() < 1e-9

@@ -81,6 +81,47 @@ def test_clf_full_size_config4(ctl_cache):
     assert (out.qp_info[:, 2] > -1e-9).all()          # delta >= 0 is never optimal to violate: cost w*delta^2, row -delta
 
 
+@pytest.mark.parametrize("case", CASES)
+def test_pc_step_matches_golden(ctl_cache, case):
+    """Passivity-constrained QP (pc_controller.py:43-255): analytic C w / Jdot against the oracle's AutoDiff-equivalent."""
+    g = np.load(GOLD / f"{case}.npz")
+    out = ctl_cache(robot_of(case)).step("pc", g["q"], g["v"], g["traj"], g["contact"], debug=True)
+    ok = g["pc_ok"]
+    assert (out.status[ok] == 0).all() and (out.status[~ok] == 64).all()
+    assert np.abs(out.tau - g["pc_tau"])[ok].max() < 1e-5
+    assert np.abs(out.vd - g["pc_vd"])[ok].max() < 1e-6
+    assert np.abs(out.f - g["pc_f"])[ok].max() < 1e-5
+    ref = g["pc_metrics"][ok]
+    assert (np.abs(out.metrics[ok] - ref)[:, [0, 1, 3]] / np.maximum(1.0, np.abs(ref[:, [0, 1, 3]]))).max() < 1e-8
+
+
+def test_pc_full_size_config4(ctl_cache):
+    """BASELINE config 4 (PC variant, 65536 instances, walk patterns): solves; constraints and passivity row hold."""
+    from quadruped_drake_b200.synth import generate
+    ctl = ctl_cache("mini_cheetah")
+    q, v, traj, contact = generate(ctl.model, 65536, 20260121, "walk", ctl.fk)
+    out = ctl.step("pc", q, v, traj, contact, debug=True)
+    assert (out.status == 0).all(), np.unique(out.status, return_counts=True)
+    dyn, con, fr = kkt_properties(ctl, q, v, traj, contact, out)
+    assert dyn.max() < 1e-7 and con.max() < 1e-7 and fr.max() < 1e-7
+    assert (out.metrics[:, 3] < 1e-7 * np.maximum(1.0, np.abs(out.metrics[:, 0]))).all()      # Vdot <= delta <= 0
+
+
+def test_coriolis_entry_matches_oracle(ctl_cache):
+    """wbc_coriolis: C = 1/2 d(Cv)/dv (CalcCoriolisMatrix) and the four foot Jdot (CalcFrameJacobianDot), 1e-9 relative."""
+    from oracle.dynamics import Plant
+    for robot, case in (("mini_cheetah", "mixed_mini_cheetah"), ("anymal_b", "cfg3_anymal_trot")):
+        g = np.load(GOLD / f"{case}.npz")
+        ctl, P = ctl_cache(robot), Plant(robot)
+        Cm, Jd = ctl.coriolis(g["q"], g["v"])
+        assert (np.abs(np.einsum("nij,nj->ni", Cm, g["v"]) - g["Cv"]).max(axis=1) < 1e-9 * np.maximum(1, np.abs(g["Cv"]).max(axis=1))).all()
+        for i in range(3):
+            Co = P.coriolis_matrix(g["q"][i], g["v"][i])
+            assert np.abs(Cm[i] - Co).max() < 1e-9 * np.abs(Co).max()
+            for k, fr in enumerate(P.foot_frames):
+                assert np.abs(Jd[i, k] - P.frame_jacobian_dot(g["q"][i], g["v"][i], fr)).max() < 1e-9
+
+
 def test_named_wrapper_and_torch_device_path(ctl_cache):
     """wbc_step_id on device pointers (torch only carries the memory and the stream) equals the host entry."""
     import ctypes as C

@@ -403,3 +403,84 @@ def proto_step_id(model, prm, q, v, traj, contact):
     for j, i in enumerate(cont):
         f[i] = z[18 + 3 * j:21 + 3 * j]
     return dict(tau=tau, vd=vd, f=f, iters=iters, flag=flag | (gflag << 1), err=err, lam=lam, cond=np.linalg.cond(Hr))
+
+
+# ----------------------------------------------------------------------------- PC step
+def proto_step_pc(model, prm, q, v, traj, contact):
+    """Kernel formulation of pc_controller.py:43-255: tau_g cancels, delta is eliminated."""
+    dyn = dynamics(model, q, v, gravity_in_bias=True)
+    vidx = [model.v_index[k] for k in range(12)]
+    to_int = lambda x: np.hstack([x[0:6], [x[i] for i in vidx]])            # noqa: E731  Drake -> internal order
+    def to_drake(x):
+        y = np.zeros(18); y[0:6] = x[0:6]
+        for k in range(12):
+            y[vidx[k]] = x[6 + k]
+        return y
+    v_int = to_int(v)
+    bias = lambda vel_int: to_int_bias(model, q, to_drake(vel_int))         # noqa: E731
+    A, b, cont = build_equalities(model, prm, dyn, v_int, contact)
+    nc = len(cont)
+    n = 18 + 3 * nc
+    z0, Z, flag = nullspace(A, b)
+    sw = [i for i in range(4) if not contact[i]]
+    m = 6 + 3 * len(sw)
+    M = dyn["M"]
+    J = np.zeros((m, 18)); J[0:6, 0:6] = np.eye(6)
+    for s_, i in enumerate(sw):
+        J[6 + 3 * s_:9 + 3 * s_] = foot_jacobian(dyn, i)
+    rpy = rpy_from_R(dyn["R0"]); N = rpy_N(rpy)
+    xt = np.hstack([rpy - traj[9:12], dyn["P"] - traj[0:3]] + [dyn["p"][i] - traj[18 + 3 * i:21 + 3 * i] for i in sw])
+    xdt = np.hstack([v[0:3] - N @ traj[12:15], v[3:6] - traj[3:6]] + [dyn["vf"][i] - traj[30 + 3 * i:33 + 3 * i] for i in sw])
+    xddn = np.hstack([N @ traj[15:18], traj[6:9]] + [traj[42 + 3 * i:45 + 3 * i] for i in sw])
+    kp = np.hstack([prm["pc_kp_body_rpy"] * np.ones(3), prm["pc_kp_body_p"] * np.ones(3), prm["pc_kp_foot"] * np.ones(3 * len(sw))])
+    kd = np.hstack([prm["pc_kd_body_rpy"] * np.ones(3), prm["pc_kd_body_p"] * np.ones(3), prm["pc_kd_foot"] * np.ones(3 * len(sw))])
+    wt = np.hstack([prm["pc_w_body"] * np.ones(6), prm["pc_w_foot"] * np.ones(3 * len(sw))])
+    X = np.linalg.solve(M, J.T)
+    Lam = np.linalg.inv(J @ X)
+    s1 = Lam @ xdt
+    w = v_int - X @ s1
+    bv = bias(v_int)
+    Cw = 0.5 * (bias(v_int + w) - bv - bias(w))
+    Jdw = np.zeros(m)
+    for s_, i in enumerate(sw):
+        Jdw[6 + 3 * s_:9 + 3 * s_] = -skew(dyn["vf"][i] - v[3:6]) @ w[0:3] + dyn["Ld"][i] @ w[6 + 3 * i:9 + 3 * i]
+    g0 = X.T @ (bv - Cw) - xddn + Jdw
+    # reduced rows
+    YJ = J @ Z[0:18, :]                 # task rows as functions of the reduced variables
+    yJ0 = J @ z0[0:18]
+    rows = []
+    Wh = np.sqrt(wt)
+    Rw = (Wh[:, None] * Lam) @ YJ
+    r0 = Wh * (Lam @ (yJ0 + g0) + kp * xt + kd * xdt)
+    nf = Z.shape[1]
+    Hr = Rw.T @ Rw
+    gr = Rw.T @ r0
+    F = Z[18:18 + 3 * nc, :]
+    Hr += prm["reg_f"] * F.T @ F
+    gr += prm["reg_f"] * F.T @ z0[18:18 + 3 * nc]
+    G, hv = [], []
+    mu = prm["mu"]
+    for j in range(nc):
+        for sx, sy in ((1, 0), (-1, 0), (0, 1), (0, -1)):
+            e = np.zeros(n); e[18 + 3 * j], e[19 + 3 * j], e[20 + 3 * j] = sx, sy, -mu
+            G.append(e @ Z); hv.append(-(e @ z0))
+    G.append(s1 @ YJ); hv.append(-(s1 @ (yJ0 + g0)) - xdt @ (kp * xt))
+    G = np.array(G); hv = np.array(hv)
+    wsol, lam, iters, gflag = gi_solve(Hr, gr, G, hv)
+    z = z0 + Z @ wsol
+    T, t0 = tau_map(model, dyn, cont, n)
+    tau_int = T @ z + t0
+    tau = np.zeros(12); vd = to_drake(z[0:18])
+    for k in range(12):
+        tau[model.act_index[k]] = tau_int[k]
+    f = np.zeros((4, 3))
+    for j, i in enumerate(cont):
+        f[i] = z[18 + 3 * j:21 + 3 * j]
+    V = 0.5 * xdt @ s1 + 0.5 * xt @ (kp * xt)
+    Vdot = s1 @ (J @ z[0:18] + g0) + xdt @ (kp * xt)
+    return dict(tau=tau, vd=vd, f=f, iters=iters, flag=flag | (gflag << 1), V=V, Vdot=Vdot, err=xt @ xt)
+
+
+def to_int_bias(model, q, v_drake):
+    d = dynamics(model, q, v_drake, gravity_in_bias=False)
+    return d["h"]
