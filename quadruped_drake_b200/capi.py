@@ -12,7 +12,10 @@ import numpy as np
 
 from .model import WbcModelStruct
 
-LIB_PATH = Path(__file__).resolve().parent / "csrc" / "libwbc_b200.so"
+import os
+
+# WBC_LIB lets experiments point at an alternative build of the same library (e.g. different launch bounds)
+LIB_PATH = Path(os.environ.get("WBC_LIB") or (Path(__file__).resolve().parent / "csrc" / "libwbc_b200.so"))
 
 WBC_CTRL_ID, WBC_CTRL_CLF, WBC_CTRL_PC = 0, 1, 2
 KINDS = {"id": WBC_CTRL_ID, "clf": WBC_CTRL_CLF, "pc": WBC_CTRL_PC}
