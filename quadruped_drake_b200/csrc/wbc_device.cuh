@@ -69,7 +69,7 @@ struct StepArgs {
   long long n; int kind;
 };
 
-// Per-warp shared memory. Everything a step needs between load and store lives here (10.1 KB).
+// Per-warp shared memory. Everything a step needs between load and store lives here (12.6 KB).
 // The inputs + dynamics block is dead once the reduced problem (Y, cw, ct) is built, so the reduced
 // Hessian / Goldfarb-Idnani workspace overlays it.
 struct WarpSmem {
@@ -96,8 +96,8 @@ struct WarpSmem {
       int act[NF];
     };
   };
-  // ---- reduced equality system: for pivot row r, z_pc[r] = Ared[r][13] - sum_w Ared[r][w] w_w (free columns compacted)
-  double Ared[AR][YS];
+  // ---- equality system and its reduction
+  double A[AR][AC];
   int rowof[AC];         // pivot row of variable c, -1 if free
   int pc[AR];
   int fcol[NF];          // free (non-pivot) columns of A in increasing order
@@ -278,8 +278,7 @@ WBC_DEV void dynamics_phase(WarpSmem& s, const wbc_model& md, int lane, int& sta
   fcn = fcn + WBC_V3_SHFL(__shfl_down_sync, fn, 1, 8) + WBC_V3_SHFL(__shfl_down_sync, fn, 2, 8);
   fcf = fcf + WBC_V3_SHFL(__shfl_down_sync, ff, 1, 8) + WBC_V3_SHFL(__shfl_down_sync, ff, 2, 8);
   // ---- mass-matrix columns of joint (leg, j)
-  const V3 axl = jl == 0 ? ax[0] : (jl == 1 ? ax[1] : ax[2]), orl = jl == 0 ? org[0] : (jl == 1 ? org[1] : org[2]);
-  const V3 a = axl, b = cross(orl, axl);
+  const V3 a = ax[jl], b = cross(org[jl], ax[jl]);
   V3 Fn, Ff;
   spi_mul(Ic, a, b, Fn, Ff);
   if (link && BIAS_ONLY) bias_out[6 + 3 * leg + j] = dot(a, fcn) + dot(b, fcf);
@@ -349,11 +348,11 @@ WBC_DEV void dynamics_phase(WarpSmem& s, const wbc_model& md, int lane, int& sta
   if (GRAV) jdv = jdv + grav;
   if (link && WITH_JD) {
     // d/dt of column j of L: (omega_parent x a_j) x (p_f - o_j) + a_j x (pdot_f - odot_j)   
-    const V3 Ldc = cross(cross(wpar, axl), rf - orl) + cross(axl, vfoot - vorg);
+    const V3 Ldc = cross(cross(wpar, ax[j]), rf - org[j]) + cross(ax[j], vfoot - vorg);
     s.Ld[leg][0][j] = Ldc.x; s.Ld[leg][1][j] = Ldc.y; s.Ld[leg][2][j] = Ldc.z;
   }
   if (link && !BIAS_ONLY) {
-    const V3 Lc = cross(axl, rf - orl);
+    const V3 Lc = cross(ax[j], rf - org[j]);
     s.L[leg][0][j] = Lc.x; s.L[leg][1][j] = Lc.y; s.L[leg][2][j] = Lc.z;
     s.rho[leg][j] = comp(rf, j);
     s.Jdv[leg][j] = comp(jdv, j);
@@ -413,40 +412,53 @@ WBC_DEV int stance_foot(unsigned cmask, int slot) {  // foot index of the slot-t
 }
 
 // Column `lane` of the tau-eliminated equality system [A|b] (SURVEY Appendix C.1 with
-// tau = M_j vd + h_j - J_c,j' f substituted), kept in REGISTERS (col[r], r static):
+// tau = M_j vd + h_j - J_c,j' f substituted):
 //   rows 0-5          M_b vd - sum_c Jb_c' f_c = -h_b          (base rows of AddDynamicsConstraint)
 //   rows 6+3s..8+3s   J_c vd = -Jdv_c - Kd J_c v               (AddContactConstraint)
-// variables: 0-5 base accel, 6-17 joint accel, 18.. contact forces (3 per stance foot), then extras; lane 31 = b.
-WBC_DEV void build_equalities(WarpSmem& s, int lane, unsigned cmask, int nc, double kd, double (&col)[AR]) {
+// variables: 0-5 base accel, 6-17 joint accel, 18.. contact forces (3 per stance foot), then extras.
+WBC_DEV void build_equalities(WarpSmem& s, int lane, unsigned cmask, int nc, double kd) {
   const int c = lane;
-  const bool isf = c >= 18 && c < 18 + 3 * nc;
-  const int fsl = isf ? (c - 18) / 3 : 0, fi = isf ? (c - 18) % 3 : 0;
-  const V3 frh = ld3(s.rho[stance_foot(cmask, fsl)]);
 #pragma unroll
-  for (int r = 0; r < 6; ++r) {
-    double val = 0.0;
-    if (c < 18) val = s.Mb[c][r];
-    else if (isf) val = r < 3 ? -skew_ent(frh, r, fi) : (r - 3 == fi ? -1.0 : 0.0);     // -Jb' e_i = -[skew(rho)[:, i]; e_i]
-    else if (c == 31) val = -s.hb[r];
-    col[r] = val;
-  }
+  for (int r = 0; r < AR; ++r) s.A[r][c] = 0.0;
+  if (c < 18) {
 #pragma unroll
-  for (int sl = 0; sl < 4; ++sl) {
-    const int k = stance_foot(cmask, sl);
-    const V3 rh = ld3(s.rho[k]);
+    for (int r = 0; r < 6; ++r) s.A[r][c] = s.Mb[c][r];
 #pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      double val = 0.0;
-      if (sl < nc) {
+    for (int k = 0; k < 4; ++k) {
+      const int sl = stance_slot(cmask, k);
+      if (sl < 0) continue;
+      const V3 rh = ld3(s.rho[k]);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        double val = 0.0;
         if (c < 3) val = -skew_ent(rh, i, c);
         else if (c < 6) val = (c - 3 == i) ? 1.0 : 0.0;
-        else if (c < 18) val = ((c - 6) / 3 == k) ? s.L[k][i][(c - 6) % 3] : 0.0;
-        else if (c == 31) val = -s.Jdv[k][i] - kd * s.vf[k][i];
+        else if ((c - 6) / 3 == k) val = s.L[k][i][(c - 6) % 3];
+        s.A[6 + 3 * sl + i][c] = val;
       }
-      col[6 + 3 * sl + i] = val;
+    }
+  } else if (c < 18 + 3 * nc) {
+    const int sl = (c - 18) / 3, i = (c - 18) % 3;
+    const V3 rh = ld3(s.rho[stance_foot(cmask, sl)]);
+    // -Jb' e_i = -[skew(rho)[:, i]; e_i]
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      s.A[r][c] = -skew_ent(rh, r, i);
+      s.A[3 + r][c] = r == i ? -1.0 : 0.0;
+    }
+  } else if (c == 31) {
+#pragma unroll
+    for (int r = 0; r < 6; ++r) s.A[r][c] = -s.hb[r];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int sl = stance_slot(cmask, k);
+      if (sl < 0) continue;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) s.A[6 + 3 * sl + i][c] = -s.Jdv[k][i] - kd * s.vf[k][i];
     }
   }
   s.rowof[c] = -1;
+  __syncwarp();
 }
 
 // Max over the warp of a non-negative double, with the owning lane: the lane index rides in the 5 lowest
@@ -462,58 +474,47 @@ WBC_DEV double warp_argmax_nonneg(double v, int lane, int& idx) {
   return __longlong_as_double((long long)(key & ~31ull));
 }
 
-// Gauss-Jordan on the register-resident columns, one pivot per row, pivot column = largest remaining entry of that
-// row; the multiplier of row i is the pivot lane's col[i], broadcast by shuffle. Finished pivot columns are left stale
-// (never read again). Returns the bit mask of pivot columns.
-WBC_DEV unsigned gauss_jordan(WarpSmem& s, int lane, int m, int n, int& status, double (&col)[AR]) {
+// Gauss-Jordan, one pivot per row, pivot column = largest remaining entry of that row.
+// Finished pivot columns are left stale (never read again). Returns the bit mask of pivot columns.
+WBC_DEV unsigned gauss_jordan(WarpSmem& s, int lane, int m, int n, int& status) {
   unsigned used = 0;
-#pragma unroll
-  for (int r = 0; r < AR; ++r) {
-    if (r < m) {
-      const double arc0 = col[r];
-      const bool eligible = lane < n && !((used >> lane) & 1);
-      int pcol;
-      const double best = warp_argmax_nonneg(eligible ? fabs(arc0) : 0.0, lane, pcol);
-      if (!(best > 1e-9)) {          // rows are O(0.01..10) (kg, kg m, lever arms): anything below is round-off
-        status |= WBC_ST_RANKDEF;
-        if (lane == 0) s.pc[r] = -1;
-      } else {
-        const double piv = shfl(arc0, pcol);
-        const double arc = arc0 / piv;
-        const bool upd = lane != pcol;
-#pragma unroll
-        for (int i = 0; i < AR; ++i) {
-          if (i != r && i < m) {
-            const double f = shfl(col[i], pcol);
-            if (upd) col[i] = fma(-f, arc, col[i]);
-          }
-        }
-        if (upd) col[r] = arc;
-        if (lane == pcol) s.rowof[lane] = r;
-        if (lane == 0) s.pc[r] = pcol;
-        used |= 1u << pcol;
-      }
+  for (int r = 0; r < m; ++r) {
+    const double arc0 = s.A[r][lane];
+    const bool eligible = lane < n && !((used >> lane) & 1);
+    int pcol;
+    const double best = warp_argmax_nonneg(eligible ? fabs(arc0) : 0.0, lane, pcol);
+    if (!(best > 1e-9)) {            // rows are O(0.01..10) (kg, kg m, lever arms): anything below is round-off
+      status |= WBC_ST_RANKDEF;
+      if (lane == 0) s.pc[r] = -1;
+      continue;
     }
+    const double piv = shfl(arc0, pcol);
+    const double arc = arc0 / piv;
+    if (lane != pcol) {
+      // row r itself is updated with factor A[r][pcol] = piv: arc0 - piv*arc = 0, so overwrite it afterwards
+#pragma unroll
+      for (int i = 0; i < AR; ++i) {
+        if (i < m) {
+          const double f = s.A[i][pcol];
+          s.A[i][lane] = fma(-f, arc, s.A[i][lane]);
+        }
+      }
+      s.A[r][lane] = arc;
+    }
+    __syncwarp();
+    if (lane == pcol) s.rowof[lane] = r;
+    if (lane == 0) s.pc[r] = pcol;
+    used |= 1u << pcol;
+    __syncwarp();
   }
   return used;
 }
 
-// Compacts the reduced system into shared memory: free column -> Ared[:, widx], right-hand side -> Ared[:, 13].
-WBC_DEV void store_reduced(WarpSmem& s, int ycol, const double (&col)[AR]) {
-  if (ycol >= 0) {
-#pragma unroll
-    for (int r = 0; r < AR; ++r) s.Ared[r][ycol] = col[r];
-  }
-  __syncwarp();
-}
-
 // Entry (var, column `lane`) of Z (free lanes) or of z0 (lane 31).
-// `ycol` = compact column of this lane (widx for a free lane, NF for lane 31, -1 otherwise).
-WBC_DEV double zent(const WarpSmem& s, int lane, int ycol, int var) {
+WBC_DEV double zent(const WarpSmem& s, int lane, int var) {
   const int r = s.rowof[var];
-  if (ycol < 0) return 0.0;
-  if (lane == 31) return r >= 0 ? s.Ared[r][NF] : 0.0;
-  return r >= 0 ? -s.Ared[r][ycol] : (var == lane ? 1.0 : 0.0);
+  if (lane == 31) return r >= 0 ? s.A[r][31] : 0.0;
+  return r >= 0 ? -s.A[r][lane] : (var == lane ? 1.0 : 0.0);
 }
 
 // ------------------------------------------------------------------------------ phase 5
@@ -835,15 +836,15 @@ WBC_DEV void put_y(WarpSmem& s, int row, int ycol, double val) { if (ycol >= 0) 
 WBC_DEV void build_common_rows(WarpSmem& s, int lane, int ycol, unsigned cmask) {
   double zb[6];
 #pragma unroll
-  for (int i = 0; i < 6; ++i) { zb[i] = zent(s, lane, ycol, i); put_y(s, i, ycol, zb[i]); }
+  for (int i = 0; i < 6; ++i) { zb[i] = zent(s, lane, i); put_y(s, i, ycol, zb[i]); }
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const int sl = stance_slot(cmask, k);
     double zl[3], zf[3];
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-      zl[i] = zent(s, lane, ycol, 6 + 3 * k + i);
-      zf[i] = sl >= 0 ? zent(s, lane, ycol, 18 + 3 * sl + i) : 0.0;
+      zl[i] = zent(s, lane, 6 + 3 * k + i);
+      zf[i] = sl >= 0 ? zent(s, lane, 18 + 3 * sl + i) : 0.0;
     }
     const V3 rh = ld3(s.rho[k]);
 #pragma unroll
@@ -922,8 +923,8 @@ WBC_DEV int swing_foot(unsigned cmask, int slot) { return stance_foot(~cmask & 1
 
 WBC_DEV void pc_precompute(WarpSmem& s, PcSmem& pc, const wbc_model& md, const wbc_params& pr, const BodyTask& bt,
                            int lane, unsigned cmask, int m, int& status, double& Vout, double& errout) {
-  double (*X)[16] = reinterpret_cast<double (*)[16]>(&s.Y[0][0]);       // 18 x 16 scratch in the Y region (Y is built later)
-  double (*T)[15] = reinterpret_cast<double (*)[15]>(&s.Y[0][0] + 18 * 16);   // 15 x 15 scratch (L^-1); 288 + 225 <= 32 * 14
+  double (*X)[16] = reinterpret_cast<double (*)[16]>(&s.A[0][0]);       // 18 x 16, dead before build_equalities
+  double (*T)[16] = X + 18;                                              // 16 x 16 scratch (L^-1)
   const bool on = lane < m;
   const int slot = lane >= 6 ? (lane - 6) / 3 : 0, ri = lane >= 6 ? (lane - 6) % 3 : 0;
   const int rk = (on && lane >= 6) ? swing_foot(cmask, slot) : -1;
@@ -1162,18 +1163,15 @@ WBC_DEV void step_instance(WarpSmem& s, const wbc_model& md, const wbc_params& p
   // ---- phases 2,3
   const int ndelta = (KIND == WBC_CTRL_CLF) ? 1 : 0;
   const int n = 18 + 3 * nc + ndelta, m = 6 + 3 * nc;
-  double col[AR];
-  build_equalities(s, lane, cmask, nc, pr.contact_damping, col);
-  const unsigned used = gauss_jordan(s, lane, m, n, status, col);
+  build_equalities(s, lane, cmask, nc, pr.contact_damping);
+  const unsigned used = gauss_jordan(s, lane, m, n, status);
   const unsigned freemask = ~used & ((n >= 32) ? 0xffffffffu : ((1u << n) - 1u));
   const int nf = __popc(freemask);
   const bool isfree = (freemask >> lane) & 1u;
   const int widx = __popc(freemask & ((1u << lane) - 1u));
   const int ycol = lane == 31 ? NF : (isfree ? widx : -1);
   bool ok = nf <= NF && pc_ok;
-  __syncwarp();
   if (ok) {
-    store_reduced(s, ycol, col);
     if (isfree) s.fcol[widx] = lane;
     // ---- phase 4
     for (int e = lane; e < YROWS * YS; e += 32) (&s.Y[0][0])[e] = 0.0;
@@ -1293,8 +1291,8 @@ WBC_DEV void step_instance(WarpSmem& s, const wbc_model& md, const wbc_params& p
         const int r = s.rowof[lane];
         double val;
         if (r >= 0) {
-          val = s.Ared[r][NF];
-          for (int w = 0; w < nf; ++w) val = fma(-s.Ared[r][w], s.x[w], val);
+          val = s.A[r][31];
+          for (int w = 0; w < nf; ++w) val = fma(-s.A[r][s.fcol[w]], s.x[w], val);
         } else val = s.x[widx];
         const int dst = lane < 6 ? lane : md.v_index[lane - 6];
         a.vd[inst * WBC_NV + dst] = val;
@@ -1341,7 +1339,7 @@ WBC_DEV void dynamics_instance(WarpSmem& s, const wbc_model& md, const double* q
   for (int i = lane; i < WBC_NQ; i += 32) s.q[i] = q[inst * WBC_NQ + i];
   for (int i = lane; i < WBC_NV; i += 32) s.v[i] = v[inst * WBC_NV + i];
   __syncwarp();
-  double* taug = &s.Y[0][0];  // scratch: 18 doubles
+  double* taug = &s.A[0][0];  // scratch: 18 doubles
   dynamics_phase<DYN_PARITY>(s, md, lane, status, taug);
   // internal -> Drake index
   auto didx = [&](int c) { return c < 6 ? c : md.v_index[c - 6]; };
