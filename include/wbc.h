@@ -64,6 +64,8 @@ extern "C" {
 #define WBC_CTRL_ID 0          /* controllers/inverse_dynamics_controller.py */
 #define WBC_CTRL_CLF 1         /* controllers/clf_controller.py              */
 #define WBC_CTRL_PC 2          /* controllers/pc_controller.py               */
+#define WBC_CTRL_MPTC 3        /* controllers/mptc_controller.py (PC without the passivity rows) */
+#define WBC_CTRL_PD 4          /* BasicController.ControlLaw, basic_controller.py:322-352 (joint PD) */
 
 /* Flattened robot: what Drake's Parser + MultibodyPlant::Finalize hold after
  * simulate.py:37-64. Body 0 = floating base, body 1+3*leg+j = link j of leg
@@ -103,6 +105,9 @@ typedef struct wbc_params {
   double reg_f, reg_tau, reg_vd;
   int32_t torque_limits;     /* 0 = reference QP; 1 = add |tau_k| <= effort_k  */
   int32_t max_iter;          /* active-set iteration cap                       */
+  /* Basic PD law (basic_controller.py:331-350): tau = -kp (theta - theta_nom) - kd thetadot, clipped */
+  double pd_kp, pd_kd, pd_clip;
+  double pd_q_nom[WBC_NU];   /* nominal joint angles in the caller's joint order (q[7:19])       */
 } wbc_params;
 
 typedef struct wbc_handle wbc_handle;
@@ -155,6 +160,10 @@ int wbc_step_clf(wbc_handle* h, int64_t n, const double* q, const double* v, con
                  const uint8_t* contact, double* tau, double* metrics, int32_t* status, void* stream);
 int wbc_step_pc(wbc_handle* h, int64_t n, const double* q, const double* v, const double* traj,
                 const uint8_t* contact, double* tau, double* metrics, int32_t* status, void* stream);
+int wbc_step_mptc(wbc_handle* h, int64_t n, const double* q, const double* v, const double* traj,
+                  const uint8_t* contact, double* tau, double* metrics, int32_t* status, void* stream);
+/* BasicController.ControlLaw (basic_controller.py:322-352); traj / contact are ignored and may be NULL. */
+int wbc_step_pd(wbc_handle* h, int64_t n, const double* q, const double* v, double* tau, void* stream);
 
 /* Same step with HOST buffers (what the Python LeafSystem shim calls): copies the
  * inputs to the device, runs wbc_step, copies tau/metrics/status (and any optional

@@ -280,7 +280,10 @@ class CLFController(OracleController):
 
 
 class PCController(OracleController):
-    """pc_controller.py:43-255 with mptc_controller.py:30-57 (AddTaskForceCost)."""
+    """pc_controller.py:43-255 with mptc_controller.py:30-57 (AddTaskForceCost).
+    `passivity_constraint=False` gives MPTCController.ControlLaw (mptc_controller.py:125-310): same task-force cost and
+    gains, no delta, no Vdot rows."""
+    passivity_constraint = True
 
     def control_law(self, q, v, trunk):
         p = self.p
@@ -316,7 +319,8 @@ class PCController(OracleController):
         ub = t.xd_tilde @ (Jbar.T @ c.tau_g - Lam @ Qm @ (Jbar @ t.xd_tilde - v) + Lam @ t.xdd_nom - Kp @ t.x_tilde)
         row2 = np.zeros(n)                                # delta <= 0 :234-237
         row2[idel] = 1.0
-        G, h = np.vstack([row[None], row2[None], G]), np.hstack([ub, 0.0, h])
+        if self.passivity_constraint:
+            G, h = np.vstack([row[None], row2[None], G]), np.hstack([ub, 0.0, h])
         P = P0.copy()
         self._regularise(P, nc, idel, p["reg_f"])
         res = solve_qp(P, q0, A, b, G, h)
@@ -329,3 +333,25 @@ class PCController(OracleController):
         self.Vdot = float(t.xd_tilde @ (fz - Jbar.T @ c.tau_g + Lam @ Qm @ (Jbar @ t.xd_tilde - v) - Lam @ t.xdd_nom + Kp @ t.x_tilde))
         out.metrics = self.metrics()
         return out
+
+
+class MPTCController(PCController):
+    """mptc_controller.py:125-310 (the unused slack column only carries the tie-break and stays 0)."""
+    passivity_constraint = False
+
+
+class BasicController:
+    """BasicController.ControlLaw (basic_controller.py:322-352): joint-space PD about the standing posture, clipped to
+    +-150. u = S tau, so only the joint rows matter (MapQDotToVelocity is the identity on them)."""
+
+    def __init__(self, robot="mini_cheetah", dof_order="depth_first", q_nom=None, kp=30.0, kd=1.5, clip=150.0):
+        self.plant = robot if isinstance(robot, Plant) else Plant(robot, dof_order)
+        self.kp, self.kd, self.clip = kp, kd, clip
+        self.q_nom = np.asarray(q_nom, float) if q_nom is not None else np.array(
+            [1.0, 0, 0, 0, 0, 0, 0.3] + [0.0, -0.8, 1.6] * 4)
+
+    def control_law(self, q, v, trunk=None):
+        S = self.plant.actuation_matrix().T
+        tau = np.zeros(18)
+        tau[6:] = -self.kp * (np.asarray(q, float)[7:] - self.q_nom[7:]) - self.kd * np.asarray(v, float)[6:]
+        return np.clip(S @ tau, -self.clip, self.clip)

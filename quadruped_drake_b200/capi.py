@@ -17,8 +17,8 @@ import os
 # WBC_LIB lets experiments point at an alternative build of the same library (e.g. different launch bounds)
 LIB_PATH = Path(os.environ.get("WBC_LIB") or (Path(__file__).resolve().parent / "csrc" / "libwbc_b200.so"))
 
-WBC_CTRL_ID, WBC_CTRL_CLF, WBC_CTRL_PC = 0, 1, 2
-KINDS = {"id": WBC_CTRL_ID, "clf": WBC_CTRL_CLF, "pc": WBC_CTRL_PC}
+WBC_CTRL_ID, WBC_CTRL_CLF, WBC_CTRL_PC, WBC_CTRL_MPTC, WBC_CTRL_PD = 0, 1, 2, 3, 4
+KINDS = {"id": WBC_CTRL_ID, "clf": WBC_CTRL_CLF, "pc": WBC_CTRL_PC, "mptc": WBC_CTRL_MPTC, "pd": WBC_CTRL_PD}
 ST_MAXITER, ST_INFEASIBLE, ST_RANKDEF, ST_GIMBAL, ST_NOTPD, ST_BADQUAT, ST_UNSUPPORTED = 1, 2, 4, 8, 16, 32, 64
 
 _PARAM_DOUBLES = [
@@ -31,7 +31,9 @@ _PARAM_DOUBLES = [
 
 class WbcParams(C.Structure):
     """ctypes mirror of `wbc_params`."""
-    _fields_ = [(n, C.c_double) for n in _PARAM_DOUBLES] + [("torque_limits", C.c_int32), ("max_iter", C.c_int32)]
+    _fields_ = [(n, C.c_double) for n in _PARAM_DOUBLES] + [("torque_limits", C.c_int32), ("max_iter", C.c_int32),
+                                                              ("pd_kp", C.c_double), ("pd_kd", C.c_double), ("pd_clip", C.c_double),
+                                                              ("pd_q_nom", C.c_double * 12)]
 
 
 # Reference constants (SURVEY.md Appendix G); kept here so the struct can be filled without the library.
@@ -43,6 +45,7 @@ DEFAULT_PARAMS = dict(
     pc_kp_body_p=100.0, pc_kd_body_p=10.0, pc_kp_body_rpy=100.0, pc_kd_body_rpy=10.0,
     pc_kp_foot=200.0, pc_kd_foot=20.0, pc_w_body=10.0, pc_w_foot=1.0,
     mu=0.7, contact_damping=100.0, reg_f=1e-6, reg_tau=0.0, reg_vd=0.0, torque_limits=0, max_iter=200,
+    pd_kp=30.0, pd_kd=1.5, pd_clip=150.0, pd_q_nom=(0.0, -0.8, 1.6) * 4,
 )
 
 
@@ -54,7 +57,11 @@ def make_params(**overrides) -> WbcParams:
     vals.update(overrides)
     p = WbcParams()
     for k, v in vals.items():
-        setattr(p, k, int(v) if k in ("torque_limits", "max_iter") else float(v))
+        if k == "pd_q_nom":
+            for i, x in enumerate(v):
+                p.pd_q_nom[i] = float(x)
+        else:
+            setattr(p, k, int(v) if k in ("torque_limits", "max_iter") else float(v))
     return p
 
 
@@ -93,8 +100,11 @@ def load_library() -> C.CDLL:
     lib.wbc_coriolis_host.argtypes = [H, i64, dp, dp, dp, dp]
     lib.wbc_coriolis_host.restype = C.c_int
     lib.wbc_step.argtypes = [H, i32, i64, C.POINTER(WbcIO), dp]
-    for name in ("wbc_step_id", "wbc_step_clf", "wbc_step_pc"):
+    for name in ("wbc_step_id", "wbc_step_clf", "wbc_step_pc", "wbc_step_mptc"):
         getattr(lib, name).argtypes = [H, i64, dp, dp, dp, dp, dp, dp, dp, dp]
+        getattr(lib, name).restype = C.c_int
+    lib.wbc_step_pd.argtypes = [H, i64, dp, dp, dp, dp]
+    lib.wbc_step_pd.restype = C.c_int
     lib.wbc_step_host.argtypes = [H, i32, i64, C.POINTER(WbcIO)]
     lib.wbc_time_step.argtypes = [H, i32, i64, C.POINTER(WbcIO), i32, dp, C.POINTER(C.c_double)]
     lib.wbc_measure_fp64_peak.argtypes = [i32, C.POINTER(C.c_double)]
@@ -114,7 +124,7 @@ def load_library() -> C.CDLL:
 
 
 EXPORTED_SYMBOLS = ["wbc_default_params", "wbc_create", "wbc_destroy", "wbc_last_error", "wbc_dynamics", "wbc_coriolis",
-                    "wbc_step", "wbc_step_id", "wbc_step_clf", "wbc_step_pc", "wbc_step_host", "wbc_time_step",
+                    "wbc_step", "wbc_step_id", "wbc_step_clf", "wbc_step_pc", "wbc_step_mptc", "wbc_step_pd", "wbc_step_host", "wbc_time_step",
                     "wbc_measure_fp64_peak", "wbc_launch_count", "wbc_dynamics_host", "wbc_coriolis_host", "wbc_host_alloc", "wbc_host_free"]
 
 

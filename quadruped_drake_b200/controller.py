@@ -111,6 +111,16 @@ class BatchedController:
         self._check(self.lib.wbc_step_host(self._h, k, n, C.byref(io)), "wbc_step_host")
         return StepOutput(tau, met, st, vd, f, qi)
 
+    def step_pd(self, q, v):
+        """BasicController.ControlLaw (basic_controller.py:322-352) for a batch of host states -> tau[N,12]."""
+        q = np.ascontiguousarray(q, dtype=np.float64).reshape(-1, NQ)
+        n = q.shape[0]
+        v = np.ascontiguousarray(v, dtype=np.float64).reshape(n, NV)
+        tau = np.empty((n, NU))
+        io = WbcIO(np_ptr(q), np_ptr(v), None, None, np_ptr(tau), None, None, None, None, None)
+        self._check(self.lib.wbc_step_host(self._h, capi.WBC_CTRL_PD, n, C.byref(io)), "wbc_step_host")
+        return tau
+
     def _step_torch(self, k, q, v, traj, contact, debug):
         import torch
         n = q.shape[0]
@@ -336,3 +346,16 @@ class PCController(_QPController):
 
     def _log(self, m):
         self.V, self.err, self.Vdot = float(m[0]), float(m[1]), float(m[3])
+
+
+class MPTCController(PCController):
+    """Drop-in for reference controllers/mptc_controller.py:MPTCController."""
+    KIND = "mptc"
+
+
+class BasicController(_QPController):
+    """Drop-in for reference controllers/basic_controller.py:BasicController (joint-space PD, :322-352)."""
+    KIND = "pd"
+
+    def ControlLaw(self, context, q, v):
+        return self.batched.step_pd(q[None], v[None])[0].copy()

@@ -78,6 +78,11 @@ __global__ void __launch_bounds__(WARPS * 32) wbc_dynamics_kernel(const DevConst
   if (inst < n) wbc::dynamics_instance(sm->w[warp], dc.md, q, v, o, inst, lane);
 }
 
+__global__ void wbc_pd_kernel(const DevConst* __restrict__ gdc, const double* q, const double* v, double* tau, long long n) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n * WBC_NU) wbc::pd_element(gdc->md, gdc->pr, q, v, tau, t / WBC_NU, (int)(t % WBC_NU));
+}
+
 // Register-resident DFMA loop: 8 independent chains per thread, 2 flop per FMA.
 __global__ void fp64_peak_kernel(double* out, int iters) {
   double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
@@ -131,6 +136,8 @@ extern "C" int wbc_default_params(wbc_params* p) {
   p->pc_kp_foot = 200; p->pc_kd_foot = 20; p->pc_w_body = 10; p->pc_w_foot = 1;
   p->mu = 0.7; p->contact_damping = 100; p->reg_f = 1e-6; p->reg_tau = 0; p->reg_vd = 0;
   p->torque_limits = 0; p->max_iter = 200;
+  p->pd_kp = 30; p->pd_kd = 1.5; p->pd_clip = 150;
+  for (int l = 0; l < 4; ++l) { p->pd_q_nom[3 * l] = 0.0; p->pd_q_nom[3 * l + 1] = -0.8; p->pd_q_nom[3 * l + 2] = 1.6; }   // basic_controller.py:335-340
   return WBC_OK;
 }
 
@@ -243,10 +250,23 @@ extern "C" int wbc_coriolis_host(wbc_handle* h, int64_t n, const double* q, cons
   return rc;
 }
 
+extern "C" int wbc_step_pd(wbc_handle* h, int64_t n, const double* q, const double* v, double* tau, void* stream) {
+  if (!h) return WBC_ERR_ARG;
+  if (n < 0 || (n > 0 && (!q || !v || !tau))) return fail_arg(h, "wbc_step_pd: null buffer");
+  if (n == 0) return WBC_OK;
+  WBC_CUDA(h, cudaSetDevice(h->device));
+  const long long total = (long long)n * WBC_NU;
+  wbc_pd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(h->d_const, q, v, tau, n);
+  h->launches++;
+  WBC_CUDA(h, cudaGetLastError());
+  return WBC_OK;
+}
+
 extern "C" int wbc_step(wbc_handle* h, int kind, int64_t n, const wbc_io* io, void* stream) {
   if (!h) return WBC_ERR_ARG;
   if (!io || n < 0) return fail_arg(h, "wbc_step: bad arguments");
   if (n == 0) return WBC_OK;
+  if (kind == WBC_CTRL_PD) return wbc_step_pd(h, n, io->q, io->v, io->tau, stream);
   if (!io->q || !io->v || !io->traj || !io->contact || !io->tau || !io->metrics || !io->status)
     return fail_arg(h, "wbc_step: q, v, traj, contact, tau, metrics and status are required");
   WBC_CUDA(h, cudaSetDevice(h->device));
@@ -258,7 +278,8 @@ extern "C" int wbc_step(wbc_handle* h, int kind, int64_t n, const wbc_io* io, vo
   switch (kind) {
     case WBC_CTRL_ID: wbc_step_kernel<WBC_CTRL_ID><<<grid, WARPS * 32, sm, st>>>(h->d_const, a); break;
     case WBC_CTRL_CLF: wbc_step_kernel<WBC_CTRL_CLF><<<grid, WARPS * 32, sm, st>>>(h->d_const, a); break;
-    case WBC_CTRL_PC: wbc_step_pc_kernel<<<grid, WARPS * 32, sizeof(SmemLayoutPC), st>>>(h->d_const, a); break;
+    case WBC_CTRL_PC:
+    case WBC_CTRL_MPTC: wbc_step_pc_kernel<<<grid, WARPS * 32, sizeof(SmemLayoutPC), st>>>(h->d_const, a); break;
     default: return fail_arg(h, "wbc_step: unknown controller kind");
   }
   h->launches++;
@@ -275,6 +296,7 @@ extern "C" int wbc_step(wbc_handle* h, int kind, int64_t n, const wbc_io* io, vo
 WBC_STEP_WRAPPER(wbc_step_id, WBC_CTRL_ID)
 WBC_STEP_WRAPPER(wbc_step_clf, WBC_CTRL_CLF)
 WBC_STEP_WRAPPER(wbc_step_pc, WBC_CTRL_PC)
+WBC_STEP_WRAPPER(wbc_step_mptc, WBC_CTRL_MPTC)
 
 static int ensure_staging(wbc_handle* h, int64_t n) {
   if (n <= h->cap) return WBC_OK;
@@ -297,7 +319,8 @@ extern "C" int wbc_step_host(wbc_handle* h, int kind, int64_t n, const wbc_io* i
   if (!h) return WBC_ERR_ARG;
   if (!io || n < 0) return fail_arg(h, "wbc_step_host: bad arguments");
   if (n == 0) return WBC_OK;
-  if (!io->q || !io->v || !io->traj || !io->contact || !io->tau || !io->metrics || !io->status)
+  const bool pd = kind == WBC_CTRL_PD;
+  if (!io->q || !io->v || !io->tau || (!pd && (!io->traj || !io->contact || !io->metrics || !io->status)))
     return fail_arg(h, "wbc_step_host: q, v, traj, contact, tau, metrics and status are required");
   WBC_CUDA(h, cudaSetDevice(h->device));
   int rc = ensure_staging(h, n);
@@ -305,18 +328,22 @@ extern "C" int wbc_step_host(wbc_handle* h, int kind, int64_t n, const wbc_io* i
   cudaStream_t st = h->stream;
   WBC_CUDA(h, cudaMemcpyAsync(h->d_q, io->q, n * WBC_NQ * sizeof(double), cudaMemcpyHostToDevice, st));
   WBC_CUDA(h, cudaMemcpyAsync(h->d_v, io->v, n * WBC_NV * sizeof(double), cudaMemcpyHostToDevice, st));
-  WBC_CUDA(h, cudaMemcpyAsync(h->d_traj, io->traj, n * WBC_NTRAJ * sizeof(double), cudaMemcpyHostToDevice, st));
-  WBC_CUDA(h, cudaMemcpyAsync(h->d_contact, io->contact, n * 4, cudaMemcpyHostToDevice, st));
+  if (!pd) {
+    WBC_CUDA(h, cudaMemcpyAsync(h->d_traj, io->traj, n * WBC_NTRAJ * sizeof(double), cudaMemcpyHostToDevice, st));
+    WBC_CUDA(h, cudaMemcpyAsync(h->d_contact, io->contact, n * 4, cudaMemcpyHostToDevice, st));
+  }
   wbc_io dio{h->d_q, h->d_v, h->d_traj, h->d_contact, h->d_tau, h->d_metrics, h->d_status,
              io->vd ? h->d_vd : nullptr, io->f ? h->d_f : nullptr, io->qp_info ? h->d_info : nullptr};
   rc = wbc_step(h, kind, n, &dio, st);
   if (rc) return rc;
   WBC_CUDA(h, cudaMemcpyAsync(io->tau, h->d_tau, n * WBC_NU * sizeof(double), cudaMemcpyDeviceToHost, st));
-  WBC_CUDA(h, cudaMemcpyAsync(io->metrics, h->d_metrics, n * WBC_NMETRIC * sizeof(double), cudaMemcpyDeviceToHost, st));
-  WBC_CUDA(h, cudaMemcpyAsync(io->status, h->d_status, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-  if (io->vd) WBC_CUDA(h, cudaMemcpyAsync(io->vd, h->d_vd, n * WBC_NV * sizeof(double), cudaMemcpyDeviceToHost, st));
-  if (io->f) WBC_CUDA(h, cudaMemcpyAsync(io->f, h->d_f, n * 12 * sizeof(double), cudaMemcpyDeviceToHost, st));
-  if (io->qp_info) WBC_CUDA(h, cudaMemcpyAsync(io->qp_info, h->d_info, n * 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (!pd) {
+    WBC_CUDA(h, cudaMemcpyAsync(io->metrics, h->d_metrics, n * WBC_NMETRIC * sizeof(double), cudaMemcpyDeviceToHost, st));
+    WBC_CUDA(h, cudaMemcpyAsync(io->status, h->d_status, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  }
+  if (!pd && io->vd) WBC_CUDA(h, cudaMemcpyAsync(io->vd, h->d_vd, n * WBC_NV * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (!pd && io->f) WBC_CUDA(h, cudaMemcpyAsync(io->f, h->d_f, n * 12 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (!pd && io->qp_info) WBC_CUDA(h, cudaMemcpyAsync(io->qp_info, h->d_info, n * 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
   WBC_CUDA(h, cudaStreamSynchronize(st));
   return WBC_OK;
 }

@@ -1265,7 +1265,8 @@ WBC_DEV void step_instance(WarpSmem& s, const wbc_model& md, const wbc_params& p
       if (lane < 6 || (lane < 18 && !((cmask >> ((lane - 6) / 3)) & 1))) { s.cw[lane] = 1.0; s.ct[lane] = 0.0; }
       else if (lane < 18) { s.cw[lane] = pr.reg_f; s.ct[lane] = 0.0; }
       else if (lane < 30) { s.cw[lane] = pr.reg_tau; s.ct[lane] = 0.0; }
-      nextra = 1; extra_bound = 0.0;
+      nextra = (a.kind == WBC_CTRL_PC) ? 1 : 0;   // MPTC (mptc_controller.py:125-310): same cost, no passivity row
+      extra_bound = 0.0;
       err = errpc;
     }
     __syncwarp();
@@ -1415,6 +1416,17 @@ WBC_DEV void coriolis_instance(WarpSmem& s, PcSmem& pc, const wbc_model& md, con
     }
   }
   __syncwarp();
+}
+
+// BasicController.ControlLaw (basic_controller.py:322-352): u = S tau, tau = -Kp (q - q_nom) - Kd v on the joint rows,
+// clipped to +-clip. One thread per (instance, joint k in internal order).
+WBC_DEV void pd_element(const wbc_model& md, const wbc_params& pr, const double* q, const double* v, double* tau,
+                        long long inst, int k) {
+  const int vi = md.v_index[k];
+  const double e = q[inst * WBC_NQ + vi + 1] - pr.pd_q_nom[vi - 6];
+  double u = -pr.pd_kp * e - pr.pd_kd * v[inst * WBC_NV + vi];
+  u = fmin(fmax(u, -pr.pd_clip), pr.pd_clip);
+  tau[inst * WBC_NU + md.act_index[k]] = u;
 }
 
 }  // namespace wbc

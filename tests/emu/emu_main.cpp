@@ -19,7 +19,7 @@ void* lane_main(void* p) {
   for (long long i = 0; i < j->n; ++i) {
     if (j->mode == 0) {
       if (j->args.kind == WBC_CTRL_ID) wbc::step_instance<WBC_CTRL_ID>(*j->sm, *j->md, *j->pr, j->dv, j->args, i, j->lane);
-      if (j->args.kind == WBC_CTRL_PC) wbc::step_instance<WBC_CTRL_PC>(*j->sm, *j->md, *j->pr, j->dv, j->args, i, j->lane, j->pcs);
+      if (j->args.kind == WBC_CTRL_PC || j->args.kind == WBC_CTRL_MPTC) wbc::step_instance<WBC_CTRL_PC>(*j->sm, *j->md, *j->pr, j->dv, j->args, i, j->lane, j->pcs);
       if (j->args.kind == WBC_CTRL_CLF) wbc::step_instance<WBC_CTRL_CLF>(*j->sm, *j->md, *j->pr, j->dv, j->args, i, j->lane);
     } else if (j->mode == 1) {
       wbc::dynamics_instance(*j->sm, *j->md, j->q, j->v, j->dyn, i, j->lane);

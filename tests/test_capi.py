@@ -28,7 +28,7 @@ def test_struct_sizes_match_header(built):
     from quadruped_drake_b200.capi import WbcIO, WbcParams
     from quadruped_drake_b200.model import WbcModelStruct
     assert C.sizeof(WbcModelStruct) == 8 * (13 + 39 + 78 + 36 + 36 + 12 + 12 + 3) + 4 * 24
-    assert C.sizeof(WbcParams) == 8 * 29 + 8
+    assert C.sizeof(WbcParams) == 8 * 29 + 8 + 8 * 3 + 8 * 12
     assert C.sizeof(WbcIO) == 80
 
 
@@ -39,7 +39,8 @@ def test_default_params_match_reference_constants(built):
     assert lib.wbc_default_params(C.byref(p)) == 0
     q = capi.make_params()
     for name, _ in capi.WbcParams._fields_:
-        assert getattr(p, name) == getattr(q, name), name
+        a, b = getattr(p, name), getattr(q, name)
+        assert (list(a) == list(b)) if name == "pd_q_nom" else (a == b), name
     assert (p.mu, p.contact_damping, p.id_kp_body_p, p.id_w_body, p.clf_w_delta, p.pc_kp_foot) == (0.7, 100, 500, 10, 1000, 200)
 
 

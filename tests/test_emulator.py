@@ -63,7 +63,7 @@ def test_emulated_id_step_matches_golden(emu, case):
     assert np.abs(met[:, 1] - g["id_metrics"][:, 1]).max() < 1e-12
 
 
-@pytest.mark.parametrize("kind", ["clf", "pc"])
+@pytest.mark.parametrize("kind", ["clf", "pc", "mptc"])
 @pytest.mark.parametrize("case", ["cfg3_anymal_trot", "cfg4_mini_cheetah_walk"])
 def test_emulated_clf_pc_steps_match_golden(emu, case, kind):
     g = np.load(GOLD / f"{case}.npz")
@@ -71,7 +71,7 @@ def test_emulated_clf_pc_steps_match_golden(emu, case, kind):
     tau, met, st, vd, f, qi = run_step(emu, robot, kind, g)
     ok = g[f"{kind}_ok"]
     assert (st[ok] == 0).all()
-    if kind == "pc":
+    if kind in ("pc", "mptc"):
         assert (st[~ok] == 64).all()                        # full flight: WBC_ST_UNSUPPORTED (the reference raises)
     assert np.abs(tau - g[f"{kind}_tau"])[ok].max() < 1e-5
     assert np.abs(vd - g[f"{kind}_vd"])[ok].max() < 1e-6

@@ -81,11 +81,14 @@ def test_clf_full_size_config4(ctl_cache):
     assert (out.qp_info[:, 2] > -1e-9).all()          # delta >= 0 is never optimal to violate: cost w*delta^2, row -delta
 
 
+@pytest.mark.parametrize("kind", ["pc", "mptc"])
 @pytest.mark.parametrize("case", CASES)
-def test_pc_step_matches_golden(ctl_cache, case):
-    """Passivity-constrained QP (pc_controller.py:43-255): analytic C w / Jdot against the oracle's AutoDiff-equivalent."""
+def test_pc_step_matches_golden(ctl_cache, case, kind):
+    """Passivity-constrained QP (pc_controller.py:43-255) and MPTC (mptc_controller.py:125-310): analytic C w / Jdot
+    against the oracle's AutoDiff-equivalent."""
     g = np.load(GOLD / f"{case}.npz")
-    out = ctl_cache(robot_of(case)).step("pc", g["q"], g["v"], g["traj"], g["contact"], debug=True)
+    out = ctl_cache(robot_of(case)).step(kind, g["q"], g["v"], g["traj"], g["contact"], debug=True)
+    g = {k.replace(kind + "_", "pc_") if k.startswith(kind + "_") else k: g[k] for k in g.files if kind == "pc" or not k.startswith("pc_")}
     ok = g["pc_ok"]
     assert (out.status[ok] == 0).all() and (out.status[~ok] == 64).all()
     assert np.abs(out.tau - g["pc_tau"])[ok].max() < 1e-5
@@ -120,6 +123,25 @@ def test_coriolis_entry_matches_oracle(ctl_cache):
             assert np.abs(Cm[i] - Co).max() < 1e-9 * np.abs(Co).max()
             for k, fr in enumerate(P.foot_frames):
                 assert np.abs(Jd[i, k] - P.frame_jacobian_dot(g["q"][i], g["v"][i], fr)).max() < 1e-9
+
+
+def test_pd_law(ctl_cache):
+    """BasicController.ControlLaw (basic_controller.py:322-352) and its LeafSystem mirror."""
+    from oracle import controllers as oc
+    from quadruped_drake_b200.controller import BasicController
+    from quadruped_drake_b200.synth import generate
+    ctl = ctl_cache("mini_cheetah")
+    q, v, traj, contact = generate(ctl.model, 257, 9, "stand", ctl.fk)
+    q[0, 7:] += 10.0                                            # drive the clip
+    tau = ctl.step_pd(q, v)
+    ref = oc.BasicController("mini_cheetah")
+    for i in (0, 1, 100, 256):
+        assert np.abs(tau[i] - ref.control_law(q[i], v[i])).max() < 1e-12
+    assert np.abs(tau[0]).max() == 150.0
+    leaf = BasicController("mini_cheetah", 5e-3)
+    ctx = leaf.CreateDefaultContext()
+    ctx.FixValue(0, np.hstack([q[1], v[1]]))
+    assert np.abs(leaf.EvalOutput(ctx, 0) - tau[1]).max() == 0.0
 
 
 def test_named_wrapper_and_torch_device_path(ctl_cache):

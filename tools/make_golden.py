@@ -26,7 +26,7 @@ CASES = [  # name, robot, pattern, n, seed (seed = 20260117 + config 
     ("cfg4_mini_cheetah_walk", "mini_cheetah", "walk", 24, 20260121),
     ("mixed_mini_cheetah", "mini_cheetah", "mixed", 32, 20260122),
 ]
-CTRL = {"id": oc.IDController, "clf": oc.CLFController, "pc": oc.PCController}
+CTRL = {"id": oc.IDController, "clf": oc.CLFController, "pc": oc.PCController, "mptc": oc.MPTCController}
 
 
 def main(kinds):
@@ -48,7 +48,7 @@ def main(kinds):
             tau, vd, f, met, obj = np.zeros((n, 12)), np.zeros((n, 18)), np.zeros((n, 4, 3)), np.zeros((n, 4)), np.zeros(n)
             ok = np.zeros(n, bool)
             for i in range(n):
-                if kind == "pc" and contact[i].sum() == 0:
+                if kind in ("pc", "mptc") and contact[i].sum() == 0:
                     continue                      # reference PC raises on full flight
                 ctl.V = ctl.err = ctl.res = ctl.Vdot = 0.0
                 o = ctl.control_law(q[i], v[i], oc.traj_to_dict(traj[i], contact[i]))
@@ -61,4 +61,4 @@ def main(kinds):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1:] or ["id", "clf", "pc"])
+    main(sys.argv[1:] or ["id", "clf", "pc", "mptc"])
