@@ -124,6 +124,32 @@ WBC_DEV V3 mul(const S6& I, V3 a) {
 }
 WBC_DEV V3 ld3(const double* p) { return mk(p[0], p[1], p[2]); }
 
+// Fast reciprocal / reciprocal square root: hardware approximation + two Newton steps (full double precision for the
+// normal-range operands that occur here; an IEEE division expands to ~25 instructions, this to ~7).
+#ifdef __CUDA_ARCH__
+WBC_DEV double frcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  return fma(r, e, r);
+}
+WBC_DEV double frsqrt(double x) {
+  double r;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  // Newton for 1/sqrt: r <- r (1.5 - 0.5 x r^2), written as r + r * (0.5 - 0.5 x r^2)
+  double h = 0.5 * x;
+  double e = fma(-h * r, r, 0.5);
+  r = fma(r, e, r);
+  e = fma(-h * r, r, 0.5);
+  return fma(r, e, r);
+}
+#else
+WBC_DEV double frcp(double x) { return 1.0 / x; }
+WBC_DEV double frsqrt(double x) { return 1.0 / sqrt(x); }
+#endif
+
 template <typename T> WBC_DEV T shfl(T v, int src) { return __shfl_sync(WBC_FULL, v, src); }
 WBC_DEV double warp_sum(double v) {
 #pragma unroll
@@ -215,7 +241,7 @@ WBC_DEV void dynamics_phase(WarpSmem& s, const wbc_model& md, int lane, int& sta
   double qw = s.q[0], qx = s.q[1], qy = s.q[2], qz = s.q[3];
   double nn = qw * qw + qx * qx + qy * qy + qz * qz;
   if (!(nn > 1e-300) || !(nn < 1e300)) { status |= WBC_ST_BADQUAT; nn = 1.0; qw = 1.0; qx = qy = qz = 0.0; }
-  double inv = 1.0 / sqrt(nn);
+  double inv = frsqrt(nn);
   qw *= inv; qx *= inv; qy *= inv; qz *= inv;
   M3 R0;
   R0.c0 = mk(1 - 2 * (qy * qy + qz * qz), 2 * (qx * qy + qw * qz), 2 * (qx * qz - qw * qy));
@@ -227,45 +253,46 @@ WBC_DEV void dynamics_phase(WarpSmem& s, const wbc_model& md, int lane, int& sta
   V3 av0 = mk(0, 0, 0) - cross(wb, vb);
   if (GRAV) av0 = av0 - grav;
 
-  // ---- leg chain (every lane of a leg group walks the whole chain; lane j keeps link j)
+  // ---- leg chain: lane j advances through joints 0..j of its leg and stops at its own link, so only one frame /
+  //      twist / acceleration is live per lane (lanes 3..7 shadow the shank lane and contribute zeros)
   M3 R = R0; V3 rho = mk(0, 0, 0);
   V3 vw = wb, vv = vb, aw = aw0, av = av0;
-  V3 ax[3], org[3];
-  V3 wpar = wb, vorg = vb;      // (WITH_JD) angular velocity of joint j's parent and velocity of its origin
-  M3 Rm = R0; V3 rhom = rho, vwm = vw, vvm = vv, awm = aw, avm = av;
+  V3 a = mk(0, 0, 0), b = mk(0, 0, 0), org = mk(0, 0, 0);
+  V3 wpar = wb, vorg = vb;      // (WITH_JD) angular velocity of the own joint's parent and velocity of its origin
 #pragma unroll
   for (int jj = 0; jj < 3; ++jj) {
-    const int k = 3 * leg + jj;
-    rho = rho + mul(R, ld3(md.joint_xyz[k]));
-    const V3 la = ld3(md.joint_axis[k]);
-    const V3 a = mul(R, la);
-    const int vi = md.v_index[k];
-    const double th = s.q[vi + 1], thd = BIAS_ONLY ? vel_int[6 + k] : s.v[vi];
-    double sn, cs; sincos(th, &sn, &cs);
-    // R <- R * Rot(la, th):  Rot e_m = cs e_m + sn (la x e_m) + (1-cs) la (la . e_m)
-    const double oc = 1.0 - cs;
-    V3 r0 = mk(cs + oc * la.x * la.x, sn * la.z + oc * la.y * la.x, -sn * la.y + oc * la.z * la.x);
-    V3 r1 = mk(-sn * la.z + oc * la.x * la.y, cs + oc * la.y * la.y, sn * la.x + oc * la.z * la.y);
-    V3 r2 = mk(sn * la.y + oc * la.x * la.z, -sn * la.x + oc * la.y * la.z, cs + oc * la.z * la.z);
-    M3 Rn; Rn.c0 = mul(R, r0); Rn.c1 = mul(R, r1); Rn.c2 = mul(R, r2);
-    R = Rn;
-    const V3 b = cross(rho, a);            // S = [a; rho x a]
-    if (WITH_JD && jj == jl) { wpar = vw; vorg = vv + cross(vw, rho); }
-    // acc += (vel x S) thd ; vel += S thd
-    aw = aw + thd * cross(vw, a);
-    av = av + thd * (cross(vw, b) + cross(vv, a));
-    vw = vw + thd * a; vv = vv + thd * b;
-    ax[jj] = a; org[jj] = rho;
-    if (jj == jl) { Rm = R; rhom = rho; vwm = vw; vvm = vv; awm = aw; avm = av; }
+    if (jj <= jl) {
+      const int k = 3 * leg + jj;
+      rho = rho + mul(R, ld3(md.joint_xyz[k]));
+      const V3 la = ld3(md.joint_axis[k]);
+      a = mul(R, la);
+      const int vi = md.v_index[k];
+      const double th = s.q[vi + 1], thd = BIAS_ONLY ? vel_int[6 + k] : s.v[vi];
+      double sn, cs; sincos(th, &sn, &cs);
+      // R <- R * Rot(la, th):  Rot e_m = cs e_m + sn (la x e_m) + (1-cs) la (la . e_m)
+      const double oc = 1.0 - cs;
+      V3 r0 = mk(cs + oc * la.x * la.x, sn * la.z + oc * la.y * la.x, -sn * la.y + oc * la.z * la.x);
+      V3 r1 = mk(-sn * la.z + oc * la.x * la.y, cs + oc * la.y * la.y, sn * la.x + oc * la.z * la.y);
+      V3 r2 = mk(sn * la.y + oc * la.x * la.z, -sn * la.x + oc * la.y * la.z, cs + oc * la.z * la.z);
+      M3 Rn; Rn.c0 = mul(R, r0); Rn.c1 = mul(R, r1); Rn.c2 = mul(R, r2);
+      R = Rn;
+      b = cross(rho, a);                     // S = [a; rho x a]
+      org = rho;
+      if (WITH_JD) { wpar = vw; vorg = vv + cross(vw, rho); }
+      // acc += (vel x S) thd ; vel += S thd
+      aw = aw + thd * cross(vw, a);
+      av = av + thd * (cross(vw, b) + cross(vv, a));
+      vw = vw + thd * a; vv = vv + thd * b;
+    }
   }
   // ---- own link: spatial inertia about P and inertial force
   const int bi = 1 + 3 * leg + jl;
-  SpI Il = link_inertia(md.mass[bi], ld3(md.com[bi]), md.inertia_com[bi], Rm, rhom);
+  SpI Il = link_inertia(md.mass[bi], ld3(md.com[bi]), md.inertia_com[bi], R, rho);
   V3 pn, pf, fn, ff;
-  spi_mul(Il, vwm, vvm, pn, pf);
-  spi_mul(Il, awm, avm, fn, ff);
-  fn = fn + cross(vwm, pn) + cross(vvm, pf);
-  ff = ff + cross(vwm, pf);
+  spi_mul(Il, vw, vv, pn, pf);
+  spi_mul(Il, aw, av, fn, ff);
+  fn = fn + cross(vw, pn) + cross(vv, pf);
+  ff = ff + cross(vw, pf);
   if (!link) {
     Il.m = 0; Il.h = mk(0, 0, 0); Il.I.xx = Il.I.yy = Il.I.zz = Il.I.xy = Il.I.xz = Il.I.yz = 0;
     fn = mk(0, 0, 0); ff = mk(0, 0, 0);
@@ -277,17 +304,19 @@ WBC_DEV void dynamics_phase(WarpSmem& s, const wbc_model& md, int lane, int& sta
   WBC_SPI_SHFL(__shfl_down_sync, Il, 2, 8); Ic = spi_add(Ic, tmp_spi);
   fcn = fcn + WBC_V3_SHFL(__shfl_down_sync, fn, 1, 8) + WBC_V3_SHFL(__shfl_down_sync, fn, 2, 8);
   fcf = fcf + WBC_V3_SHFL(__shfl_down_sync, ff, 1, 8) + WBC_V3_SHFL(__shfl_down_sync, ff, 2, 8);
-  // ---- mass-matrix columns of joint (leg, j)
-  const V3 a = ax[jl], b = cross(org[jl], ax[jl]);
+  // ---- mass-matrix columns of joint (leg, j): F_j = I^c_j S_j; leg block entries S_i . F_j with the ancestors' screw
+  //      axes S_i = [a_i; b_i] fetched from lanes j-1, j-2 of the leg group
   V3 Fn, Ff;
   spi_mul(Ic, a, b, Fn, Ff);
+  const V3 a1 = WBC_V3_SHFL(__shfl_up_sync, a, 1, 8), b1 = WBC_V3_SHFL(__shfl_up_sync, b, 1, 8);
+  const V3 a2 = WBC_V3_SHFL(__shfl_up_sync, a, 2, 8), b2 = WBC_V3_SHFL(__shfl_up_sync, b, 2, 8);
   if (link && BIAS_ONLY) bias_out[6 + 3 * leg + j] = dot(a, fcn) + dot(b, fcf);
   if (link && !BIAS_ONLY) {
     const int c = 6 + 3 * leg + j;
     s.Mb[c][0] = Fn.x; s.Mb[c][1] = Fn.y; s.Mb[c][2] = Fn.z; s.Mb[c][3] = Ff.x; s.Mb[c][4] = Ff.y; s.Mb[c][5] = Ff.z;
-#pragma unroll
-    for (int i = 0; i < 3; ++i)
-      if (i <= j) s.Mleg[leg][sym3(i, j)] = dot(ax[i], Fn) + dot(cross(org[i], ax[i]), Ff);
+    s.Mleg[leg][sym3(j, j)] = dot(a, Fn) + dot(b, Ff);
+    if (j >= 1) s.Mleg[leg][sym3(j - 1, j)] = dot(a1, Fn) + dot(b1, Ff);
+    if (j >= 2) s.Mleg[leg][sym3(j - 2, j)] = dot(a2, Fn) + dot(b2, Ff);
     s.hj[3 * leg + j] = dot(a, fcn) + dot(b, fcf);
     if (!GRAV && taug_sm) {
       // controller-sign gravity term: -S . [h x g ; m g]
@@ -341,18 +370,21 @@ WBC_DEV void dynamics_phase(WarpSmem& s, const wbc_model& md, int lane, int& sta
       taug_sm[c] = c < 3 ? -comp(tg, c) : -It.m * comp(grav, c - 3);
     }
   }
-  // ---- foot point (shank = last link of the chain; every lane of the leg has it)
-  const V3 rf = rho + mul(R, ld3(md.foot_xyz[leg]));
-  const V3 vfoot = vv + cross(vw, rf);
+  // ---- foot point: computed on the shank lane (j == 2 holds the full chain), broadcast inside the leg group
+  V3 rf = rho + mul(R, ld3(md.foot_xyz[leg]));
+  V3 vfoot = vv + cross(vw, rf);
   V3 jdv = av + cross(aw, rf) + cross(vw, vfoot);
   if (GRAV) jdv = jdv + grav;
+  rf = WBC_V3_SHFL(__shfl_sync, rf, 2, 8);
+  vfoot = WBC_V3_SHFL(__shfl_sync, vfoot, 2, 8);
+  jdv = WBC_V3_SHFL(__shfl_sync, jdv, 2, 8);
   if (link && WITH_JD) {
     // d/dt of column j of L: (omega_parent x a_j) x (p_f - o_j) + a_j x (pdot_f - odot_j)   
-    const V3 Ldc = cross(cross(wpar, ax[j]), rf - org[j]) + cross(ax[j], vfoot - vorg);
+    const V3 Ldc = cross(cross(wpar, a), rf - org) + cross(a, vfoot - vorg);
     s.Ld[leg][0][j] = Ldc.x; s.Ld[leg][1][j] = Ldc.y; s.Ld[leg][2][j] = Ldc.z;
   }
   if (link && !BIAS_ONLY) {
-    const V3 Lc = cross(ax[j], rf - org[j]);
+    const V3 Lc = cross(a, rf - org);
     s.L[leg][0][j] = Lc.x; s.L[leg][1][j] = Lc.y; s.L[leg][2][j] = Lc.z;
     s.rho[leg][j] = comp(rf, j);
     s.Jdv[leg][j] = comp(jdv, j);
@@ -489,7 +521,7 @@ WBC_DEV unsigned gauss_jordan(WarpSmem& s, int lane, int m, int n, int& status) 
       continue;
     }
     const double piv = shfl(arc0, pcol);
-    const double arc = arc0 / piv;
+    const double arc = arc0 * frcp(piv);
     if (lane != pcol) {
       // row r itself is updated with factor A[r][pcol] = piv: arc0 - piv*arc = 0, so overwrite it afterwards
 #pragma unroll
@@ -563,9 +595,10 @@ WBC_DEV void factor_and_start(WarpSmem& s, int lane, int& status, const TriPairs
   for (int j = 0; j < NF; ++j) {
     const double dj = s.H[j][j];
     if (!(dj > 1e-300)) { status |= WBC_ST_NOTPD; }
-    const double inv = 1.0 / sqrt(dj > 1e-300 ? dj : 1.0);
+    const double inv = frsqrt(dj > 1e-300 ? dj : 1.0);
     __syncwarp();
     if (lane < NF && lane >= j) s.H[lane][j] *= inv;
+    if (lane == 0) s.d[j] = inv;                    // 1 / L[j][j], reused by the triangular inverse below
     __syncwarp();
 #pragma unroll
     for (int h = 0; h < 3; ++h) {
@@ -583,7 +616,7 @@ WBC_DEV void factor_and_start(WarpSmem& s, int lane, int& status, const TriPairs
 #pragma unroll
       for (int mm = 0; mm < NF; ++mm)
         if (mm < i) acc = fma(-s.H[i][mm], xcol[mm], acc);
-      xcol[i] = acc / s.H[i][i];
+      xcol[i] = acc * s.d[i];
     }
     __syncwarp();            // every lane is done reading L before J overwrites it
 #pragma unroll
@@ -734,8 +767,10 @@ WBC_DEV int gi_solve(WarpSmem& s, int lane, const IneqSet& S, int max_iter, int&
       }
       // step lengths
       int l;
-      const double t1 = warp_argmin_nonneg((lane < q && rk > 0.0) ? fmax(s.u[li] / rk, 0.0) : INFINITY, lane, l);
-      const double t2 = (zn > 1e-14 * fmax(dd, 1e-300)) ? -sp / zn : INFINITY;
+      const double t1 = warp_argmin_nonneg((lane < q && rk > 0.0) ? fmax(s.u[li] * frcp(rk), 0.0) : INFINITY, lane, l);
+      const bool zok = zn > 1e-14 * fmax(dd, 1e-300);
+      const double izn = frcp(zok ? zn : 1.0);
+      const double t2 = zok ? -sp * izn : INFINITY;
       const double t = fmin(t1, t2);
       if (!(t < INFINITY)) { status |= WBC_ST_INFEASIBLE; fail = true; break; }
       const bool dual_only = !(t2 < INFINITY);
@@ -756,7 +791,7 @@ WBC_DEV int gi_solve(WarpSmem& s, int lane, const IneqSet& S, int max_iter, int&
       __syncwarp();
       if (!dual_only && t2 <= t1) {
         // ---- full step: add p. Householder on d[q:] -> (alpha, 0, ..), J[:, q:] <- J[:, q:] (I - 2 v v'/v'v)
-        const double nrm = sqrt(zn);
+        const double nrm = zn * frsqrt(zn);
         const double dq = s.d[q];
         const double alpha = dq > 0.0 ? -nrm : nrm;
         double rqq = dq;
@@ -770,7 +805,7 @@ WBC_DEV int gi_solve(WarpSmem& s, int lane, const IneqSet& S, int max_iter, int&
               vk[k] = k > q ? s.d[k] : (k == q ? dq - alpha : 0.0);
               if (k & 1) dt1 = fma(s.J[li][k], vk[k], dt1); else dt = fma(s.J[li][k], vk[k], dt);
             }
-            const double sc = 2.0 * (dt + dt1) / vv;
+            const double sc = 2.0 * (dt + dt1) * frcp(vv);
             if (row) {
 #pragma unroll
               for (int k = 0; k < NF; ++k) s.J[lane][k] = fma(-sc, vk[k], s.J[lane][k]);
@@ -779,7 +814,7 @@ WBC_DEV int gi_solve(WarpSmem& s, int lane, const IneqSet& S, int max_iter, int&
           rqq = alpha;
         }
         if (lane < q) s.R[lane][q] = dl;
-        if (lane == q) { s.R[q][q] = rqq; s.r[q] = 1.0 / rqq; s.u[q] = up; s.act[q] = p; }
+        if (lane == q) { s.R[q][q] = rqq; s.r[q] = frcp(rqq); s.u[q] = up; s.act[q] = p; }
         activemask |= 1ull << p;
         ++q;
         __syncwarp();
@@ -803,14 +838,15 @@ WBC_DEV int gi_solve(WarpSmem& s, int lane, const IneqSet& S, int max_iter, int&
         // Givens rotations restoring the triangle; same rotations on the columns of J
         for (int k = l; k < q - 1; ++k) {
           const double a = s.R[k][k], b = s.R[k + 1][k];
-          const double rr = sqrt(a * a + b * b);
+          const double r2 = a * a + b * b;
           __syncwarp();
-          if (rr > 0.0) {
-            const double c = a / rr, sn = b / rr;
+          if (r2 > 0.0) {
+            const double irr = frsqrt(r2);
+            const double c = a * irr, sn = b * irr;
             if (row) {
               const double r0 = s.R[k][lane], r1 = s.R[k + 1][lane];
               s.R[k][lane] = c * r0 + sn * r1; s.R[k + 1][lane] = -sn * r0 + c * r1;
-              if (lane == k) s.r[k] = 1.0 / (c * r0 + sn * r1);
+              if (lane == k) s.r[k] = frcp(c * r0 + sn * r1);
               const double j0 = s.J[lane][k], j1 = s.J[lane][k + 1];
               s.J[lane][k] = c * j0 + sn * j1; s.J[lane][k + 1] = -sn * j0 + c * j1;
             }

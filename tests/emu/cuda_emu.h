@@ -38,6 +38,10 @@ template <typename T> static inline T __shfl_down_sync(unsigned, T v, int delta,
   const int pos = emu_lane & (width - 1);
   return emu_exchange(v, pos + delta < width ? emu_lane + delta : emu_lane);
 }
+template <typename T> static inline T __shfl_up_sync(unsigned, T v, int delta, int width = 32) {
+  const int pos = emu_lane & (width - 1);
+  return emu_exchange(v, pos - delta >= 0 ? emu_lane - delta : emu_lane);
+}
 template <typename T> static inline T __shfl_xor_sync(unsigned, T v, int mask, int width = 32) {
   (void)width;
   return emu_exchange(v, emu_lane ^ mask);
