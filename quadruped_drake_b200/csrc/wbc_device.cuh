@@ -92,7 +92,7 @@ struct WarpSmem {
       union { double H[NF][NF]; double J[NF][NF]; };
       double g[NF];
       double R[NF][NF];
-      double d[NF], r[NF], x[NF], u[NF], npv[NF], y[YROWS];
+      double d[NF], r[NF], x[NF], u[NF], npv[NF], dm[NF], y[YROWS];
       int act[NF];
     };
   };
@@ -444,17 +444,18 @@ WBC_DEV int stance_foot(unsigned cmask, int slot) {  // foot index of the slot-t
 }
 
 // Column `lane` of the tau-eliminated equality system [A|b] (SURVEY Appendix C.1 with
-// tau = M_j vd + h_j - J_c,j' f substituted):
-//   rows 0-5          M_b vd - sum_c Jb_c' f_c = -h_b          (base rows of AddDynamicsConstraint)
-//   rows 6+3s..8+3s   J_c vd = -Jdv_c - Kd J_c v               (AddContactConstraint)
+// tau = M_j vd + h_j - J_c,j' f substituted). Row order: contact rows first, then the base rows, so that the
+// elimination can pivot each contact row inside its own leg's 3x3 block and touch only 8 rows per pivot:
+//   rows 3s..3s+2     J_c vd = -Jdv_c - Kd J_c v               (AddContactConstraint, s-th stance foot)
+//   rows 3nc..3nc+5   M_b vd - sum_c Jb_c' f_c = -h_b          (base rows of AddDynamicsConstraint)
 // variables: 0-5 base accel, 6-17 joint accel, 18.. contact forces (3 per stance foot), then extras.
 WBC_DEV void build_equalities(WarpSmem& s, int lane, unsigned cmask, int nc, double kd) {
-  const int c = lane;
+  const int c = lane, rb = 3 * nc;
 #pragma unroll
   for (int r = 0; r < AR; ++r) s.A[r][c] = 0.0;
   if (c < 18) {
 #pragma unroll
-    for (int r = 0; r < 6; ++r) s.A[r][c] = s.Mb[c][r];
+    for (int r = 0; r < 6; ++r) s.A[rb + r][c] = s.Mb[c][r];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int sl = stance_slot(cmask, k);
@@ -466,7 +467,7 @@ WBC_DEV void build_equalities(WarpSmem& s, int lane, unsigned cmask, int nc, dou
         if (c < 3) val = -skew_ent(rh, i, c);
         else if (c < 6) val = (c - 3 == i) ? 1.0 : 0.0;
         else if ((c - 6) / 3 == k) val = s.L[k][i][(c - 6) % 3];
-        s.A[6 + 3 * sl + i][c] = val;
+        s.A[3 * sl + i][c] = val;
       }
     }
   } else if (c < 18 + 3 * nc) {
@@ -475,18 +476,18 @@ WBC_DEV void build_equalities(WarpSmem& s, int lane, unsigned cmask, int nc, dou
     // -Jb' e_i = -[skew(rho)[:, i]; e_i]
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
-      s.A[r][c] = -skew_ent(rh, r, i);
-      s.A[3 + r][c] = r == i ? -1.0 : 0.0;
+      s.A[rb + r][c] = -skew_ent(rh, r, i);
+      s.A[rb + 3 + r][c] = r == i ? -1.0 : 0.0;
     }
   } else if (c == 31) {
 #pragma unroll
-    for (int r = 0; r < 6; ++r) s.A[r][c] = -s.hb[r];
+    for (int r = 0; r < 6; ++r) s.A[rb + r][c] = -s.hb[r];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int sl = stance_slot(cmask, k);
       if (sl < 0) continue;
 #pragma unroll
-      for (int i = 0; i < 3; ++i) s.A[6 + 3 * sl + i][c] = -s.Jdv[k][i] - kd * s.vf[k][i];
+      for (int i = 0; i < 3; ++i) s.A[3 * sl + i][c] = -s.Jdv[k][i] - kd * s.vf[k][i];
     }
   }
   s.rowof[c] = -1;
@@ -506,15 +507,23 @@ WBC_DEV double warp_argmax_nonneg(double v, int lane, int& idx) {
   return __longlong_as_double((long long)(key & ~31ull));
 }
 
-// Gauss-Jordan, one pivot per row, pivot column = largest remaining entry of that row.
-// Finished pivot columns are left stale (never read again). Returns the bit mask of pivot columns.
-WBC_DEV unsigned gauss_jordan(WarpSmem& s, int lane, int m, int n, int& status) {
+// Gauss-Jordan, one pivot per row. A contact row first looks for its pivot among the three joint columns of its own
+// leg (largest entry; falls back to any remaining column if that 3x3 block is singular), base rows pivot on the largest
+// remaining entry. Rows whose multiplier is exactly zero are skipped (the system is sparse: a leg pivot only reaches
+// the base rows and its own foot's rows). Finished pivot columns are left stale (never read again).
+// Returns the bit mask of pivot columns.
+WBC_DEV unsigned gauss_jordan(WarpSmem& s, int lane, int m, int n, unsigned cmask, int nc, int& status) {
   unsigned used = 0;
   for (int r = 0; r < m; ++r) {
     const double arc0 = s.A[r][lane];
     const bool eligible = lane < n && !((used >> lane) & 1);
     int pcol;
-    const double best = warp_argmax_nonneg(eligible ? fabs(arc0) : 0.0, lane, pcol);
+    double best = 0.0;
+    if (r < 3 * nc) {
+      const int c0 = 6 + 3 * stance_foot(cmask, r / 3);
+      best = warp_argmax_nonneg((eligible && lane >= c0 && lane < c0 + 3) ? fabs(arc0) : 0.0, lane, pcol);
+    }
+    if (!(best > 1e-9)) best = warp_argmax_nonneg(eligible ? fabs(arc0) : 0.0, lane, pcol);
     if (!(best > 1e-9)) {            // rows are O(0.01..10) (kg, kg m, lever arms): anything below is round-off
       status |= WBC_ST_RANKDEF;
       if (lane == 0) s.pc[r] = -1;
@@ -528,7 +537,7 @@ WBC_DEV unsigned gauss_jordan(WarpSmem& s, int lane, int m, int n, int& status) 
       for (int i = 0; i < AR; ++i) {
         if (i < m) {
           const double f = s.A[i][pcol];
-          s.A[i][lane] = fma(-f, arc, s.A[i][lane]);
+          if (f != 0.0) s.A[i][lane] = fma(-f, arc, s.A[i][lane]);
         }
       }
       s.A[r][lane] = arc;
@@ -567,7 +576,7 @@ WBC_DEV TriPairs tri_pairs(int lane) {
 }
 
 // H = sum_r cw_r Y_r' Y_r (+ identity on padded dims), g = sum_r cw_r Y_r (y0_r - ct_r) + glin
-WBC_DEV void reduced_hessian(WarpSmem& s, int lane, int nf, int nrows, const TriPairs& tp) {
+WBC_DEV void reduced_hessian(WarpSmem& s, int lane, int nf, int nrows, bool extra, const TriPairs& tp) {
 #pragma unroll
   for (int h = 0; h < 3; ++h) {
     const int i = tp.i[h], k = tp.k[h];
@@ -579,12 +588,14 @@ WBC_DEV void reduced_hessian(WarpSmem& s, int lane, int nf, int nrows, const Tri
       acc1 = fma(s.cw[r + 1] * s.Y[r + 1][i], s.Y[r + 1][k], acc1);
     }
     acc += acc1;
+    if (extra) acc = fma(s.cw[30] * s.Y[30][i], s.Y[30][k], fma(s.cw[31] * s.Y[31][i], s.Y[31][k], acc));
     if (i >= nf) acc = (i == k) ? 1.0 : 0.0;
     s.H[i][k] = acc;
   }
   if (lane < NF) {
     double acc = (lane < nf) ? s.glin[lane] : 0.0;
     for (int r = 0; r < nrows; ++r) acc = fma(s.cw[r] * s.Y[r][lane], s.Y[r][NF] - s.ct[r], acc);
+    if (extra) acc = fma(s.cw[30] * s.Y[30][lane], s.Y[30][NF] - s.ct[30], fma(s.cw[31] * s.Y[31][lane], s.Y[31][NF] - s.ct[31], acc));
     s.g[lane] = (lane < nf) ? acc : 0.0;
   }
   __syncwarp();
@@ -746,6 +757,7 @@ WBC_DEV int gi_solve(WarpSmem& s, int lane, const IneqSet& S, int max_iter, int&
       dl = row ? dl + (dl1 + dl2) : 0.0;
       if (row) s.d[lane] = dl;
       const double dm = lane >= q ? dl : 0.0;           // d masked to the free part
+      if (row) s.dm[lane] = dm;
       const double zn = warp_sum(dm * dm);
       if (dd < 0.0) dd = (q == 0) ? zn : warp_sum(dl * dl);
       __syncwarp();
@@ -753,9 +765,9 @@ WBC_DEV int gi_solve(WarpSmem& s, int lane, const IneqSet& S, int max_iter, int&
       double zi = 0.0, zi1 = 0.0, zi2 = 0.0;
 #pragma unroll
       for (int k = 0; k < NF; k += 3) {
-        zi = fma(s.J[li][k], (k >= q ? s.d[k] : 0.0), zi);
-        if (k + 1 < NF) zi1 = fma(s.J[li][k + 1], (k + 1 >= q ? s.d[k + 1] : 0.0), zi1);
-        if (k + 2 < NF) zi2 = fma(s.J[li][k + 2], (k + 2 >= q ? s.d[k + 2] : 0.0), zi2);
+        zi = fma(s.J[li][k], s.dm[k], zi);
+        if (k + 1 < NF) zi1 = fma(s.J[li][k + 1], s.dm[k + 1], zi1);
+        if (k + 2 < NF) zi2 = fma(s.J[li][k + 2], s.dm[k + 2], zi2);
       }
       zi += zi1 + zi2;
       const double sp = cp.bound - cp.ca * s.y[cp.ra] - cp.cb * s.y[cp.rb];
@@ -798,17 +810,18 @@ WBC_DEV int gi_solve(WarpSmem& s, int lane, const IneqSet& S, int max_iter, int&
         if (q < NF - 1) {
           const double vv = 2.0 * (zn - dq * alpha);   // |v|^2 with v = d[q:] - alpha e_q
           if (vv > 0.0) {
-            double vk[NF];
+            // v = masked d with v_q = d_q - alpha, kept in s.dm (all lanes are past their reads of s.dm)
+            if (lane == q) s.dm[q] = dq - alpha;
+            __syncwarp();
             double dt = 0.0, dt1 = 0.0;
 #pragma unroll
             for (int k = 0; k < NF; ++k) {
-              vk[k] = k > q ? s.d[k] : (k == q ? dq - alpha : 0.0);
-              if (k & 1) dt1 = fma(s.J[li][k], vk[k], dt1); else dt = fma(s.J[li][k], vk[k], dt);
+              if (k & 1) dt1 = fma(s.J[li][k], s.dm[k], dt1); else dt = fma(s.J[li][k], s.dm[k], dt);
             }
             const double sc = 2.0 * (dt + dt1) * frcp(vv);
             if (row) {
 #pragma unroll
-              for (int k = 0; k < NF; ++k) s.J[lane][k] = fma(-sc, vk[k], s.J[lane][k]);
+              for (int k = 0; k < NF; ++k) s.J[lane][k] = fma(-sc, s.dm[k], s.J[lane][k]);
             }
           }
           rqq = alpha;
@@ -1200,7 +1213,7 @@ WBC_DEV void step_instance(WarpSmem& s, const wbc_model& md, const wbc_params& p
   const int ndelta = (KIND == WBC_CTRL_CLF) ? 1 : 0;
   const int n = 18 + 3 * nc + ndelta, m = 6 + 3 * nc;
   build_equalities(s, lane, cmask, nc, pr.contact_damping);
-  const unsigned used = gauss_jordan(s, lane, m, n, status);
+  const unsigned used = gauss_jordan(s, lane, m, n, cmask, nc, status);
   const unsigned freemask = ~used & ((n >= 32) ? 0xffffffffu : ((1u << n) - 1u));
   const int nf = __popc(freemask);
   const bool isfree = (freemask >> lane) & 1u;
@@ -1308,7 +1321,7 @@ WBC_DEV void step_instance(WarpSmem& s, const wbc_model& md, const wbc_params& p
     __syncwarp();
     // ---- phase 5
     const TriPairs tp = tri_pairs(lane);
-    reduced_hessian(s, lane, nf, KIND == WBC_CTRL_ID ? 30 : 32, tp);
+    reduced_hessian(s, lane, nf, pr.reg_tau != 0.0 ? 30 : 18, KIND != WBC_CTRL_ID, tp);
     factor_and_start(s, lane, status, tp);
     // ---- phase 6
     IneqSet S;
