@@ -444,18 +444,17 @@ WBC_DEV int stance_foot(unsigned cmask, int slot) {  // foot index of the slot-t
 }
 
 // Column `lane` of the tau-eliminated equality system [A|b] (SURVEY Appendix C.1 with
-// tau = M_j vd + h_j - J_c,j' f substituted). Row order: contact rows first, then the base rows, so that the
-// elimination can pivot each contact row inside its own leg's 3x3 block and touch only 8 rows per pivot:
-//   rows 3s..3s+2     J_c vd = -Jdv_c - Kd J_c v               (AddContactConstraint, s-th stance foot)
-//   rows 3nc..3nc+5   M_b vd - sum_c Jb_c' f_c = -h_b          (base rows of AddDynamicsConstraint)
+// tau = M_j vd + h_j - J_c,j' f substituted):
+//   rows 0-5          M_b vd - sum_c Jb_c' f_c = -h_b          (base rows of AddDynamicsConstraint)
+//   rows 6+3s..8+3s   J_c vd = -Jdv_c - Kd J_c v               (AddContactConstraint)
 // variables: 0-5 base accel, 6-17 joint accel, 18.. contact forces (3 per stance foot), then extras.
 WBC_DEV void build_equalities(WarpSmem& s, int lane, unsigned cmask, int nc, double kd) {
-  const int c = lane, rb = 3 * nc;
+  const int c = lane;
 #pragma unroll
   for (int r = 0; r < AR; ++r) s.A[r][c] = 0.0;
   if (c < 18) {
 #pragma unroll
-    for (int r = 0; r < 6; ++r) s.A[rb + r][c] = s.Mb[c][r];
+    for (int r = 0; r < 6; ++r) s.A[r][c] = s.Mb[c][r];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int sl = stance_slot(cmask, k);
@@ -467,7 +466,7 @@ WBC_DEV void build_equalities(WarpSmem& s, int lane, unsigned cmask, int nc, dou
         if (c < 3) val = -skew_ent(rh, i, c);
         else if (c < 6) val = (c - 3 == i) ? 1.0 : 0.0;
         else if ((c - 6) / 3 == k) val = s.L[k][i][(c - 6) % 3];
-        s.A[3 * sl + i][c] = val;
+        s.A[6 + 3 * sl + i][c] = val;
       }
     }
   } else if (c < 18 + 3 * nc) {
@@ -476,18 +475,18 @@ WBC_DEV void build_equalities(WarpSmem& s, int lane, unsigned cmask, int nc, dou
     // -Jb' e_i = -[skew(rho)[:, i]; e_i]
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
-      s.A[rb + r][c] = -skew_ent(rh, r, i);
-      s.A[rb + 3 + r][c] = r == i ? -1.0 : 0.0;
+      s.A[r][c] = -skew_ent(rh, r, i);
+      s.A[3 + r][c] = r == i ? -1.0 : 0.0;
     }
   } else if (c == 31) {
 #pragma unroll
-    for (int r = 0; r < 6; ++r) s.A[rb + r][c] = -s.hb[r];
+    for (int r = 0; r < 6; ++r) s.A[r][c] = -s.hb[r];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int sl = stance_slot(cmask, k);
       if (sl < 0) continue;
 #pragma unroll
-      for (int i = 0; i < 3; ++i) s.A[3 * sl + i][c] = -s.Jdv[k][i] - kd * s.vf[k][i];
+      for (int i = 0; i < 3; ++i) s.A[6 + 3 * sl + i][c] = -s.Jdv[k][i] - kd * s.vf[k][i];
     }
   }
   s.rowof[c] = -1;
@@ -507,23 +506,15 @@ WBC_DEV double warp_argmax_nonneg(double v, int lane, int& idx) {
   return __longlong_as_double((long long)(key & ~31ull));
 }
 
-// Gauss-Jordan, one pivot per row. A contact row first looks for its pivot among the three joint columns of its own
-// leg (largest entry; falls back to any remaining column if that 3x3 block is singular), base rows pivot on the largest
-// remaining entry. Rows whose multiplier is exactly zero are skipped (the system is sparse: a leg pivot only reaches
-// the base rows and its own foot's rows). Finished pivot columns are left stale (never read again).
-// Returns the bit mask of pivot columns.
-WBC_DEV unsigned gauss_jordan(WarpSmem& s, int lane, int m, int n, unsigned cmask, int nc, int& status) {
+// Gauss-Jordan, one pivot per row, pivot column = largest remaining entry of that row.
+// Finished pivot columns are left stale (never read again). Returns the bit mask of pivot columns.
+WBC_DEV unsigned gauss_jordan(WarpSmem& s, int lane, int m, int n, int& status) {
   unsigned used = 0;
   for (int r = 0; r < m; ++r) {
     const double arc0 = s.A[r][lane];
     const bool eligible = lane < n && !((used >> lane) & 1);
     int pcol;
-    double best = 0.0;
-    if (r < 3 * nc) {
-      const int c0 = 6 + 3 * stance_foot(cmask, r / 3);
-      best = warp_argmax_nonneg((eligible && lane >= c0 && lane < c0 + 3) ? fabs(arc0) : 0.0, lane, pcol);
-    }
-    if (!(best > 1e-9)) best = warp_argmax_nonneg(eligible ? fabs(arc0) : 0.0, lane, pcol);
+    const double best = warp_argmax_nonneg(eligible ? fabs(arc0) : 0.0, lane, pcol);
     if (!(best > 1e-9)) {            // rows are O(0.01..10) (kg, kg m, lever arms): anything below is round-off
       status |= WBC_ST_RANKDEF;
       if (lane == 0) s.pc[r] = -1;
@@ -537,7 +528,7 @@ WBC_DEV unsigned gauss_jordan(WarpSmem& s, int lane, int m, int n, unsigned cmas
       for (int i = 0; i < AR; ++i) {
         if (i < m) {
           const double f = s.A[i][pcol];
-          if (f != 0.0) s.A[i][lane] = fma(-f, arc, s.A[i][lane]);
+          s.A[i][lane] = fma(-f, arc, s.A[i][lane]);
         }
       }
       s.A[r][lane] = arc;
@@ -1213,7 +1204,7 @@ WBC_DEV void step_instance(WarpSmem& s, const wbc_model& md, const wbc_params& p
   const int ndelta = (KIND == WBC_CTRL_CLF) ? 1 : 0;
   const int n = 18 + 3 * nc + ndelta, m = 6 + 3 * nc;
   build_equalities(s, lane, cmask, nc, pr.contact_damping);
-  const unsigned used = gauss_jordan(s, lane, m, n, cmask, nc, status);
+  const unsigned used = gauss_jordan(s, lane, m, n, status);
   const unsigned freemask = ~used & ((n >= 32) ? 0xffffffffu : ((1u << n) - 1u));
   const int nf = __popc(freemask);
   const bool isfree = (freemask >> lane) & 1u;
