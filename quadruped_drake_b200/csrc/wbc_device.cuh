@@ -17,6 +17,7 @@
 #pragma once
 #include <stdint.h>
 #include <math.h>
+#include <stddef.h>
 #include "wbc.h"
 
 #ifndef WBC_DEV
@@ -31,7 +32,7 @@ namespace wbc {
 constexpr int NF = 13;      // reduced dimension (12 free variables for ID/PC, 13 for CLF; padded to 13)
 constexpr int YS = 14;      // row stride of Y: 13 coefficients + constant
 constexpr int YROWS = 32;   // 0-5 a_b | 6-17 leg rows (f of a stance leg / task accel of a swing leg) | 18-29 tau | 30,31 extra
-constexpr int AR = 18;      // max equality rows
+constexpr int AR = 6;       // rows of the reduced base system (the stance-leg rows are eliminated analytically)
 constexpr int AC = 32;      // columns of [A|b]: lane c owns column c, lane 31 the right-hand side
 
 // Host-precomputed constants (wbc_create): per-channel CARE solution of the double integrator and the
@@ -96,15 +97,15 @@ struct WarpSmem {
       int act[NF];
     };
   };
-  // ---- equality system and its reduction
+  // ---- reduced base system [B | c0] over u = [a_b(6); per leg f_k (stance) or a_k (swing)] and its reduction
   double A[AR][AC];
+  double AK[4][3][7];    // stance leg k: a_k = AK[k][:, 6] - AK[k][:, 0:6] a_b   (= L_k^-1 (r_k - Jb_k a_b))
   int rowof[AC];         // pivot row of variable c, -1 if free
   int pc[AR];
   int fcol[NF];          // free (non-pivot) columns of A in increasing order
   // ---- reduced problem
   double Y[YROWS][YS];
   double cw[YROWS], ct[YROWS];   // cost weight / target of each Y row: 1/2 cw (y - ct)^2
-  double glin[NF];               // extra linear cost term on w
 };
 
 // ------------------------------------------------------------------ small vector helpers
@@ -443,52 +444,69 @@ WBC_DEV int stance_foot(unsigned cmask, int slot) {  // foot index of the slot-t
   return k;
 }
 
-// Column `lane` of the tau-eliminated equality system [A|b] (SURVEY Appendix C.1 with
-// tau = M_j vd + h_j - J_c,j' f substituted):
-//   rows 0-5          M_b vd - sum_c Jb_c' f_c = -h_b          (base rows of AddDynamicsConstraint)
-//   rows 6+3s..8+3s   J_c vd = -Jdv_c - Kd J_c v               (AddContactConstraint)
-// variables: 0-5 base accel, 6-17 joint accel, 18.. contact forces (3 per stance foot), then extras.
-WBC_DEV void build_equalities(WarpSmem& s, int lane, unsigned cmask, int nc, double kd) {
-  const int c = lane;
-#pragma unroll
-  for (int r = 0; r < AR; ++r) s.A[r][c] = 0.0;
-  if (c < 18) {
-#pragma unroll
-    for (int r = 0; r < 6; ++r) s.A[r][c] = s.Mb[c][r];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int sl = stance_slot(cmask, k);
-      if (sl < 0) continue;
+// Equality constraints of the tau-eliminated QP (SURVEY Appendix C.1 with tau = M_j vd + h_j - L' f substituted):
+//   contact rows  Jb_k a_b + L_k a_k = r_k := -Jdv_k - Kd J_k v     (AddContactConstraint, stance feet)
+//   base rows     M_bb a_b + sum_k M_bk a_k - sum_stance Jb_k' f_k = -h_b   (base rows of AddDynamicsConstraint)
+// The contact rows are solved analytically for the stance-leg joint accelerations through the leg's own 3x3 Jacobian
+// block, a_k = L_k^-1 (r_k - Jb_k a_b) (stored as AK), which leaves 6 base rows over the 18 variables
+// u = [a_b; per leg: f_k if stance, a_k if swing] (+ delta for CLF). Column `lane` of that 6 x 18 system [B | c0]
+// (c0 in lane 31) goes to shared memory for the pivoted Gauss-Jordan below.
+WBC_DEV void build_base_system(WarpSmem& s, int lane, unsigned cmask, double kd, int& status) {
+  // ---- AK rows: lane 3k+i computes row i of L_k^-1 = (c_{i+1} x c_{i+2}) / det, c_j the columns of L_k
+  bool bad = false;
+  if (lane < 12) {
+    const int k = lane / 3, i = lane % 3;
+    if ((cmask >> k) & 1) {
+      const int i1 = (i + 1) % 3, i2 = (i + 2) % 3;
+      const V3 ci = mk(s.L[k][0][i], s.L[k][1][i], s.L[k][2][i]);
+      const V3 c1 = mk(s.L[k][0][i1], s.L[k][1][i1], s.L[k][2][i1]);
+      const V3 c2 = mk(s.L[k][0][i2], s.L[k][1][i2], s.L[k][2][i2]);
+      const V3 cx = cross(c1, c2);
+      const double det = dot(ci, cx);
+      bad = !(fabs(det) > 1e-12);                              // singular stance leg (stretched knee)
+      const V3 li = frcp(fabs(det) > 1e-12 ? det : 1.0) * cx;  // row i of L_k^-1
       const V3 rh = ld3(s.rho[k]);
-#pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        double val = 0.0;
-        if (c < 3) val = -skew_ent(rh, i, c);
-        else if (c < 6) val = (c - 3 == i) ? 1.0 : 0.0;
-        else if ((c - 6) / 3 == k) val = s.L[k][i][(c - 6) % 3];
-        s.A[6 + 3 * sl + i][c] = val;
-      }
-    }
-  } else if (c < 18 + 3 * nc) {
-    const int sl = (c - 18) / 3, i = (c - 18) % 3;
-    const V3 rh = ld3(s.rho[stance_foot(cmask, sl)]);
-    // -Jb' e_i = -[skew(rho)[:, i]; e_i]
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-      s.A[r][c] = -skew_ent(rh, r, i);
-      s.A[3 + r][c] = r == i ? -1.0 : 0.0;
-    }
-  } else if (c == 31) {
-#pragma unroll
-    for (int r = 0; r < 6; ++r) s.A[r][c] = -s.hb[r];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int sl = stance_slot(cmask, k);
-      if (sl < 0) continue;
-#pragma unroll
-      for (int i = 0; i < 3; ++i) s.A[6 + 3 * sl + i][c] = -s.Jdv[k][i] - kd * s.vf[k][i];
+      // Li Jb = [-Li skew(rho) | Li];  li' skew(rho) = (li x rho)'  ->  row of -Li skew(rho) = rho x li
+      const V3 lxr = cross(rh, li);
+      s.AK[k][i][0] = lxr.x; s.AK[k][i][1] = lxr.y; s.AK[k][i][2] = lxr.z;
+      s.AK[k][i][3] = li.x; s.AK[k][i][4] = li.y; s.AK[k][i][5] = li.z;
+      const V3 r = mk(-s.Jdv[k][0] - kd * s.vf[k][0], -s.Jdv[k][1] - kd * s.vf[k][1], -s.Jdv[k][2] - kd * s.vf[k][2]);
+      s.AK[k][i][6] = dot(li, r);
     }
   }
+  if (__any_sync(WBC_FULL, bad)) status |= WBC_ST_RANKDEF;
+  __syncwarp();
+  const int c = lane;
+  double col[AR];
+#pragma unroll
+  for (int r = 0; r < AR; ++r) col[r] = 0.0;
+  if (c < 6 || c == 31) {
+    const int cc = c < 6 ? c : 6;                              // AK column: 0-5 -> S_b, 6 -> right-hand side
+#pragma unroll
+    for (int r = 0; r < 6; ++r) col[r] = c < 6 ? s.Mb[c][r] : -s.hb[r];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (!((cmask >> k) & 1)) continue;
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        const double ak = s.AK[k][a][cc];
+#pragma unroll
+        for (int r = 0; r < 6; ++r) col[r] = fma(-s.Mb[6 + 3 * k + a][r], ak, col[r]);
+      }
+    }
+  } else if (c < 18) {
+    const int k = (c - 6) / 3, i = (c - 6) % 3;
+    if ((cmask >> k) & 1) {
+      const V3 rh = ld3(s.rho[k]);                             // -Jb_k' e_i = [skew(rho)[i][0:3] ; -e_i]
+#pragma unroll
+      for (int r = 0; r < 3; ++r) { col[r] = skew_ent(rh, i, r); col[3 + r] = (r == i) ? -1.0 : 0.0; }
+    } else {
+#pragma unroll
+      for (int r = 0; r < 6; ++r) col[r] = s.Mb[c][r];
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < AR; ++r) s.A[r][c] = col[r];
   s.rowof[c] = -1;
   __syncwarp();
 }
@@ -584,7 +602,7 @@ WBC_DEV void reduced_hessian(WarpSmem& s, int lane, int nf, int nrows, bool extr
     s.H[i][k] = acc;
   }
   if (lane < NF) {
-    double acc = (lane < nf) ? s.glin[lane] : 0.0;
+    double acc = 0.0;
     for (int r = 0; r < nrows; ++r) acc = fma(s.cw[r] * s.Y[r][lane], s.Y[r][NF] - s.ct[r], acc);
     if (extra) acc = fma(s.cw[30] * s.Y[30][lane], s.Y[30][NF] - s.ct[30], fma(s.cw[31] * s.Y[31][lane], s.Y[31][NF] - s.ct[31], acc));
     s.g[lane] = (lane < nf) ? acc : 0.0;
@@ -871,33 +889,36 @@ WBC_DEV int gi_solve(WarpSmem& s, int lane, const IneqSet& S, int max_iter, int&
 // value at z0 (lane 31) are accumulated by the caller with zent(); this stores one result.
 WBC_DEV void put_y(WarpSmem& s, int row, int ycol, double val) { if (ycol >= 0) s.Y[row][ycol] = val; }
 
-// Rows 0-29 of Y for all three controllers: a_b, per-leg rows (contact force of a stance leg,
-// task acceleration J_s vd of a swing leg), joint torques tau = M_j vd + h_j - L' f.
+// Rows 0-29 of Y for all controllers: a_b, per-leg rows (contact force of a stance leg, task acceleration J_s vd of a
+// swing leg), joint torques tau = M_j vd + h_j - L' f. Variables: 0-5 a_b, 6+3k+i = f_k,i (stance) or a_k,i (swing).
 WBC_DEV void build_common_rows(WarpSmem& s, int lane, int ycol, unsigned cmask) {
   double zb[6];
 #pragma unroll
   for (int i = 0; i < 6; ++i) { zb[i] = zent(s, lane, i); put_y(s, i, ycol, zb[i]); }
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    const int sl = stance_slot(cmask, k);
-    double zl[3], zf[3];
+    const bool stance = (cmask >> k) & 1;
+    double zl[3], ak[3];
 #pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      zl[i] = zent(s, lane, 6 + 3 * k + i);
-      zf[i] = sl >= 0 ? zent(s, lane, 18 + 3 * sl + i) : 0.0;
-    }
+    for (int i = 0; i < 3; ++i) zl[i] = zent(s, lane, 6 + 3 * k + i);
     const V3 rh = ld3(s.rho[k]);
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
       double val;
-      if (sl >= 0) val = zf[i];
-      else {
+      if (stance) {
+        val = zl[i];                                       // the contact force itself
+        double a = (lane == 31) ? s.AK[k][i][6] : 0.0;     // a_k = AK[:,6] - AK[:,0:6] a_b
+#pragma unroll
+        for (int r = 0; r < 6; ++r) a = fma(-s.AK[k][i][r], zb[r], a);
+        ak[i] = a;
+      } else {
         // row i of J_k = [-skew(rho) | 1 | L_k]
         val = zb[3 + i];
 #pragma unroll
         for (int c = 0; c < 3; ++c) val = fma(-skew_ent(rh, i, c), zb[c], val);
 #pragma unroll
         for (int c = 0; c < 3; ++c) val = fma(s.L[k][i][c], zl[c], val);
+        ak[i] = zl[i];
       }
       put_y(s, 6 + 3 * k + i, ycol, val);
     }
@@ -908,10 +929,10 @@ WBC_DEV void build_common_rows(WarpSmem& s, int lane, int ycol, unsigned cmask) 
 #pragma unroll
       for (int r = 0; r < 6; ++r) val = fma(s.Mb[6 + kk][r], zb[r], val);
 #pragma unroll
-      for (int i = 0; i < 3; ++i) val = fma(s.Mleg[k][sym3(i < j ? i : j, i < j ? j : i)], zl[i], val);
-      if (sl >= 0) {
+      for (int i = 0; i < 3; ++i) val = fma(s.Mleg[k][sym3(i < j ? i : j, i < j ? j : i)], ak[i], val);
+      if (stance) {
 #pragma unroll
-        for (int i = 0; i < 3; ++i) val = fma(-s.L[k][i][j], zf[i], val);
+        for (int i = 0; i < 3; ++i) val = fma(-s.L[k][i][j], zl[i], val);
       }
       put_y(s, 18 + kk, ycol, val);
     }
@@ -963,8 +984,10 @@ WBC_DEV int swing_foot(unsigned cmask, int slot) { return stance_foot(~cmask & 1
 
 WBC_DEV void pc_precompute(WarpSmem& s, PcSmem& pc, const wbc_model& md, const wbc_params& pr, const BodyTask& bt,
                            int lane, unsigned cmask, int m, int& status, double& Vout, double& errout) {
-  double (*X)[16] = reinterpret_cast<double (*)[16]>(&s.A[0][0]);       // 18 x 16, dead before build_equalities
-  double (*T)[16] = X + 18;                                              // 16 x 16 scratch (L^-1)
+  double (*X)[16] = reinterpret_cast<double (*)[16]>(&s.Y[0][0]);       // 18 x 16 scratch in the Y region (Y is built later)
+  // 15 x 15 scratch (L^-1) right after the last used entry of X (17*16+14): 287 + 225 = 512 doubles = Y + cw + ct
+  static_assert(offsetof(WarpSmem, ct) + sizeof(double) * YROWS - offsetof(WarpSmem, Y) >= 512 * sizeof(double), "PC scratch");
+  double (*T)[15] = reinterpret_cast<double (*)[15]>(&s.Y[0][0] + 287);
   const bool on = lane < m;
   const int slot = lane >= 6 ? (lane - 6) / 3 : 0, ri = lane >= 6 ? (lane - 6) % 3 : 0;
   const int rk = (on && lane >= 6) ? swing_foot(cmask, slot) : -1;
@@ -1202,8 +1225,8 @@ WBC_DEV void step_instance(WarpSmem& s, const wbc_model& md, const wbc_params& p
   }
   // ---- phases 2,3
   const int ndelta = (KIND == WBC_CTRL_CLF) ? 1 : 0;
-  const int n = 18 + 3 * nc + ndelta, m = 6 + 3 * nc;
-  build_equalities(s, lane, cmask, nc, pr.contact_damping);
+  const int n = 18 + ndelta, m = 6;
+  build_base_system(s, lane, cmask, pr.contact_damping, status);
   const unsigned used = gauss_jordan(s, lane, m, n, status);
   const unsigned freemask = ~used & ((n >= 32) ? 0xffffffffu : ((1u << n) - 1u));
   const int nf = __popc(freemask);
@@ -1216,7 +1239,6 @@ WBC_DEV void step_instance(WarpSmem& s, const wbc_model& md, const wbc_params& p
     // ---- phase 4
     for (int e = lane; e < YROWS * YS; e += 32) (&s.Y[0][0])[e] = 0.0;
     s.cw[lane] = 0.0; s.ct[lane] = 0.0;
-    if (lane < NF) s.glin[lane] = 0.0;
     __syncwarp();
     build_common_rows(s, lane, ycol, cmask);
     // ---- costs
@@ -1288,7 +1310,7 @@ WBC_DEV void step_instance(WarpSmem& s, const wbc_model& md, const wbc_params& p
       Vl = warp_sum(Vl); PFl = warp_sum(PFl); csum = warp_sum(csum); err = warp_sum(err);
       __syncwarp();
       // extra rows: 30 = 2 kappa' J vd - delta  (Vdot constraint, :27-45), 31 = delta
-      const int cdel = 18 + 3 * nc;                      // delta's column: never a pivot (all-zero column of A)
+      const int cdel = 18;                               // delta's column: never a pivot (all-zero column of A)
       if (ycol >= 0) {
         double acc = 0.0;
         for (int r = 0; r < 18; ++r) acc = fma(2.0 * s.y[r], s.Y[r][ycol], acc);
@@ -1328,13 +1350,28 @@ WBC_DEV void step_instance(WarpSmem& s, const wbc_model& md, const wbc_params& p
       if (a.f) a.f[inst * 12 + lane] = ((cmask >> (lane / 3)) & 1) ? s.y[6 + lane] : 0.0;
     }
     if (a.vd) {
+      // u = [a_b; leg variables] from the reduced base system (not from Y: the PC kernel overwrites its task rows)
+      double uval = 0.0;
       if (lane < 18) {
         const int r = s.rowof[lane];
-        double val;
         if (r >= 0) {
-          val = s.A[r][31];
-          for (int w = 0; w < nf; ++w) val = fma(-s.A[r][s.fcol[w]], s.x[w], val);
-        } else val = s.x[widx];
+          uval = s.A[r][31];
+          for (int w = 0; w < nf; ++w) uval = fma(-s.A[r][s.fcol[w]], s.x[w], uval);
+        } else uval = s.x[widx];
+      }
+      double ab[6];
+#pragma unroll
+      for (int r = 0; r < 6; ++r) ab[r] = shfl(uval, r);
+      if (lane < 18) {
+        double val = uval;
+        if (lane >= 6) {
+          const int k = (lane - 6) / 3, i = (lane - 6) % 3;
+          if ((cmask >> k) & 1) {                          // stance leg: a_k = AK[:,6] - AK[:,0:6] a_b
+            val = s.AK[k][i][6];
+#pragma unroll
+            for (int r = 0; r < 6; ++r) val = fma(-s.AK[k][i][r], ab[r], val);
+          }
+        }
         const int dst = lane < 6 ? lane : md.v_index[lane - 6];
         a.vd[inst * WBC_NV + dst] = val;
       }

@@ -46,6 +46,11 @@ template <typename T> static inline T __shfl_xor_sync(unsigned, T v, int mask, i
   (void)width;
   return emu_exchange(v, emu_lane ^ mask);
 }
+static inline int __any_sync(unsigned, int pred) {
+  int acc = 0;
+  for (int l = 0; l < 32; ++l) acc |= emu_exchange(pred ? 1 : 0, l);
+  return acc;
+}
 static inline void __syncwarp(unsigned = 0xffffffffu) { emu_sync(); }
 static inline long long __double_as_longlong(double v) { long long r; memcpy(&r, &v, 8); return r; }
 static inline double __longlong_as_double(long long v) { double r; memcpy(&r, &v, 8); return r; }

@@ -484,3 +484,80 @@ def proto_step_pc(model, prm, q, v, traj, contact):
 def to_int_bias(model, q, v_drake):
     d = dynamics(model, q, v_drake, gravity_in_bias=False)
     return d["h"]
+
+
+# --------------------------------------------------------------- structured elimination (kernel v2)
+def structured_nullspace(model, prm, dyn, contact):
+    """z = z0 + Z w with w = [per leg: f_k (stance) or a_k (swing)] (12), using the block structure instead of a
+    generic Gauss-Jordan: stance legs a_k = Li_k (r_k - Jb_k a_b); base rows give a 6x6 system for a_b."""
+    cont = [i for i in range(4) if contact[i]]
+    nc = len(cont)
+    n = 18 + 3 * nc
+    M, h = dyn["M"], dyn["h"]
+    Sb = M[0:6, 0:6].copy()
+    C = np.zeros((6, 12))
+    c0 = -h[0:6].copy()
+    AK = {}
+    for k in range(4):
+        Jb = np.hstack([-skew(dyn["rho"][k]), np.eye(3)])
+        Mbk = M[0:6, 6 + 3 * k:9 + 3 * k]
+        if contact[k]:
+            Li = np.linalg.inv(dyn["L"][k])
+            r = -dyn["Jdv"][k] - prm["contact_damping"] * dyn["vf"][k]
+            AK[k] = (Li @ Jb, Li @ r)
+            Sb -= Mbk @ AK[k][0]
+            c0 -= Mbk @ AK[k][1]
+            C[:, 3 * k:3 * k + 3] = Jb.T
+        else:
+            C[:, 3 * k:3 * k + 3] = -Mbk
+    Bw = np.linalg.solve(Sb, C)          # a_b = Bw w + b0
+    b0 = np.linalg.solve(Sb, c0)
+    Z = np.zeros((n, 12)); z0 = np.zeros(n)
+    Z[0:6] = Bw; z0[0:6] = b0
+    for k in range(4):
+        if contact[k]:
+            s = cont.index(k)
+            Z[6 + 3 * k:9 + 3 * k] = -AK[k][0] @ Bw
+            z0[6 + 3 * k:9 + 3 * k] = AK[k][1] - AK[k][0] @ b0
+            Z[18 + 3 * s:21 + 3 * s, 3 * k:3 * k + 3] = np.eye(3)
+        else:
+            Z[6 + 3 * k:9 + 3 * k, 3 * k:3 * k + 3] = np.eye(3)
+    return z0, Z
+
+
+def hybrid_nullspace(model, prm, dyn, contact):
+    """Kernel v2 reduction: stance-leg joint accelerations analytically (a_k = Li_k (r_k - Jb_k a_b)), then pivoted
+    Gauss-Jordan on the 6 base rows over u = [a_b(6); per leg: f_k (stance) or a_k (swing)] (18 columns)."""
+    cont = [i for i in range(4) if contact[i]]
+    nc = len(cont)
+    n = 18 + 3 * nc
+    M, h = dyn["M"], dyn["h"]
+    B = np.zeros((6, 18)); c0 = -h[0:6].copy()
+    B[:, 0:6] = M[0:6, 0:6]
+    AK = {}
+    for k in range(4):
+        Jb = np.hstack([-skew(dyn["rho"][k]), np.eye(3)])
+        Mbk = M[0:6, 6 + 3 * k:9 + 3 * k]
+        if contact[k]:
+            Li = np.linalg.inv(dyn["L"][k])
+            r = -dyn["Jdv"][k] - prm["contact_damping"] * dyn["vf"][k]
+            AK[k] = (Li @ Jb, Li @ r)
+            B[:, 0:6] -= Mbk @ AK[k][0]
+            c0 -= Mbk @ AK[k][1]
+            B[:, 6 + 3 * k:9 + 3 * k] = -Jb.T
+        else:
+            B[:, 6 + 3 * k:9 + 3 * k] = Mbk
+    u0, Zu, flag = nullspace(B, c0)          # u = u0 + Zu w, 12 free
+    Z = np.zeros((n, 12)); z0 = np.zeros(n)
+    Z[0:6] = Zu[0:6]; z0[0:6] = u0[0:6]
+    for k in range(4):
+        if contact[k]:
+            s = cont.index(k)
+            Z[6 + 3 * k:9 + 3 * k] = -AK[k][0] @ Zu[0:6]
+            z0[6 + 3 * k:9 + 3 * k] = AK[k][1] - AK[k][0] @ u0[0:6]
+            Z[18 + 3 * s:21 + 3 * s] = Zu[6 + 3 * k:9 + 3 * k]
+            z0[18 + 3 * s:21 + 3 * s] = u0[6 + 3 * k:9 + 3 * k]
+        else:
+            Z[6 + 3 * k:9 + 3 * k] = Zu[6 + 3 * k:9 + 3 * k]
+            z0[6 + 3 * k:9 + 3 * k] = u0[6 + 3 * k:9 + 3 * k]
+    return z0, Z
