@@ -39,8 +39,13 @@ __device__ __forceinline__ const DevConst& stage_consts(L* sm, const DevConst* g
   return sm->dc;
 }
 
+#if WBC_MIN_CTAS > 0
+#define WBC_STEP_BOUNDS __launch_bounds__(WARPS * 32, WBC_MIN_CTAS)
+#else
+#define WBC_STEP_BOUNDS __maxnreg__(WBC_MAXNREG)                     // experiments: explicit register budget
+#endif
 template <int KIND>
-__global__ void __launch_bounds__(WARPS * 32, WBC_MIN_CTAS) wbc_step_kernel(const DevConst* __restrict__ gdc, wbc::StepArgs a) {
+__global__ void WBC_STEP_BOUNDS wbc_step_kernel(const DevConst* __restrict__ gdc, wbc::StepArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SmemLayout* sm = reinterpret_cast<SmemLayout*>(smem_raw);
   const DevConst& dc = stage_consts(sm, gdc);
