@@ -188,6 +188,41 @@ int wbc_time_step(wbc_handle* h, int kind, int64_t n, const wbc_io* io, int reps
  * resident DFMA loop over all SMs), used as the FP64 roofline denominator. */
 int wbc_measure_fp64_peak(int device, double* tflops);
 
+/* ---- LCM wire codecs: the byte formats either side of the control step. Messages are packed back
+ * to back, `msgs` must be 16-byte aligned; any optional pointer may be NULL. Per-message problems go to status[i]. */
+#define WBC_LCM_TRUNK_STATE_BYTES 549   /* lcm_types/trunk_state_t.lcm:1-50: 8 fingerprint + 8 + 1 + 18*24 + 4 + 4*24 */
+#define WBC_LCM_ROBOT_STATE_BYTES 204   /* lcm_types/robot_state_control_lcmt.lcm:1-7: 8 fingerprint + 4*(19+18+12)   */
+#define WBC_WIRE_BADFINGERPRINT 1       /* the generated decoders raise ValueError("Decode error")                    */
+#define WBC_WIRE_OVERFLOW 2             /* finite double beyond float32 range: struct.pack('>f') raises OverflowError */
+
+/* trunk_state_t.decode (lcm_types/trunklcm/trunk_state_t.py:79-120) + the field copy of planners/towr.py:112-145:
+ * n messages -> traj [N][54], contact [N][4] (wbc.h layout), optional timestamp [N], finished [N], planned forces
+ * f_plan [N][12] (LF RF LH RH, unused by every controller), status [N]. Device pointers. */
+int wbc_lcm_decode_trunk_state(wbc_handle* h, int64_t n, const uint8_t* msgs, double* timestamp, uint8_t* finished,
+                               double* traj, uint8_t* contact, double* f_plan, int32_t* status, void* stream);
+/* trunk_state_t.encode (trunk_state_t.py:54-77), what towr/trunk_mpc.cpp:19-68 publishes per sample. */
+int wbc_lcm_encode_trunk_state(wbc_handle* h, int64_t n, const double* timestamp, const uint8_t* finished,
+                               const double* traj, const uint8_t* contact, const double* f_plan, uint8_t* msgs, void* stream);
+/* robot_state_control_lcmt.decode (lcm_types/cheetahlcm/robot_state_control_lcmt.py:35-47) as used by
+ * BasicController.lcm_callback (basic_controller.py:79-87): float32 wire values widened to q [N][19], v [N][18],
+ * optional tau [N][12]. */
+int wbc_lcm_decode_robot_state(wbc_handle* h, int64_t n, const uint8_t* msgs, double* q, double* v, double* tau,
+                               int32_t* status, void* stream);
+/* robot_state_control_lcmt.encode (:24-33). q / v may be NULL (zeros: the controller publishes a fresh message that
+ * carries only the torques, basic_controller.py:309-314). tau_in_actuator_order != 0: `tau` is the step output of
+ * this library (actuator order) and is sent in velocity order like the reference's (S.T @ u)[-12:]; 0: copied as is. */
+int wbc_lcm_encode_robot_state(wbc_handle* h, int64_t n, const double* q, const double* v, const double* tau,
+                               int tau_in_actuator_order, uint8_t* msgs, int32_t* status, void* stream);
+/* The same four with HOST buffers (copies inside, synchronous). */
+int wbc_lcm_decode_trunk_state_host(wbc_handle* h, int64_t n, const uint8_t* msgs, double* timestamp, uint8_t* finished,
+                                    double* traj, uint8_t* contact, double* f_plan, int32_t* status);
+int wbc_lcm_encode_trunk_state_host(wbc_handle* h, int64_t n, const double* timestamp, const uint8_t* finished,
+                                    const double* traj, const uint8_t* contact, const double* f_plan, uint8_t* msgs);
+int wbc_lcm_decode_robot_state_host(wbc_handle* h, int64_t n, const uint8_t* msgs, double* q, double* v, double* tau,
+                                    int32_t* status);
+int wbc_lcm_encode_robot_state_host(wbc_handle* h, int64_t n, const double* q, const double* v, const double* tau,
+                                    int tau_in_actuator_order, uint8_t* msgs, int32_t* status);
+
 /* Number of kernel launches issued through this handle since creation. */
 int64_t wbc_launch_count(const wbc_handle* h);
 

@@ -114,6 +114,17 @@ def load_library() -> C.CDLL:
     lib.wbc_host_alloc.restype = C.c_void_p
     lib.wbc_host_free.argtypes = [C.c_void_p]
     lib.wbc_host_free.restype = None
+    u8 = dp
+    lib.wbc_lcm_decode_trunk_state.argtypes = [H, i64, u8, dp, dp, dp, dp, dp, dp, dp]
+    lib.wbc_lcm_encode_trunk_state.argtypes = [H, i64, dp, dp, dp, dp, dp, u8, dp]
+    lib.wbc_lcm_decode_robot_state.argtypes = [H, i64, u8, dp, dp, dp, dp, dp]
+    lib.wbc_lcm_encode_robot_state.argtypes = [H, i64, dp, dp, dp, i32, u8, dp, dp]
+    lib.wbc_lcm_decode_trunk_state_host.argtypes = [H, i64, u8, dp, dp, dp, dp, dp, dp]
+    lib.wbc_lcm_encode_trunk_state_host.argtypes = [H, i64, dp, dp, dp, dp, dp, u8]
+    lib.wbc_lcm_decode_robot_state_host.argtypes = [H, i64, u8, dp, dp, dp, dp]
+    lib.wbc_lcm_encode_robot_state_host.argtypes = [H, i64, dp, dp, dp, i32, u8, dp]
+    for name in WIRE_SYMBOLS:
+        getattr(lib, name).restype = C.c_int
     lib.wbc_launch_count.argtypes = [H]
     lib.wbc_launch_count.restype = C.c_int64
     for name in ("wbc_default_params", "wbc_create", "wbc_destroy", "wbc_dynamics", "wbc_coriolis", "wbc_step",
@@ -123,7 +134,10 @@ def load_library() -> C.CDLL:
     return lib
 
 
-EXPORTED_SYMBOLS = ["wbc_default_params", "wbc_create", "wbc_destroy", "wbc_last_error", "wbc_dynamics", "wbc_coriolis",
+WIRE_SYMBOLS = ["wbc_lcm_decode_trunk_state", "wbc_lcm_encode_trunk_state", "wbc_lcm_decode_robot_state", "wbc_lcm_encode_robot_state",
+                "wbc_lcm_decode_trunk_state_host", "wbc_lcm_encode_trunk_state_host", "wbc_lcm_decode_robot_state_host",
+                "wbc_lcm_encode_robot_state_host"]
+EXPORTED_SYMBOLS = WIRE_SYMBOLS + ["wbc_default_params", "wbc_create", "wbc_destroy", "wbc_last_error", "wbc_dynamics", "wbc_coriolis",
                     "wbc_step", "wbc_step_id", "wbc_step_clf", "wbc_step_pc", "wbc_step_mptc", "wbc_step_pd", "wbc_step_host", "wbc_time_step",
                     "wbc_measure_fp64_peak", "wbc_launch_count", "wbc_dynamics_host", "wbc_coriolis_host", "wbc_host_alloc", "wbc_host_free"]
 

@@ -41,6 +41,21 @@ def dict_to_traj(d):
     return t, np.array([1 if c else 0 for c in d["contact_states"]], dtype=np.uint8)
 
 
+def traj_to_dict(traj, contact, f_plan=None, u2_max=0.0):
+    """(traj[54], contact[4]) -> the reference trunk dict (planners/simple.py:45-85, planners/towr.py:112-148)."""
+    t = np.asarray(traj, float).ravel()
+    d = {"p_body": t[0:3].copy(), "pd_body": t[3:6].copy(), "pdd_body": t[6:9].copy(),
+         "rpy_body": t[9:12].copy(), "rpyd_body": t[12:15].copy(), "rpydd_body": t[15:18].copy()}
+    for i, f in enumerate(FEET):
+        d["p_" + f] = t[18 + 3 * i:21 + 3 * i].copy()
+        d["pd_" + f] = t[30 + 3 * i:33 + 3 * i].copy()
+        d["pdd_" + f] = t[42 + 3 * i:45 + 3 * i].copy()
+    d["contact_states"] = [bool(c) for c in np.asarray(contact).ravel()]
+    d["f_cj"] = np.zeros((3, 4)) if f_plan is None else np.asarray(f_plan, float).reshape(4, 3).T.copy()
+    d["u2_max"] = u2_max
+    return d
+
+
 def _is_torch(x):
     return type(x).__module__.startswith("torch")
 
@@ -291,8 +306,6 @@ class _QPController(LeafSystem):
 
     def __init__(self, plant, dt, use_lcm=False, device=0, dof_order="depth_first", **params):
         LeafSystem.__init__(self)
-        if use_lcm:
-            raise NotImplementedError("the LCM bridge (basic_controller.py:291-317) is outside the accelerated path")
         self.dt = dt
         self.plant = plant
         robot = plant if isinstance(plant, (str, RobotModel)) else getattr(plant, "wbc_robot", "mini_cheetah")
@@ -303,11 +316,51 @@ class _QPController(LeafSystem):
         self.DeclareVectorOutputPort("output_metrics", BasicVector(4), self.SetLoggingOutputs)
         self.DeclareAbstractInputPort("trunk_input", AbstractValue.Make({}))
         self.last_status = 0
+        # LCM bridge (basic_controller.py:54-61): messages are decoded / encoded by the device codecs of wire.py. The
+        # LCM runtime itself is optional: without it, feed `lcm_callback` yourself and read `published`.
+        self.use_lcm = use_lcm
+        self.q, self.v = np.zeros(NQ), np.zeros(NV)
+        self.published = []
+        self.lc = None
+        if use_lcm:
+            from .wire import WireCodec
+            self.wire = WireCodec(self.batched)
+            try:  # pragma: no cover - no LCM runtime in the build image
+                import lcm
+                self.lc = lcm.LCM()
+                self.lc.subscribe("robot_current_state", self.lcm_callback)
+            except ImportError:
+                self.lc = None
+
+    def lcm_callback(self, channel, data):
+        """basic_controller.py:79-87: latest robot state from a `robot_state_control_lcmt` message."""
+        msg = np.frombuffer(bytes(data), np.uint8)
+        if msg.size != 204:
+            raise ValueError("Decode error")
+        d = self.wire.decode_robot_state(msg[None])
+        if d["status"][0] != 0:
+            raise ValueError("Decode error")          # robot_state_control_lcmt.py:40
+        self.q, self.v = d["q"][0].copy(), d["v"][0].copy()
 
     def SetLoggingOutputs(self, context, output):
         output.SetFromVector(np.asarray([self.V, self.err, self.res, self.Vdot]))
 
     def DoSetControlTorques(self, context, output):
+        if self.use_lcm:
+            # basic_controller.py:291-297,307-317: state from LCM, torques out over LCM (velocity order), zeros to Drake
+            if self.lc is not None:  # pragma: no cover
+                self.lc.handle()
+            u = self.ControlLaw(context, self.q, self.v)
+            msgs, st = self.wire.encode_robot_state(None, None, np.asarray(u, float)[None], tau_in_actuator_order=True)
+            if st[0] != 0:
+                raise OverflowError("float too large to pack with f format")
+            data = msgs[0].tobytes()
+            self.published.append(("robot_control_input", data))
+            del self.published[:-16]
+            if self.lc is not None:  # pragma: no cover
+                self.lc.publish("robot_control_input", data)
+            output.SetFromVector(np.zeros(NU))
+            return
         state = np.asarray(self.EvalVectorInput(context, 0).get_value(), float)
         q, v = state[:NQ], state[-NV:]
         output.SetFromVector(self.ControlLaw(context, q, v))

@@ -7,6 +7,7 @@
 #include <string>
 
 #include "wbc_device.cuh"
+#include "wbc_wire.cuh"
 
 namespace {
 
@@ -107,6 +108,8 @@ struct wbc_handle {
   wbc_params params;
   std::string err;
   int64_t launches = 0;
+  int sm_count = 148;
+  int* d_tau_map = nullptr;            // message slot (velocity order) -> actuator index, for wbc_lcm_encode_robot_state
   cudaStream_t stream = nullptr;       // used by the host entry points
   // device staging for wbc_step_host
   int64_t cap = 0;
@@ -183,6 +186,15 @@ extern "C" int wbc_create(const wbc_model* model, const wbc_params* params, int 
   if (e != cudaSuccess) { h->err = std::string("cudaMemcpy: ") + cudaGetErrorString(e); return bail(WBC_ERR_CUDA); }
   e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) { h->err = std::string("cudaStreamCreate: ") + cudaGetErrorString(e); return bail(WBC_ERR_CUDA); }
+  {
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) h->sm_count = prop.multiProcessorCount;
+    int tmap[WBC_NU];
+    for (int k = 0; k < WBC_NU; ++k) tmap[model->v_index[k] - 6] = model->act_index[k];
+    e = cudaMalloc(&h->d_tau_map, sizeof(tmap));
+    if (e == cudaSuccess) e = cudaMemcpy(h->d_tau_map, tmap, sizeof(tmap), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { h->err = std::string("tau map upload: ") + cudaGetErrorString(e); return bail(WBC_ERR_CUDA); }
+  }
   rc = set_smem_attr(h);
   *out = h;
   return rc;
@@ -200,6 +212,7 @@ extern "C" int wbc_destroy(wbc_handle* h) {
   cudaSetDevice(h->device);
   free_staging(h);
   if (h->d_const) cudaFree(h->d_const);
+  if (h->d_tau_map) cudaFree(h->d_tau_map);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return WBC_OK;
@@ -403,6 +416,187 @@ extern "C" int wbc_time_step(wbc_handle* h, int kind, int64_t n, const wbc_io* i
   WBC_CUDA(h, cudaEventElapsedTime(&ms, e0, e1));
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   *ms_per_launch = (double)ms / reps;
+  return WBC_OK;
+}
+
+// ------------------------------------------------------------------------------ LCM wire codecs (wbc_wire.cuh)
+static unsigned wire_grid(const wbc_handle* h, int64_t n, int tile) {
+  const int64_t tiles = (n + tile - 1) / tile, cap = (int64_t)h->sm_count * 8;     // grid-stride over tiles
+  return (unsigned)(tiles < cap ? tiles : cap);
+}
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+extern "C" int wbc_lcm_decode_trunk_state(wbc_handle* h, int64_t n, const uint8_t* msgs, double* timestamp, uint8_t* finished,
+                                          double* traj, uint8_t* contact, double* f_plan, int32_t* status, void* stream) {
+  if (!h) return WBC_ERR_ARG;
+  if (n < 0 || (n > 0 && (!msgs || !traj || !contact))) return fail_arg(h, "wbc_lcm_decode_trunk_state: msgs, traj and contact are required");
+  if (!aligned16(msgs)) return fail_arg(h, "wbc_lcm_decode_trunk_state: msgs must be 16-byte aligned");
+  if (n == 0) return WBC_OK;
+  WBC_CUDA(h, cudaSetDevice(h->device));
+  wbcwire::decode_trunk_kernel<<<wire_grid(h, n, wbcwire::TILE), wbcwire::THREADS, 0, (cudaStream_t)stream>>>(
+      msgs, n, timestamp, finished, traj, contact, f_plan, status);
+  h->launches++;
+  WBC_CUDA(h, cudaGetLastError());
+  return WBC_OK;
+}
+
+extern "C" int wbc_lcm_encode_trunk_state(wbc_handle* h, int64_t n, const double* timestamp, const uint8_t* finished,
+                                          const double* traj, const uint8_t* contact, const double* f_plan, uint8_t* msgs,
+                                          void* stream) {
+  if (!h) return WBC_ERR_ARG;
+  if (n < 0 || (n > 0 && (!msgs || !traj || !contact))) return fail_arg(h, "wbc_lcm_encode_trunk_state: msgs, traj and contact are required");
+  if (!aligned16(msgs)) return fail_arg(h, "wbc_lcm_encode_trunk_state: msgs must be 16-byte aligned");
+  if (n == 0) return WBC_OK;
+  WBC_CUDA(h, cudaSetDevice(h->device));
+  wbcwire::encode_trunk_kernel<<<wire_grid(h, n, wbcwire::TILE), wbcwire::THREADS, 0, (cudaStream_t)stream>>>(
+      msgs, n, timestamp, finished, traj, contact, f_plan);
+  h->launches++;
+  WBC_CUDA(h, cudaGetLastError());
+  return WBC_OK;
+}
+
+extern "C" int wbc_lcm_decode_robot_state(wbc_handle* h, int64_t n, const uint8_t* msgs, double* q, double* v, double* tau,
+                                          int32_t* status, void* stream) {
+  if (!h) return WBC_ERR_ARG;
+  if (n < 0 || (n > 0 && (!msgs || !q || !v))) return fail_arg(h, "wbc_lcm_decode_robot_state: msgs, q and v are required");
+  if (!aligned16(msgs)) return fail_arg(h, "wbc_lcm_decode_robot_state: msgs must be 16-byte aligned");
+  if (n == 0) return WBC_OK;
+  WBC_CUDA(h, cudaSetDevice(h->device));
+  wbcwire::decode_robot_kernel<<<wire_grid(h, n, wbcwire::RTILE), wbcwire::THREADS, 0, (cudaStream_t)stream>>>(msgs, n, q, v, tau, status);
+  h->launches++;
+  WBC_CUDA(h, cudaGetLastError());
+  return WBC_OK;
+}
+
+extern "C" int wbc_lcm_encode_robot_state(wbc_handle* h, int64_t n, const double* q, const double* v, const double* tau,
+                                          int tau_in_actuator_order, uint8_t* msgs, int32_t* status, void* stream) {
+  if (!h) return WBC_ERR_ARG;
+  if (n < 0 || (n > 0 && (!msgs || !tau))) return fail_arg(h, "wbc_lcm_encode_robot_state: msgs and tau are required");
+  if (!aligned16(msgs)) return fail_arg(h, "wbc_lcm_encode_robot_state: msgs must be 16-byte aligned");
+  if (n == 0) return WBC_OK;
+  WBC_CUDA(h, cudaSetDevice(h->device));
+  wbcwire::encode_robot_kernel<<<wire_grid(h, n, wbcwire::RTILE), wbcwire::THREADS, 0, (cudaStream_t)stream>>>(
+      msgs, n, q, v, tau, tau_in_actuator_order ? h->d_tau_map : nullptr, status);
+  h->launches++;
+  WBC_CUDA(h, cudaGetLastError());
+  return WBC_OK;
+}
+
+namespace {
+// Scratch device buffers of the host-buffer codec entries: freed when the scope ends.
+struct DevScratch {
+  void* p[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int used = 0;
+  cudaError_t err = cudaSuccess;
+  template <typename T> T* in(const T* host, size_t count, cudaStream_t st) {      // NULL stays NULL
+    if (!host || err != cudaSuccess) return nullptr;
+    T* d = out<T>(host, count);
+    if (d) err = cudaMemcpyAsync(d, host, count * sizeof(T), cudaMemcpyHostToDevice, st);
+    return d;
+  }
+  template <typename T> T* out(const T* host, size_t count) {
+    if (!host || err != cudaSuccess) return nullptr;
+    void* d = nullptr;
+    err = cudaMalloc(&d, count * sizeof(T) > 0 ? count * sizeof(T) : 1);
+    if (err != cudaSuccess) return nullptr;
+    p[used++] = d;
+    return static_cast<T*>(d);
+  }
+  template <typename T> void back(T* host, const T* dev, size_t count, cudaStream_t st) {
+    if (host && dev && err == cudaSuccess) err = cudaMemcpyAsync(host, dev, count * sizeof(T), cudaMemcpyDeviceToHost, st);
+  }
+  ~DevScratch() { for (int i = 0; i < used; ++i) cudaFree(p[i]); }
+};
+}  // namespace
+
+#define WBC_SCRATCH_CHECK(h, s)                                                                  \
+  do {                                                                                           \
+    if ((s).err != cudaSuccess) { (h)->err = std::string("wire codec host path: ") + cudaGetErrorString((s).err); return WBC_ERR_CUDA; } \
+  } while (0)
+
+extern "C" int wbc_lcm_decode_trunk_state_host(wbc_handle* h, int64_t n, const uint8_t* msgs, double* timestamp, uint8_t* finished,
+                                               double* traj, uint8_t* contact, double* f_plan, int32_t* status) {
+  if (!h) return WBC_ERR_ARG;
+  if (n < 0 || (n > 0 && (!msgs || !traj || !contact))) return fail_arg(h, "wbc_lcm_decode_trunk_state_host: msgs, traj and contact are required");
+  if (n == 0) return WBC_OK;
+  WBC_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  DevScratch s;
+  const size_t N = (size_t)n;
+  uint8_t* dm = s.in(msgs, N * WBC_LCM_TRUNK_STATE_BYTES, st);
+  double* dts = s.out(timestamp, N); uint8_t* dfin = s.out(finished, N);
+  double* dtr = s.out(traj, N * WBC_NTRAJ); uint8_t* dc = s.out(contact, N * 4);
+  double* dfp = s.out(f_plan, N * 12); int32_t* dst = s.out(status, N);
+  WBC_SCRATCH_CHECK(h, s);
+  int rc = wbc_lcm_decode_trunk_state(h, n, dm, dts, dfin, dtr, dc, dfp, dst, st);
+  if (rc) return rc;
+  s.back(timestamp, dts, N, st); s.back(finished, dfin, N, st); s.back(traj, dtr, N * WBC_NTRAJ, st);
+  s.back(contact, dc, N * 4, st); s.back(f_plan, dfp, N * 12, st); s.back(status, dst, N, st);
+  WBC_SCRATCH_CHECK(h, s);
+  WBC_CUDA(h, cudaStreamSynchronize(st));
+  return WBC_OK;
+}
+
+extern "C" int wbc_lcm_encode_trunk_state_host(wbc_handle* h, int64_t n, const double* timestamp, const uint8_t* finished,
+                                               const double* traj, const uint8_t* contact, const double* f_plan, uint8_t* msgs) {
+  if (!h) return WBC_ERR_ARG;
+  if (n < 0 || (n > 0 && (!msgs || !traj || !contact))) return fail_arg(h, "wbc_lcm_encode_trunk_state_host: msgs, traj and contact are required");
+  if (n == 0) return WBC_OK;
+  WBC_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  DevScratch s;
+  const size_t N = (size_t)n;
+  const double* dts = s.in(timestamp, N, st); const uint8_t* dfin = s.in(finished, N, st);
+  const double* dtr = s.in(traj, N * WBC_NTRAJ, st); const uint8_t* dc = s.in(contact, N * 4, st);
+  const double* dfp = s.in(f_plan, N * 12, st);
+  uint8_t* dm = s.out(msgs, N * WBC_LCM_TRUNK_STATE_BYTES);
+  WBC_SCRATCH_CHECK(h, s);
+  int rc = wbc_lcm_encode_trunk_state(h, n, dts, dfin, dtr, dc, dfp, dm, st);
+  if (rc) return rc;
+  s.back(msgs, dm, N * WBC_LCM_TRUNK_STATE_BYTES, st);
+  WBC_SCRATCH_CHECK(h, s);
+  WBC_CUDA(h, cudaStreamSynchronize(st));
+  return WBC_OK;
+}
+
+extern "C" int wbc_lcm_decode_robot_state_host(wbc_handle* h, int64_t n, const uint8_t* msgs, double* q, double* v, double* tau,
+                                               int32_t* status) {
+  if (!h) return WBC_ERR_ARG;
+  if (n < 0 || (n > 0 && (!msgs || !q || !v))) return fail_arg(h, "wbc_lcm_decode_robot_state_host: msgs, q and v are required");
+  if (n == 0) return WBC_OK;
+  WBC_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  DevScratch s;
+  const size_t N = (size_t)n;
+  uint8_t* dm = s.in(msgs, N * WBC_LCM_ROBOT_STATE_BYTES, st);
+  double* dq = s.out(q, N * WBC_NQ); double* dv = s.out(v, N * WBC_NV); double* dt = s.out(tau, N * WBC_NU);
+  int32_t* dst = s.out(status, N);
+  WBC_SCRATCH_CHECK(h, s);
+  int rc = wbc_lcm_decode_robot_state(h, n, dm, dq, dv, dt, dst, st);
+  if (rc) return rc;
+  s.back(q, dq, N * WBC_NQ, st); s.back(v, dv, N * WBC_NV, st); s.back(tau, dt, N * WBC_NU, st); s.back(status, dst, N, st);
+  WBC_SCRATCH_CHECK(h, s);
+  WBC_CUDA(h, cudaStreamSynchronize(st));
+  return WBC_OK;
+}
+
+extern "C" int wbc_lcm_encode_robot_state_host(wbc_handle* h, int64_t n, const double* q, const double* v, const double* tau,
+                                               int tau_in_actuator_order, uint8_t* msgs, int32_t* status) {
+  if (!h) return WBC_ERR_ARG;
+  if (n < 0 || (n > 0 && (!msgs || !tau))) return fail_arg(h, "wbc_lcm_encode_robot_state_host: msgs and tau are required");
+  if (n == 0) return WBC_OK;
+  WBC_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  DevScratch s;
+  const size_t N = (size_t)n;
+  const double* dq = s.in(q, N * WBC_NQ, st); const double* dv = s.in(v, N * WBC_NV, st); const double* dt = s.in(tau, N * WBC_NU, st);
+  uint8_t* dm = s.out(msgs, N * WBC_LCM_ROBOT_STATE_BYTES); int32_t* dst = s.out(status, N);
+  WBC_SCRATCH_CHECK(h, s);
+  int rc = wbc_lcm_encode_robot_state(h, n, dq, dv, dt, tau_in_actuator_order, dm, dst, st);
+  if (rc) return rc;
+  s.back(msgs, dm, N * WBC_LCM_ROBOT_STATE_BYTES, st); s.back(status, dst, N, st);
+  WBC_SCRATCH_CHECK(h, s);
+  WBC_CUDA(h, cudaStreamSynchronize(st));
   return WBC_OK;
 }
 
