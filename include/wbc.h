@@ -223,6 +223,46 @@ int wbc_lcm_decode_robot_state_host(wbc_handle* h, int64_t n, const uint8_t* msg
 int wbc_lcm_encode_robot_state_host(wbc_handle* h, int64_t n, const double* q, const double* v, const double* tau,
                                     int tau_in_actuator_order, uint8_t* msgs, int32_t* status);
 
+/* ---- Trunk-trajectory sampler: TOWR spline solution -> controller input on the device.
+ * A plan is what towr's SplineHolder holds after the solve (towr/trunk_mpc.cpp:151-156): cubic Hermite node splines for
+ * base position, base Euler angles (rpy), 4 foot positions, 4 foot forces, and the per-foot phase durations. */
+#define WBC_TRAJ_CLAMPED 1   /* t outside [0, total]: evaluated at the nearest end (the reference asserts / runs off) */
+#define WBC_TRAJ_BADPLAN 2   /* plan index out of range: plan 0 used                                                  */
+
+typedef struct wbc_spline_desc {
+  int32_t n_poly;            /* number of cubic polynomials                                                        */
+  const double* durations;   /* [n_poly]           polynomial durations (Spline::GetPolyDurations)                 */
+  const double* nodes;       /* [n_poly + 1][6]    node position (3) and velocity (3), towr Node                   */
+} wbc_spline_desc;
+
+typedef struct wbc_plan_desc {
+  wbc_spline_desc base_linear, base_angular;   /* SplineHolder::base_linear_, base_angular_                        */
+  wbc_spline_desc ee_motion[WBC_NLEG];         /* SplineHolder::ee_motion_ (LF RF LH RH)                           */
+  wbc_spline_desc ee_force[WBC_NLEG];          /* SplineHolder::ee_force_                                          */
+  int32_t n_phase[WBC_NLEG];                   /* PhaseDurations::GetPhaseDurations().size()                       */
+  const double* phase_durations[WBC_NLEG];     /* [n_phase] alternating contact / swing phases of the foot         */
+  uint8_t contact_at_start[WBC_NLEG];          /* GaitGenerator::IsInContactAtStart                                */
+  /* Planner semantics of planners/towr.py:92-148 (optional, n_grid = 0 -> evaluate the splines at t itself):       */
+  int32_t n_grid;                              /* number of stored samples (5001 for trunk_mpc's 1 kHz x 5 s)      */
+  const double* grid_timestamps;               /* [n_grid] increasing timestamps of the stored samples             */
+  double wait_time;                            /* stand this long before the motion starts (planners/towr.py:35)   */
+  double standing[WBC_NTRAJ];                  /* SimpleStanding reference (planners/simple.py:39-85) while waiting */
+} wbc_plan_desc;
+
+typedef struct wbc_plan wbc_plan;
+
+/* Upload n_plans plans (host descriptors) and build their device tables; Hermite coefficients
+ * (towr/src/polynomial.cc:98-104) are computed on the device. */
+int wbc_plan_create(wbc_handle* h, int32_t n_plans, const wbc_plan_desc* plans, wbc_plan** out);
+int wbc_plan_destroy(wbc_plan* plan);
+/* publish_trunk_state (towr/trunk_mpc.cpp:19-68) + TowrTrunkPlanner.SetTrunkOutputs (planners/towr.py:92-148) for n
+ * (plan, time) pairs: traj [N][54], contact [N][4]; optional plan_index [N] (NULL = plan 0), f_plan [N][12],
+ * t_eval [N] (the spline time actually evaluated, -1 while standing), status [N]. Device pointers. */
+int wbc_sample_trajectory(wbc_handle* h, const wbc_plan* plan, int64_t n, const int32_t* plan_index, const double* t,
+                          double* traj, uint8_t* contact, double* f_plan, double* t_eval, int32_t* status, void* stream);
+int wbc_sample_trajectory_host(wbc_handle* h, const wbc_plan* plan, int64_t n, const int32_t* plan_index, const double* t,
+                               double* traj, uint8_t* contact, double* f_plan, double* t_eval, int32_t* status);
+
 /* Number of kernel launches issued through this handle since creation. */
 int64_t wbc_launch_count(const wbc_handle* h);
 

@@ -123,6 +123,11 @@ def load_library() -> C.CDLL:
     lib.wbc_lcm_encode_trunk_state_host.argtypes = [H, i64, dp, dp, dp, dp, dp, u8]
     lib.wbc_lcm_decode_robot_state_host.argtypes = [H, i64, u8, dp, dp, dp, dp]
     lib.wbc_lcm_encode_robot_state_host.argtypes = [H, i64, dp, dp, dp, i32, u8, dp]
+    lib.wbc_plan_destroy.argtypes = [dp]
+    lib.wbc_plan_destroy.restype = C.c_int
+    lib.wbc_sample_trajectory.argtypes = [H, dp, i64, dp, dp, dp, dp, dp, dp, dp, dp]
+    lib.wbc_sample_trajectory_host.argtypes = [H, dp, i64, dp, dp, dp, dp, dp, dp, dp]
+    lib.wbc_sample_trajectory.restype = lib.wbc_sample_trajectory_host.restype = lib.wbc_plan_create.restype = C.c_int
     for name in WIRE_SYMBOLS:
         getattr(lib, name).restype = C.c_int
     lib.wbc_launch_count.argtypes = [H]
@@ -137,7 +142,8 @@ def load_library() -> C.CDLL:
 WIRE_SYMBOLS = ["wbc_lcm_decode_trunk_state", "wbc_lcm_encode_trunk_state", "wbc_lcm_decode_robot_state", "wbc_lcm_encode_robot_state",
                 "wbc_lcm_decode_trunk_state_host", "wbc_lcm_encode_trunk_state_host", "wbc_lcm_decode_robot_state_host",
                 "wbc_lcm_encode_robot_state_host"]
-EXPORTED_SYMBOLS = WIRE_SYMBOLS + ["wbc_default_params", "wbc_create", "wbc_destroy", "wbc_last_error", "wbc_dynamics", "wbc_coriolis",
+TRAJ_SYMBOLS = ["wbc_plan_create", "wbc_plan_destroy", "wbc_sample_trajectory", "wbc_sample_trajectory_host"]
+EXPORTED_SYMBOLS = WIRE_SYMBOLS + TRAJ_SYMBOLS + ["wbc_default_params", "wbc_create", "wbc_destroy", "wbc_last_error", "wbc_dynamics", "wbc_coriolis",
                     "wbc_step", "wbc_step_id", "wbc_step_clf", "wbc_step_pc", "wbc_step_mptc", "wbc_step_pd", "wbc_step_host", "wbc_time_step",
                     "wbc_measure_fp64_peak", "wbc_launch_count", "wbc_dynamics_host", "wbc_coriolis_host", "wbc_host_alloc", "wbc_host_free"]
 

@@ -8,6 +8,8 @@
 
 #include "wbc_device.cuh"
 #include "wbc_wire.cuh"
+#include "wbc_traj.cuh"
+#include <vector>
 
 namespace {
 
@@ -595,6 +597,150 @@ extern "C" int wbc_lcm_encode_robot_state_host(wbc_handle* h, int64_t n, const d
   int rc = wbc_lcm_encode_robot_state(h, n, dq, dv, dt, tau_in_actuator_order, dm, dst, st);
   if (rc) return rc;
   s.back(msgs, dm, N * WBC_LCM_ROBOT_STATE_BYTES, st); s.back(status, dst, N, st);
+  WBC_SCRATCH_CHECK(h, s);
+  WBC_CUDA(h, cudaStreamSynchronize(st));
+  return WBC_OK;
+}
+
+// ------------------------------------------------------------------------------ trajectory sampler (wbc_traj.cuh)
+struct wbc_plan {
+  wbc_handle* h = nullptr;
+  wbctraj::PlanTables t{};
+  std::vector<void*> bufs;
+};
+
+extern "C" int wbc_plan_destroy(wbc_plan* p) {
+  if (!p) return WBC_OK;
+  if (p->h) cudaSetDevice(p->h->device);
+  for (void* b : p->bufs) cudaFree(b);
+  delete p;
+  return WBC_OK;
+}
+
+extern "C" int wbc_plan_create(wbc_handle* h, int32_t n_plans, const wbc_plan_desc* plans, wbc_plan** out) {
+  if (!h) return WBC_ERR_ARG;
+  if (!out || !plans || n_plans <= 0) return fail_arg(h, "wbc_plan_create: bad arguments");
+  *out = nullptr;
+  using wbctraj::NSPLINE;
+  // ---- flatten on the host: offsets, running sums of the durations (in the reference's summation order), nodes
+  std::vector<int> poly_off, phase_off, grid_off, node_of_poly;
+  std::vector<unsigned char> cstart;
+  std::vector<double> tend, dur, nodes, phase_tend, grid_ts, wait, standing;
+  grid_off.push_back(0);
+  for (int p = 0; p < n_plans; ++p) {
+    const wbc_plan_desc& d = plans[p];
+    const wbc_spline_desc* sp[NSPLINE] = {&d.base_linear, &d.base_angular, &d.ee_motion[0], &d.ee_motion[1], &d.ee_motion[2],
+                                          &d.ee_motion[3], &d.ee_force[0], &d.ee_force[1], &d.ee_force[2], &d.ee_force[3]};
+    for (int s = 0; s < NSPLINE; ++s) {
+      if (sp[s]->n_poly <= 0 || !sp[s]->durations || !sp[s]->nodes) return fail_arg(h, "wbc_plan_create: empty spline");
+      poly_off.push_back((int)tend.size());
+      double acc = 0.0;
+      const int node0 = (int)(nodes.size() / 6);
+      for (int i = 0; i < sp[s]->n_poly; ++i) {
+        if (!(sp[s]->durations[i] > 0.0)) return fail_arg(h, "wbc_plan_create: polynomial duration must be > 0");
+        acc += sp[s]->durations[i];
+        tend.push_back(acc);
+        dur.push_back(sp[s]->durations[i]);
+        node_of_poly.push_back(node0 + i);
+      }
+      nodes.insert(nodes.end(), sp[s]->nodes, sp[s]->nodes + (size_t)(sp[s]->n_poly + 1) * 6);
+    }
+    poly_off.push_back((int)tend.size());
+    for (int k = 0; k < WBC_NLEG; ++k) {
+      if (d.n_phase[k] <= 0 || !d.phase_durations[k]) return fail_arg(h, "wbc_plan_create: empty phase list");
+      phase_off.push_back((int)phase_tend.size());
+      double acc = 0.0;
+      for (int i = 0; i < d.n_phase[k]; ++i) { acc += d.phase_durations[k][i]; phase_tend.push_back(acc); }
+      cstart.push_back(d.contact_at_start[k] ? 1 : 0);
+    }
+    phase_off.push_back((int)phase_tend.size());
+    if (d.n_grid < 0 || (d.n_grid > 0 && !d.grid_timestamps)) return fail_arg(h, "wbc_plan_create: bad sample grid");
+    for (int i = 0; i < d.n_grid; ++i) {
+      if (i > 0 && !(d.grid_timestamps[i] > d.grid_timestamps[i - 1])) return fail_arg(h, "wbc_plan_create: grid timestamps must increase");
+      grid_ts.push_back(d.grid_timestamps[i]);
+    }
+    grid_off.push_back((int)grid_ts.size());
+    wait.push_back(d.wait_time);
+    standing.insert(standing.end(), d.standing, d.standing + WBC_NTRAJ);
+  }
+  if (grid_ts.empty()) grid_ts.push_back(0.0);
+  WBC_CUDA(h, cudaSetDevice(h->device));
+  wbc_plan* pl = new (std::nothrow) wbc_plan();
+  if (!pl) return WBC_ERR_NOMEM;
+  pl->h = h;
+  cudaError_t err = cudaSuccess;
+  auto up = [&](const void* src, size_t bytes) -> void* {
+    void* dptr = nullptr;
+    if (err != cudaSuccess) return nullptr;
+    err = cudaMalloc(&dptr, bytes ? bytes : 1);
+    if (err != cudaSuccess) return nullptr;
+    pl->bufs.push_back(dptr);
+    if (src) err = cudaMemcpy(dptr, src, bytes, cudaMemcpyHostToDevice);
+    return dptr;
+  };
+  const int n_poly_total = (int)tend.size();
+  pl->t.n_plans = n_plans;
+  pl->t.poly_off = (const int*)up(poly_off.data(), poly_off.size() * sizeof(int));
+  pl->t.phase_off = (const int*)up(phase_off.data(), phase_off.size() * sizeof(int));
+  pl->t.grid_off = (const int*)up(grid_off.data(), grid_off.size() * sizeof(int));
+  pl->t.contact_start = (const unsigned char*)up(cstart.data(), cstart.size());
+  pl->t.tend = (const double*)up(tend.data(), tend.size() * sizeof(double));
+  pl->t.phase_tend = (const double*)up(phase_tend.data(), phase_tend.size() * sizeof(double));
+  pl->t.grid_ts = (const double*)up(grid_ts.data(), grid_ts.size() * sizeof(double));
+  pl->t.wait_time = (const double*)up(wait.data(), wait.size() * sizeof(double));
+  pl->t.standing = (const double*)up(standing.data(), standing.size() * sizeof(double));
+  double* d_coef = (double*)up(nullptr, (size_t)n_poly_total * 12 * sizeof(double));
+  pl->t.coef = d_coef;
+  const int* d_node_of = (const int*)up(node_of_poly.data(), node_of_poly.size() * sizeof(int));
+  const double* d_nodes = (const double*)up(nodes.data(), nodes.size() * sizeof(double));
+  const double* d_dur = (const double*)up(dur.data(), dur.size() * sizeof(double));
+  if (err == cudaSuccess) {
+    wbctraj::hermite_coeff_kernel<<<(n_poly_total * 3 + 255) / 256, 256, 0, h->stream>>>(n_poly_total, d_node_of, d_nodes, d_dur, d_coef);
+    h->launches++;
+    err = cudaGetLastError();
+    if (err == cudaSuccess) err = cudaStreamSynchronize(h->stream);
+  }
+  if (err != cudaSuccess) {
+    h->err = std::string("wbc_plan_create: ") + cudaGetErrorString(err);
+    wbc_plan_destroy(pl);
+    return WBC_ERR_CUDA;
+  }
+  *out = pl;
+  return WBC_OK;
+}
+
+extern "C" int wbc_sample_trajectory(wbc_handle* h, const wbc_plan* plan, int64_t n, const int32_t* plan_index, const double* t,
+                                     double* traj, uint8_t* contact, double* f_plan, double* t_eval, int32_t* status, void* stream) {
+  if (!h) return WBC_ERR_ARG;
+  if (!plan || n < 0 || (n > 0 && (!t || !traj || !contact))) return fail_arg(h, "wbc_sample_trajectory: plan, t, traj and contact are required");
+  if (n == 0) return WBC_OK;
+  WBC_CUDA(h, cudaSetDevice(h->device));
+  const long long total = (long long)n * wbctraj::NELEM, cap = (long long)h->sm_count * 16;
+  const long long blocks = (total + 255) / 256;
+  wbctraj::sample_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(plan->t, n, plan_index, t, traj, contact,
+                                                                                                  f_plan, t_eval, status);
+  h->launches++;
+  WBC_CUDA(h, cudaGetLastError());
+  return WBC_OK;
+}
+
+extern "C" int wbc_sample_trajectory_host(wbc_handle* h, const wbc_plan* plan, int64_t n, const int32_t* plan_index, const double* t,
+                                          double* traj, uint8_t* contact, double* f_plan, double* t_eval, int32_t* status) {
+  if (!h) return WBC_ERR_ARG;
+  if (!plan || n < 0 || (n > 0 && (!t || !traj || !contact))) return fail_arg(h, "wbc_sample_trajectory_host: plan, t, traj and contact are required");
+  if (n == 0) return WBC_OK;
+  WBC_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  DevScratch s;
+  const size_t N = (size_t)n;
+  const int32_t* dpi = s.in(plan_index, N, st); const double* dt = s.in(t, N, st);
+  double* dtr = s.out(traj, N * WBC_NTRAJ); uint8_t* dc = s.out(contact, N * 4); double* dfp = s.out(f_plan, N * 12);
+  double* dte = s.out(t_eval, N); int32_t* dst = s.out(status, N);
+  WBC_SCRATCH_CHECK(h, s);
+  int rc = wbc_sample_trajectory(h, plan, n, dpi, dt, dtr, dc, dfp, dte, dst, st);
+  if (rc) return rc;
+  s.back(traj, dtr, N * WBC_NTRAJ, st); s.back(contact, dc, N * 4, st); s.back(f_plan, dfp, N * 12, st);
+  s.back(t_eval, dte, N, st); s.back(status, dst, N, st);
   WBC_SCRATCH_CHECK(h, s);
   WBC_CUDA(h, cudaStreamSynchronize(st));
   return WBC_OK;

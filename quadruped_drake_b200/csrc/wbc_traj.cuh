@@ -1,0 +1,140 @@
+// wbc_traj.cuh — trunk-trajectory sampler on the device.
+//
+// Turns a TOWR spline solution (cubic Hermite node splines + per-foot phase durations) into the controller input
+// traj[54] / contact[4] (+ planned forces) for N (plan, time) pairs per launch, i.e. what
+//   towr/trunk_mpc.cpp:19-68        publish_trunk_state (GetPoint of base_linear, base_angular, ee_motion, ee_force;
+//                                   IsContactPhase) and
+//   planners/towr.py:92-148         TowrTrunkPlanner.SetTrunkOutputs (stand for wait_time, then NEAREST stored 1 kHz sample)
+// do one sample at a time on the host. Restated arithmetic: towr/src/polynomial.cc:49-63,98-104 (cubic Hermite),
+// towr/src/spline.cc:49-90 (segment lookup, "previous polynomial at junctions", eps 1e-10),
+// towr/src/phase_durations.cc:120-124 (contact flag).
+//
+// HBM-bound: 12 B in (t, plan index), 436 (+96) B out per instance; the spline tables (tens of KB per plan) stay in
+// L1/L2. One thread per output element, so the stores of a warp are consecutive doubles of traj.
+#pragma once
+#include <stdint.h>
+#include "wbc.h"
+
+namespace wbctraj {
+
+constexpr int NSPLINE = 10;          // 0 base linear, 1 base angular, 2-5 foot motion LF RF LH RH, 6-9 foot force
+constexpr int NELEM = 54 + 4 + 12;   // virtual output elements per instance: traj, contact, planned force
+
+// Device-resident tables of a set of plans (built by wbc_plan_create).
+struct PlanTables {
+  int n_plans;
+  const int* poly_off;        // [n_plans][NSPLINE + 1] -> first polynomial of spline s in tend / coef (last = end)
+  const int* phase_off;       // [n_plans][4 + 1]       -> first phase of foot k in phase_tend
+  const int* grid_off;        // [n_plans + 1]          -> first stored timestamp of the plan (0 entries = continuous)
+  const unsigned char* contact_start;   // [n_plans][4]
+  const double* tend;         // running sum of the polynomial durations inside each spline (spline.cc:55-58)
+  const double* coef;         // [poly][3][4]: A B C D of each dimension (polynomial.cc:98-104)
+  const double* phase_tend;   // running sum of the phase durations of each foot
+  const double* grid_ts;      // timestamps of the stored samples (trunk_mpc.cpp:168-174)
+  const double* wait_time;    // [n_plans] planners/towr.py:35
+  const double* standing;     // [n_plans][54] SimpleStanding (planners/simple.py:39-85) used while t < wait_time
+};
+
+// CubicHermitePolynomial::UpdateCoeff for every (polynomial, dimension): nodes[(poly + spline index)][6] = p, v.
+__global__ void hermite_coeff_kernel(int n_poly_total, const int* __restrict__ node_of_poly, const double* __restrict__ nodes,
+                                     const double* __restrict__ dur, double* __restrict__ coef) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_poly_total * 3) return;
+  const int p = idx / 3, d = idx - 3 * p;
+  const double* n0 = nodes + (size_t)node_of_poly[p] * 6;
+  const double* n1 = n0 + 6;
+  const double T = dur[p], p0 = n0[d], v0 = n0[3 + d], p1 = n1[d], v1 = n1[3 + d];
+  double* c = coef + (size_t)idx * 4;
+  c[0] = p0;
+  c[1] = v0;
+  c[2] = -(3.0 * (p0 - p1) + T * (2.0 * v0 + v1)) / (T * T);
+  c[3] = (2.0 * (p0 - p1) + T * (v0 + v1)) / (T * T * T);
+}
+
+// Spline::GetSegmentID on the running sums: first i with tend[i] >= t - 1e-10 (clamped to the last segment).
+__device__ __forceinline__ int segment_of(const double* __restrict__ tend, int n, double t) {
+  const double key = t - 1e-10;
+  int lo = 0, hi = n - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(tend + mid) >= key) hi = mid; else lo = mid + 1;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(256) sample_kernel(PlanTables pt, long long n, const int* __restrict__ plan_index,
+                                                     const double* __restrict__ tin, double* __restrict__ traj,
+                                                     unsigned char* __restrict__ contact, double* __restrict__ fplan,
+                                                     double* __restrict__ t_eval_out, int* __restrict__ status) {
+  const long long total = n * NELEM;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const long long inst = idx / NELEM;
+    const int e = (int)(idx - inst * NELEM);
+    if (e >= 58 && !fplan) continue;
+    int pl = plan_index ? plan_index[inst] : 0;
+    int st = 0;
+    if (pl < 0 || pl >= pt.n_plans) { pl = 0; st |= WBC_TRAJ_BADPLAN; }
+    double t = tin[inst];
+    // ---- planner semantics (planners/towr.py:96-110): stand while t < wait_time, then the nearest stored sample
+    const int g0 = pt.grid_off[pl], gn = pt.grid_off[pl + 1] - g0;
+    bool standing = false;
+    if (gn > 0) {
+      const double wait = pt.wait_time[pl];
+      if (t < wait) standing = true;
+      else {
+        const double tq = t - wait;
+        const double* ts = pt.grid_ts + g0;
+        // np.abs(ts - tq).argmin(): ts is increasing, so the minimum is next to the insertion point; first minimum wins
+        int lo = 0, hi = gn - 1;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (__ldg(ts + mid) >= tq) hi = mid; else lo = mid + 1; }
+        int best = lo;
+        if (lo > 0 && fabs(__ldg(ts + lo - 1) - tq) <= fabs(__ldg(ts + lo) - tq)) best = lo - 1;
+        t = __ldg(ts + best);
+      }
+    }
+    const int* po = pt.poly_off + pl * (NSPLINE + 1);
+    const double t_total = __ldg(pt.tend + po[1] - 1);            // Spline::GetTotalTime of the base spline
+    if (!standing) {
+      if (!(t >= 0.0)) { t = 0.0; st |= WBC_TRAJ_CLAMPED; }       // the reference asserts t >= 0 (spline.cc:52) ...
+      if (t > t_total + 1e-10) { t = t_total; st |= WBC_TRAJ_CLAMPED; }   // ... and runs off the end (spline.cc:65)
+    }
+    if (e == 0) {
+      if (status) status[inst] = st;
+      if (t_eval_out) t_eval_out[inst] = standing ? -1.0 : t;
+    }
+    if (e >= 54 && e < 58) {
+      // ---- contact flag of foot k (phase_durations.cc:120-124)
+      const int k = e - 54;
+      unsigned char c = 1;
+      if (!standing) {
+        const int* fo = pt.phase_off + pl * 5;
+        const int ph = segment_of(pt.phase_tend + fo[k], fo[k + 1] - fo[k], t);
+        const bool c0 = pt.contact_start[pl * 4 + k] != 0;
+        c = (ph & 1) ? !c0 : c0;
+      }
+      contact[inst * 4 + k] = c;
+      continue;
+    }
+    // ---- which spline / derivative / dimension this element is (wbc.h traj order = trunk_state_t member order)
+    int s, deriv, dim;
+    if (e < 18) { s = e / 9; deriv = (e % 9) / 3; dim = e % 3; }
+    else if (e < 54) { const int r = e - 18; deriv = r / 12; s = 2 + (r % 12) / 3; dim = r % 3; }
+    else { const int r = e - 58; deriv = 0; s = 6 + r / 3; dim = r % 3; }
+    double val;
+    if (standing) val = e < 54 ? pt.standing[pl * 54 + e] : 0.0;
+    else {
+      const int p0 = po[s], np_ = po[s + 1] - p0;
+      const int i = segment_of(pt.tend + p0, np_, t);
+      const double tl = t - (i > 0 ? __ldg(pt.tend + p0 + i - 1) : 0.0);
+      const double2* c2 = reinterpret_cast<const double2*>(pt.coef + ((size_t)(p0 + i) * 3 + dim) * 4);
+      const double2 ab = __ldg(c2), cd = __ldg(c2 + 1);            // A B | C D
+      if (deriv == 0) val = fma(fma(fma(cd.y, tl, cd.x), tl, ab.y), tl, ab.x);
+      else if (deriv == 1) val = fma(fma(3.0 * cd.y, tl, 2.0 * cd.x), tl, ab.y);
+      else val = fma(6.0 * cd.y, tl, 2.0 * cd.x);
+    }
+    if (e < 54) traj[inst * 54 + e] = val;
+    else fplan[inst * 12 + (e - 58)] = val;
+  }
+}
+
+}  // namespace wbctraj

@@ -78,3 +78,8 @@ def generate(model: RobotModel, n: int, seed: int, pattern="stand", fk=None):
     idx = rng.choice(len(pats), size=n, p=np.asarray(wts) / np.sum(wts))
     contact = np.asarray(pats, dtype=np.uint8)[idx]
     return q, v, traj, contact
+
+
+def nominal_state(model: RobotModel, n: int):
+    """n copies of the nominal standing configuration at rest -> q[n,19], v[n,18]."""
+    return np.tile(model.nominal_q(), (n, 1)), np.zeros((n, NV))
