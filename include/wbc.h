@@ -59,6 +59,7 @@ extern "C" {
 #define WBC_ST_NOTPD 16        /* reduced Hessian not positive definite                   */
 #define WBC_ST_BADQUAT 32      /* zero / non-finite quaternion                            */
 #define WBC_ST_UNSUPPORTED 64  /* PC controller with no stance foot (the reference raises too) */
+#define WBC_ST_DIVERGED 128    /* rollout only: non-finite / runaway velocity, instance frozen   */
 
 /* controller kinds: reference controllers/__init__.py:1-5 */
 #define WBC_CTRL_ID 0          /* controllers/inverse_dynamics_controller.py */
@@ -262,6 +263,31 @@ int wbc_sample_trajectory(wbc_handle* h, const wbc_plan* plan, int64_t n, const 
                           double* traj, uint8_t* contact, double* f_plan, double* t_eval, int32_t* status, void* stream);
 int wbc_sample_trajectory_host(wbc_handle* h, const wbc_plan* plan, int64_t n, const int32_t* plan_index, const double* t,
                                double* traj, uint8_t* contact, double* f_plan, double* t_eval, int32_t* status);
+
+/* ---- Closed-loop batched rollout: the caller of the control step, simulate.py:160-182.
+ * wbc_integrate: semi-implicit Euler step of n states with the accelerations vd returned by wbc_step
+ * (v += dt vd; q += dt N(q) v, quaternion renormalised); t [N] (optional) is advanced by dt. Device pointers. */
+int wbc_integrate(wbc_handle* h, int64_t n, double dt, double* q, double* v, const double* vd, double* t, void* stream);
+
+typedef struct wbc_rollout_io {
+  double* q;              /* [N][19] in: initial state (simulate.py:171-179), out: final state                  */
+  double* v;              /* [N][18]                                                                             */
+  double* t;              /* [N]     in: start time of each instance, out: end time                              */
+  const int32_t* plan_index; /* [N] or NULL (plan 0)                                                             */
+  double* tau;            /* [N][12] torques of the last step                                                    */
+  double* metrics;        /* [N][4]  metrics of the last step                                                    */
+  int32_t* status_or;     /* [N]     OR of the per-step status words (optional)                                  */
+  double* err_max;        /* [N]     max over the steps of the tracking-error metric (optional)                  */
+  double* metrics_log;    /* [n_steps][N][4] every step's output_metrics, what simulate.py:142 logs (optional)   */
+} wbc_rollout_io;
+
+/* n_steps control steps of n robots, entirely on the device: sample the plan at t (wbc_sample_trajectory), run the
+ * controller `kind` (wbc_step), integrate (wbc_integrate). No host synchronisation inside; with use_graph != 0 the
+ * per-step launches are captured once into a CUDA graph and replayed. Device pointers. */
+int wbc_rollout(wbc_handle* h, int kind, const wbc_plan* plan, int64_t n, int32_t n_steps, double dt,
+                const wbc_rollout_io* io, int use_graph, void* stream);
+int wbc_rollout_host(wbc_handle* h, int kind, const wbc_plan* plan, int64_t n, int32_t n_steps, double dt,
+                     const wbc_rollout_io* host_io, int use_graph);
 
 /* Number of kernel launches issued through this handle since creation. */
 int64_t wbc_launch_count(const wbc_handle* h);

@@ -278,7 +278,7 @@ NOMINAL_STANCE = {                        # towr/include/towr/models/examples/{m
 }
 
 
-def make_gait_plan(robot="mini_cheetah", combo=0, total_duration=5.0, goal=(1.5, 0.0), swing_height=0.05, yaw_goal=0.0):
+def make_gait_plan(robot="mini_cheetah", combo=0, total_duration=5.0, goal=(1.5, 0.0), swing_height=0.05, yaw_goal=0.0, base_height=None):
     """Synthetic stand-in for the IPOPT solution: same variable layout as TOWR (base nodes every 0.1 s, one constant
     polynomial per stance phase, two per swing phase with a lifted mid node whose vertical velocity is zero, three force
     polynomials per stance phase), node values from a simple heuristic: base on a straight line with constant velocity
@@ -287,7 +287,8 @@ def make_gait_plan(robot="mini_cheetah", combo=0, total_duration=5.0, goal=(1.5,
     x, y, z, mass = NOMINAL_STANCE[robot]
     stance = np.array([[x, y, z], [x, -y, z], [-x, y, z], [-x, -y, z]])
     T = float(total_duration)
-    p_init, p_goal = np.array([0.0, 0.0, -z]), np.array([goal[0], goal[1], -z])
+    bh = -z if base_height is None else float(base_height)
+    p_init, p_goal = np.array([0.0, 0.0, bh]), np.array([goal[0], goal[1], bh])
     bd = base_poly_durations(T)
     nb = len(bd) + 1
     dp = p_goal - p_init

@@ -72,6 +72,11 @@ class WbcIO(C.Structure):
                 ("vd", C.c_void_p), ("f", C.c_void_p), ("qp_info", C.c_void_p)]
 
 
+class WbcRolloutIO(C.Structure):
+    """ctypes mirror of `wbc_rollout_io`."""
+    _fields_ = [(n, C.c_void_p) for n in ("q", "v", "t", "plan_index", "tau", "metrics", "status_or", "err_max", "metrics_log")]
+
+
 def np_ptr(a: np.ndarray):
     return C.c_void_p(a.ctypes.data)
 
@@ -128,6 +133,10 @@ def load_library() -> C.CDLL:
     lib.wbc_sample_trajectory.argtypes = [H, dp, i64, dp, dp, dp, dp, dp, dp, dp, dp]
     lib.wbc_sample_trajectory_host.argtypes = [H, dp, i64, dp, dp, dp, dp, dp, dp, dp]
     lib.wbc_sample_trajectory.restype = lib.wbc_sample_trajectory_host.restype = lib.wbc_plan_create.restype = C.c_int
+    lib.wbc_integrate.argtypes = [H, i64, C.c_double, dp, dp, dp, dp, dp]
+    lib.wbc_rollout.argtypes = [H, i32, dp, i64, C.c_int32, C.c_double, C.POINTER(WbcRolloutIO), i32, dp]
+    lib.wbc_rollout_host.argtypes = [H, i32, dp, i64, C.c_int32, C.c_double, C.POINTER(WbcRolloutIO), i32]
+    lib.wbc_integrate.restype = lib.wbc_rollout.restype = lib.wbc_rollout_host.restype = C.c_int
     for name in WIRE_SYMBOLS:
         getattr(lib, name).restype = C.c_int
     lib.wbc_launch_count.argtypes = [H]
@@ -142,7 +151,8 @@ def load_library() -> C.CDLL:
 WIRE_SYMBOLS = ["wbc_lcm_decode_trunk_state", "wbc_lcm_encode_trunk_state", "wbc_lcm_decode_robot_state", "wbc_lcm_encode_robot_state",
                 "wbc_lcm_decode_trunk_state_host", "wbc_lcm_encode_trunk_state_host", "wbc_lcm_decode_robot_state_host",
                 "wbc_lcm_encode_robot_state_host"]
-TRAJ_SYMBOLS = ["wbc_plan_create", "wbc_plan_destroy", "wbc_sample_trajectory", "wbc_sample_trajectory_host"]
+ROLLOUT_SYMBOLS = ["wbc_integrate", "wbc_rollout", "wbc_rollout_host"]
+TRAJ_SYMBOLS = ROLLOUT_SYMBOLS + ["wbc_plan_create", "wbc_plan_destroy", "wbc_sample_trajectory", "wbc_sample_trajectory_host"]
 EXPORTED_SYMBOLS = WIRE_SYMBOLS + TRAJ_SYMBOLS + ["wbc_default_params", "wbc_create", "wbc_destroy", "wbc_last_error", "wbc_dynamics", "wbc_coriolis",
                     "wbc_step", "wbc_step_id", "wbc_step_clf", "wbc_step_pc", "wbc_step_mptc", "wbc_step_pd", "wbc_step_host", "wbc_time_step",
                     "wbc_measure_fp64_peak", "wbc_launch_count", "wbc_dynamics_host", "wbc_coriolis_host", "wbc_host_alloc", "wbc_host_free"]

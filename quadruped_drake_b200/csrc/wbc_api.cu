@@ -9,6 +9,7 @@
 #include "wbc_device.cuh"
 #include "wbc_wire.cuh"
 #include "wbc_traj.cuh"
+#include "wbc_rollout.cuh"
 #include <vector>
 
 namespace {
@@ -119,6 +120,12 @@ struct wbc_handle {
          *d_f = nullptr, *d_info = nullptr;
   uint8_t* d_contact = nullptr;
   int32_t* d_status = nullptr;
+  // scratch of wbc_rollout (sized for ro_cap instances)
+  int64_t ro_cap = 0;
+  double *ro_traj = nullptr, *ro_vd = nullptr, *ro_metrics = nullptr, *ro_tau = nullptr, *ro_t = nullptr;
+  uint8_t* ro_contact = nullptr;
+  int32_t* ro_status = nullptr;
+  int* ro_counter = nullptr;
 };
 
 #define WBC_CUDA(h, call)                                                                       \
@@ -215,6 +222,8 @@ extern "C" int wbc_destroy(wbc_handle* h) {
   free_staging(h);
   if (h->d_const) cudaFree(h->d_const);
   if (h->d_tau_map) cudaFree(h->d_tau_map);
+  cudaFree(h->ro_traj); cudaFree(h->ro_vd); cudaFree(h->ro_metrics); cudaFree(h->ro_tau); cudaFree(h->ro_t);
+  cudaFree(h->ro_contact); cudaFree(h->ro_status); cudaFree(h->ro_counter);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return WBC_OK;
@@ -742,6 +751,123 @@ extern "C" int wbc_sample_trajectory_host(wbc_handle* h, const wbc_plan* plan, i
   s.back(traj, dtr, N * WBC_NTRAJ, st); s.back(contact, dc, N * 4, st); s.back(f_plan, dfp, N * 12, st);
   s.back(t_eval, dte, N, st); s.back(status, dst, N, st);
   WBC_SCRATCH_CHECK(h, s);
+  WBC_CUDA(h, cudaStreamSynchronize(st));
+  return WBC_OK;
+}
+
+// ------------------------------------------------------------------------------ closed-loop rollout (wbc_rollout.cuh)
+extern "C" int wbc_integrate(wbc_handle* h, int64_t n, double dt, double* q, double* v, const double* vd, double* t, void* stream) {
+  if (!h) return WBC_ERR_ARG;
+  if (n < 0 || (n > 0 && (!q || !v || !vd))) return fail_arg(h, "wbc_integrate: q, v and vd are required");
+  if (n == 0) return WBC_OK;
+  WBC_CUDA(h, cudaSetDevice(h->device));
+  wbcroll::integrate_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n, dt, q, v, vd, t, nullptr, nullptr, nullptr,
+                                                                                          nullptr, nullptr, nullptr);
+  h->launches++;
+  WBC_CUDA(h, cudaGetLastError());
+  return WBC_OK;
+}
+
+static int ensure_rollout_scratch(wbc_handle* h, int64_t n) {
+  if (!h->ro_counter) WBC_CUDA(h, cudaMalloc(&h->ro_counter, sizeof(int)));
+  if (n <= h->ro_cap) return WBC_OK;
+  cudaFree(h->ro_traj); cudaFree(h->ro_vd); cudaFree(h->ro_metrics); cudaFree(h->ro_tau); cudaFree(h->ro_t);
+  cudaFree(h->ro_contact); cudaFree(h->ro_status);
+  h->ro_traj = h->ro_vd = h->ro_metrics = h->ro_tau = h->ro_t = nullptr; h->ro_contact = nullptr; h->ro_status = nullptr; h->ro_cap = 0;
+  WBC_CUDA(h, cudaMalloc(&h->ro_traj, n * WBC_NTRAJ * sizeof(double)));
+  WBC_CUDA(h, cudaMalloc(&h->ro_vd, n * WBC_NV * sizeof(double)));
+  WBC_CUDA(h, cudaMalloc(&h->ro_metrics, n * WBC_NMETRIC * sizeof(double)));
+  WBC_CUDA(h, cudaMalloc(&h->ro_tau, n * WBC_NU * sizeof(double)));
+  WBC_CUDA(h, cudaMalloc(&h->ro_t, n * sizeof(double)));
+  WBC_CUDA(h, cudaMalloc(&h->ro_contact, n * 4));
+  WBC_CUDA(h, cudaMalloc(&h->ro_status, n * sizeof(int32_t)));
+  h->ro_cap = n;
+  return WBC_OK;
+}
+
+extern "C" int wbc_rollout(wbc_handle* h, int kind, const wbc_plan* plan, int64_t n, int32_t n_steps, double dt,
+                           const wbc_rollout_io* io, int use_graph, void* stream) {
+  if (!h) return WBC_ERR_ARG;
+  if (!plan || !io || n < 0 || n_steps < 0 || !(dt > 0.0)) return fail_arg(h, "wbc_rollout: bad arguments");
+  if (kind == WBC_CTRL_PD) return fail_arg(h, "wbc_rollout: the PD law returns no accelerations to integrate");
+  if (n > 0 && (!io->q || !io->v || !io->t)) return fail_arg(h, "wbc_rollout: q, v and t are required");
+  if (n == 0 || n_steps == 0) return WBC_OK;
+  WBC_CUDA(h, cudaSetDevice(h->device));
+  int rc = ensure_rollout_scratch(h, n);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  double* tau = io->tau ? io->tau : h->ro_tau;
+  double* metrics = io->metrics ? io->metrics : h->ro_metrics;
+  WBC_CUDA(h, cudaMemsetAsync(h->ro_counter, 0, sizeof(int), st));
+  if (io->status_or) WBC_CUDA(h, cudaMemsetAsync(io->status_or, 0, n * sizeof(int32_t), st));
+  if (io->err_max) WBC_CUDA(h, cudaMemsetAsync(io->err_max, 0, n * sizeof(double), st));
+  wbc_io sio{io->q, io->v, h->ro_traj, h->ro_contact, tau, metrics, h->ro_status, h->ro_vd, nullptr, nullptr};
+  auto one_step = [&]() -> int {
+    int r = wbc_sample_trajectory(h, plan, n, io->plan_index, io->t, h->ro_traj, h->ro_contact, nullptr, nullptr, nullptr, st);
+    if (r) return r;
+    r = wbc_step(h, kind, n, &sio, st);
+    if (r) return r;
+    wbcroll::integrate_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, dt, io->q, io->v, h->ro_vd, io->t, h->ro_status, io->status_or,
+                                                                         metrics, io->err_max, io->metrics_log, h->ro_counter);
+    h->launches++;
+    if (io->metrics_log) { wbcroll::bump_counter_kernel<<<1, 1, 0, st>>>(h->ro_counter); h->launches++; }
+    return WBC_OK;
+  };
+  if (use_graph && n_steps > 1 && st != nullptr && st != cudaStreamLegacy) {   // the legacy default stream cannot be captured
+    // capture one control step (3-4 kernels) once, replay it n_steps times: one graph launch per step instead of 3-4 kernel launches
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    const int64_t launches0 = h->launches;
+    WBC_CUDA(h, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    rc = one_step();
+    cudaError_t e = cudaStreamEndCapture(st, &graph);
+    const int64_t per_step = h->launches - launches0;
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (e != cudaSuccess) { h->err = std::string("wbc_rollout: graph capture: ") + cudaGetErrorString(e); return WBC_ERR_CUDA; }
+    e = cudaGraphInstantiate(&exec, graph, 0);
+    if (e != cudaSuccess) { cudaGraphDestroy(graph); h->err = std::string("wbc_rollout: graph instantiate: ") + cudaGetErrorString(e); return WBC_ERR_CUDA; }
+    h->launches = launches0;
+    for (int k = 0; k < n_steps && e == cudaSuccess; ++k) { e = cudaGraphLaunch(exec, st); h->launches += per_step; }
+    // the exec graph must outlive its launches: wait for the stream before destroying it
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaGraphExecDestroy(exec);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) { h->err = std::string("wbc_rollout: graph launch: ") + cudaGetErrorString(e); return WBC_ERR_CUDA; }
+  } else {
+    for (int k = 0; k < n_steps; ++k) {
+      rc = one_step();
+      if (rc) return rc;
+    }
+  }
+  WBC_CUDA(h, cudaGetLastError());
+  return WBC_OK;
+}
+
+extern "C" int wbc_rollout_host(wbc_handle* h, int kind, const wbc_plan* plan, int64_t n, int32_t n_steps, double dt,
+                                const wbc_rollout_io* io, int use_graph) {
+  if (!h) return WBC_ERR_ARG;
+  if (!plan || !io || n < 0 || n_steps < 0) return fail_arg(h, "wbc_rollout_host: bad arguments");
+  if (n > 0 && (!io->q || !io->v || !io->t)) return fail_arg(h, "wbc_rollout_host: q, v and t are required");
+  if (n == 0) return WBC_OK;
+  WBC_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  DevScratch s;
+  const size_t N = (size_t)n;
+  wbc_rollout_io d{};
+  d.q = s.in(io->q, N * WBC_NQ, st); d.v = s.in(io->v, N * WBC_NV, st); d.t = s.in(io->t, N, st);
+  d.plan_index = s.in(io->plan_index, N, st);
+  DevScratch s2;     // DevScratch holds 8 buffers
+  d.tau = s2.out(io->tau, N * WBC_NU); d.metrics = s2.out(io->metrics, N * WBC_NMETRIC);
+  d.status_or = s2.out(io->status_or, N); d.err_max = s2.out(io->err_max, N);
+  d.metrics_log = s2.out(io->metrics_log, N * WBC_NMETRIC * (size_t)n_steps);
+  WBC_SCRATCH_CHECK(h, s); WBC_SCRATCH_CHECK(h, s2);
+  int rc = wbc_rollout(h, kind, plan, n, n_steps, dt, &d, use_graph, st);
+  if (rc) return rc;
+  s.back(io->q, d.q, N * WBC_NQ, st); s.back(io->v, d.v, N * WBC_NV, st); s.back(io->t, d.t, N, st);
+  s2.back(io->tau, d.tau, N * WBC_NU, st); s2.back(io->metrics, d.metrics, N * WBC_NMETRIC, st);
+  s2.back(io->status_or, d.status_or, N, st); s2.back(io->err_max, d.err_max, N, st);
+  s2.back(io->metrics_log, d.metrics_log, N * WBC_NMETRIC * (size_t)n_steps, st);
+  WBC_SCRATCH_CHECK(h, s); WBC_SCRATCH_CHECK(h, s2);
   WBC_CUDA(h, cudaStreamSynchronize(st));
   return WBC_OK;
 }

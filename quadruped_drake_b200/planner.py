@@ -162,7 +162,7 @@ def simple_standing(robot="mini_cheetah"):
 
 
 def make_gait_plan(robot="mini_cheetah", combo="walk", total_duration=5.0, goal=(1.5, 0.0), swing_height=0.05, yaw_goal=0.0,
-                   sample_dt=0.0, wait_time=0.0):
+                   sample_dt=0.0, wait_time=0.0, base_height=None):
     """Synthetic stand-in for the IPOPT solution in TOWR's variable layout: base nodes every 0.1 s on a straight line at
     constant velocity (SetByLinearInterpolation, nodes_variables.cc:127-149); per foot one constant polynomial per stance
     phase and two per swing phase with a lifted apex node (vertical velocity 0, nodes_variables_phase_based.cc:208-216);
@@ -170,7 +170,8 @@ def make_gait_plan(robot="mini_cheetah", combo="walk", total_duration=5.0, goal=
     x, y, z, mass = NOMINAL_STANCE[robot]
     stance = np.array([[x, y, z], [x, -y, z], [-x, y, z], [-x, -y, z]])
     T = float(total_duration)
-    p0, p1 = np.array([0.0, 0.0, -z]), np.array([goal[0], goal[1], -z])
+    bh = -z if base_height is None else float(base_height)
+    p0, p1 = np.array([0.0, 0.0, bh]), np.array([goal[0], goal[1], bh])
     dp = p1 - p0
     bd = base_poly_durations(T)
     nb = len(bd) + 1
@@ -222,6 +223,55 @@ def make_gait_plan(robot="mini_cheetah", combo="walk", total_duration=5.0, goal=
         c0s.append(c0)
     return GaitPlan(SplineTable(bd, lin), SplineTable(bd, ang), motions, forces, pds, c0s, sample_dt=sample_dt, wait_time=wait_time,
                     standing=simple_standing(robot)[0], total_duration=T)
+
+
+def make_motion_plan(robot="mini_cheetah", motion="standing", total_duration=6.0, base_height=None, phase=0.0):
+    """The reference's manual test motions (planners/simple.py:87-115) as a plan for the device sampler: the analytic base
+    reference is sampled into Hermite nodes every 0.1 s (position and velocity exact at the nodes, O(h^4) in between).
+    motion: "standing" (SimpleStanding), "orientation" (OrientationTest), "edge" (EdgeTest), "raise_foot" (RaiseFoot: the
+    reference steps the RF target up by 0.1 m at t = 1 s; here it is lifted smoothly over the first half of its swing phase).
+    `phase` shifts the time argument of the sinusoids (different robots of a batch at different phases)."""
+    feet, height = SIMPLE_STANDING[robot]
+    bh = height if base_height is None else float(base_height)
+    T = float(total_duration)
+    bd = base_poly_durations(T)
+    tn = np.concatenate([[0.0], np.cumsum(bd)]) + phase
+    nb = len(tn)
+    lin, ang = np.zeros((nb, 6)), np.zeros((nb, 6))
+    lin[:, 2] = bh
+    if motion == "orientation":           # rpy = [0, 0.4 sin t, 0.4 cos t]
+        ang[:, 1], ang[:, 2], ang[:, 4], ang[:, 5] = 0.4 * np.sin(tn), 0.4 * np.cos(tn), 0.4 * np.cos(tn), -0.4 * np.sin(tn)
+    elif motion == "edge":                # p_body z += 0.1 sin t
+        lin[:, 2] += 0.1 * np.sin(tn)
+        lin[:, 5] = 0.1 * np.cos(tn)
+    elif motion == "raise_foot":          # p_body += [-0.1, 0.05, 0]
+        lin[:, 0], lin[:, 1] = -0.1, 0.05
+    elif motion != "standing":
+        raise KeyError(motion)
+    motions, forces, pds, c0s = [], [], [], []
+    mass = NOMINAL_STANCE[robot][3]
+    for ee in range(4):
+        if motion == "raise_foot" and ee == 1:       # RF: stance for 1 s, then in the air at +0.1 m
+            pd = [1.0, T - 1.0]
+            md = split_phases(pd, True, 2)
+            nodes = np.zeros((4, 6))
+            nodes[:, :3] = feet[ee]
+            nodes[2:, 2] = 0.1
+            fd = split_phases(pd, False, 3)
+            fn = np.zeros((5, 6))
+            fn[:3, 2] = mass * 9.81 / 4.0
+        else:
+            pd = [T]
+            md, fd = [T], split_phases(pd, False, 3)
+            nodes = np.zeros((2, 6))
+            nodes[:, :3] = feet[ee]
+            fn = np.zeros((4, 6))
+            fn[:, 2] = mass * 9.81 / 4.0
+        motions.append(SplineTable(md, nodes))
+        forces.append(SplineTable(fd, fn))
+        pds.append(pd)
+        c0s.append(True)
+    return GaitPlan(SplineTable(bd, lin), SplineTable(bd, ang), motions, forces, pds, c0s, standing=simple_standing(robot)[0], total_duration=T)
 
 
 # ------------------------------------------------------------------------------ C ABI mirrors
