@@ -333,7 +333,16 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH, help="instances per launch per GPU (default: the BASELINE config, 4096)")
     ap.add_argument("--pattern", default=PATTERN, choices=["stand", "trot", "walk", "mixed"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (experiments only)")
+    ap.add_argument("--workload", default="step", choices=["step", "wire", "traj", "rollout"],
+                    help="step = the BASELINE metric (default); wire / traj / rollout = the rows next to it (tools/bench_aux.py)")
     args = ap.parse_args()
+    if args.workload != "step":
+        import __graft_entry__ as g
+        g.build()
+        sys.path.insert(0, str(ROOT / "tools"))
+        import bench_aux
+        bench_aux.run(args.workload, steps=min(args.steps, 50), warmup=args.warmup)
+        return
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -724,10 +724,10 @@ extern "C" int wbc_sample_trajectory(wbc_handle* h, const wbc_plan* plan, int64_
   if (!plan || n < 0 || (n > 0 && (!t || !traj || !contact))) return fail_arg(h, "wbc_sample_trajectory: plan, t, traj and contact are required");
   if (n == 0) return WBC_OK;
   WBC_CUDA(h, cudaSetDevice(h->device));
-  const long long total = (long long)n * wbctraj::NELEM, cap = (long long)h->sm_count * 16;
-  const long long blocks = (total + 255) / 256;
-  wbctraj::sample_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(plan->t, n, plan_index, t, traj, contact,
-                                                                                                  f_plan, t_eval, status);
+  if (reinterpret_cast<uintptr_t>(contact) & 3u) return fail_arg(h, "wbc_sample_trajectory: contact must be 4-byte aligned");
+  const long long chunks = (n + 31) / 32, blocks = (chunks + wbctraj::SAMPLE_WARPS - 1) / wbctraj::SAMPLE_WARPS, cap = (long long)h->sm_count * 16;
+  wbctraj::sample_kernel<<<(unsigned)(blocks < cap ? blocks : cap), wbctraj::SAMPLE_WARPS * 32, 0, (cudaStream_t)stream>>>(
+      plan->t, n, plan_index, t, traj, contact, f_plan, t_eval, status);
   h->launches++;
   WBC_CUDA(h, cudaGetLastError());
   return WBC_OK;

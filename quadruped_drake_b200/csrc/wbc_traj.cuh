@@ -10,7 +10,7 @@
 // towr/src/phase_durations.cc:120-124 (contact flag).
 //
 // HBM-bound: 12 B in (t, plan index), 436 (+96) B out per instance; the spline tables (tens of KB per plan) stay in
-// L1/L2. One thread per output element, so the stores of a warp are consecutive doubles of traj.
+// L1/L2. See sample_kernel for the thread mapping.
 #pragma once
 #include <stdint.h>
 #include "wbc.h"
@@ -18,7 +18,6 @@
 namespace wbctraj {
 
 constexpr int NSPLINE = 10;          // 0 base linear, 1 base angular, 2-5 foot motion LF RF LH RH, 6-9 foot force
-constexpr int NELEM = 54 + 4 + 12;   // virtual output elements per instance: traj, contact, planned force
 
 // Device-resident tables of a set of plans (built by wbc_plan_create).
 struct PlanTables {
@@ -62,78 +61,124 @@ __device__ __forceinline__ int segment_of(const double* __restrict__ tend, int n
   return lo;
 }
 
-__global__ void __launch_bounds__(256) sample_kernel(PlanTables pt, long long n, const int* __restrict__ plan_index,
-                                                     const double* __restrict__ tin, double* __restrict__ traj,
-                                                     unsigned char* __restrict__ contact, double* __restrict__ fplan,
-                                                     double* __restrict__ t_eval_out, int* __restrict__ status) {
-  const long long total = n * NELEM;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    const long long inst = idx / NELEM;
-    const int e = (int)(idx - inst * NELEM);
-    if (e >= 58 && !fplan) continue;
-    int pl = plan_index ? plan_index[inst] : 0;
-    int st = 0;
-    if (pl < 0 || pl >= pt.n_plans) { pl = 0; st |= WBC_TRAJ_BADPLAN; }
-    double t = tin[inst];
-    // ---- planner semantics (planners/towr.py:96-110): stand while t < wait_time, then the nearest stored sample
-    const int g0 = pt.grid_off[pl], gn = pt.grid_off[pl + 1] - g0;
-    bool standing = false;
-    if (gn > 0) {
-      const double wait = pt.wait_time[pl];
-      if (t < wait) standing = true;
-      else {
-        const double tq = t - wait;
-        const double* ts = pt.grid_ts + g0;
-        // np.abs(ts - tq).argmin(): ts is increasing, so the minimum is next to the insertion point; first minimum wins
-        int lo = 0, hi = gn - 1;
-        while (lo < hi) { const int mid = (lo + hi) >> 1; if (__ldg(ts + mid) >= tq) hi = mid; else lo = mid + 1; }
-        int best = lo;
-        if (lo > 0 && fabs(__ldg(ts + lo - 1) - tq) <= fabs(__ldg(ts + lo) - tq)) best = lo - 1;
-        t = __ldg(ts + best);
+// Two stages per chunk of 32 instances (one warp per chunk):
+//   A  lane = instance: planner time logic (wait / nearest stored sample), the 10 spline segment lookups and the 4 contact
+//      flags, done ONCE per instance; (polynomial index, local time) of every spline go to shared memory;
+//   B  lane = output element: consecutive lanes write consecutive doubles of traj (coalesced), each evaluating one cubic
+//      (or its first / second derivative) from the staged segment info and a 32-byte coefficient record.
+constexpr int SAMPLE_WARPS = 4;
+struct SampleSmem {
+  double tl[32][NSPLINE];
+  int poly[32][NSPLINE];
+  int plan[32];
+  unsigned char standing[32];
+};
+
+__global__ void __launch_bounds__(SAMPLE_WARPS * 32) sample_kernel(PlanTables pt, long long n, const int* __restrict__ plan_index,
+                                                                   const double* __restrict__ tin, double* __restrict__ traj,
+                                                                   unsigned char* __restrict__ contact, double* __restrict__ fplan,
+                                                                   double* __restrict__ t_eval_out, int* __restrict__ status) {
+  __shared__ SampleSmem smem[SAMPLE_WARPS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  SampleSmem& sm = smem[warp];
+  const long long n_chunks = (n + 31) / 32;
+  for (long long chunk = (long long)blockIdx.x * SAMPLE_WARPS + warp; chunk < n_chunks; chunk += (long long)gridDim.x * SAMPLE_WARPS) {
+    const long long i0 = chunk * 32;
+    const int cnt = (int)((n - i0) < 32 ? (n - i0) : 32);
+    __syncwarp();
+    // ---------------------------------------------------------------- stage A
+    if (lane < cnt) {
+      const long long inst = i0 + lane;
+      int pl = plan_index ? plan_index[inst] : 0;
+      int st = 0;
+      if (pl < 0 || pl >= pt.n_plans) { pl = 0; st |= WBC_TRAJ_BADPLAN; }
+      double t = tin[inst];
+      // planner semantics (planners/towr.py:96-110): stand while t < wait_time, then the nearest stored sample
+      const int g0 = __ldg(pt.grid_off + pl), gn = __ldg(pt.grid_off + pl + 1) - g0;
+      bool standing = false;
+      if (gn > 0) {
+        const double wait = __ldg(pt.wait_time + pl);
+        if (t < wait) standing = true;
+        else {
+          const double tq = t - wait;
+          const double* ts = pt.grid_ts + g0;
+          // np.abs(ts - tq).argmin(): ts is increasing, so the minimum is next to the insertion point; first minimum wins
+          int lo = 0, hi = gn - 1;
+          while (lo < hi) { const int mid = (lo + hi) >> 1; if (__ldg(ts + mid) >= tq) hi = mid; else lo = mid + 1; }
+          int best = lo;
+          if (lo > 0 && fabs(__ldg(ts + lo - 1) - tq) <= fabs(__ldg(ts + lo) - tq)) best = lo - 1;
+          t = __ldg(ts + best);
+        }
       }
-    }
-    const int* po = pt.poly_off + pl * (NSPLINE + 1);
-    const double t_total = __ldg(pt.tend + po[1] - 1);            // Spline::GetTotalTime of the base spline
-    if (!standing) {
-      if (!(t >= 0.0)) { t = 0.0; st |= WBC_TRAJ_CLAMPED; }       // the reference asserts t >= 0 (spline.cc:52) ...
-      if (t > t_total + 1e-10) { t = t_total; st |= WBC_TRAJ_CLAMPED; }   // ... and runs off the end (spline.cc:65)
-    }
-    if (e == 0) {
+      const int* po = pt.poly_off + pl * (NSPLINE + 1);
+      if (!standing) {
+        const double t_total = __ldg(pt.tend + __ldg(po + 1) - 1);      // Spline::GetTotalTime of the base spline
+        if (!(t >= 0.0)) { t = 0.0; st |= WBC_TRAJ_CLAMPED; }           // the reference asserts t >= 0 (spline.cc:52) ...
+        if (t > t_total + 1e-10) { t = t_total; st |= WBC_TRAJ_CLAMPED; }   // ... and runs off the end (spline.cc:65)
+      }
       if (status) status[inst] = st;
       if (t_eval_out) t_eval_out[inst] = standing ? -1.0 : t;
-    }
-    if (e >= 54 && e < 58) {
-      // ---- contact flag of foot k (phase_durations.cc:120-124)
-      const int k = e - 54;
-      unsigned char c = 1;
+      sm.plan[lane] = pl;
+      sm.standing[lane] = standing ? 1 : 0;
+      unsigned cbits = 0x01010101u;
       if (!standing) {
+        const int ns = fplan ? NSPLINE : 6;
+        for (int s = 0; s < ns; ++s) {
+          const int p0 = __ldg(po + s), np_ = __ldg(po + s + 1) - p0;
+          const int i = segment_of(pt.tend + p0, np_, t);
+          sm.poly[lane][s] = p0 + i;
+          sm.tl[lane][s] = t - (i > 0 ? __ldg(pt.tend + p0 + i - 1) : 0.0);
+        }
+        // contact flags (phase_durations.cc:120-124)
         const int* fo = pt.phase_off + pl * 5;
-        const int ph = segment_of(pt.phase_tend + fo[k], fo[k + 1] - fo[k], t);
-        const bool c0 = pt.contact_start[pl * 4 + k] != 0;
-        c = (ph & 1) ? !c0 : c0;
+        cbits = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int f0 = __ldg(fo + k);
+          const int ph = segment_of(pt.phase_tend + f0, __ldg(fo + k + 1) - f0, t);
+          const bool c0 = __ldg(pt.contact_start + pl * 4 + k) != 0;
+          cbits |= (unsigned)(((ph & 1) ? !c0 : c0) ? 1 : 0) << (8 * k);
+        }
       }
-      contact[inst * 4 + k] = c;
-      continue;
+      reinterpret_cast<unsigned*>(contact)[inst] = cbits;              // 4 flags as one aligned 32-bit store
     }
-    // ---- which spline / derivative / dimension this element is (wbc.h traj order = trunk_state_t member order)
-    int s, deriv, dim;
-    if (e < 18) { s = e / 9; deriv = (e % 9) / 3; dim = e % 3; }
-    else if (e < 54) { const int r = e - 18; deriv = r / 12; s = 2 + (r % 12) / 3; dim = r % 3; }
-    else { const int r = e - 58; deriv = 0; s = 6 + r / 3; dim = r % 3; }
-    double val;
-    if (standing) val = e < 54 ? pt.standing[pl * 54 + e] : 0.0;
-    else {
-      const int p0 = po[s], np_ = po[s + 1] - p0;
-      const int i = segment_of(pt.tend + p0, np_, t);
-      const double tl = t - (i > 0 ? __ldg(pt.tend + p0 + i - 1) : 0.0);
-      const double2* c2 = reinterpret_cast<const double2*>(pt.coef + ((size_t)(p0 + i) * 3 + dim) * 4);
-      const double2 ab = __ldg(c2), cd = __ldg(c2 + 1);            // A B | C D
-      if (deriv == 0) val = fma(fma(fma(cd.y, tl, cd.x), tl, ab.y), tl, ab.x);
-      else if (deriv == 1) val = fma(fma(3.0 * cd.y, tl, 2.0 * cd.x), tl, ab.y);
-      else val = fma(6.0 * cd.y, tl, 2.0 * cd.x);
+    __syncwarp();
+    // ---------------------------------------------------------------- stage B
+    // lane = (instance, spline, dimension): one coefficient record gives position, velocity and acceleration; the three
+    // stores of neighbouring lanes fill whole 24-byte groups of the row, which L2 merges into full sectors
+    double* out = traj + i0 * WBC_NTRAJ;
+    for (int idx = lane; idx < cnt * 18; idx += 32) {
+      const int il = idx / 18, r = idx - il * 18, s = r / 3, dim = r - 3 * s;
+      const int e0 = s < 2 ? 9 * s + dim : 18 + 3 * (s - 2) + dim, stride = s < 2 ? 3 : 12;
+      double p, v, a;
+      if (sm.standing[il]) {
+        const double* st = pt.standing + sm.plan[il] * WBC_NTRAJ + e0;
+        p = __ldg(st); v = __ldg(st + stride); a = __ldg(st + 2 * stride);
+      } else {
+        const double tl = sm.tl[il][s];
+        const double2* c2 = reinterpret_cast<const double2*>(pt.coef + ((size_t)sm.poly[il][s] * 3 + dim) * 4);
+        const double2 ab = __ldg(c2), cd = __ldg(c2 + 1);            // A B | C D
+        p = fma(fma(fma(cd.y, tl, cd.x), tl, ab.y), tl, ab.x);
+        v = fma(fma(3.0 * cd.y, tl, 2.0 * cd.x), tl, ab.y);
+        a = fma(6.0 * cd.y, tl, 2.0 * cd.x);
+      }
+      double* o = out + il * WBC_NTRAJ + e0;
+      o[0] = p; o[stride] = v; o[2 * stride] = a;
     }
-    if (e < 54) traj[inst * 54 + e] = val;
-    else fplan[inst * 12 + (e - 58)] = val;
+    if (fplan) {
+      double* fo = fplan + i0 * 12;
+      for (int idx = lane; idx < cnt * 12; idx += 32) {
+        const int il = idx / 12, r = idx - il * 12, s = 6 + r / 3, dim = r % 3;
+        double val = 0.0;
+        if (!sm.standing[il]) {
+          const double tl = sm.tl[il][s];
+          const double2* c2 = reinterpret_cast<const double2*>(pt.coef + ((size_t)sm.poly[il][s] * 3 + dim) * 4);
+          const double2 ab = __ldg(c2), cd = __ldg(c2 + 1);
+          val = fma(fma(fma(cd.y, tl, cd.x), tl, ab.y), tl, ab.x);
+        }
+        fo[idx] = val;
+      }
+    }
   }
 }
 

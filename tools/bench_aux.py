@@ -1,0 +1,118 @@
+#!/usr/bin/env python
+"""Device-timed throughput of the rows next to the control step: LCM wire codecs, trajectory sampler,
+closed-loop rollout. One JSON line per workload, same keys as bench.py (`python bench.py --workload wire|traj|rollout` calls
+this). Inputs are resident in HBM and larger than the 126 MB L2 (no flush needed); CUDA events on the launch stream."""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+
+
+def _time(fn, steps, warmup):
+    import torch
+    for _ in range(max(warmup, 3)):
+        fn()
+    torch.cuda.synchronize()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for e0, e1 in evs:
+        e0.record()
+        fn()
+        e1.record()
+    torch.cuda.synchronize()
+    return np.array([a.elapsed_time(b) for a, b in evs])
+
+
+def _line(metric, unit, n, per_ms, bytes_per_unit, workload, steps, warmup, launches, extra=None):
+    from bench import measured_peaks
+    peak, src = measured_peaks()
+    ms = float(per_ms.mean())
+    ach = bytes_per_unit * n / (ms * 1e-3) / 1e9
+    d = {"metric": metric, "value": n / (ms * 1e-3), "unit": unit, "n_gpus": 1, "steps": steps, "warmup": max(warmup, 3), "ms_per_step": ms,
+         "p50_ms_per_step": float(np.median(per_ms)), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/f64",
+         "data": "synthetic", "config": {"workload": workload, "units_per_launch": n, "l2": "inputs + outputs larger than L2"},
+         "gpu_launches": launches,
+         "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                      "algorithmic_bytes_per_unit": bytes_per_unit, "peak_source": src}}
+    if extra:
+        d.update(extra)
+    return d
+
+
+def run(workload, steps=50, warmup=5, n=1 << 20):
+    import torch
+    from oracle import lcm_codec as lc          # checker only: builds a seeded reference batch of wire bytes
+    from quadruped_drake_b200 import planner as pl
+    from quadruped_drake_b200.controller import BatchedController
+    from quadruped_drake_b200.wire import WireCodec
+    ctl = BatchedController("mini_cheetah", device=0)
+    out = []
+    rng = np.random.default_rng(0)
+    if workload == "wire":
+        w = WireCodec(ctl)
+        traj, f = rng.normal(0, 3, (n, 54)), rng.normal(0, 40, (n, 12))
+        contact = rng.integers(0, 2, (n, 4)).astype(np.uint8)
+        msgs = torch.from_numpy(lc.encode_trunk_state(np.arange(n) * 1e-3, np.zeros(n, np.uint8), traj, contact, f)).cuda()
+        d = w.decode_trunk_state(msgs)
+        l0 = ctl.launches
+        per = _time(lambda: w.decode_trunk_state(msgs), steps, warmup)
+        out.append(_line("trunk_state_t messages decoded/sec", "messages/s", n, per, 549 + 545, "wbc_lcm_decode_trunk_state, 1Mi messages", steps, warmup, ctl.launches - l0))
+        per = _time(lambda: w.encode_trunk_state(d["timestamp"], d["finished"], d["traj"], d["contact"], d["f"]), steps, warmup)
+        out.append(_line("trunk_state_t messages encoded/sec", "messages/s", n, per, 541 + 549, "wbc_lcm_encode_trunk_state, 1Mi messages", steps, warmup, steps))
+        tau = torch.from_numpy(rng.normal(0, 10, (n, 12))).cuda()
+        rm, _ = w.encode_robot_state(None, None, tau, tau_in_actuator_order=True)
+        per = _time(lambda: w.encode_robot_state(None, None, tau, tau_in_actuator_order=True), steps, warmup)
+        out.append(_line("robot_state_control_lcmt torque messages encoded/sec", "messages/s", n, per, 96 + 204 + 4, "wbc_lcm_encode_robot_state (torques only), 1Mi messages", steps, warmup, steps))
+        per = _time(lambda: w.decode_robot_state(rm), steps, warmup)
+        out.append(_line("robot_state_control_lcmt messages decoded/sec", "messages/s", n, per, 204 + 49 * 8 + 4, "wbc_lcm_decode_robot_state, 1Mi messages", steps, warmup, steps))
+    elif workload == "traj":
+        plans = [pl.make_gait_plan("mini_cheetah", c) for c in ("walk", "trot", "pace", "bound")]
+        s = pl.TrajectorySampler(ctl, plans)
+        t = torch.from_numpy(rng.uniform(0, 5, n)).cuda()
+        pi = torch.from_numpy(rng.integers(0, 4, n).astype(np.int32)).cuda()
+        per = _time(lambda: s.sample(t, pi), steps, warmup)
+        out.append(_line("trunk-trajectory samples/sec", "samples/s", n, per, 12 + 432 + 4 + 8 + 4, "wbc_sample_trajectory, 4 gait plans, 1Mi (plan, t) pairs", steps, warmup, steps))
+    elif workload == "rollout":
+        from quadruped_drake_b200.rollout import Q0_MINI_CHEETAH as Q0, rollout
+        nr, k = 4096, 200
+        bh = Q0[6] - ctl.dynamics(Q0[None], np.zeros((1, 18)))["p_feet"][0, :, 2].mean()
+        plans = [pl.make_motion_plan("mini_cheetah", m, 6.0, base_height=bh, phase=ph) for m in ("orientation", "edge", "raise_foot")
+                 for ph in np.linspace(0, 2 * np.pi, 8, endpoint=False)]
+        s = pl.TrajectorySampler(ctl, plans)
+        q0 = np.tile(Q0, (nr, 1)); q0[:, 6] = bh
+        pi = torch.from_numpy(rng.integers(0, len(plans), nr).astype(np.int32)).cuda()
+        res = {}
+        for graph in (True, False):
+            def once():
+                q, v, t = (torch.from_numpy(x).cuda() for x in (q0, np.zeros((nr, 18)), np.zeros(nr)))
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                r = rollout(ctl, s, "id", q, v, t, k, 5e-3, plan_index=pi, use_graph=graph)
+                e1.record()
+                torch.cuda.synchronize()
+                assert int(r.status_or.max().item()) == 0
+                return e0.elapsed_time(e1)
+            with torch.cuda.stream(torch.cuda.Stream()):
+                for _ in range(2):
+                    once()
+                res[graph] = np.array([once() for _ in range(5)])
+        per = res[True]
+        d = _line("closed-loop robot control steps/sec (sample + ID-QP + integrate)", "robot-steps/s", nr * k, per, 860 + 2 * 444 + 2 * 296 + 144,
+                  "wbc_rollout: 4096 robots x 200 steps, reference test motions, CUDA-graph replay", 5, 2, 3 * k * 5,
+                  {"without_graph_robot_steps_per_s": nr * k / (float(res[False].mean()) * 1e-3)})
+        out.append(d)
+    else:
+        raise SystemExit(f"unknown workload {workload}")
+    for d in out:
+        print(json.dumps(d))
+    ctl.close()
+
+
+if __name__ == "__main__":
+    run(sys.argv[1] if len(sys.argv) > 1 else "wire")
