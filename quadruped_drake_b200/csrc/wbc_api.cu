@@ -114,6 +114,7 @@ struct wbc_handle {
   int sm_count = 148;
   int* d_tau_map = nullptr;            // message slot (velocity order) -> actuator index, for wbc_lcm_encode_robot_state
   cudaStream_t stream = nullptr;       // used by the host entry points
+  cudaStream_t stream2 = nullptr;      // second lane of the chunked wbc_step_host pipeline
   // device staging for wbc_step_host
   int64_t cap = 0;
   double *d_q = nullptr, *d_v = nullptr, *d_traj = nullptr, *d_tau = nullptr, *d_metrics = nullptr, *d_vd = nullptr,
@@ -194,6 +195,7 @@ extern "C" int wbc_create(const wbc_model* model, const wbc_params* params, int 
   e = cudaMemcpy(h->d_const, &hc, sizeof(DevConst), cudaMemcpyHostToDevice);
   if (e != cudaSuccess) { h->err = std::string("cudaMemcpy: ") + cudaGetErrorString(e); return bail(WBC_ERR_CUDA); }
   e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking);
   if (e != cudaSuccess) { h->err = std::string("cudaStreamCreate: ") + cudaGetErrorString(e); return bail(WBC_ERR_CUDA); }
   {
     cudaDeviceProp prop;
@@ -225,6 +227,7 @@ extern "C" int wbc_destroy(wbc_handle* h) {
   cudaFree(h->ro_traj); cudaFree(h->ro_vd); cudaFree(h->ro_metrics); cudaFree(h->ro_tau); cudaFree(h->ro_t);
   cudaFree(h->ro_contact); cudaFree(h->ro_status); cudaFree(h->ro_counter);
   if (h->stream) cudaStreamDestroy(h->stream);
+  if (h->stream2) cudaStreamDestroy(h->stream2);
   delete h;
   return WBC_OK;
 }
@@ -352,28 +355,66 @@ extern "C" int wbc_step_host(wbc_handle* h, int kind, int64_t n, const wbc_io* i
   if (!io->q || !io->v || !io->tau || (!pd && (!io->traj || !io->contact || !io->metrics || !io->status)))
     return fail_arg(h, "wbc_step_host: q, v, traj, contact, tau, metrics and status are required");
   WBC_CUDA(h, cudaSetDevice(h->device));
-  int rc = ensure_staging(h, n);
-  if (rc) return rc;
-  cudaStream_t st = h->stream;
-  WBC_CUDA(h, cudaMemcpyAsync(h->d_q, io->q, n * WBC_NQ * sizeof(double), cudaMemcpyHostToDevice, st));
-  WBC_CUDA(h, cudaMemcpyAsync(h->d_v, io->v, n * WBC_NV * sizeof(double), cudaMemcpyHostToDevice, st));
-  if (!pd) {
-    WBC_CUDA(h, cudaMemcpyAsync(h->d_traj, io->traj, n * WBC_NTRAJ * sizeof(double), cudaMemcpyHostToDevice, st));
-    WBC_CUDA(h, cudaMemcpyAsync(h->d_contact, io->contact, n * 4, cudaMemcpyHostToDevice, st));
+  int rc = WBC_OK;
+  // Zero-copy path: when every buffer is page-locked host memory (wbc_host_alloc / cudaHostRegister) the kernel reads
+  // its 732 B of inputs and writes its 132 B of outputs per instance straight over the host link - one launch, no
+  // staging copies, the transfers of one warp overlap the arithmetic of the others.
+  {
+    int mode = 1;
+    if (const char* env = getenv("WBC_HOST_ZEROCOPY")) mode = atoi(env);
+    const void* ptrs[10] = {io->q, io->v, io->traj, io->contact, io->tau, io->metrics, io->status, io->vd, io->f, io->qp_info};
+    void* dev[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool pinned = mode != 0;
+    for (int i = 0; i < 10 && pinned; ++i) {
+      if (!ptrs[i]) continue;
+      cudaPointerAttributes at;
+      if (cudaPointerGetAttributes(&at, ptrs[i]) != cudaSuccess || at.type != cudaMemoryTypeHost || !at.devicePointer) { pinned = false; cudaGetLastError(); }
+      else dev[i] = at.devicePointer;
+    }
+    if (pinned) {
+      wbc_io dio{(const double*)dev[0], (const double*)dev[1], (const double*)dev[2], (const uint8_t*)dev[3], (double*)dev[4],
+                 (double*)dev[5], (int32_t*)dev[6], (double*)dev[7], (double*)dev[8], (double*)dev[9]};
+      rc = wbc_step(h, kind, n, &dio, h->stream);
+      if (rc) return rc;
+      WBC_CUDA(h, cudaStreamSynchronize(h->stream));
+      return WBC_OK;
+    }
   }
-  wbc_io dio{h->d_q, h->d_v, h->d_traj, h->d_contact, h->d_tau, h->d_metrics, h->d_status,
-             io->vd ? h->d_vd : nullptr, io->f ? h->d_f : nullptr, io->qp_info ? h->d_info : nullptr};
-  rc = wbc_step(h, kind, n, &dio, st);
+  rc = ensure_staging(h, n);
   if (rc) return rc;
-  WBC_CUDA(h, cudaMemcpyAsync(io->tau, h->d_tau, n * WBC_NU * sizeof(double), cudaMemcpyDeviceToHost, st));
-  if (!pd) {
-    WBC_CUDA(h, cudaMemcpyAsync(io->metrics, h->d_metrics, n * WBC_NMETRIC * sizeof(double), cudaMemcpyDeviceToHost, st));
-    WBC_CUDA(h, cudaMemcpyAsync(io->status, h->d_status, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  // Chunked two-stream pipeline: the upload of chunk c + 1 overlaps the kernel of chunk c, the download of chunk c the
+  // kernel of chunk c + 1 (separate copy engines); small batches go through in one piece.
+  int n_chunks = n >= 2048 ? 2 : 1;
+  if (const char* env = getenv("WBC_HOST_CHUNKS")) { const int v = atoi(env); if (v >= 1 && v <= 16) n_chunks = v; }
+  if ((int64_t)n_chunks > n) n_chunks = (int)n;
+  const int64_t per = (n + n_chunks - 1) / n_chunks;
+  cudaStream_t lanes[2] = {h->stream, h->stream2};
+  for (int c = 0; c < n_chunks; ++c) {
+    const int64_t o = c * per, m = (o + per <= n) ? per : n - o;
+    if (m <= 0) break;
+    cudaStream_t st = lanes[c & 1];
+    WBC_CUDA(h, cudaMemcpyAsync(h->d_q + o * WBC_NQ, io->q + o * WBC_NQ, m * WBC_NQ * sizeof(double), cudaMemcpyHostToDevice, st));
+    WBC_CUDA(h, cudaMemcpyAsync(h->d_v + o * WBC_NV, io->v + o * WBC_NV, m * WBC_NV * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (!pd) {
+      WBC_CUDA(h, cudaMemcpyAsync(h->d_traj + o * WBC_NTRAJ, io->traj + o * WBC_NTRAJ, m * WBC_NTRAJ * sizeof(double), cudaMemcpyHostToDevice, st));
+      WBC_CUDA(h, cudaMemcpyAsync(h->d_contact + o * 4, io->contact + o * 4, m * 4, cudaMemcpyHostToDevice, st));
+    }
+    wbc_io dio{h->d_q + o * WBC_NQ, h->d_v + o * WBC_NV, h->d_traj + o * WBC_NTRAJ, h->d_contact + o * 4, h->d_tau + o * WBC_NU,
+               h->d_metrics + o * WBC_NMETRIC, h->d_status + o,
+               io->vd ? h->d_vd + o * WBC_NV : nullptr, io->f ? h->d_f + o * 12 : nullptr, io->qp_info ? h->d_info + o * 4 : nullptr};
+    rc = wbc_step(h, kind, m, &dio, st);
+    if (rc) return rc;
+    WBC_CUDA(h, cudaMemcpyAsync(io->tau + o * WBC_NU, h->d_tau + o * WBC_NU, m * WBC_NU * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (!pd) {
+      WBC_CUDA(h, cudaMemcpyAsync(io->metrics + o * WBC_NMETRIC, h->d_metrics + o * WBC_NMETRIC, m * WBC_NMETRIC * sizeof(double), cudaMemcpyDeviceToHost, st));
+      WBC_CUDA(h, cudaMemcpyAsync(io->status + o, h->d_status + o, m * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+      if (io->vd) WBC_CUDA(h, cudaMemcpyAsync(io->vd + o * WBC_NV, h->d_vd + o * WBC_NV, m * WBC_NV * sizeof(double), cudaMemcpyDeviceToHost, st));
+      if (io->f) WBC_CUDA(h, cudaMemcpyAsync(io->f + o * 12, h->d_f + o * 12, m * 12 * sizeof(double), cudaMemcpyDeviceToHost, st));
+      if (io->qp_info) WBC_CUDA(h, cudaMemcpyAsync(io->qp_info + o * 4, h->d_info + o * 4, m * 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
   }
-  if (!pd && io->vd) WBC_CUDA(h, cudaMemcpyAsync(io->vd, h->d_vd, n * WBC_NV * sizeof(double), cudaMemcpyDeviceToHost, st));
-  if (!pd && io->f) WBC_CUDA(h, cudaMemcpyAsync(io->f, h->d_f, n * 12 * sizeof(double), cudaMemcpyDeviceToHost, st));
-  if (!pd && io->qp_info) WBC_CUDA(h, cudaMemcpyAsync(io->qp_info, h->d_info, n * 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
-  WBC_CUDA(h, cudaStreamSynchronize(st));
+  WBC_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (n_chunks > 1) WBC_CUDA(h, cudaStreamSynchronize(h->stream2));
   return WBC_OK;
 }
 
