@@ -262,3 +262,25 @@ def test_leafsystem_mirror_standing(built):
     assert np.abs(tau - ref.tau).max() < 1e-5
     met = ctl.EvalOutput(ctx, 1)
     assert abs(met[1] - ref.metrics[1]) < 1e-12
+
+
+@pytest.mark.gpu
+def test_host_entry_paths_agree(ctl_cache):
+    """wbc_step_host: pageable buffers (staged, two-stream chunked copies) and page-locked buffers (zero-copy: the kernel
+    reads / writes host memory directly) give bit-identical results, for sizes around the chunking threshold."""
+    import ctypes as C
+    from quadruped_drake_b200 import capi
+    from quadruped_drake_b200.synth import generate
+    ctl = ctl_cache("mini_cheetah")
+    for n in (1, 5, 2047, 2048, 4099):
+        q, v, traj, contact = generate(ctl.model, n, 77 + n, "mixed", ctl.fk)
+        a = ctl.step("id", q, v, traj, contact, debug=True)                      # numpy arrays: pageable path
+        hq, hv, ht = capi.pinned_empty((n, 19)), capi.pinned_empty((n, 18)), capi.pinned_empty((n, 54))
+        hc = capi.pinned_empty((n, 4), np.uint8)
+        hq[:], hv[:], ht[:], hc[:] = q, v, traj, contact
+        tau, met, st = capi.pinned_empty((n, 12)), capi.pinned_empty((n, 4)), capi.pinned_empty((n,), np.int32)
+        vd = capi.pinned_empty((n, 18))
+        io = capi.WbcIO(capi.np_ptr(hq), capi.np_ptr(hv), capi.np_ptr(ht), capi.np_ptr(hc), capi.np_ptr(tau), capi.np_ptr(met),
+                        capi.np_ptr(st), capi.np_ptr(vd), None, None)
+        assert ctl.lib.wbc_step_host(ctl._h, capi.WBC_CTRL_ID, n, C.byref(io)) == 0
+        assert np.array_equal(tau, a.tau) and np.array_equal(met, a.metrics) and np.array_equal(st, a.status) and np.array_equal(vd, a.vd)
