@@ -568,24 +568,25 @@ WBC_DEV double zent(const WarpSmem& s, int lane, int var) {
 }
 
 // ------------------------------------------------------------------------------ phase 5
-// Lower-triangle pairs (i >= k) of a 13x13 owned by a lane: entries e = lane, lane+32, lane+64 of the 91.
+// Lower-triangle pairs (i >= k) of an N x N matrix owned by a lane: entries e = lane, lane+32, lane+64 of the N (N + 1) / 2
+// (N = active reduced dimension: 12 for ID / PC / MPTC, 13 for CLF; the storage stride stays NF).
 struct TriPairs { int i[3], k[3]; };
-WBC_DEV TriPairs tri_pairs(int lane) {
+template <int N> WBC_DEV TriPairs tri_pairs(int lane) {
   TriPairs t;
 #pragma unroll
   for (int h = 0; h < 3; ++h) {
     const int e = lane + 32 * h;
     int ii = 0;
 #pragma unroll
-    for (int c = 1; c < NF; ++c) ii += (c * (c + 1) / 2 <= e) ? 1 : 0;
-    t.i[h] = e < NF * (NF + 1) / 2 ? ii : -1;
+    for (int c = 1; c < N; ++c) ii += (c * (c + 1) / 2 <= e) ? 1 : 0;
+    t.i[h] = e < N * (N + 1) / 2 ? ii : -1;
     t.k[h] = e - ii * (ii + 1) / 2;
   }
   return t;
 }
 
 // H = sum_r cw_r Y_r' Y_r (+ identity on padded dims), g = sum_r cw_r Y_r (y0_r - ct_r) + glin
-WBC_DEV void reduced_hessian(WarpSmem& s, int lane, int nf, int nrows, bool extra, const TriPairs& tp) {
+template <int N> WBC_DEV void reduced_hessian(WarpSmem& s, int lane, int nf, int nrows, bool extra, const TriPairs& tp) {
 #pragma unroll
   for (int h = 0; h < 3; ++h) {
     const int i = tp.i[h], k = tp.k[h];
@@ -601,7 +602,7 @@ WBC_DEV void reduced_hessian(WarpSmem& s, int lane, int nf, int nrows, bool extr
     if (i >= nf) acc = (i == k) ? 1.0 : 0.0;
     s.H[i][k] = acc;
   }
-  if (lane < NF) {
+  if (lane < N) {
     double acc = 0.0;
     for (int r = 0; r < nrows; ++r) acc = fma(s.cw[r] * s.Y[r][lane], s.Y[r][NF] - s.ct[r], acc);
     if (extra) acc = fma(s.cw[30] * s.Y[30][lane], s.Y[30][NF] - s.ct[30], fma(s.cw[31] * s.Y[31][lane], s.Y[31][NF] - s.ct[31], acc));
@@ -611,13 +612,13 @@ WBC_DEV void reduced_hessian(WarpSmem& s, int lane, int nf, int nrows, bool extr
 }
 
 // In-place Cholesky (lower) of s.H, then J = L^-T (J J' = H^-1) and the unconstrained minimiser x.
-WBC_DEV void factor_and_start(WarpSmem& s, int lane, int& status, const TriPairs& tp) {
-  for (int j = 0; j < NF; ++j) {
+template <int N> WBC_DEV void factor_and_start(WarpSmem& s, int lane, int& status, const TriPairs& tp) {
+  for (int j = 0; j < N; ++j) {
     const double dj = s.H[j][j];
     if (!(dj > 1e-300)) { status |= WBC_ST_NOTPD; }
     const double inv = frsqrt(dj > 1e-300 ? dj : 1.0);
     __syncwarp();
-    if (lane < NF && lane >= j) s.H[lane][j] *= inv;
+    if (lane < N && lane >= j) s.H[lane][j] *= inv;
     if (lane == 0) s.d[j] = inv;                    // 1 / L[j][j], reused by the triangular inverse below
     __syncwarp();
 #pragma unroll
@@ -628,33 +629,33 @@ WBC_DEV void factor_and_start(WarpSmem& s, int lane, int& status, const TriPairs
     __syncwarp();
   }
   // column `lane` of X = L^-1 is row `lane` of J = X'
-  if (lane < NF) {
-    double xcol[NF];
+  if (lane < N) {
+    double xcol[N];
 #pragma unroll
-    for (int i = 0; i < NF; ++i) {
+    for (int i = 0; i < N; ++i) {
       double acc = (i == lane) ? 1.0 : 0.0;
 #pragma unroll
-      for (int mm = 0; mm < NF; ++mm)
+      for (int mm = 0; mm < N; ++mm)
         if (mm < i) acc = fma(-s.H[i][mm], xcol[mm], acc);
       xcol[i] = acc * s.d[i];
     }
     __syncwarp();            // every lane is done reading L before J overwrites it
 #pragma unroll
-    for (int i = 0; i < NF; ++i) s.J[lane][i] = (i >= lane) ? xcol[i] : 0.0;
+    for (int i = 0; i < N; ++i) s.J[lane][i] = (i >= lane) ? xcol[i] : 0.0;
   } else {
     __syncwarp();
   }
   __syncwarp();
   // x = -J J' g
-  if (lane < NF) {
+  if (lane < N) {
     double t = 0.0;
-    for (int i = 0; i < NF; ++i) t = fma(s.J[i][lane], s.g[i], t);
+    for (int i = 0; i < N; ++i) t = fma(s.J[i][lane], s.g[i], t);
     s.d[lane] = t;
   }
   __syncwarp();
-  if (lane < NF) {
+  if (lane < N) {
     double t = 0.0;
-    for (int k = 0; k < NF; ++k) t = fma(s.J[lane][k], s.d[k], t);
+    for (int k = 0; k < N; ++k) t = fma(s.J[lane][k], s.d[k], t);
     s.x[lane] = -t;
   }
   __syncwarp();
@@ -701,12 +702,12 @@ WBC_DEV double warp_argmin_nonneg(double v, int payload, int& out) {
 
 // Goldfarb-Idnani dual active-set method on  min 1/2 w'Hw + g'w  s.t. the IneqSet.
 // On entry s.J, s.x hold L^-T and the unconstrained minimiser. Returns iterations; multipliers in s.u.
-// All loops over the reduced dimension are fixed-length and branch-free: lanes >= NF compute on a clamped
+// All loops over the reduced dimension are fixed-length and branch-free: lanes >= N compute on a clamped
 // row (results discarded), entries left of the active count q are masked to zero instead of skipped.
-WBC_DEV int gi_solve(WarpSmem& s, int lane, const IneqSet& S, int max_iter, int& status, int& q_out, double& minslack) {
+template <int N> WBC_DEV int gi_solve(WarpSmem& s, int lane, const IneqSet& S, int max_iter, int& status, int& q_out, double& minslack) {
   const int mi = S.nfric + S.nextra + S.ntl;
-  const int li = lane < NF ? lane : NF - 1;     // clamped row for loads
-  const bool row = lane < NF;
+  const int li = lane < N ? lane : N - 1;     // clamped row for loads
+  const bool row = lane < N;
   // the (up to) two inequalities this lane watches, hoisted out of the loop
   Ineq c0 = get_ineq(S, lane < mi ? lane : 0), c1 = get_ineq(S, lane + 32 < mi ? lane + 32 : 0);
   const bool have0 = lane < mi, have1 = lane + 32 < mi;
@@ -716,7 +717,7 @@ WBC_DEV int gi_solve(WarpSmem& s, int lane, const IneqSet& S, int max_iter, int&
   {  // y = Y x + y0 (kept current after every primal step)
     double acc = s.Y[lane][NF];
 #pragma unroll
-    for (int k = 0; k < NF; ++k) acc = fma(s.Y[lane][k], s.x[k], acc);
+    for (int k = 0; k < N; ++k) acc = fma(s.Y[lane][k], s.x[k], acc);
     s.y[lane] = acc;
   }
   __syncwarp();
@@ -758,10 +759,10 @@ WBC_DEV int gi_solve(WarpSmem& s, int lane, const IneqSet& S, int max_iter, int&
       // d = J' n ; s.d keeps d, s.npv is untouched
       double dl = 0.0, dl1 = 0.0, dl2 = 0.0;
 #pragma unroll
-      for (int i = 0; i < NF; i += 3) {
+      for (int i = 0; i < N; i += 3) {
         dl = fma(s.J[i][li], s.npv[i], dl);
-        if (i + 1 < NF) dl1 = fma(s.J[i + 1][li], s.npv[i + 1], dl1);
-        if (i + 2 < NF) dl2 = fma(s.J[i + 2][li], s.npv[i + 2], dl2);
+        if (i + 1 < N) dl1 = fma(s.J[i + 1][li], s.npv[i + 1], dl1);
+        if (i + 2 < N) dl2 = fma(s.J[i + 2][li], s.npv[i + 2], dl2);
       }
       dl = row ? dl + (dl1 + dl2) : 0.0;
       if (row) s.d[lane] = dl;
@@ -773,10 +774,10 @@ WBC_DEV int gi_solve(WarpSmem& s, int lane, const IneqSet& S, int max_iter, int&
       // z = J[:, q:] d[q:]
       double zi = 0.0, zi1 = 0.0, zi2 = 0.0;
 #pragma unroll
-      for (int k = 0; k < NF; k += 3) {
+      for (int k = 0; k < N; k += 3) {
         zi = fma(s.J[li][k], s.dm[k], zi);
-        if (k + 1 < NF) zi1 = fma(s.J[li][k + 1], s.dm[k + 1], zi1);
-        if (k + 2 < NF) zi2 = fma(s.J[li][k + 2], s.dm[k + 2], zi2);
+        if (k + 1 < N) zi1 = fma(s.J[li][k + 1], s.dm[k + 1], zi1);
+        if (k + 2 < N) zi2 = fma(s.J[li][k + 2], s.dm[k + 2], zi2);
       }
       zi += zi1 + zi2;
       const double sp = cp.bound - cp.ca * s.y[cp.ra] - cp.cb * s.y[cp.rb];
@@ -802,10 +803,10 @@ WBC_DEV int gi_solve(WarpSmem& s, int lane, const IneqSet& S, int max_iter, int&
         __syncwarp();
         double acc = s.Y[lane][NF], acc1 = 0.0, acc2 = 0.0;
 #pragma unroll
-        for (int k = 0; k < NF; k += 3) {
+        for (int k = 0; k < N; k += 3) {
           acc = fma(s.Y[lane][k], s.x[k], acc);
-          if (k + 1 < NF) acc1 = fma(s.Y[lane][k + 1], s.x[k + 1], acc1);
-          if (k + 2 < NF) acc2 = fma(s.Y[lane][k + 2], s.x[k + 2], acc2);
+          if (k + 1 < N) acc1 = fma(s.Y[lane][k + 1], s.x[k + 1], acc1);
+          if (k + 2 < N) acc2 = fma(s.Y[lane][k + 2], s.x[k + 2], acc2);
         }
         s.y[lane] = acc + (acc1 + acc2);
       }
@@ -816,7 +817,7 @@ WBC_DEV int gi_solve(WarpSmem& s, int lane, const IneqSet& S, int max_iter, int&
         const double dq = s.d[q];
         const double alpha = dq > 0.0 ? -nrm : nrm;
         double rqq = dq;
-        if (q < NF - 1) {
+        if (q < N - 1) {
           const double vv = 2.0 * (zn - dq * alpha);   // |v|^2 with v = d[q:] - alpha e_q
           if (vv > 0.0) {
             // v = masked d with v_q = d_q - alpha, kept in s.dm (all lanes are past their reads of s.dm)
@@ -824,13 +825,13 @@ WBC_DEV int gi_solve(WarpSmem& s, int lane, const IneqSet& S, int max_iter, int&
             __syncwarp();
             double dt = 0.0, dt1 = 0.0;
 #pragma unroll
-            for (int k = 0; k < NF; ++k) {
+            for (int k = 0; k < N; ++k) {
               if (k & 1) dt1 = fma(s.J[li][k], s.dm[k], dt1); else dt = fma(s.J[li][k], s.dm[k], dt);
             }
             const double sc = 2.0 * (dt + dt1) * frcp(vv);
             if (row) {
 #pragma unroll
-              for (int k = 0; k < NF; ++k) s.J[lane][k] = fma(-sc, s.dm[k], s.J[lane][k]);
+              for (int k = 0; k < N; ++k) s.J[lane][k] = fma(-sc, s.dm[k], s.J[lane][k]);
             }
           }
           rqq = alpha;
@@ -1233,7 +1234,8 @@ WBC_DEV void step_instance(WarpSmem& s, const wbc_model& md, const wbc_params& p
   const bool isfree = (freemask >> lane) & 1u;
   const int widx = __popc(freemask & ((1u << lane) - 1u));
   const int ycol = lane == 31 ? NF : (isfree ? widx : -1);
-  bool ok = nf <= NF && pc_ok;
+  constexpr int NA = (KIND == WBC_CTRL_CLF) ? NF : NF - 1;   // active reduced dimension: the loops of phases 5-6 run to NA
+  bool ok = nf <= NA && pc_ok;
   if (ok) {
     if (isfree) s.fcol[widx] = lane;
     // ---- phase 4
@@ -1333,16 +1335,16 @@ WBC_DEV void step_instance(WarpSmem& s, const wbc_model& md, const wbc_params& p
     }
     __syncwarp();
     // ---- phase 5
-    const TriPairs tp = tri_pairs(lane);
-    reduced_hessian(s, lane, nf, pr.reg_tau != 0.0 ? 30 : 18, KIND != WBC_CTRL_ID, tp);
-    factor_and_start(s, lane, status, tp);
+    const TriPairs tp = tri_pairs<NA>(lane);
+    reduced_hessian<NA>(s, lane, nf, pr.reg_tau != 0.0 ? 30 : 18, KIND != WBC_CTRL_ID, tp);
+    factor_and_start<NA>(s, lane, status, tp);
     // ---- phase 6
     IneqSet S;
     S.cmask = cmask; S.nc = nc; S.mu = pr.mu; S.nfric = 4 * nc; S.nextra = nextra; S.ntl = pr.torque_limits ? 24 : 0;
     S.effort = md.effort; S.dummy = nullptr; S.extra_bound[0] = extra_bound; S.extra_bound[1] = 0.0;
     int qact = 0; double minslack = 0.0;
     int iters = 0;
-    if (!(status & WBC_ST_NOTPD)) iters = gi_solve(s, lane, S, pr.max_iter, status, qact, minslack);
+    if (!(status & WBC_ST_NOTPD)) iters = gi_solve<NA>(s, lane, S, pr.max_iter, status, qact, minslack);
     // ---- phase 7: y = Y x + y0 is current in s.y
     const double res = minslack < 0.0 ? -minslack : 0.0;
     if (lane < 12) {

@@ -47,7 +47,6 @@ def _line(metric, unit, n, per_ms, bytes_per_unit, workload, steps, warmup, laun
 
 def run(workload, steps=50, warmup=5, n=1 << 20):
     import torch
-    from oracle import lcm_codec as lc          # checker only: builds a seeded reference batch of wire bytes
     from quadruped_drake_b200 import planner as pl
     from quadruped_drake_b200.controller import BatchedController
     from quadruped_drake_b200.wire import WireCodec
@@ -58,8 +57,10 @@ def run(workload, steps=50, warmup=5, n=1 << 20):
         w = WireCodec(ctl)
         traj, f = rng.normal(0, 3, (n, 54)), rng.normal(0, 40, (n, 12))
         contact = rng.integers(0, 2, (n, 4)).astype(np.uint8)
-        msgs = torch.from_numpy(lc.encode_trunk_state(np.arange(n) * 1e-3, np.zeros(n, np.uint8), traj, contact, f)).cuda()
+        tt = lambda a: torch.from_numpy(a).cuda()  # noqa: E731
+        msgs = w.encode_trunk_state(tt(np.arange(n) * 1e-3), tt(np.zeros(n, np.uint8)), tt(traj), tt(contact), tt(f))   # synthetic wire bytes
         d = w.decode_trunk_state(msgs)
+        assert int(d["status"].max().item()) == 0 and torch.equal(d["traj"], tt(traj))
         l0 = ctl.launches
         per = _time(lambda: w.decode_trunk_state(msgs), steps, warmup)
         out.append(_line("trunk_state_t messages decoded/sec", "messages/s", n, per, 549 + 545, "wbc_lcm_decode_trunk_state, 1Mi messages", steps, warmup, ctl.launches - l0))
