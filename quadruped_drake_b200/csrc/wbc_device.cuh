@@ -172,6 +172,24 @@ WBC_DEV void warp_argmin(double& v, int& idx) {
   }
 }
 
+// Arg-max / arg-min of a NON-NEGATIVE double over the warp with two 32-bit redux.sync reductions (IEEE order of
+// non-negative doubles = unsigned order of their bit patterns): high words first, then the low words of the lanes that
+// tie on the high word; the winner is the lowest such lane. Returns the extreme value (exact) and its lane.
+WBC_DEV double warp_max_lane(double v, int& lane_out) {
+  const unsigned hi = (unsigned)__double2hiint(v), lo = (unsigned)__double2loint(v);
+  const unsigned mhi = __reduce_max_sync(WBC_FULL, hi);
+  const unsigned mlo = __reduce_max_sync(WBC_FULL, hi == mhi ? lo : 0u);
+  lane_out = __ffs((int)__ballot_sync(WBC_FULL, hi == mhi && lo == mlo)) - 1;
+  return __hiloint2double((int)mhi, (int)mlo);
+}
+WBC_DEV double warp_min_lane(double v, int& lane_out) {
+  const unsigned hi = (unsigned)__double2hiint(v), lo = (unsigned)__double2loint(v);
+  const unsigned mhi = __reduce_min_sync(WBC_FULL, hi);
+  const unsigned mlo = __reduce_min_sync(WBC_FULL, hi == mhi ? lo : 0xffffffffu);
+  lane_out = __ffs((int)__ballot_sync(WBC_FULL, hi == mhi && lo == mlo)) - 1;
+  return __hiloint2double((int)mhi, (int)mlo);
+}
+
 // Spatial inertia about the base origin P, world axes: mass, first moment h = m c, rotational part.
 struct SpI { double m; V3 h; S6 I; };
 // World-frame spatial inertia of a link with body-frame CoM `com`, inertia about CoM `Ic`,
@@ -511,19 +529,6 @@ WBC_DEV void build_base_system(WarpSmem& s, int lane, unsigned cmask, double kd,
   __syncwarp();
 }
 
-// Max over the warp of a non-negative double, with the owning lane: the lane index rides in the 5 lowest
-// mantissa bits (IEEE order of non-negative doubles = integer order), so one 64-bit butterfly does both.
-WBC_DEV double warp_argmax_nonneg(double v, int lane, int& idx) {
-  unsigned long long key = ((unsigned long long)__double_as_longlong(v) & ~31ull) | (unsigned long long)(31 - lane);
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const unsigned long long other = __shfl_xor_sync(WBC_FULL, key, o);
-    key = other > key ? other : key;
-  }
-  idx = 31 - (int)(key & 31ull);
-  return __longlong_as_double((long long)(key & ~31ull));
-}
-
 // Gauss-Jordan, one pivot per row, pivot column = largest remaining entry of that row.
 // Finished pivot columns are left stale (never read again). Returns the bit mask of pivot columns.
 WBC_DEV unsigned gauss_jordan(WarpSmem& s, int lane, int m, int n, int& status) {
@@ -532,7 +537,7 @@ WBC_DEV unsigned gauss_jordan(WarpSmem& s, int lane, int m, int n, int& status) 
     const double arc0 = s.A[r][lane];
     const bool eligible = lane < n && !((used >> lane) & 1);
     int pcol;
-    const double best = warp_argmax_nonneg(eligible ? fabs(arc0) : 0.0, lane, pcol);
+    const double best = warp_max_lane(eligible ? fabs(arc0) : 0.0, pcol);
     if (!(best > 1e-9)) {            // rows are O(0.01..10) (kg, kg m, lever arms): anything below is round-off
       status |= WBC_ST_RANKDEF;
       if (lane == 0) s.pc[r] = -1;
@@ -688,18 +693,6 @@ WBC_DEV Ineq get_ineq(const IneqSet& S, int i) {
   return q;
 }
 
-// Min over the warp of a non-negative double with a 6-bit payload (lowest mantissa bits), one butterfly.
-WBC_DEV double warp_argmin_nonneg(double v, int payload, int& out) {
-  unsigned long long key = ((unsigned long long)__double_as_longlong(v) & ~63ull) | (unsigned long long)payload;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const unsigned long long other = __shfl_xor_sync(WBC_FULL, key, o);
-    key = other < key ? other : key;
-  }
-  out = (int)(key & 63ull);
-  return __longlong_as_double((long long)(key & ~63ull));
-}
-
 // Goldfarb-Idnani dual active-set method on  min 1/2 w'Hw + g'w  s.t. the IneqSet.
 // On entry s.J, s.x hold L^-T and the unconstrained minimiser. Returns iterations; multipliers in s.u.
 // All loops over the reduced dimension are fixed-length and branch-free: lanes >= N compute on a clamped
@@ -735,16 +728,10 @@ template <int N> WBC_DEV int gi_solve(WarpSmem& s, int lane, const IneqSet& S, i
       if (sl < -1e-10 * (1.0 + fabs(c1.bound) + fabs(ta) + fabs(tb)) && -sl > viol) { viol = -sl; who = lane + 32; }
     }
     int p;
-    {  // arg-max of a non-negative double: complement trick on the min butterfly is not order preserving, so
-       // run a max butterfly with the payload in the low bits
-      unsigned long long key = ((unsigned long long)__double_as_longlong(viol) & ~63ull) | (unsigned long long)who;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const unsigned long long other = __shfl_xor_sync(WBC_FULL, key, o);
-        key = other > key ? other : key;
-      }
-      p = (int)(key & 63ull);
-      viol = __longlong_as_double((long long)(key & ~63ull));
+    {  // most violated constraint of the warp; ties go to the lowest lane
+      int wl;
+      viol = warp_max_lane(viol, wl);
+      p = shfl(who, wl);
     }
     minslack = -viol;
     if (!(viol > 0.0)) break;
@@ -789,7 +776,7 @@ template <int N> WBC_DEV int gi_solve(WarpSmem& s, int lane, const IneqSet& S, i
       }
       // step lengths
       int l;
-      const double t1 = warp_argmin_nonneg((lane < q && rk > 0.0) ? fmax(s.u[li] * frcp(rk), 0.0) : INFINITY, lane, l);
+      const double t1 = warp_min_lane((lane < q && rk > 0.0) ? fmax(s.u[li] * frcp(rk), 0.0) + 0.0 : INFINITY, l);   // + 0.0: never -0.0
       const bool zok = zn > 1e-14 * fmax(dd, 1e-300);
       const double izn = frcp(zok ? zn : 1.0);
       const double t2 = zok ? -sp * izn : INFINITY;

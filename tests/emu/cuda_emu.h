@@ -51,6 +51,25 @@ static inline int __any_sync(unsigned, int pred) {
   for (int l = 0; l < 32; ++l) acc |= emu_exchange(pred ? 1 : 0, l);
   return acc;
 }
+static inline unsigned __reduce_max_sync(unsigned, unsigned v) {
+  unsigned acc = 0;
+  for (int l = 0; l < 32; ++l) { const unsigned o = emu_exchange(v, l); acc = o > acc ? o : acc; }
+  return acc;
+}
+static inline unsigned __reduce_min_sync(unsigned, unsigned v) {
+  unsigned acc = 0xffffffffu;
+  for (int l = 0; l < 32; ++l) { const unsigned o = emu_exchange(v, l); acc = o < acc ? o : acc; }
+  return acc;
+}
+static inline unsigned __ballot_sync(unsigned, int pred) {
+  unsigned acc = 0;
+  for (int l = 0; l < 32; ++l) acc |= (unsigned)(emu_exchange(pred ? 1 : 0, l) & 1) << l;
+  return acc;
+}
+static inline int __ffs(int v) { return __builtin_ffs(v); }
+static inline int __double2hiint(double v) { long long r; memcpy(&r, &v, 8); return (int)(r >> 32); }
+static inline int __double2loint(double v) { long long r; memcpy(&r, &v, 8); return (int)(r & 0xffffffffll); }
+static inline double __hiloint2double(int hi, int lo) { long long r = ((long long)hi << 32) | (unsigned)lo; double d; memcpy(&d, &r, 8); return d; }
 static inline void __syncwarp(unsigned = 0xffffffffu) { emu_sync(); }
 static inline long long __double_as_longlong(double v) { long long r; memcpy(&r, &v, 8); return r; }
 static inline double __longlong_as_double(long long v) { double r; memcpy(&r, &v, 8); return r; }
