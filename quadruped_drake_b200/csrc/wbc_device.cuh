@@ -151,6 +151,20 @@ WBC_DEV double frcp(double x) { return 1.0 / x; }
 WBC_DEV double frsqrt(double x) { return 1.0 / sqrt(x); }
 #endif
 
+// Asynchronous 8-byte global -> shared copy (LDGSTS): the trajectory row is requested at the start of a step and only
+// waited for after the dynamics phase, so its latency (microseconds when the buffers live in page-locked host memory)
+// hides behind the arithmetic that does not need it.
+#ifdef __CUDA_ARCH__
+WBC_DEV void async_copy8(double* smem_dst, const double* gsrc) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gsrc) : "memory");
+}
+WBC_DEV void async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+#else
+WBC_DEV void async_copy8(double* smem_dst, const double* gsrc) { *smem_dst = *gsrc; }
+WBC_DEV void async_wait_all() {}
+#endif
+
 template <typename T> WBC_DEV T shfl(T v, int src) { return __shfl_sync(WBC_FULL, v, src); }
 WBC_DEV double warp_sum(double v) {
 #pragma unroll
@@ -1193,7 +1207,7 @@ WBC_DEV void step_instance(WarpSmem& s, const wbc_model& md, const wbc_params& p
   // ---- phase 0: coalesced loads into shared memory
   for (int i = lane; i < WBC_NQ; i += 32) s.q[i] = a.q[inst * WBC_NQ + i];
   for (int i = lane; i < WBC_NV; i += 32) s.v[i] = a.v[inst * WBC_NV + i];
-  for (int i = lane; i < WBC_NTRAJ; i += 32) s.traj[i] = a.traj[inst * WBC_NTRAJ + i];
+  for (int i = lane; i < WBC_NTRAJ; i += 32) async_copy8(&s.traj[i], a.traj + inst * WBC_NTRAJ + i);   // waited for after phase 1
   unsigned cmask = 0;
 #pragma unroll
   for (int k = 0; k < 4; ++k) cmask |= (a.contact[inst * 4 + k] ? 1u : 0u) << k;
@@ -1201,6 +1215,8 @@ WBC_DEV void step_instance(WarpSmem& s, const wbc_model& md, const wbc_params& p
   __syncwarp();
   // ---- phase 1
   dynamics_phase<(KIND == WBC_CTRL_PC) ? DYN_STEP_JD : DYN_STEP>(s, md, lane, status, nullptr);
+  async_wait_all();
+  __syncwarp();
   BodyTask bt;
   body_task(s, lane, status, bt);
   // ---- PC: operational-space quantities (uses the A region as scratch, so it runs before the equalities are built)
