@@ -19,7 +19,7 @@ constexpr int WARPS = 4;  // instances (warps) per CTA
 #define WBC_MIN_CTAS 4
 #endif
 
-struct DevConst { wbc_model md; wbc_params pr; wbc::Derived dv; };
+struct alignas(16) DevConst { wbc_model md; wbc_params pr; wbc::Derived dv; };
 
 struct SmemLayout {
   DevConst dc;
@@ -56,6 +56,109 @@ __global__ void WBC_STEP_BOUNDS wbc_step_kernel(const DevConst* __restrict__ gdc
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long inst = (long long)blockIdx.x * WARPS + warp;
   if (inst < a.n) wbc::step_instance<KIND>(sm->w[warp], dc.md, dc.pr, dc.dv, a, inst, lane);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Split path (ID / CLF): the step is launched as two kernels with their own register / occupancy budgets.
+//   wbc_reduce_kernel  phases 0-4 (dynamics, equality elimination, reduced rows): register hungry (128 regs, 16 warps / SM);
+//                      leaves [Y | cw | ct] + 16 carry words per instance in a hand-over record (4224 B, device scratch).
+//   wbc_solve_kernel   phases 5-7 (reduced Hessian, Cholesky, Goldfarb-Idnani, outputs): 72 registers and 7.8 KB of shared
+//                      memory per warp -> 28 warps / SM, so the dependent-instruction latency of the active-set iterations is
+//                      hidden by 1.75x more resident instances than the fused kernel could hold.
+// The 4 KB block moves shared -> global and global -> shared with one bulk asynchronous copy each (TMA 1-D), issued by one
+// lane; the solve warp waits on an mbarrier.
+#ifndef WBC_SOLVE_CTAS
+#define WBC_SOLVE_CTAS 7
+#endif
+struct SmemLayoutSolve { wbc::SolveSmem w[WARPS]; };
+static_assert(sizeof(wbc::SolveSmem) % 16 == 0, "SolveSmem must keep 16-byte alignment per warp");
+static_assert(offsetof(wbc::WarpSmem, Y) % 16 == 0 && sizeof(wbc::WarpSmem) % 16 == 0 && sizeof(DevConst) % 16 == 0, "bulk copy alignment");
+static_assert(offsetof(wbc::WarpSmem, cw) == offsetof(wbc::WarpSmem, Y) + sizeof(double) * wbc::YROWS * wbc::YS &&
+              offsetof(wbc::WarpSmem, ct) == offsetof(wbc::WarpSmem, cw) + sizeof(double) * wbc::YROWS, "[Y | cw | ct] must be contiguous");
+static_assert(offsetof(wbc::SolveSmem, cw) == sizeof(double) * wbc::YROWS * wbc::YS &&
+              offsetof(wbc::SolveSmem, ct) == offsetof(wbc::SolveSmem, cw) + sizeof(double) * wbc::YROWS, "[Y | cw | ct] must be contiguous");
+constexpr unsigned REC_Y_BYTES = wbc::REC_Y * sizeof(double);
+
+__device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+// shared -> global bulk copy of `bytes` (multiple of 16), issued by the calling thread; returns once the source may be reused
+__device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, unsigned bytes) {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes of the warp -> visible to the copy engine
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_addr(ssrc)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+// global -> shared bulk copy completing on an mbarrier (armed here by the issuing thread)
+__device__ __forceinline__ void bulk_load(void* sdst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+  const unsigned b = smem_addr(bar);
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(sdst)),
+               "l"(gsrc), "r"(bytes), "r"(b)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  const unsigned b = smem_addr(bar);
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(b), "r"(parity)
+      : "memory");
+}
+
+template <int KIND>
+__global__ void WBC_STEP_BOUNDS wbc_reduce_kernel(const DevConst* __restrict__ gdc, wbc::StepArgs a, double* __restrict__ rec,
+                                                  double* __restrict__ vdmap) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SmemLayout* sm = reinterpret_cast<SmemLayout*>(smem_raw);
+  const DevConst& dc = stage_consts(sm, gdc);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long inst = (long long)blockIdx.x * WARPS + warp;
+  if (inst >= a.n) return;
+  wbc::WarpSmem& s = sm->w[warp];
+  wbc::StepCarry c;
+  wbc::reduce_instance<KIND>(s, dc.md, dc.pr, dc.dv, a, inst, lane, c, nullptr, vdmap ? vdmap + inst * wbc::VDMAP_DOUBLES : nullptr);
+  double* r = rec + inst * wbc::REC_DOUBLES;
+  __syncwarp();
+  if (lane == 0) {
+    double2* m = reinterpret_cast<double2*>(r + wbc::REC_Y);
+    m[0] = make_double2((double)c.status, (double)c.cmask);
+    m[1] = make_double2((double)c.nf, (double)c.nextra);
+    m[2] = make_double2(c.ok ? 1.0 : 0.0, c.pc_ok ? 1.0 : 0.0);
+    m[3] = make_double2(c.extra_bound, c.err);
+    m[4] = make_double2(c.Vl, c.PFl);
+    m[5] = make_double2(c.csum, c.Vpc);
+    if (c.ok) bulk_store(r, &s.Y[0][0], REC_Y_BYTES);
+  }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(WARPS * 32, WBC_SOLVE_CTAS) wbc_solve_kernel(const DevConst* __restrict__ gdc, wbc::StepArgs a,
+                                                                               const double* __restrict__ rec,
+                                                                               const double* __restrict__ vdmap) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SmemLayoutSolve* sm = reinterpret_cast<SmemLayoutSolve*>(smem_raw);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long inst = (long long)blockIdx.x * WARPS + warp;
+  if (inst >= a.n) return;
+  wbc::SolveSmem& s = sm->w[warp];
+  const double* r = rec + inst * wbc::REC_DOUBLES;
+  const double2* m = reinterpret_cast<const double2*>(r + wbc::REC_Y);
+  const double2 m2 = m[2];
+  const bool ok = m2.x != 0.0;
+  if (ok && lane == 0) bulk_load(&s.Y[0][0], r, REC_Y_BYTES, &s.mbar);
+  const double2 m0 = m[0], m1 = m[1], m3 = m[3], m4 = m[4], m5 = m[5];
+  wbc::StepCarry c;
+  c.status = (int)m0.x; c.cmask = (unsigned)m0.y; c.nf = (int)m1.x; c.nextra = (int)m1.y; c.widx = 0;
+  c.ok = ok; c.pc_ok = m2.y != 0.0; c.extra_bound = m3.x; c.err = m3.y; c.Vl = m4.x; c.PFl = m4.y; c.csum = m5.x; c.Vpc = m5.y;
+  __syncwarp();                    // the barrier is initialised before any lane polls it
+  if (ok) mbar_wait(&s.mbar, 0);
+  wbc::solve_instance<KIND, wbc::SolveSmem>(s, gdc->md, gdc->pr, a, inst, lane, c, vdmap ? vdmap + inst * wbc::VDMAP_DOUBLES : nullptr);
 }
 
 __global__ void __launch_bounds__(WARPS * 32, 3) wbc_step_pc_kernel(const DevConst* __restrict__ gdc, wbc::StepArgs a) {
@@ -127,6 +230,10 @@ struct wbc_handle {
   uint8_t* ro_contact = nullptr;
   int32_t* ro_status = nullptr;
   int* ro_counter = nullptr;
+  // hand-over records of the split step (reduce -> solve), one slot per internal stream lane
+  double* d_rec[2] = {nullptr, nullptr};
+  double* d_vdmap[2] = {nullptr, nullptr};
+  int64_t rec_cap[2] = {0, 0}, vdmap_cap[2] = {0, 0};
 };
 
 #define WBC_CUDA(h, call)                                                                       \
@@ -163,6 +270,10 @@ static int set_smem_attr(wbc_handle* h) {
   const int bytes = (int)sizeof(SmemLayout);
   WBC_CUDA(h, cudaFuncSetAttribute(wbc_step_kernel<WBC_CTRL_ID>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   WBC_CUDA(h, cudaFuncSetAttribute(wbc_step_kernel<WBC_CTRL_CLF>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  WBC_CUDA(h, cudaFuncSetAttribute(wbc_reduce_kernel<WBC_CTRL_ID>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  WBC_CUDA(h, cudaFuncSetAttribute(wbc_reduce_kernel<WBC_CTRL_CLF>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  WBC_CUDA(h, cudaFuncSetAttribute(wbc_solve_kernel<WBC_CTRL_ID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemLayoutSolve)));
+  WBC_CUDA(h, cudaFuncSetAttribute(wbc_solve_kernel<WBC_CTRL_CLF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemLayoutSolve)));
   WBC_CUDA(h, cudaFuncSetAttribute(wbc_step_pc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemLayoutPC)));
   WBC_CUDA(h, cudaFuncSetAttribute(wbc_coriolis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemLayoutPC)));
   WBC_CUDA(h, cudaFuncSetAttribute(wbc_dynamics_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
@@ -226,6 +337,7 @@ extern "C" int wbc_destroy(wbc_handle* h) {
   if (h->d_tau_map) cudaFree(h->d_tau_map);
   cudaFree(h->ro_traj); cudaFree(h->ro_vd); cudaFree(h->ro_metrics); cudaFree(h->ro_tau); cudaFree(h->ro_t);
   cudaFree(h->ro_contact); cudaFree(h->ro_status); cudaFree(h->ro_counter);
+  for (int i = 0; i < 2; ++i) { cudaFree(h->d_rec[i]); cudaFree(h->d_vdmap[i]); }
   if (h->stream) cudaStreamDestroy(h->stream);
   if (h->stream2) cudaStreamDestroy(h->stream2);
   delete h;
@@ -294,6 +406,80 @@ extern "C" int wbc_step_pd(wbc_handle* h, int64_t n, const double* q, const doub
   return WBC_OK;
 }
 
+// Instances per reduce / solve launch pair of the split path: bounds the hand-over scratch (4224 B per instance) at 1.1 GB
+// while each kernel still runs for milliseconds, so the drain at the kernel boundaries stays below ~1 % of the step.
+constexpr int64_t SPLIT_CHUNK = 262144;
+
+static int split_mode() {   // WBC_SPLIT=0 forces the fused single-kernel step (experiments / A-B comparisons)
+  static int mode = -1;
+  if (mode < 0) { const char* e = getenv("WBC_SPLIT"); mode = e ? atoi(e) : 1; }
+  return mode;
+}
+
+// Grows the hand-over scratch of `slot` to `n` instances (never inside a stream capture: callers that capture call this first).
+static int ensure_split_scratch(wbc_handle* h, int slot, int64_t n, bool with_vd) {
+  const int64_t m = n < SPLIT_CHUNK ? n : SPLIT_CHUNK;
+  if (m > h->rec_cap[slot]) {
+    cudaFree(h->d_rec[slot]); h->d_rec[slot] = nullptr; h->rec_cap[slot] = 0;
+    WBC_CUDA(h, cudaMalloc(&h->d_rec[slot], m * wbc::REC_DOUBLES * sizeof(double)));
+    h->rec_cap[slot] = m;
+  }
+  if (with_vd && m > h->vdmap_cap[slot]) {
+    cudaFree(h->d_vdmap[slot]); h->d_vdmap[slot] = nullptr; h->vdmap_cap[slot] = 0;
+    WBC_CUDA(h, cudaMalloc(&h->d_vdmap[slot], m * wbc::VDMAP_DOUBLES * sizeof(double)));
+    h->vdmap_cap[slot] = m;
+  }
+  return WBC_OK;
+}
+
+static wbc::StepArgs offset_args(const wbc_io* io, int64_t o, int64_t m, int kind) {
+  return wbc::StepArgs{io->q + o * WBC_NQ, io->v + o * WBC_NV, io->traj + o * WBC_NTRAJ, io->contact + o * 4, io->tau + o * WBC_NU,
+                       io->metrics + o * WBC_NMETRIC, io->status + o, io->vd ? io->vd + o * WBC_NV : nullptr,
+                       io->f ? io->f + o * 12 : nullptr, io->qp_info ? io->qp_info + o * 4 : nullptr, (long long)m, kind};
+}
+
+template <int KIND>
+static int launch_split(wbc_handle* h, int64_t n, const wbc_io* io, cudaStream_t st, int slot) {
+  int rc = ensure_split_scratch(h, slot, n, io->vd != nullptr);
+  if (rc) return rc;
+  double* vdmap = io->vd ? h->d_vdmap[slot] : nullptr;
+  for (int64_t o = 0; o < n; o += SPLIT_CHUNK) {
+    const int64_t m = (n - o) < SPLIT_CHUNK ? (n - o) : SPLIT_CHUNK;
+    const wbc::StepArgs a = offset_args(io, o, m, KIND);
+    const unsigned grid = (unsigned)((m + WARPS - 1) / WARPS);
+    wbc_reduce_kernel<KIND><<<grid, WARPS * 32, sizeof(SmemLayout), st>>>(h->d_const, a, h->d_rec[slot], vdmap);
+    wbc_solve_kernel<KIND><<<grid, WARPS * 32, sizeof(SmemLayoutSolve), st>>>(h->d_const, a, h->d_rec[slot], vdmap);
+    h->launches += 2;
+  }
+  return WBC_OK;
+}
+
+static int step_launch(wbc_handle* h, int kind, int64_t n, const wbc_io* io, cudaStream_t st, int slot) {
+  const unsigned grid = (unsigned)((n + WARPS - 1) / WARPS);
+  const size_t sm = sizeof(SmemLayout);
+  const bool split = split_mode() != 0;
+  int rc = WBC_OK;
+  switch (kind) {
+    case WBC_CTRL_ID:
+      if (split) rc = launch_split<WBC_CTRL_ID>(h, n, io, st, slot);
+      else { wbc_step_kernel<WBC_CTRL_ID><<<grid, WARPS * 32, sm, st>>>(h->d_const, offset_args(io, 0, n, kind)); h->launches++; }
+      break;
+    case WBC_CTRL_CLF:
+      if (split) rc = launch_split<WBC_CTRL_CLF>(h, n, io, st, slot);
+      else { wbc_step_kernel<WBC_CTRL_CLF><<<grid, WARPS * 32, sm, st>>>(h->d_const, offset_args(io, 0, n, kind)); h->launches++; }
+      break;
+    case WBC_CTRL_PC:
+    case WBC_CTRL_MPTC:
+      wbc_step_pc_kernel<<<grid, WARPS * 32, sizeof(SmemLayoutPC), st>>>(h->d_const, offset_args(io, 0, n, kind));
+      h->launches++;
+      break;
+    default: return fail_arg(h, "wbc_step: unknown controller kind");
+  }
+  if (rc) return rc;
+  WBC_CUDA(h, cudaGetLastError());
+  return WBC_OK;
+}
+
 extern "C" int wbc_step(wbc_handle* h, int kind, int64_t n, const wbc_io* io, void* stream) {
   if (!h) return WBC_ERR_ARG;
   if (!io || n < 0) return fail_arg(h, "wbc_step: bad arguments");
@@ -302,21 +488,7 @@ extern "C" int wbc_step(wbc_handle* h, int kind, int64_t n, const wbc_io* io, vo
   if (!io->q || !io->v || !io->traj || !io->contact || !io->tau || !io->metrics || !io->status)
     return fail_arg(h, "wbc_step: q, v, traj, contact, tau, metrics and status are required");
   WBC_CUDA(h, cudaSetDevice(h->device));
-  wbc::StepArgs a{io->q, io->v, io->traj, io->contact, io->tau, io->metrics, io->status, io->vd, io->f, io->qp_info,
-                  (long long)n, kind};
-  const unsigned grid = (unsigned)((n + WARPS - 1) / WARPS);
-  const size_t sm = sizeof(SmemLayout);
-  cudaStream_t st = (cudaStream_t)stream;
-  switch (kind) {
-    case WBC_CTRL_ID: wbc_step_kernel<WBC_CTRL_ID><<<grid, WARPS * 32, sm, st>>>(h->d_const, a); break;
-    case WBC_CTRL_CLF: wbc_step_kernel<WBC_CTRL_CLF><<<grid, WARPS * 32, sm, st>>>(h->d_const, a); break;
-    case WBC_CTRL_PC:
-    case WBC_CTRL_MPTC: wbc_step_pc_kernel<<<grid, WARPS * 32, sizeof(SmemLayoutPC), st>>>(h->d_const, a); break;
-    default: return fail_arg(h, "wbc_step: unknown controller kind");
-  }
-  h->launches++;
-  WBC_CUDA(h, cudaGetLastError());
-  return WBC_OK;
+  return step_launch(h, kind, n, io, (cudaStream_t)stream, 0);
 }
 
 #define WBC_STEP_WRAPPER(name, kind)                                                                               \
@@ -402,7 +574,7 @@ extern "C" int wbc_step_host(wbc_handle* h, int kind, int64_t n, const wbc_io* i
     wbc_io dio{h->d_q + o * WBC_NQ, h->d_v + o * WBC_NV, h->d_traj + o * WBC_NTRAJ, h->d_contact + o * 4, h->d_tau + o * WBC_NU,
                h->d_metrics + o * WBC_NMETRIC, h->d_status + o,
                io->vd ? h->d_vd + o * WBC_NV : nullptr, io->f ? h->d_f + o * 12 : nullptr, io->qp_info ? h->d_info + o * 4 : nullptr};
-    rc = wbc_step(h, kind, m, &dio, st);
+    rc = pd ? wbc_step_pd(h, m, dio.q, dio.v, dio.tau, st) : step_launch(h, kind, m, &dio, st, c & 1);
     if (rc) return rc;
     WBC_CUDA(h, cudaMemcpyAsync(io->tau + o * WBC_NU, h->d_tau + o * WBC_NU, m * WBC_NU * sizeof(double), cudaMemcpyDeviceToHost, st));
     if (!pd) {
@@ -836,6 +1008,7 @@ extern "C" int wbc_rollout(wbc_handle* h, int kind, const wbc_plan* plan, int64_
   WBC_CUDA(h, cudaSetDevice(h->device));
   int rc = ensure_rollout_scratch(h, n);
   if (rc) return rc;
+  if (kind == WBC_CTRL_ID || kind == WBC_CTRL_CLF) { rc = ensure_split_scratch(h, 0, n, true); if (rc) return rc; }
   cudaStream_t st = (cudaStream_t)stream;
   double* tau = io->tau ? io->tau : h->ro_tau;
   double* metrics = io->metrics ? io->metrics : h->ro_metrics;

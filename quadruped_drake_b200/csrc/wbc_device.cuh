@@ -18,6 +18,7 @@
 #include <stdint.h>
 #include <math.h>
 #include <stddef.h>
+#include <type_traits>
 #include "wbc.h"
 
 #ifndef WBC_DEV
@@ -73,7 +74,7 @@ struct StepArgs {
 // Per-warp shared memory. Everything a step needs between load and store lives here (12.6 KB).
 // The inputs + dynamics block is dead once the reduced problem (Y, cw, ct) is built, so the reduced
 // Hessian / Goldfarb-Idnani workspace overlays it.
-struct WarpSmem {
+struct alignas(16) WarpSmem {
   union {
     struct {
       // ---- inputs
@@ -103,10 +104,28 @@ struct WarpSmem {
   int rowof[AC];         // pivot row of variable c, -1 if free
   int pc[AR];
   int fcol[NF];          // free (non-pivot) columns of A in increasing order
-  // ---- reduced problem
-  double Y[YROWS][YS];
+  // ---- reduced problem ([Y | cw | ct] contiguous and 16-byte aligned: one bulk copy in the split path)
+  alignas(16) double Y[YROWS][YS];
   double cw[YROWS], ct[YROWS];   // cost weight / target of each Y row: 1/2 cw (y - ct)^2
 };
+
+// Per-warp shared memory of the solve kernel of the split path (phases 5-7 only): the reduced problem (Y, cw, ct - one
+// contiguous 4 KB block, filled by a single bulk copy of the record the reduce kernel wrote) and the Goldfarb-Idnani state.
+// Member names match WarpSmem so that reduced_hessian / factor_and_start / gi_solve / solve_instance run on either.
+struct alignas(16) SolveSmem {
+  alignas(16) double Y[YROWS][YS];
+  double cw[YROWS], ct[YROWS];
+  union { double H[NF][NF]; double J[NF][NF]; };
+  double g[NF];
+  double R[NF][NF];
+  double d[NF], r[NF], x[NF], u[NF], npv[NF], dm[NF], y[YROWS];
+  int act[NF];
+  alignas(8) unsigned long long mbar;   // completion barrier of the bulk copy
+};
+constexpr int REC_Y = YROWS * YS + 2 * YROWS;   // doubles of [Y | cw | ct]
+constexpr int REC_MISC = 16;                    // status, cmask, nf, nextra, ok, extra_bound, err, Vl, PFl, csum, Vpc
+constexpr int REC_DOUBLES = REC_Y + REC_MISC;   // one record of the reduce -> solve hand-over (4224 B)
+constexpr int VDMAP_DOUBLES = 12 * YS;          // joint accelerations as affine maps of w (only when vd is requested)
 
 // ------------------------------------------------------------------ small vector helpers
 struct V3 { double x, y, z; };
@@ -605,7 +624,7 @@ template <int N> WBC_DEV TriPairs tri_pairs(int lane) {
 }
 
 // H = sum_r cw_r Y_r' Y_r (+ identity on padded dims), g = sum_r cw_r Y_r (y0_r - ct_r) + glin
-template <int N> WBC_DEV void reduced_hessian(WarpSmem& s, int lane, int nf, int nrows, bool extra, const TriPairs& tp) {
+template <int N, class SM> WBC_DEV void reduced_hessian(SM& s, int lane, int nf, int nrows, bool extra, const TriPairs& tp) {
 #pragma unroll
   for (int h = 0; h < 3; ++h) {
     const int i = tp.i[h], k = tp.k[h];
@@ -631,7 +650,7 @@ template <int N> WBC_DEV void reduced_hessian(WarpSmem& s, int lane, int nf, int
 }
 
 // In-place Cholesky (lower) of s.H, then J = L^-T (J J' = H^-1) and the unconstrained minimiser x.
-template <int N> WBC_DEV void factor_and_start(WarpSmem& s, int lane, int& status, const TriPairs& tp) {
+template <int N, class SM> WBC_DEV void factor_and_start(SM& s, int lane, int& status, const TriPairs& tp) {
   for (int j = 0; j < N; ++j) {
     const double dj = s.H[j][j];
     if (!(dj > 1e-300)) { status |= WBC_ST_NOTPD; }
@@ -711,7 +730,7 @@ WBC_DEV Ineq get_ineq(const IneqSet& S, int i) {
 // On entry s.J, s.x hold L^-T and the unconstrained minimiser. Returns iterations; multipliers in s.u.
 // All loops over the reduced dimension are fixed-length and branch-free: lanes >= N compute on a clamped
 // row (results discarded), entries left of the active count q are masked to zero instead of skipped.
-template <int N> WBC_DEV int gi_solve(WarpSmem& s, int lane, const IneqSet& S, int max_iter, int& status, int& q_out, double& minslack) {
+template <int N, class SM> WBC_DEV int gi_solve(SM& s, int lane, const IneqSet& S, int max_iter, int& status, int& q_out, double& minslack) {
   const int mi = S.nfric + S.nextra + S.ntl;
   const int li = lane < N ? lane : N - 1;     // clamped row for loads
   const bool row = lane < N;
@@ -893,7 +912,7 @@ WBC_DEV void put_y(WarpSmem& s, int row, int ycol, double val) { if (ycol >= 0) 
 
 // Rows 0-29 of Y for all controllers: a_b, per-leg rows (contact force of a stance leg, task acceleration J_s vd of a
 // swing leg), joint torques tau = M_j vd + h_j - L' f. Variables: 0-5 a_b, 6+3k+i = f_k,i (stance) or a_k,i (swing).
-WBC_DEV void build_common_rows(WarpSmem& s, int lane, int ycol, unsigned cmask) {
+WBC_DEV void build_common_rows(WarpSmem& s, int lane, int ycol, unsigned cmask, double* vdmap = nullptr) {
   double zb[6];
 #pragma unroll
   for (int i = 0; i < 6; ++i) { zb[i] = zent(s, lane, i); put_y(s, i, ycol, zb[i]); }
@@ -923,6 +942,7 @@ WBC_DEV void build_common_rows(WarpSmem& s, int lane, int ycol, unsigned cmask) 
         ak[i] = zl[i];
       }
       put_y(s, 6 + 3 * k + i, ycol, val);
+      if (vdmap && ycol >= 0) vdmap[(3 * k + i) * YS + ycol] = ak[i];
     }
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
@@ -1200,9 +1220,17 @@ WBC_DEV void pc_rows(WarpSmem& s, const PcSmem& pc, int lane, int ycol, int m) {
 // ------------------------------------------------------------------------------ the step
 // One control step of instance `inst` (DoSetControlTorques -> ControlLaw,
 // basic_controller.py:286-320). KIND selects the cost / extra rows.
+// What the solve half needs from the reduce half besides [Y | cw | ct]: registers in the fused kernels, the `misc` words of
+// the hand-over record in the split path.
+struct StepCarry {
+  int status; unsigned cmask; int nf, nextra, widx; bool ok, pc_ok;
+  double extra_bound, err, Vl, PFl, csum, Vpc;
+};
+
+// Phases 0-4 + cost rows: state -> reduced problem [Y | cw | ct] in s (and the joint-acceleration maps in `vdmap`, if given).
 template <int KIND>
-WBC_DEV void step_instance(WarpSmem& s, const wbc_model& md, const wbc_params& pr, const Derived& dv, const StepArgs& a,
-                           long long inst, int lane, PcSmem* pcs = nullptr) {
+WBC_DEV void reduce_instance(WarpSmem& s, const wbc_model& md, const wbc_params& pr, const Derived& dv, const StepArgs& a,
+                             long long inst, int lane, StepCarry& c, PcSmem* pcs = nullptr, double* vdmap = nullptr) {
   int status = 0;
   // ---- phase 0: coalesced loads into shared memory
   for (int i = lane; i < WBC_NQ; i += 32) s.q[i] = a.q[inst * WBC_NQ + i];
@@ -1238,19 +1266,19 @@ WBC_DEV void step_instance(WarpSmem& s, const wbc_model& md, const wbc_params& p
   const int widx = __popc(freemask & ((1u << lane) - 1u));
   const int ycol = lane == 31 ? NF : (isfree ? widx : -1);
   constexpr int NA = (KIND == WBC_CTRL_CLF) ? NF : NF - 1;   // active reduced dimension: the loops of phases 5-6 run to NA
-  bool ok = nf <= NA && pc_ok;
+  const bool ok = nf <= NA && pc_ok;
+  double err = 0.0;
+  int nextra = 0;
+  double extra_bound = 0.0, Vl = 0.0, PFl = 0.0, csum = 0.0;
   if (ok) {
     if (isfree) s.fcol[widx] = lane;
     // ---- phase 4
     for (int e = lane; e < YROWS * YS; e += 32) (&s.Y[0][0])[e] = 0.0;
     s.cw[lane] = 0.0; s.ct[lane] = 0.0;
     __syncwarp();
-    build_common_rows(s, lane, ycol, cmask);
+    build_common_rows(s, lane, ycol, cmask, vdmap);
     // ---- costs
     const double* tr = s.traj;
-    double err = 0.0;
-    int nextra = 0;
-    double extra_bound = 0.0, Vl = 0.0, PFl = 0.0, csum = 0.0;
     if (KIND == WBC_CTRL_ID) {
       // inverse_dynamics_controller.py:187-197 task-space PD
       double rdd[3], add[3];
@@ -1337,6 +1365,23 @@ WBC_DEV void step_instance(WarpSmem& s, const wbc_model& md, const wbc_params& p
       err = errpc;
     }
     __syncwarp();
+  }
+  c.status = status; c.cmask = cmask; c.nf = nf; c.nextra = nextra; c.widx = widx; c.ok = ok; c.pc_ok = pc_ok;
+  c.extra_bound = extra_bound; c.err = err; c.Vl = Vl; c.PFl = PFl; c.csum = csum; c.Vpc = Vpc;
+}
+
+// Phases 5-7: reduced problem in s -> torques, metrics, status. Runs on the full WarpSmem (fused kernels: PC / MPTC, the
+// host emulator) or on the compact SolveSmem of the split path, where the joint accelerations come from `vdmap`.
+template <int KIND, class SM>
+WBC_DEV void solve_instance(SM& s, const wbc_model& md, const wbc_params& pr, const StepArgs& a, long long inst, int lane,
+                            const StepCarry& c, const double* vdmap = nullptr) {
+  constexpr int NA = (KIND == WBC_CTRL_CLF) ? NF : NF - 1;
+  constexpr bool FUSED = std::is_same<SM, WarpSmem>::value;
+  int status = c.status;
+  const unsigned cmask = c.cmask;
+  const int nc = __popc(cmask), nf = c.nf, nextra = c.nextra;
+  const double extra_bound = c.extra_bound, err = c.err, Vl = c.Vl, PFl = c.PFl, csum = c.csum, Vpc = c.Vpc;
+  if (c.ok) {
     // ---- phase 5
     const TriPairs tp = tri_pairs<NA>(lane);
     reduced_hessian<NA>(s, lane, nf, pr.reg_tau != 0.0 ? 30 : 18, KIND != WBC_CTRL_ID, tp);
@@ -1355,30 +1400,46 @@ WBC_DEV void step_instance(WarpSmem& s, const wbc_model& md, const wbc_params& p
       if (a.f) a.f[inst * 12 + lane] = ((cmask >> (lane / 3)) & 1) ? s.y[6 + lane] : 0.0;
     }
     if (a.vd) {
-      // u = [a_b; leg variables] from the reduced base system (not from Y: the PC kernel overwrites its task rows)
-      double uval = 0.0;
-      if (lane < 18) {
-        const int r = s.rowof[lane];
-        if (r >= 0) {
-          uval = s.A[r][31];
-          for (int w = 0; w < nf; ++w) uval = fma(-s.A[r][s.fcol[w]], s.x[w], uval);
-        } else uval = s.x[widx];
-      }
-      double ab[6];
-#pragma unroll
-      for (int r = 0; r < 6; ++r) ab[r] = shfl(uval, r);
-      if (lane < 18) {
-        double val = uval;
-        if (lane >= 6) {
-          const int k = (lane - 6) / 3, i = (lane - 6) % 3;
-          if ((cmask >> k) & 1) {                          // stance leg: a_k = AK[:,6] - AK[:,0:6] a_b
-            val = s.AK[k][i][6];
-#pragma unroll
-            for (int r = 0; r < 6; ++r) val = fma(-s.AK[k][i][r], ab[r], val);
-          }
+      if constexpr (FUSED) {
+        const int widx = c.widx;
+        // u = [a_b; leg variables] from the reduced base system (not from Y: the PC kernel overwrites its task rows)
+        double uval = 0.0;
+        if (lane < 18) {
+          const int r = s.rowof[lane];
+          if (r >= 0) {
+            uval = s.A[r][31];
+            for (int w = 0; w < nf; ++w) uval = fma(-s.A[r][s.fcol[w]], s.x[w], uval);
+          } else uval = s.x[widx];
         }
-        const int dst = lane < 6 ? lane : md.v_index[lane - 6];
-        a.vd[inst * WBC_NV + dst] = val;
+        double ab[6];
+  #pragma unroll
+        for (int r = 0; r < 6; ++r) ab[r] = shfl(uval, r);
+        if (lane < 18) {
+          double val = uval;
+          if (lane >= 6) {
+            const int k = (lane - 6) / 3, i = (lane - 6) % 3;
+            if ((cmask >> k) & 1) {                          // stance leg: a_k = AK[:,6] - AK[:,0:6] a_b
+              val = s.AK[k][i][6];
+  #pragma unroll
+              for (int r = 0; r < 6; ++r) val = fma(-s.AK[k][i][r], ab[r], val);
+            }
+          }
+          const int dst = lane < 6 ? lane : md.v_index[lane - 6];
+          a.vd[inst * WBC_NV + dst] = val;
+        }
+      } else {
+        // a_b = y[0:6]; joint accelerations from the affine maps the reduce kernel stored
+        if (lane < 18) {
+          double val;
+          if (lane < 6) val = s.y[lane];
+          else {
+            const double* mrow = vdmap + (lane - 6) * YS;
+            val = mrow[NF];
+            for (int w = 0; w < nf; ++w) val = fma(mrow[w], s.x[w], val);
+          }
+          const int dst = lane < 6 ? lane : md.v_index[lane - 6];
+          a.vd[inst * WBC_NV + dst] = val;
+        }
       }
     }
     // reference objective 1/2 x'P0x + q0'x (constants dropped, E.5b): rows with a reference cost
@@ -1404,7 +1465,7 @@ WBC_DEV void step_instance(WarpSmem& s, const wbc_model& md, const wbc_params& p
       if (a.qp_info) { double* qi = a.qp_info + inst * 4; qi[0] = obj; qi[1] = res; qi[2] = delta; qi[3] = (double)iters; }
     }
   } else {
-    if (pc_ok) status |= WBC_ST_RANKDEF;
+    if (c.pc_ok) status |= WBC_ST_RANKDEF;
     if (lane < 12) { a.tau[inst * WBC_NU + lane] = 0.0; if (a.f) a.f[inst * 12 + lane] = 0.0; }
     if (a.vd && lane < 18) a.vd[inst * WBC_NV + lane] = 0.0;
     if (lane < 4) a.metrics[inst * WBC_NMETRIC + lane] = 0.0;
@@ -1412,6 +1473,18 @@ WBC_DEV void step_instance(WarpSmem& s, const wbc_model& md, const wbc_params& p
   }
   if (lane == 0) a.status[inst] = status;
   __syncwarp();
+}
+
+
+// One control step of instance `inst` (DoSetControlTorques -> ControlLaw, basic_controller.py:286-320) inside one warp:
+// reduce + solve on the same shared-memory block (PC / MPTC kernels and the host emulator; ID / CLF launch the two halves
+// as separate kernels with their own register / occupancy budgets, see wbc_api.cu).
+template <int KIND>
+WBC_DEV void step_instance(WarpSmem& s, const wbc_model& md, const wbc_params& pr, const Derived& dv, const StepArgs& a,
+                           long long inst, int lane, PcSmem* pcs = nullptr) {
+  StepCarry c;
+  reduce_instance<KIND>(s, md, pr, dv, a, inst, lane, c, pcs, nullptr);
+  solve_instance<KIND, WarpSmem>(s, md, pr, a, inst, lane, c, nullptr);
 }
 
 // ---------------------------------------------------------------- dynamics parity entry
