@@ -48,16 +48,6 @@ __device__ __forceinline__ const DevConst& stage_consts(L* sm, const DevConst* g
 #else
 #define WBC_STEP_BOUNDS __maxnreg__(WBC_MAXNREG)                     // experiments: explicit register budget
 #endif
-template <int KIND>
-__global__ void WBC_STEP_BOUNDS wbc_step_kernel(const DevConst* __restrict__ gdc, wbc::StepArgs a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  SmemLayout* sm = reinterpret_cast<SmemLayout*>(smem_raw);
-  const DevConst& dc = stage_consts(sm, gdc);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long inst = (long long)blockIdx.x * WARPS + warp;
-  if (inst < a.n) wbc::step_instance<KIND>(sm->w[warp], dc.md, dc.pr, dc.dv, a, inst, lane);
-}
-
 // ---------------------------------------------------------------------------------------------------------------------
 // Split path (ID / CLF): the step is launched as two kernels with their own register / occupancy budgets.
 //   wbc_reduce_kernel  phases 0-4 (dynamics, equality elimination, reduced rows): register hungry (128 regs, 16 warps / SM);
@@ -111,6 +101,18 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
       : "memory");
 }
 
+// Hand-over record of one instance: [Y | cw | ct] by one bulk copy + the carry words (called by one lane).
+__device__ __forceinline__ void store_record(double* r, const wbc::StepCarry& c, const wbc::WarpSmem& s) {
+  double2* m = reinterpret_cast<double2*>(r + wbc::REC_Y);
+  m[0] = make_double2((double)c.status, (double)c.cmask);
+  m[1] = make_double2((double)c.nf, (double)c.nextra);
+  m[2] = make_double2(c.ok ? 1.0 : 0.0, c.pc_ok ? 1.0 : 0.0);
+  m[3] = make_double2(c.extra_bound, c.err);
+  m[4] = make_double2(c.Vl, c.PFl);
+  m[5] = make_double2(c.csum, c.Vpc);
+  if (c.ok) bulk_store(r, &s.Y[0][0], REC_Y_BYTES);
+}
+
 template <int KIND>
 __global__ void WBC_STEP_BOUNDS wbc_reduce_kernel(const DevConst* __restrict__ gdc, wbc::StepArgs a, double* __restrict__ rec,
                                                   double* __restrict__ vdmap) {
@@ -123,18 +125,8 @@ __global__ void WBC_STEP_BOUNDS wbc_reduce_kernel(const DevConst* __restrict__ g
   wbc::WarpSmem& s = sm->w[warp];
   wbc::StepCarry c;
   wbc::reduce_instance<KIND>(s, dc.md, dc.pr, dc.dv, a, inst, lane, c, nullptr, vdmap ? vdmap + inst * wbc::VDMAP_DOUBLES : nullptr);
-  double* r = rec + inst * wbc::REC_DOUBLES;
   __syncwarp();
-  if (lane == 0) {
-    double2* m = reinterpret_cast<double2*>(r + wbc::REC_Y);
-    m[0] = make_double2((double)c.status, (double)c.cmask);
-    m[1] = make_double2((double)c.nf, (double)c.nextra);
-    m[2] = make_double2(c.ok ? 1.0 : 0.0, c.pc_ok ? 1.0 : 0.0);
-    m[3] = make_double2(c.extra_bound, c.err);
-    m[4] = make_double2(c.Vl, c.PFl);
-    m[5] = make_double2(c.csum, c.Vpc);
-    if (c.ok) bulk_store(r, &s.Y[0][0], REC_Y_BYTES);
-  }
+  if (lane == 0) store_record(rec + inst * wbc::REC_DOUBLES, c, s);
 }
 
 template <int KIND>
@@ -154,20 +146,27 @@ __global__ void __launch_bounds__(WARPS * 32, WBC_SOLVE_CTAS) wbc_solve_kernel(c
   if (ok && lane == 0) bulk_load(&s.Y[0][0], r, REC_Y_BYTES, &s.mbar);
   const double2 m0 = m[0], m1 = m[1], m3 = m[3], m4 = m[4], m5 = m[5];
   wbc::StepCarry c;
-  c.status = (int)m0.x; c.cmask = (unsigned)m0.y; c.nf = (int)m1.x; c.nextra = (int)m1.y; c.widx = 0;
+  c.status = (int)m0.x; c.cmask = (unsigned)m0.y; c.nf = (int)m1.x; c.nextra = (int)m1.y;
   c.ok = ok; c.pc_ok = m2.y != 0.0; c.extra_bound = m3.x; c.err = m3.y; c.Vl = m4.x; c.PFl = m4.y; c.csum = m5.x; c.Vpc = m5.y;
   __syncwarp();                    // the barrier is initialised before any lane polls it
   if (ok) mbar_wait(&s.mbar, 0);
-  wbc::solve_instance<KIND, wbc::SolveSmem>(s, gdc->md, gdc->pr, a, inst, lane, c, vdmap ? vdmap + inst * wbc::VDMAP_DOUBLES : nullptr);
+  wbc::solve_instance<KIND, wbc::SolveSmem>(s, gdc->md, gdc->pr, a, inst, lane, c, vdmap ? vdmap + inst * wbc::VDMAP_DOUBLES : nullptr, r);
 }
 
-__global__ void __launch_bounds__(WARPS * 32, 3) wbc_step_pc_kernel(const DevConst* __restrict__ gdc, wbc::StepArgs a) {
+// PC / MPTC reduce half: same hand-over, extra operational-space workspace per warp (3 CTAs / SM).
+__global__ void __launch_bounds__(WARPS * 32, 3) wbc_reduce_pc_kernel(const DevConst* __restrict__ gdc, wbc::StepArgs a,
+                                                                      double* __restrict__ rec, double* __restrict__ vdmap) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SmemLayoutPC* sm = reinterpret_cast<SmemLayoutPC*>(smem_raw);
   const DevConst& dc = stage_consts(sm, gdc);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long inst = (long long)blockIdx.x * WARPS + warp;
-  if (inst < a.n) wbc::step_instance<WBC_CTRL_PC>(sm->w[warp], dc.md, dc.pr, dc.dv, a, inst, lane, &sm->pc[warp]);
+  if (inst >= a.n) return;
+  wbc::WarpSmem& s = sm->w[warp];
+  wbc::StepCarry c;
+  wbc::reduce_instance<WBC_CTRL_PC>(s, dc.md, dc.pr, dc.dv, a, inst, lane, c, &sm->pc[warp], vdmap ? vdmap + inst * wbc::VDMAP_DOUBLES : nullptr);
+  __syncwarp();
+  if (lane == 0) store_record(rec + inst * wbc::REC_DOUBLES, c, s);
 }
 
 __global__ void __launch_bounds__(WARPS * 32, 3) wbc_coriolis_kernel(const DevConst* __restrict__ gdc, const double* q,
@@ -268,13 +267,12 @@ extern "C" int wbc_default_params(wbc_params* p) {
 
 static int set_smem_attr(wbc_handle* h) {
   const int bytes = (int)sizeof(SmemLayout);
-  WBC_CUDA(h, cudaFuncSetAttribute(wbc_step_kernel<WBC_CTRL_ID>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-  WBC_CUDA(h, cudaFuncSetAttribute(wbc_step_kernel<WBC_CTRL_CLF>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   WBC_CUDA(h, cudaFuncSetAttribute(wbc_reduce_kernel<WBC_CTRL_ID>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   WBC_CUDA(h, cudaFuncSetAttribute(wbc_reduce_kernel<WBC_CTRL_CLF>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  WBC_CUDA(h, cudaFuncSetAttribute(wbc_reduce_pc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemLayoutPC)));
   WBC_CUDA(h, cudaFuncSetAttribute(wbc_solve_kernel<WBC_CTRL_ID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemLayoutSolve)));
   WBC_CUDA(h, cudaFuncSetAttribute(wbc_solve_kernel<WBC_CTRL_CLF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemLayoutSolve)));
-  WBC_CUDA(h, cudaFuncSetAttribute(wbc_step_pc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemLayoutPC)));
+  WBC_CUDA(h, cudaFuncSetAttribute(wbc_solve_kernel<WBC_CTRL_PC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemLayoutSolve)));
   WBC_CUDA(h, cudaFuncSetAttribute(wbc_coriolis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemLayoutPC)));
   WBC_CUDA(h, cudaFuncSetAttribute(wbc_dynamics_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   return WBC_OK;
@@ -410,12 +408,6 @@ extern "C" int wbc_step_pd(wbc_handle* h, int64_t n, const double* q, const doub
 // while each kernel still runs for milliseconds, so the drain at the kernel boundaries stays below ~1 % of the step.
 constexpr int64_t SPLIT_CHUNK = 262144;
 
-static int split_mode() {   // WBC_SPLIT=0 forces the fused single-kernel step (experiments / A-B comparisons)
-  static int mode = -1;
-  if (mode < 0) { const char* e = getenv("WBC_SPLIT"); mode = e ? atoi(e) : 1; }
-  return mode;
-}
-
 // Grows the hand-over scratch of `slot` to `n` instances (never inside a stream capture: callers that capture call this first).
 static int ensure_split_scratch(wbc_handle* h, int slot, int64_t n, bool with_vd) {
   const int64_t m = n < SPLIT_CHUNK ? n : SPLIT_CHUNK;
@@ -439,40 +431,31 @@ static wbc::StepArgs offset_args(const wbc_io* io, int64_t o, int64_t m, int kin
 }
 
 template <int KIND>
-static int launch_split(wbc_handle* h, int64_t n, const wbc_io* io, cudaStream_t st, int slot) {
+static int launch_split(wbc_handle* h, int kind, int64_t n, const wbc_io* io, cudaStream_t st, int slot) {
   int rc = ensure_split_scratch(h, slot, n, io->vd != nullptr);
   if (rc) return rc;
   double* vdmap = io->vd ? h->d_vdmap[slot] : nullptr;
   for (int64_t o = 0; o < n; o += SPLIT_CHUNK) {
     const int64_t m = (n - o) < SPLIT_CHUNK ? (n - o) : SPLIT_CHUNK;
-    const wbc::StepArgs a = offset_args(io, o, m, KIND);
+    const wbc::StepArgs a = offset_args(io, o, m, kind);
     const unsigned grid = (unsigned)((m + WARPS - 1) / WARPS);
-    wbc_reduce_kernel<KIND><<<grid, WARPS * 32, sizeof(SmemLayout), st>>>(h->d_const, a, h->d_rec[slot], vdmap);
+    if constexpr (KIND == WBC_CTRL_PC) wbc_reduce_pc_kernel<<<grid, WARPS * 32, sizeof(SmemLayoutPC), st>>>(h->d_const, a, h->d_rec[slot], vdmap);
+    else wbc_reduce_kernel<KIND><<<grid, WARPS * 32, sizeof(SmemLayout), st>>>(h->d_const, a, h->d_rec[slot], vdmap);
     wbc_solve_kernel<KIND><<<grid, WARPS * 32, sizeof(SmemLayoutSolve), st>>>(h->d_const, a, h->d_rec[slot], vdmap);
     h->launches += 2;
   }
   return WBC_OK;
 }
 
+// One control step = reduce kernel (per controller kind) + solve kernel, stream ordered; `slot` selects the hand-over scratch
+// (the host pipelines run two streams side by side).
 static int step_launch(wbc_handle* h, int kind, int64_t n, const wbc_io* io, cudaStream_t st, int slot) {
-  const unsigned grid = (unsigned)((n + WARPS - 1) / WARPS);
-  const size_t sm = sizeof(SmemLayout);
-  const bool split = split_mode() != 0;
   int rc = WBC_OK;
   switch (kind) {
-    case WBC_CTRL_ID:
-      if (split) rc = launch_split<WBC_CTRL_ID>(h, n, io, st, slot);
-      else { wbc_step_kernel<WBC_CTRL_ID><<<grid, WARPS * 32, sm, st>>>(h->d_const, offset_args(io, 0, n, kind)); h->launches++; }
-      break;
-    case WBC_CTRL_CLF:
-      if (split) rc = launch_split<WBC_CTRL_CLF>(h, n, io, st, slot);
-      else { wbc_step_kernel<WBC_CTRL_CLF><<<grid, WARPS * 32, sm, st>>>(h->d_const, offset_args(io, 0, n, kind)); h->launches++; }
-      break;
+    case WBC_CTRL_ID: rc = launch_split<WBC_CTRL_ID>(h, kind, n, io, st, slot); break;
+    case WBC_CTRL_CLF: rc = launch_split<WBC_CTRL_CLF>(h, kind, n, io, st, slot); break;
     case WBC_CTRL_PC:
-    case WBC_CTRL_MPTC:
-      wbc_step_pc_kernel<<<grid, WARPS * 32, sizeof(SmemLayoutPC), st>>>(h->d_const, offset_args(io, 0, n, kind));
-      h->launches++;
-      break;
+    case WBC_CTRL_MPTC: rc = launch_split<WBC_CTRL_PC>(h, kind, n, io, st, slot); break;   // MPTC: a.kind drops the passivity row
     default: return fail_arg(h, "wbc_step: unknown controller kind");
   }
   if (rc) return rc;
@@ -546,9 +529,27 @@ extern "C" int wbc_step_host(wbc_handle* h, int kind, int64_t n, const wbc_io* i
     if (pinned) {
       wbc_io dio{(const double*)dev[0], (const double*)dev[1], (const double*)dev[2], (const uint8_t*)dev[3], (double*)dev[4],
                  (double*)dev[5], (int32_t*)dev[6], (double*)dev[7], (double*)dev[8], (double*)dev[9]};
-      rc = wbc_step(h, kind, n, &dio, h->stream);
-      if (rc) return rc;
-      WBC_CUDA(h, cudaStreamSynchronize(h->stream));
+      // The batch goes through in chunks alternating between two streams (each with its own hand-over scratch), so that the
+      // input-bound reduce kernel of one chunk overlaps the solve kernel of the previous one and the host link stays busy.
+      int zc = 1;
+      if (const char* env = getenv("WBC_ZC_CHUNKS")) { const int v = atoi(env); if (v >= 1 && v <= 64) zc = v; }
+      if ((int64_t)zc > n) zc = (int)n;
+      const int64_t per = ((n + zc - 1) / zc + 3) & ~(int64_t)3;
+      cudaStream_t lanes[2] = {h->stream, h->stream2};
+      int used = 0;
+      for (int c = 0; c < zc; ++c) {
+        const int64_t o = c * per, m = (o + per <= n) ? per : n - o;
+        if (m <= 0) break;
+        const wbc_io cio{dio.q + o * WBC_NQ, dio.v + o * WBC_NV, dio.traj ? dio.traj + o * WBC_NTRAJ : nullptr,
+                         dio.contact ? dio.contact + o * 4 : nullptr, dio.tau + o * WBC_NU,
+                         dio.metrics ? dio.metrics + o * WBC_NMETRIC : nullptr, dio.status ? dio.status + o : nullptr,
+                         dio.vd ? dio.vd + o * WBC_NV : nullptr, dio.f ? dio.f + o * 12 : nullptr, dio.qp_info ? dio.qp_info + o * 4 : nullptr};
+        rc = pd ? wbc_step_pd(h, m, cio.q, cio.v, cio.tau, lanes[c & 1]) : step_launch(h, kind, m, &cio, lanes[c & 1], c & 1);
+        if (rc) return rc;
+        used |= 1 << (c & 1);
+      }
+      if (used & 1) WBC_CUDA(h, cudaStreamSynchronize(h->stream));
+      if (used & 2) WBC_CUDA(h, cudaStreamSynchronize(h->stream2));
       return WBC_OK;
     }
   }
@@ -1008,7 +1009,8 @@ extern "C" int wbc_rollout(wbc_handle* h, int kind, const wbc_plan* plan, int64_
   WBC_CUDA(h, cudaSetDevice(h->device));
   int rc = ensure_rollout_scratch(h, n);
   if (rc) return rc;
-  if (kind == WBC_CTRL_ID || kind == WBC_CTRL_CLF) { rc = ensure_split_scratch(h, 0, n, true); if (rc) return rc; }
+  rc = ensure_split_scratch(h, 0, n, true);
+  if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   double* tau = io->tau ? io->tau : h->ro_tau;
   double* metrics = io->metrics ? io->metrics : h->ro_metrics;

@@ -31,7 +31,7 @@
 namespace wbc {
 
 constexpr int NF = 13;      // reduced dimension (12 free variables for ID/PC, 13 for CLF; padded to 13)
-constexpr int YS = 14;      // row stride of Y: 13 coefficients + constant
+constexpr int YS = 15;      // row stride of Y: 13 coefficients + constant + 1 pad (odd stride: row-per-lane access is bank-conflict free)
 constexpr int YROWS = 32;   // 0-5 a_b | 6-17 leg rows (f of a stance leg / task accel of a swing leg) | 18-29 tau | 30,31 extra
 constexpr int AR = 6;       // rows of the reduced base system (the stance-leg rows are eliminated analytically)
 constexpr int AC = 32;      // columns of [A|b]: lane c owns column c, lane 31 the right-hand side
@@ -71,33 +71,21 @@ struct StepArgs {
   long long n; int kind;
 };
 
-// Per-warp shared memory. Everything a step needs between load and store lives here (12.6 KB).
-// The inputs + dynamics block is dead once the reduced problem (Y, cw, ct) is built, so the reduced
-// Hessian / Goldfarb-Idnani workspace overlays it.
+// Per-warp shared memory of the reduce half (phases 0-4): inputs, dynamics block, the reduced base system and the reduced
+// problem it leaves behind (9.9 KB).
 struct alignas(16) WarpSmem {
-  union {
-    struct {
-      // ---- inputs
-      double q[WBC_NQ], v[WBC_NV], traj[WBC_NTRAJ];
-      // ---- dynamics block (internal joint order k = 3*leg + j)
-      double Mb[18][6];      // Mb[c][r] = M[r][c] for r < 6 (base rows of the mass matrix, column major)
-      double Mleg[4][6];     // per-leg 3x3 block, upper triangle (0,0)(0,1)(0,2)(1,1)(1,2)(2,2)
-      double hb[6], hj[12];  // bias: C v + tau_g (controller sign)
-      double rho[4][3];      // foot position relative to the base origin, world axes
-      double L[4][3][3];     // leg block of the foot Jacobian: L[leg][row][joint]
-      double Jdv[4][3], vf[4][3];
-      double Ld[4][3][3];    // time derivative of L (PC only): Ld[leg][row][joint]
-      double task[16];       // 7-15: base rotation matrix (column major)
-    };
-    struct {
-      // ---- reduced Hessian -> Cholesky factor -> J = L^-T (in place), then Goldfarb-Idnani state
-      union { double H[NF][NF]; double J[NF][NF]; };
-      double g[NF];
-      double R[NF][NF];
-      double d[NF], r[NF], x[NF], u[NF], npv[NF], dm[NF], y[YROWS];
-      int act[NF];
-    };
-  };
+  // ---- inputs
+  double q[WBC_NQ], v[WBC_NV], traj[WBC_NTRAJ];
+  // ---- dynamics block (internal joint order k = 3*leg + j)
+  double Mb[18][6];      // Mb[c][r] = M[r][c] for r < 6 (base rows of the mass matrix, column major)
+  double Mleg[4][6];     // per-leg 3x3 block, upper triangle (0,0)(0,1)(0,2)(1,1)(1,2)(2,2)
+  double hb[6], hj[12];  // bias: C v + tau_g (controller sign)
+  double rho[4][3];      // foot position relative to the base origin, world axes
+  double L[4][3][3];     // leg block of the foot Jacobian: L[leg][row][joint]
+  double Jdv[4][3], vf[4][3];
+  double Ld[4][3][3];    // time derivative of L (PC only): Ld[leg][row][joint]
+  double task[16];       // 7-15: base rotation matrix (column major)
+  double y[YROWS];       // scratch (CLF: kappa per task row)
   // ---- reduced base system [B | c0] over u = [a_b(6); per leg f_k (stance) or a_k (swing)] and its reduction
   double A[AR][AC];
   double AK[4][3][7];    // stance leg k: a_k = AK[k][:, 6] - AK[k][:, 0:6] a_b   (= L_k^-1 (r_k - Jb_k a_b))
@@ -111,21 +99,20 @@ struct alignas(16) WarpSmem {
 
 // Per-warp shared memory of the solve kernel of the split path (phases 5-7 only): the reduced problem (Y, cw, ct - one
 // contiguous 4 KB block, filled by a single bulk copy of the record the reduce kernel wrote) and the Goldfarb-Idnani state.
-// Member names match WarpSmem so that reduced_hessian / factor_and_start / gi_solve / solve_instance run on either.
 struct alignas(16) SolveSmem {
   alignas(16) double Y[YROWS][YS];
   double cw[YROWS], ct[YROWS];
   union { double H[NF][NF]; double J[NF][NF]; };
   double g[NF];
   double R[NF][NF];
-  double d[NF], r[NF], x[NF], u[NF], npv[NF], dm[NF], y[YROWS];
+  double d[NF], x[NF], u[NF], npv[NF], dm[NF], y[YROWS];
   int act[NF];
   alignas(8) unsigned long long mbar;   // completion barrier of the bulk copy
 };
 constexpr int REC_Y = YROWS * YS + 2 * YROWS;   // doubles of [Y | cw | ct]
 constexpr int REC_MISC = 16;                    // status, cmask, nf, nextra, ok, extra_bound, err, Vl, PFl, csum, Vpc
 constexpr int REC_DOUBLES = REC_Y + REC_MISC;   // one record of the reduce -> solve hand-over (4224 B)
-constexpr int VDMAP_DOUBLES = 12 * YS;          // joint accelerations as affine maps of w (only when vd is requested)
+constexpr int VDMAP_DOUBLES = 18 * YS;          // accelerations [a_b; joints] as affine maps of w (only when vd is requested)
 
 // ------------------------------------------------------------------ small vector helpers
 struct V3 { double x, y, z; };
@@ -650,7 +637,7 @@ template <int N, class SM> WBC_DEV void reduced_hessian(SM& s, int lane, int nf,
 }
 
 // In-place Cholesky (lower) of s.H, then J = L^-T (J J' = H^-1) and the unconstrained minimiser x.
-template <int N, class SM> WBC_DEV void factor_and_start(SM& s, int lane, int& status, const TriPairs& tp) {
+template <int N, class SM> WBC_DEV void cholesky_factor(SM& s, int lane, int& status, const TriPairs& tp) {
   for (int j = 0; j < N; ++j) {
     const double dj = s.H[j][j];
     if (!(dj > 1e-300)) { status |= WBC_ST_NOTPD; }
@@ -666,39 +653,7 @@ template <int N, class SM> WBC_DEV void factor_and_start(SM& s, int lane, int& s
     }
     __syncwarp();
   }
-  // column `lane` of X = L^-1 is row `lane` of J = X'
-  if (lane < N) {
-    double xcol[N];
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
-      double acc = (i == lane) ? 1.0 : 0.0;
-#pragma unroll
-      for (int mm = 0; mm < N; ++mm)
-        if (mm < i) acc = fma(-s.H[i][mm], xcol[mm], acc);
-      xcol[i] = acc * s.d[i];
-    }
-    __syncwarp();            // every lane is done reading L before J overwrites it
-#pragma unroll
-    for (int i = 0; i < N; ++i) s.J[lane][i] = (i >= lane) ? xcol[i] : 0.0;
-  } else {
-    __syncwarp();
-  }
-  __syncwarp();
-  // x = -J J' g
-  if (lane < N) {
-    double t = 0.0;
-    for (int i = 0; i < N; ++i) t = fma(s.J[i][lane], s.g[i], t);
-    s.d[lane] = t;
-  }
-  __syncwarp();
-  if (lane < N) {
-    double t = 0.0;
-    for (int k = 0; k < N; ++k) t = fma(s.J[lane][k], s.d[k], t);
-    s.x[lane] = -t;
-  }
-  __syncwarp();
 }
-
 // ------------------------------------------------------------------------------ phase 6
 // Inequality i is  ca*y[ra] + cb*y[rb] <= bound  with y = Y w + y0.
 struct Ineq { int ra, rb; double ca, cb, bound; };
@@ -726,42 +681,106 @@ WBC_DEV Ineq get_ineq(const IneqSet& S, int i) {
   return q;
 }
 
-// Goldfarb-Idnani dual active-set method on  min 1/2 w'Hw + g'w  s.t. the IneqSet.
-// On entry s.J, s.x hold L^-T and the unconstrained minimiser. Returns iterations; multipliers in s.u.
-// All loops over the reduced dimension are fixed-length and branch-free: lanes >= N compute on a clamped
-// row (results discarded), entries left of the active count q are masked to zero instead of skipped.
-template <int N, class SM> WBC_DEV int gi_solve(SM& s, int lane, const IneqSet& S, int max_iter, int& status, int& q_out, double& minslack) {
-  const int mi = S.nfric + S.nextra + S.ntl;
-  const int li = lane < N ? lane : N - 1;     // clamped row for loads
+// Triangular solves with the Cholesky factor L (s.H lower triangle in place, s.d its inverse diagonal): lane k owns
+// component k, the finished component is broadcast by shuffle.
+template <int N, class SM> WBC_DEV double tri_fwd_lane(const SM& s, int lane, double rhs) {
+  // solves L b = rhs (rhs_k in lane k < N); returns b_lane
   const bool row = lane < N;
-  // the (up to) two inequalities this lane watches, hoisted out of the loop
-  Ineq c0 = get_ineq(S, lane < mi ? lane : 0), c1 = get_ineq(S, lane + 32 < mi ? lane + 32 : 0);
-  const bool have0 = lane < mi, have1 = lane + 32 < mi;
+  const int li = row ? lane : N - 1;
+  const double dinv = s.d[li];
+  double acc = row ? rhs : 0.0, bl = 0.0;
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    const double bj = shfl(acc * dinv, j);
+    if (lane == j) bl = bj;
+    else if (lane > j) acc = fma(-s.H[li][j], bj, acc);
+  }
+  return bl;
+}
+template <int N, class SM> WBC_DEV double tri_bwd_lane(const SM& s, int lane, double rhs) {
+  // solves L' x = rhs; returns x_lane
+  const bool row = lane < N;
+  const int li = row ? lane : N - 1;
+  const double dinv = s.d[li];
+  double acc = row ? rhs : 0.0, xl = 0.0;
+#pragma unroll
+  for (int j = N - 1; j >= 0; --j) {
+    const double xj = shfl(acc * dinv, j);
+    if (lane == j) xl = xj;
+    else if (lane < j) acc = fma(-s.H[j][li], xj, acc);
+  }
+  return xl;
+}
+
+// ------------------------------------------------------------------------------ phase 6: Goldfarb-Idnani on W = Y J
+// Dual active-set method on  min 1/2 w'Hw + g'w  s.t. the IneqSet (exact optimum; replaces OsqpSolver().Solve,
+// inverse_dynamics_controller.py:223), written on W = Y J (32 x N, J J' = H^-1) instead of on J itself. Every quantity an
+// iteration needs is a function of W:
+//   d = J'n_p = -(ca W[ra] + cb W[rb])             two rows of W (the constraint combines two rows of Y)
+//   Y z = W[:, q:] d[q:]                           -> y += t Y z is one FMA per lane; w itself is never formed
+//   J <- J Q (Householder on add, Givens on drop)  -> W <- W Q, a row update that keeps all 32 lanes busy
+// so the N x N matrix-vector products, the J update and the y = Y w + y0 product of the textbook form (about 265
+// shared-memory wavefronts per iteration, the limiter measured on that form) reduce to ~85 wavefronts and half the
+// instructions. W is built IN PLACE over Y (W = Y L^-T, forward substitution along each row); the free-part chains enter an
+// unrolled sequence at column q (q is warp uniform) with static shared-memory offsets - no masks, no selects.
+// On entry s.H holds the Cholesky factor L (lower, in place), s.d its inverse diagonal, s.g the reduced gradient.
+// On exit s.y = Y w + y0 and the multipliers are in s.u / s.act; w is recovered (x = H^-1 Y' C (y - y0), Y read back from
+// the hand-over record `Yg`) only when the caller asks for the accelerations.
+template <int N, class SM> WBC_DEV int gi_solve_ws(SM& s, int lane, const IneqSet& S, int max_iter, int& status, int& q_out,
+                                                  double& minslack, const double* Yg) {
+  const int mi = S.nfric + S.nextra + S.ntl;
+  const bool row = lane < N;
+  const int li = row ? lane : N - 1;
+  const Ineq c0 = get_ineq(S, lane < mi ? lane : 0);
+  const bool have0 = lane < mi;
+  double* Wl = &s.Y[lane][0];                    // row `lane` of W (after the substitution below)
+  // ---- W = Y L^-T in place: forward substitution along the row, L broadcast from shared memory
+  {
+    double w[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      double acc = Wl[k];
+#pragma unroll
+      for (int j = 0; j < k; ++j) acc = fma(-w[j], s.H[k][j], acc);
+      w[k] = acc * s.d[k];
+    }
+    // ---- unconstrained minimiser in y: b = L^-1 g, y = y0 - W b
+    const double bl = tri_fwd_lane<N>(s, lane, s.g[li]);
+    if (row) s.npv[lane] = bl;
+    __syncwarp();
+    double acc = Wl[NF], acc1 = 0.0;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      Wl[k] = w[k];
+      if (k & 1) acc1 = fma(-w[k], s.npv[k], acc1); else acc = fma(-w[k], s.npv[k], acc);
+    }
+    s.y[lane] = acc + acc1;
+  }
+  double yl = s.y[lane];
   int q = 0, iters = 0;
   unsigned long long activemask = 0ull;
+  double ul = 0.0, rinvl = 0.0;     // lane k < q: multiplier and 1 / R[k][k] of active slot k
+  int actl = 0;                     // constraint id in slot `lane`
   minslack = 0.0;
-  {  // y = Y x + y0 (kept current after every primal step)
-    double acc = s.Y[lane][NF];
-#pragma unroll
-    for (int k = 0; k < N; ++k) acc = fma(s.Y[lane][k], s.x[k], acc);
-    s.y[lane] = acc;
-  }
   __syncwarp();
   for (;;) {
-    // most violated inequality: largest (-slack) beyond tolerance
+    // most violated inequality (y lives in shared memory: every lane reads the two rows its constraint combines)
     double viol = 0.0; int who = 0;
     if (have0 && !((activemask >> lane) & 1ull)) {
       const double ta = c0.ca * s.y[c0.ra], tb = c0.cb * s.y[c0.rb];
       const double sl = c0.bound - ta - tb;
       if (sl < -1e-10 * (1.0 + fabs(c0.bound) + fabs(ta) + fabs(tb))) { viol = -sl; who = lane; }
     }
-    if (have1 && !((activemask >> (lane + 32)) & 1ull)) {
-      const double ta = c1.ca * s.y[c1.ra], tb = c1.cb * s.y[c1.rb];
-      const double sl = c1.bound - ta - tb;
-      if (sl < -1e-10 * (1.0 + fabs(c1.bound) + fabs(ta) + fabs(tb)) && -sl > viol) { viol = -sl; who = lane + 32; }
+    if (mi > 32) {
+      const Ineq c1 = get_ineq(S, lane + 32 < mi ? lane + 32 : 0);
+      if (lane + 32 < mi && !((activemask >> (lane + 32)) & 1ull)) {
+        const double ta = c1.ca * s.y[c1.ra], tb = c1.cb * s.y[c1.rb];
+        const double sl = c1.bound - ta - tb;
+        if (sl < -1e-10 * (1.0 + fabs(c1.bound) + fabs(ta) + fabs(tb)) && -sl > viol) { viol = -sl; who = lane + 32; }
+      }
     }
     int p;
-    {  // most violated constraint of the warp; ties go to the lowest lane
+    {
       int wl;
       viol = warp_max_lane(viol, wl);
       p = shfl(who, wl);
@@ -769,95 +788,77 @@ template <int N, class SM> WBC_DEV int gi_solve(SM& s, int lane, const IneqSet& 
     minslack = -viol;
     if (!(viol > 0.0)) break;
     const Ineq cp = get_ineq(S, p);
-    if (row) s.npv[lane] = -(cp.ca * s.Y[cp.ra][lane] + cp.cb * s.Y[cp.rb][lane]);
+    const double nca = -cp.ca, ncb = -cp.cb;
     double up = 0.0;
-    __syncwarp();
     bool fail = false;
-    double dd = -1.0;   // |J'n|^2 = n'H^-1 n: invariant under the orthogonal column updates of J
+    double dd = -1.0;   // |J'n|^2: invariant under the orthogonal column updates
     for (;;) {
       if (++iters > max_iter) { status |= WBC_ST_MAXITER; fail = true; break; }
-      // d = J' n ; s.d keeps d, s.npv is untouched
-      double dl = 0.0, dl1 = 0.0, dl2 = 0.0;
-#pragma unroll
-      for (int i = 0; i < N; i += 3) {
-        dl = fma(s.J[i][li], s.npv[i], dl);
-        if (i + 1 < N) dl1 = fma(s.J[i + 1][li], s.npv[i + 1], dl1);
-        if (i + 2 < N) dl2 = fma(s.J[i + 2][li], s.npv[i + 2], dl2);
-      }
-      dl = row ? dl + (dl1 + dl2) : 0.0;
-      if (row) s.d[lane] = dl;
-      const double dm = lane >= q ? dl : 0.0;           // d masked to the free part
-      if (row) s.dm[lane] = dm;
-      const double zn = warp_sum(dm * dm);
-      if (dd < 0.0) dd = (q == 0) ? zn : warp_sum(dl * dl);
+      // ---- d = J'n = -(ca W[ra] + cb W[rb]); lane k owns d_k and publishes it
+      const double dself = fma(nca, s.Y[cp.ra][li], ncb * s.Y[cp.rb][li]);
+      if (row) s.dm[lane] = dself;
+      if (dd < 0.0) dd = warp_sum(row ? dself * dself : 0.0);
       __syncwarp();
-      // z = J[:, q:] d[q:]
-      double zi = 0.0, zi1 = 0.0, zi2 = 0.0;
-#pragma unroll
-      for (int k = 0; k < N; k += 3) {
-        zi = fma(s.J[li][k], s.dm[k], zi);
-        if (k + 1 < N) zi1 = fma(s.J[li][k + 1], s.dm[k + 1], zi1);
-        if (k + 2 < N) zi2 = fma(s.J[li][k + 2], s.dm[k + 2], zi2);
+      // free part k >= q: the unrolled chain is entered at k = q
+      double zn = 0.0, zn1 = 0.0, wd = 0.0, wd1 = 0.0;    // |d[q:]|^2 and (Y z)_lane = W[lane][q:] . d[q:]
+      switch (q) {
+#define WBC_ACC(K)                                                                                   \
+        case K:                                                                                      \
+          if (K < N) {                                                                               \
+            const double dk_ = s.dm[K < N ? K : 0];                                                  \
+            if (K & 1) { zn1 = fma(dk_, dk_, zn1); wd1 = fma(Wl[K < N ? K : 0], dk_, wd1); }         \
+            else { zn = fma(dk_, dk_, zn); wd = fma(Wl[K < N ? K : 0], dk_, wd); }                   \
+          }
+        WBC_ACC(0) WBC_ACC(1) WBC_ACC(2) WBC_ACC(3) WBC_ACC(4) WBC_ACC(5) WBC_ACC(6) WBC_ACC(7) WBC_ACC(8) WBC_ACC(9) WBC_ACC(10)
+        WBC_ACC(11) WBC_ACC(12)
+#undef WBC_ACC
+        default: break;
       }
-      zi += zi1 + zi2;
+      zn += zn1; wd += wd1;
+      const int qc = q < N ? q : N - 1;
+      const double dq = s.dm[qc], wq = Wl[qc];
       const double sp = cp.bound - cp.ca * s.y[cp.ra] - cp.cb * s.y[cp.rb];
-      // r = R^-1 d[:q]  (back substitution; lane k owns r_k)
-      double rk = dl;
+      // r = R^-1 d[:q]  (back substitution; lane k owns r_k; R is kept transposed: R[col][row])
+      double rk = dself;
       for (int jj = q - 1; jj >= 0; --jj) {
-        const double rj = shfl(rk, jj) * s.r[jj];          // s.r[jj] = 1 / R[jj][jj]
-        rk = (lane == jj) ? rj : ((lane < jj) ? fma(-s.R[li][jj], rj, rk) : rk);
+        const double rl = s.R[jj][li];
+        const double rj = shfl(rk * rinvl, jj);
+        if (lane < jj) rk = fma(-rl, rj, rk);
       }
-      // step lengths
+      rk *= rinvl;
       int l;
-      const double t1 = warp_min_lane((lane < q && rk > 0.0) ? fmax(s.u[li] * frcp(rk), 0.0) + 0.0 : INFINITY, l);   // + 0.0: never -0.0
+      const double t1 = warp_min_lane((lane < q && rk > 0.0) ? fmax(ul * frcp(rk), 0.0) + 0.0 : INFINITY, l);
       const bool zok = zn > 1e-14 * fmax(dd, 1e-300);
       const double izn = frcp(zok ? zn : 1.0);
       const double t2 = zok ? -sp * izn : INFINITY;
       const double t = fmin(t1, t2);
       if (!(t < INFINITY)) { status |= WBC_ST_INFEASIBLE; fail = true; break; }
       const bool dual_only = !(t2 < INFINITY);
-      if (lane < q) s.u[lane] -= t * rk;
+      if (lane < q) ul -= t * rk;
       up += t;
-      if (!dual_only) {
-        if (row) s.x[lane] = fma(t, zi, s.x[lane]);
-        __syncwarp();
-        double acc = s.Y[lane][NF], acc1 = 0.0, acc2 = 0.0;
-#pragma unroll
-        for (int k = 0; k < N; k += 3) {
-          acc = fma(s.Y[lane][k], s.x[k], acc);
-          if (k + 1 < N) acc1 = fma(s.Y[lane][k + 1], s.x[k + 1], acc1);
-          if (k + 2 < N) acc2 = fma(s.Y[lane][k + 2], s.x[k + 2], acc2);
-        }
-        s.y[lane] = acc + (acc1 + acc2);
-      }
-      __syncwarp();
+      if (!dual_only) { yl = fma(t, wd, yl); s.y[lane] = yl; }
       if (!dual_only && t2 <= t1) {
-        // ---- full step: add p. Householder on d[q:] -> (alpha, 0, ..), J[:, q:] <- J[:, q:] (I - 2 v v'/v'v)
+        // ---- full step: add p. Householder on d[q:] -> (alpha, 0, ..), W[:, q:] <- W[:, q:] (I - 2 v v'/v'v), v = d[q:] - alpha e_q
         const double nrm = zn * frsqrt(zn);
-        const double dq = s.d[q];
         const double alpha = dq > 0.0 ? -nrm : nrm;
         double rqq = dq;
         if (q < N - 1) {
-          const double vv = 2.0 * (zn - dq * alpha);   // |v|^2 with v = d[q:] - alpha e_q
+          const double vv = 2.0 * (zn - dq * alpha);       // |v|^2
           if (vv > 0.0) {
-            // v = masked d with v_q = d_q - alpha, kept in s.dm (all lanes are past their reads of s.dm)
-            if (lane == q) s.dm[q] = dq - alpha;
-            __syncwarp();
-            double dt = 0.0, dt1 = 0.0;
-#pragma unroll
-            for (int k = 0; k < N; ++k) {
-              if (k & 1) dt1 = fma(s.J[li][k], s.dm[k], dt1); else dt = fma(s.J[li][k], s.dm[k], dt);
+            const double sc = 2.0 * (wd - alpha * wq) * frcp(vv);   // W[lane] . v = wd - alpha W[lane][q]
+            switch (q) {                                   // W[k] -= sc d_k, k >= q
+#define WBC_UPD(K) case K: if (K < N) Wl[K < N ? K : 0] = fma(-sc, s.dm[K < N ? K : 0], Wl[K < N ? K : 0]);
+              WBC_UPD(0) WBC_UPD(1) WBC_UPD(2) WBC_UPD(3) WBC_UPD(4) WBC_UPD(5) WBC_UPD(6) WBC_UPD(7) WBC_UPD(8) WBC_UPD(9) WBC_UPD(10)
+              WBC_UPD(11) WBC_UPD(12)
+#undef WBC_UPD
+              default: break;
             }
-            const double sc = 2.0 * (dt + dt1) * frcp(vv);
-            if (row) {
-#pragma unroll
-              for (int k = 0; k < N; ++k) s.J[lane][k] = fma(-sc, s.dm[k], s.J[lane][k]);
-            }
+            Wl[qc] = fma(sc, alpha, Wl[qc]);               // column q: v_q = d_q - alpha
           }
           rqq = alpha;
         }
-        if (lane < q) s.R[lane][q] = dl;
-        if (lane == q) { s.R[q][q] = rqq; s.r[q] = frcp(rqq); s.u[q] = up; s.act[q] = p; }
+        if (lane < q) s.R[q][lane] = dself;
+        if (lane == q) { s.R[q][q] = rqq; rinvl = frcp(rqq); ul = up; actl = p; }
         activemask |= 1ull << p;
         ++q;
         __syncwarp();
@@ -865,34 +866,31 @@ template <int N, class SM> WBC_DEV int gi_solve(SM& s, int lane, const IneqSet& 
       }
       // ---- drop the blocking constraint l (position in the active list)
       {
-        const int dropped = s.act[l];
-        __syncwarp();
+        const int dropped = shfl(actl, l);
         activemask &= ~(1ull << dropped);
-        // shift R columns, u, act left from l
         if (row) {
-          for (int jj = l; jj < q - 1; ++jj) s.R[lane][jj] = s.R[lane][jj + 1];
-          s.R[lane][q - 1] = 0.0;
+          for (int jj = l; jj < q - 1; ++jj) s.R[jj][lane] = s.R[jj + 1][lane];
+          s.R[q - 1][lane] = 0.0;
         }
-        double un = 0.0; int an = 0;
-        if (lane >= l && lane < q - 1) { un = s.u[lane + 1]; an = s.act[lane + 1]; }
+        const double un = __shfl_down_sync(WBC_FULL, ul, 1);
+        const int an = __shfl_down_sync(WBC_FULL, actl, 1);
+        if (lane >= l && lane < q - 1) { ul = un; actl = an; }
         __syncwarp();
-        if (lane >= l && lane < q - 1) { s.u[lane] = un; s.act[lane] = an; }
-        __syncwarp();
-        // Givens rotations restoring the triangle; same rotations on the columns of J
+        // Givens rotations restoring the triangle; same rotations on the columns of W
         for (int k = l; k < q - 1; ++k) {
-          const double a = s.R[k][k], b = s.R[k + 1][k];
+          const double a = s.R[k][k], b = s.R[k][k + 1];   // R[k][k], R[k+1][k]
           const double r2 = a * a + b * b;
           __syncwarp();
           if (r2 > 0.0) {
             const double irr = frsqrt(r2);
             const double c = a * irr, sn = b * irr;
             if (row) {
-              const double r0 = s.R[k][lane], r1 = s.R[k + 1][lane];
-              s.R[k][lane] = c * r0 + sn * r1; s.R[k + 1][lane] = -sn * r0 + c * r1;
-              if (lane == k) s.r[k] = frcp(c * r0 + sn * r1);
-              const double j0 = s.J[lane][k], j1 = s.J[lane][k + 1];
-              s.J[lane][k] = c * j0 + sn * j1; s.J[lane][k + 1] = -sn * j0 + c * j1;
+              const double r0 = s.R[lane][k], r1 = s.R[lane][k + 1];
+              s.R[lane][k] = c * r0 + sn * r1; s.R[lane][k + 1] = -sn * r0 + c * r1;
+              if (lane == k) rinvl = frcp(c * r0 + sn * r1);
             }
+            const double w0 = Wl[k], w1 = Wl[k + 1];
+            Wl[k] = c * w0 + sn * w1; Wl[k + 1] = -sn * w0 + c * w1;
           }
           __syncwarp();
         }
@@ -901,6 +899,20 @@ template <int N, class SM> WBC_DEV int gi_solve(SM& s, int lane, const IneqSet& 
     }
     if (fail) break;
   }
+  if (lane < q) { s.u[lane] = ul; s.act[lane] = actl; }
+  if (Yg) {
+    // x = H^-1 Y' C (y - y0)   (exact: y - y0 = Y x and H = Y' C Y); the original Y is read back from the record
+    s.R[0][lane] = s.cw[lane] * (yl - Wl[NF]);            // R is free now: 32 doubles of scratch
+    __syncwarp();
+    double gk = 0.0;
+    const double* ev = &s.R[0][0];
+    for (int r = 0; r < YROWS; ++r) gk = fma(Yg[r * YS + li], ev[r], gk);
+    const double bl = tri_fwd_lane<N>(s, lane, gk);
+    const double xl = tri_bwd_lane<N>(s, lane, bl);
+    if (row) s.x[lane] = xl;
+    if (lane >= N && lane < NF) s.x[lane] = 0.0;
+  }
+  __syncwarp();
   q_out = q;
   return iters;
 }
@@ -915,7 +927,10 @@ WBC_DEV void put_y(WarpSmem& s, int row, int ycol, double val) { if (ycol >= 0) 
 WBC_DEV void build_common_rows(WarpSmem& s, int lane, int ycol, unsigned cmask, double* vdmap = nullptr) {
   double zb[6];
 #pragma unroll
-  for (int i = 0; i < 6; ++i) { zb[i] = zent(s, lane, i); put_y(s, i, ycol, zb[i]); }
+  for (int i = 0; i < 6; ++i) {
+    zb[i] = zent(s, lane, i); put_y(s, i, ycol, zb[i]);
+    if (vdmap && ycol >= 0) vdmap[i * YS + ycol] = zb[i];
+  }
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const bool stance = (cmask >> k) & 1;
@@ -942,7 +957,7 @@ WBC_DEV void build_common_rows(WarpSmem& s, int lane, int ycol, unsigned cmask, 
         ak[i] = zl[i];
       }
       put_y(s, 6 + 3 * k + i, ycol, val);
-      if (vdmap && ycol >= 0) vdmap[(3 * k + i) * YS + ycol] = ak[i];
+      if (vdmap && ycol >= 0) vdmap[(6 + 3 * k + i) * YS + ycol] = ak[i];
     }
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
@@ -1223,7 +1238,7 @@ WBC_DEV void pc_rows(WarpSmem& s, const PcSmem& pc, int lane, int ycol, int m) {
 // What the solve half needs from the reduce half besides [Y | cw | ct]: registers in the fused kernels, the `misc` words of
 // the hand-over record in the split path.
 struct StepCarry {
-  int status; unsigned cmask; int nf, nextra, widx; bool ok, pc_ok;
+  int status; unsigned cmask; int nf, nextra; bool ok, pc_ok;
   double extra_bound, err, Vl, PFl, csum, Vpc;
 };
 
@@ -1366,17 +1381,16 @@ WBC_DEV void reduce_instance(WarpSmem& s, const wbc_model& md, const wbc_params&
     }
     __syncwarp();
   }
-  c.status = status; c.cmask = cmask; c.nf = nf; c.nextra = nextra; c.widx = widx; c.ok = ok; c.pc_ok = pc_ok;
+  c.status = status; c.cmask = cmask; c.nf = nf; c.nextra = nextra; c.ok = ok; c.pc_ok = pc_ok;
   c.extra_bound = extra_bound; c.err = err; c.Vl = Vl; c.PFl = PFl; c.csum = csum; c.Vpc = Vpc;
 }
 
-// Phases 5-7: reduced problem in s -> torques, metrics, status. Runs on the full WarpSmem (fused kernels: PC / MPTC, the
-// host emulator) or on the compact SolveSmem of the split path, where the joint accelerations come from `vdmap`.
+// Phases 5-7: reduced problem in s ([Y | cw | ct], bulk-copied from the hand-over record) -> torques, metrics, status.
+// `vdmap` are the 18 acceleration rows the reduce half stored (null unless vd is requested), `yrec` the record itself.
 template <int KIND, class SM>
 WBC_DEV void solve_instance(SM& s, const wbc_model& md, const wbc_params& pr, const StepArgs& a, long long inst, int lane,
-                            const StepCarry& c, const double* vdmap = nullptr) {
+                            const StepCarry& c, const double* vdmap = nullptr, const double* yrec = nullptr) {
   constexpr int NA = (KIND == WBC_CTRL_CLF) ? NF : NF - 1;
-  constexpr bool FUSED = std::is_same<SM, WarpSmem>::value;
   int status = c.status;
   const unsigned cmask = c.cmask;
   const int nc = __popc(cmask), nf = c.nf, nextra = c.nextra;
@@ -1385,62 +1399,28 @@ WBC_DEV void solve_instance(SM& s, const wbc_model& md, const wbc_params& pr, co
     // ---- phase 5
     const TriPairs tp = tri_pairs<NA>(lane);
     reduced_hessian<NA>(s, lane, nf, pr.reg_tau != 0.0 ? 30 : 18, KIND != WBC_CTRL_ID, tp);
-    factor_and_start<NA>(s, lane, status, tp);
+    cholesky_factor<NA>(s, lane, status, tp);
     // ---- phase 6
     IneqSet S;
     S.cmask = cmask; S.nc = nc; S.mu = pr.mu; S.nfric = 4 * nc; S.nextra = nextra; S.ntl = pr.torque_limits ? 24 : 0;
     S.effort = md.effort; S.dummy = nullptr; S.extra_bound[0] = extra_bound; S.extra_bound[1] = 0.0;
     int qact = 0; double minslack = 0.0;
     int iters = 0;
-    if (!(status & WBC_ST_NOTPD)) iters = gi_solve<NA>(s, lane, S, pr.max_iter, status, qact, minslack);
+    if (!(status & WBC_ST_NOTPD)) {
+      iters = gi_solve_ws<NA>(s, lane, S, pr.max_iter, status, qact, minslack, a.vd != nullptr ? yrec : nullptr);
+    }
     // ---- phase 7: y = Y x + y0 is current in s.y
     const double res = minslack < 0.0 ? -minslack : 0.0;
     if (lane < 12) {
       a.tau[inst * WBC_NU + md.act_index[lane]] = s.y[18 + lane];
       if (a.f) a.f[inst * 12 + lane] = ((cmask >> (lane / 3)) & 1) ? s.y[6 + lane] : 0.0;
     }
-    if (a.vd) {
-      if constexpr (FUSED) {
-        const int widx = c.widx;
-        // u = [a_b; leg variables] from the reduced base system (not from Y: the PC kernel overwrites its task rows)
-        double uval = 0.0;
-        if (lane < 18) {
-          const int r = s.rowof[lane];
-          if (r >= 0) {
-            uval = s.A[r][31];
-            for (int w = 0; w < nf; ++w) uval = fma(-s.A[r][s.fcol[w]], s.x[w], uval);
-          } else uval = s.x[widx];
-        }
-        double ab[6];
-  #pragma unroll
-        for (int r = 0; r < 6; ++r) ab[r] = shfl(uval, r);
-        if (lane < 18) {
-          double val = uval;
-          if (lane >= 6) {
-            const int k = (lane - 6) / 3, i = (lane - 6) % 3;
-            if ((cmask >> k) & 1) {                          // stance leg: a_k = AK[:,6] - AK[:,0:6] a_b
-              val = s.AK[k][i][6];
-  #pragma unroll
-              for (int r = 0; r < 6; ++r) val = fma(-s.AK[k][i][r], ab[r], val);
-            }
-          }
-          const int dst = lane < 6 ? lane : md.v_index[lane - 6];
-          a.vd[inst * WBC_NV + dst] = val;
-        }
-      } else {
-        // a_b = y[0:6]; joint accelerations from the affine maps the reduce kernel stored
-        if (lane < 18) {
-          double val;
-          if (lane < 6) val = s.y[lane];
-          else {
-            const double* mrow = vdmap + (lane - 6) * YS;
-            val = mrow[NF];
-            for (int w = 0; w < nf; ++w) val = fma(mrow[w], s.x[w], val);
-          }
-          const int dst = lane < 6 ? lane : md.v_index[lane - 6];
-          a.vd[inst * WBC_NV + dst] = val;
-        }
-      }
+    if (a.vd && lane < 18) {
+      // accelerations as affine maps of w (rows stored by the reduce half: a_b, then the joints in internal order)
+      const double* mrow = vdmap + lane * YS;
+      double val = mrow[NF];
+      for (int w = 0; w < nf; ++w) val = fma(mrow[w], s.x[w], val);
+      a.vd[inst * WBC_NV + (lane < 6 ? lane : md.v_index[lane - 6])] = val;
     }
     // reference objective 1/2 x'P0x + q0'x (constants dropped, E.5b): rows with a reference cost
     double obj = 0.0;
@@ -1475,17 +1455,6 @@ WBC_DEV void solve_instance(SM& s, const wbc_model& md, const wbc_params& pr, co
   __syncwarp();
 }
 
-
-// One control step of instance `inst` (DoSetControlTorques -> ControlLaw, basic_controller.py:286-320) inside one warp:
-// reduce + solve on the same shared-memory block (PC / MPTC kernels and the host emulator; ID / CLF launch the two halves
-// as separate kernels with their own register / occupancy budgets, see wbc_api.cu).
-template <int KIND>
-WBC_DEV void step_instance(WarpSmem& s, const wbc_model& md, const wbc_params& pr, const Derived& dv, const StepArgs& a,
-                           long long inst, int lane, PcSmem* pcs = nullptr) {
-  StepCarry c;
-  reduce_instance<KIND>(s, md, pr, dv, a, inst, lane, c, pcs, nullptr);
-  solve_instance<KIND, WarpSmem>(s, md, pr, a, inst, lane, c, nullptr);
-}
 
 // ---------------------------------------------------------------- dynamics parity entry
 // CalcDynamics + CalcFramePositionQuantities x4 for instance `inst`, written in Drake order.

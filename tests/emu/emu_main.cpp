@@ -9,18 +9,31 @@ thread_local EmuWarp* emu_warp;
 
 namespace {
 struct Job {
-  EmuWarp* warp; int lane; wbc::WarpSmem* sm; wbc::PcSmem* pcs; double* Cout; double* Jdout; const wbc_model* md; const wbc_params* pr; wbc::Derived dv;
+  EmuWarp* warp; int lane; wbc::WarpSmem* sm; wbc::SolveSmem* ssm; double* rec; double* vdmap; wbc::PcSmem* pcs; double* Cout; double* Jdout; const wbc_model* md; const wbc_params* pr; wbc::Derived dv;
   wbc::StepArgs args; wbc::DynOut dyn; const double* q; const double* v; long long n; int mode;
 };
+template <int KIND> void split_step(Job* j, long long i) {
+  wbc::StepCarry c;
+  double* vd = j->args.vd ? j->vdmap : nullptr;
+  wbc::reduce_instance<KIND>(*j->sm, *j->md, *j->pr, j->dv, j->args, i, j->lane, c, KIND == WBC_CTRL_PC ? j->pcs : nullptr, vd);
+  __syncwarp();
+  if (j->lane == 0) memcpy(j->rec, &j->sm->Y[0][0], sizeof(double) * wbc::REC_Y);
+  __syncwarp();
+  if (j->lane == 0) memcpy(&j->ssm->Y[0][0], j->rec, sizeof(double) * wbc::REC_Y);
+  __syncwarp();
+  wbc::solve_instance<KIND, wbc::SolveSmem>(*j->ssm, *j->md, *j->pr, j->args, i, j->lane, c, vd, j->rec);
+  __syncwarp();
+}
 void* lane_main(void* p) {
   Job* j = (Job*)p;
   emu_lane = j->lane;
   emu_warp = j->warp;
   for (long long i = 0; i < j->n; ++i) {
     if (j->mode == 0) {
-      if (j->args.kind == WBC_CTRL_ID) wbc::step_instance<WBC_CTRL_ID>(*j->sm, *j->md, *j->pr, j->dv, j->args, i, j->lane);
-      if (j->args.kind == WBC_CTRL_PC || j->args.kind == WBC_CTRL_MPTC) wbc::step_instance<WBC_CTRL_PC>(*j->sm, *j->md, *j->pr, j->dv, j->args, i, j->lane, j->pcs);
-      if (j->args.kind == WBC_CTRL_CLF) wbc::step_instance<WBC_CTRL_CLF>(*j->sm, *j->md, *j->pr, j->dv, j->args, i, j->lane);
+      // reduce on the full block, hand-over record (what the reduce / solve kernels do with bulk copies), solve on the compact block
+      if (j->args.kind == WBC_CTRL_ID) split_step<WBC_CTRL_ID>(j, i);
+      else if (j->args.kind == WBC_CTRL_CLF) split_step<WBC_CTRL_CLF>(j, i);
+      else split_step<WBC_CTRL_PC>(j, i);
     } else if (j->mode == 1) {
       wbc::dynamics_instance(*j->sm, *j->md, j->q, j->v, j->dyn, i, j->lane);
     } else {
@@ -36,16 +49,20 @@ int run(Job proto) {
   memset(sm, 0, sizeof(*sm));
   wbc::PcSmem* pcs = new wbc::PcSmem();
   memset(pcs, 0, sizeof(*pcs));
+  wbc::SolveSmem* ssm = new wbc::SolveSmem();
+  memset(ssm, 0, sizeof(*ssm));
+  std::vector<double> rec(wbc::REC_DOUBLES), vdmap(wbc::VDMAP_DOUBLES);
   std::vector<Job> jobs(32, proto);
   std::vector<pthread_t> th(32);
   for (int l = 0; l < 32; ++l) {
-    jobs[l].warp = &warp; jobs[l].lane = l; jobs[l].sm = sm; jobs[l].pcs = pcs;
+    jobs[l].warp = &warp; jobs[l].lane = l; jobs[l].sm = sm; jobs[l].pcs = pcs; jobs[l].ssm = ssm; jobs[l].rec = rec.data(); jobs[l].vdmap = vdmap.data();
     pthread_create(&th[l], nullptr, lane_main, &jobs[l]);
   }
   for (int l = 0; l < 32; ++l) pthread_join(th[l], nullptr);
   pthread_barrier_destroy(&warp.bar);
   delete sm;
   delete pcs;
+  delete ssm;
   return 0;
 }
 }  // namespace

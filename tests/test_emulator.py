@@ -28,7 +28,7 @@ def run_step(emu, robot, kind, g, **params):
     tau, met, st = np.zeros((n, 12)), np.zeros((n, 4)), np.zeros(n, np.int32)
     vd, f, qi = np.zeros((n, 18)), np.zeros((n, 4, 3)), np.zeros((n, 4))
     io = WbcIO(np_ptr(q), np_ptr(v), np_ptr(traj), np_ptr(contact), np_ptr(tau), np_ptr(met), np_ptr(st), np_ptr(vd), np_ptr(f), np_ptr(qi))
-    assert emu.emu_step(C.byref(ms), C.byref(pr), KINDS[kind], n, C.byref(io)) == 0
+    assert emu.emu_step(C.byref(ms), C.byref(pr), KINDS[kind], n, C.byref(io)) == 0     # reduce -> record -> solve, as on the GPU
     return tau, met, st, vd, f, qi
 
 

@@ -8,6 +8,7 @@ joins that with `ncu --page source --csv` (per-instruction counters of the first
 import collections
 import csv
 import io
+import os
 import re
 import subprocess
 import sys
@@ -22,7 +23,8 @@ def main():
     top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
     cub = "/tmp/ncu_lines.cubin"
     subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-cubin",
-                    f"-I{ROOT}/include", str(ROOT / "quadruped_drake_b200/csrc/wbc_api.cu"), "-o", cub], check=True)
+                    f"-I{ROOT}/include", *os.environ.get("NCU_LINES_FLAGS", "").split(),   # e.g. -DWBC_SOLVE_CTAS=4 for a variant build
+                    str(ROOT / "quadruped_drake_b200/csrc/wbc_api.cu"), "-o", cub], check=True)
     sass = subprocess.run(["nvdisasm", "-g", "-c", cub], capture_output=True, text=True).stdout.split("\n")
     start = next(i for i, l in enumerate(sass) if l.startswith(".text.") and kern in l)
     cur, off2line = None, {}
