@@ -21,13 +21,30 @@ constexpr int WARPS = 4;  // instances (warps) per CTA
 
 struct alignas(16) DevConst { wbc_model md; wbc_params pr; wbc::Derived dv; };
 
+// CTA-level input staging of the reduce kernels: the rows of the CTA's WARPS consecutive instances are contiguous in the
+// caller's arrays, so each array arrives with ONE bulk copy (608 + 576 + 1728 + 16 bytes) instead of 8-byte loads per lane -
+// few large requests, which is what the host link wants when the buffers are page-locked host memory (zero-copy path).
+struct alignas(16) InStage {
+  double q[WARPS * WBC_NQ];
+  double v[WARPS * WBC_NV];
+  double traj[WARPS * WBC_NTRAJ];
+  uint8_t contact[WARPS * 4];
+  uint8_t pad[16 - (WARPS * 4) % 16];
+  unsigned long long mbar;
+  unsigned long long pad2;
+};
+static_assert((WARPS * WBC_NQ * 8) % 16 == 0 && (WARPS * WBC_NV * 8) % 16 == 0 && (WARPS * WBC_NTRAJ * 8) % 16 == 0 && (WARPS * 4) % 16 == 0,
+              "per-CTA input blocks must be multiples of 16 bytes for the bulk copies");
+
 struct SmemLayout {
   DevConst dc;
+  InStage in;
   wbc::WarpSmem w[WARPS];
 };
 
 struct SmemLayoutPC {       // PC controller / Coriolis entry: extra operational-space workspace per warp
   DevConst dc;
+  InStage in;
   wbc::WarpSmem w[WARPS];
   wbc::PcSmem pc[WARPS];
 };
@@ -57,10 +74,14 @@ __device__ __forceinline__ const DevConst& stage_consts(L* sm, const DevConst* g
 //                      hidden by 1.75x more resident instances than the fused kernel could hold.
 // The 4 KB block moves shared -> global and global -> shared with one bulk asynchronous copy each (TMA 1-D), issued by one
 // lane; the solve warp waits on an mbarrier.
+#ifndef WBC_SOLVE_WARPS
+#define WBC_SOLVE_WARPS 1      // one warp per CTA: the shared-memory block sits at a compile-time address, so no per-warp base
+#endif                         // (thread index -> warp -> offset) has to be kept live or re-derived under the 72-register budget
 #ifndef WBC_SOLVE_CTAS
-#define WBC_SOLVE_CTAS 7
+#define WBC_SOLVE_CTAS (28 / WBC_SOLVE_WARPS)
 #endif
-struct SmemLayoutSolve { wbc::SolveSmem w[WARPS]; };
+constexpr int SOLVE_WARPS = WBC_SOLVE_WARPS;
+struct SmemLayoutSolve { wbc::SolveSmem w[SOLVE_WARPS]; };
 static_assert(sizeof(wbc::SolveSmem) % 16 == 0, "SolveSmem must keep 16-byte alignment per warp");
 static_assert(offsetof(wbc::WarpSmem, Y) % 16 == 0 && sizeof(wbc::WarpSmem) % 16 == 0 && sizeof(DevConst) % 16 == 0, "bulk copy alignment");
 static_assert(offsetof(wbc::WarpSmem, cw) == offsetof(wbc::WarpSmem, Y) + sizeof(double) * wbc::YROWS * wbc::YS &&
@@ -85,6 +106,11 @@ __device__ __forceinline__ void bulk_load(void* sdst, const void* gsrc, unsigned
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(sdst)),
                "l"(gsrc), "r"(bytes), "r"(b)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_load_on(void* sdst, const void* gsrc, unsigned bytes, unsigned bar_smem) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(sdst)),
+               "l"(gsrc), "r"(bytes), "r"(bar_smem)
                : "memory");
 }
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
@@ -113,30 +139,54 @@ __device__ __forceinline__ void store_record(double* r, const wbc::StepCarry& c,
   if (c.ok) bulk_store(r, &s.Y[0][0], REC_Y_BYTES);
 }
 
+// Issues the CTA's four input bulk copies (thread 0) - call before stage_consts so that they fly during the constant staging -
+// and, after the CTA barrier inside stage_consts, waits for them. Returns false when this CTA must use the per-lane path
+// (tail CTA with fewer than WARPS instances, or buffers that are not 16-byte aligned: `bulk_ok` from the host).
+__device__ __forceinline__ bool stage_inputs_issue(InStage& in, const wbc::StepArgs& a, bool bulk_ok) {
+  const long long first = (long long)blockIdx.x * WARPS;
+  const bool full = bulk_ok && first + WARPS <= a.n;
+  if (full && threadIdx.x == 0) {
+    const unsigned b = smem_addr(&in.mbar);
+    const unsigned bytes = WARPS * (WBC_NQ + WBC_NV + WBC_NTRAJ) * 8 + WARPS * 4;
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+    bulk_load_on(in.q, a.q + first * WBC_NQ, WARPS * WBC_NQ * 8, b);
+    bulk_load_on(in.v, a.v + first * WBC_NV, WARPS * WBC_NV * 8, b);
+    bulk_load_on(in.traj, a.traj + first * WBC_NTRAJ, WARPS * WBC_NTRAJ * 8, b);
+    bulk_load_on(in.contact, a.contact + first * 4, WARPS * 4, b);
+  }
+  return full;
+}
+
 template <int KIND>
 __global__ void WBC_STEP_BOUNDS wbc_reduce_kernel(const DevConst* __restrict__ gdc, wbc::StepArgs a, double* __restrict__ rec,
-                                                  double* __restrict__ vdmap) {
+                                                  double* __restrict__ vdmap, int bulk_ok) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SmemLayout* sm = reinterpret_cast<SmemLayout*>(smem_raw);
+  const bool staged = stage_inputs_issue(sm->in, a, bulk_ok != 0);
   const DevConst& dc = stage_consts(sm, gdc);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long inst = (long long)blockIdx.x * WARPS + warp;
   if (inst >= a.n) return;
   wbc::WarpSmem& s = sm->w[warp];
   wbc::StepCarry c;
-  wbc::reduce_instance<KIND>(s, dc.md, dc.pr, dc.dv, a, inst, lane, c, nullptr, vdmap ? vdmap + inst * wbc::VDMAP_DOUBLES : nullptr);
+  wbc::StagedInputs in{sm->in.q + warp * WBC_NQ, sm->in.v + warp * WBC_NV, sm->in.traj + warp * WBC_NTRAJ, sm->in.contact + warp * 4};
+  if (staged) mbar_wait(&sm->in.mbar, 0);
+  wbc::reduce_instance<KIND>(s, dc.md, dc.pr, dc.dv, a, inst, lane, c, nullptr, vdmap ? vdmap + inst * wbc::VDMAP_DOUBLES : nullptr,
+                             staged ? &in : nullptr);
   __syncwarp();
   if (lane == 0) store_record(rec + inst * wbc::REC_DOUBLES, c, s);
 }
 
 template <int KIND>
-__global__ void __launch_bounds__(WARPS * 32, WBC_SOLVE_CTAS) wbc_solve_kernel(const DevConst* __restrict__ gdc, wbc::StepArgs a,
+__global__ void __launch_bounds__(SOLVE_WARPS * 32, WBC_SOLVE_CTAS) wbc_solve_kernel(const DevConst* __restrict__ gdc, wbc::StepArgs a,
                                                                                const double* __restrict__ rec,
                                                                                const double* __restrict__ vdmap) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SmemLayoutSolve* sm = reinterpret_cast<SmemLayoutSolve*>(smem_raw);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long inst = (long long)blockIdx.x * WARPS + warp;
+  const int warp = SOLVE_WARPS == 1 ? 0 : (int)(threadIdx.x >> 5), lane = threadIdx.x & 31;
+  const long long inst = (long long)blockIdx.x * SOLVE_WARPS + warp;
   if (inst >= a.n) return;
   wbc::SolveSmem& s = sm->w[warp];
   const double* r = rec + inst * wbc::REC_DOUBLES;
@@ -155,16 +205,21 @@ __global__ void __launch_bounds__(WARPS * 32, WBC_SOLVE_CTAS) wbc_solve_kernel(c
 
 // PC / MPTC reduce half: same hand-over, extra operational-space workspace per warp (3 CTAs / SM).
 __global__ void __launch_bounds__(WARPS * 32, 3) wbc_reduce_pc_kernel(const DevConst* __restrict__ gdc, wbc::StepArgs a,
-                                                                      double* __restrict__ rec, double* __restrict__ vdmap) {
+                                                                      double* __restrict__ rec, double* __restrict__ vdmap,
+                                                                      int bulk_ok) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SmemLayoutPC* sm = reinterpret_cast<SmemLayoutPC*>(smem_raw);
+  const bool staged = stage_inputs_issue(sm->in, a, bulk_ok != 0);
   const DevConst& dc = stage_consts(sm, gdc);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long inst = (long long)blockIdx.x * WARPS + warp;
   if (inst >= a.n) return;
   wbc::WarpSmem& s = sm->w[warp];
   wbc::StepCarry c;
-  wbc::reduce_instance<WBC_CTRL_PC>(s, dc.md, dc.pr, dc.dv, a, inst, lane, c, &sm->pc[warp], vdmap ? vdmap + inst * wbc::VDMAP_DOUBLES : nullptr);
+  wbc::StagedInputs in{sm->in.q + warp * WBC_NQ, sm->in.v + warp * WBC_NV, sm->in.traj + warp * WBC_NTRAJ, sm->in.contact + warp * 4};
+  if (staged) mbar_wait(&sm->in.mbar, 0);
+  wbc::reduce_instance<WBC_CTRL_PC>(s, dc.md, dc.pr, dc.dv, a, inst, lane, c, &sm->pc[warp], vdmap ? vdmap + inst * wbc::VDMAP_DOUBLES : nullptr,
+                                    staged ? &in : nullptr);
   __syncwarp();
   if (lane == 0) store_record(rec + inst * wbc::REC_DOUBLES, c, s);
 }
@@ -430,6 +485,13 @@ static wbc::StepArgs offset_args(const wbc_io* io, int64_t o, int64_t m, int kin
                        io->f ? io->f + o * 12 : nullptr, io->qp_info ? io->qp_info + o * 4 : nullptr, (long long)m, kind};
 }
 
+static bool aligned16p(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+static int bulk_in_mode() {   // WBC_BULK_IN=0: per-lane input loads everywhere (A/B comparisons)
+  static int mode = -1;
+  if (mode < 0) { const char* e = getenv("WBC_BULK_IN"); mode = e ? atoi(e) : 1; }
+  return mode;
+}
+
 template <int KIND>
 static int launch_split(wbc_handle* h, int kind, int64_t n, const wbc_io* io, cudaStream_t st, int slot) {
   int rc = ensure_split_scratch(h, slot, n, io->vd != nullptr);
@@ -439,9 +501,11 @@ static int launch_split(wbc_handle* h, int kind, int64_t n, const wbc_io* io, cu
     const int64_t m = (n - o) < SPLIT_CHUNK ? (n - o) : SPLIT_CHUNK;
     const wbc::StepArgs a = offset_args(io, o, m, kind);
     const unsigned grid = (unsigned)((m + WARPS - 1) / WARPS);
-    if constexpr (KIND == WBC_CTRL_PC) wbc_reduce_pc_kernel<<<grid, WARPS * 32, sizeof(SmemLayoutPC), st>>>(h->d_const, a, h->d_rec[slot], vdmap);
-    else wbc_reduce_kernel<KIND><<<grid, WARPS * 32, sizeof(SmemLayout), st>>>(h->d_const, a, h->d_rec[slot], vdmap);
-    wbc_solve_kernel<KIND><<<grid, WARPS * 32, sizeof(SmemLayoutSolve), st>>>(h->d_const, a, h->d_rec[slot], vdmap);
+    // bulk input staging needs 16-byte aligned rows at the CTA boundaries (chunk offsets are multiples of WARPS)
+    const int bulk_ok = bulk_in_mode() && aligned16p(a.q) && aligned16p(a.v) && aligned16p(a.traj) && aligned16p(a.contact);
+    if constexpr (KIND == WBC_CTRL_PC) wbc_reduce_pc_kernel<<<grid, WARPS * 32, sizeof(SmemLayoutPC), st>>>(h->d_const, a, h->d_rec[slot], vdmap, bulk_ok);
+    else wbc_reduce_kernel<KIND><<<grid, WARPS * 32, sizeof(SmemLayout), st>>>(h->d_const, a, h->d_rec[slot], vdmap, bulk_ok);
+    wbc_solve_kernel<KIND><<<(unsigned)((m + SOLVE_WARPS - 1) / SOLVE_WARPS), SOLVE_WARPS * 32, sizeof(SmemLayoutSolve), st>>>(h->d_const, a, h->d_rec[slot], vdmap);
     h->launches += 2;
   }
   return WBC_OK;
@@ -515,10 +579,14 @@ extern "C" int wbc_step_host(wbc_handle* h, int kind, int64_t n, const wbc_io* i
   // its 732 B of inputs and writes its 132 B of outputs per instance straight over the host link - one launch, no
   // staging copies, the transfers of one warp overlap the arithmetic of the others.
   {
-    int mode = 1;
+    int mode = -1;   // auto; WBC_HOST_ZEROCOPY=0 / 1 forces the staged / zero-copy path (experiments)
     if (const char* env = getenv("WBC_HOST_ZEROCOPY")) mode = atoi(env);
     const void* ptrs[10] = {io->q, io->v, io->traj, io->contact, io->tau, io->metrics, io->status, io->vd, io->f, io->qp_info};
     void* dev[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    // Measured on B200 (profiles/README.md): zero-copy wins up to ~10^5 instances per call (no staging copies, no extra API
+    // calls; the host link delivers ~32 GB/s to the SMs); above that the copy engines (~55 GB/s) in a chunked two-stream
+    // pipeline win, so large page-locked batches take the staged path below with 65536-instance chunks.
+    if (mode < 0) mode = n >= 131072 ? 0 : 1;
     bool pinned = mode != 0;
     for (int i = 0; i < 10 && pinned; ++i) {
       if (!ptrs[i]) continue;
@@ -557,8 +625,8 @@ extern "C" int wbc_step_host(wbc_handle* h, int kind, int64_t n, const wbc_io* i
   if (rc) return rc;
   // Chunked two-stream pipeline: the upload of chunk c + 1 overlaps the kernel of chunk c, the download of chunk c the
   // kernel of chunk c + 1 (separate copy engines); small batches go through in one piece.
-  int n_chunks = n >= 2048 ? 2 : 1;
-  if (const char* env = getenv("WBC_HOST_CHUNKS")) { const int v = atoi(env); if (v >= 1 && v <= 16) n_chunks = v; }
+  int n_chunks = n >= 131072 ? (int)((n + 65535) / 65536 > 64 ? 64 : (n + 65535) / 65536) : (n >= 2048 ? 2 : 1);
+  if (const char* env = getenv("WBC_HOST_CHUNKS")) { const int v = atoi(env); if (v >= 1 && v <= 64) n_chunks = v; }
   if ((int64_t)n_chunks > n) n_chunks = (int)n;
   const int64_t per = (n + n_chunks - 1) / n_chunks;
   cudaStream_t lanes[2] = {h->stream, h->stream2};

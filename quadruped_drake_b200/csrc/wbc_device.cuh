@@ -102,13 +102,19 @@ struct alignas(16) WarpSmem {
 struct alignas(16) SolveSmem {
   alignas(16) double Y[YROWS][YS];
   double cw[YROWS], ct[YROWS];
-  union { double H[NF][NF]; double J[NF][NF]; };
-  double g[NF];
-  double R[NF][NF];
-  double d[NF], x[NF], u[NF], npv[NF], dm[NF], y[YROWS];
+  double H[NF][NF];                       // reduced Hessian -> its Cholesky factor L (lower triangle, in place)
+  double Rp[NF * (NF + 3) / 2];           // R of the active set, transposed and packed: column c keeps rows 0..c+1 (the
+                                          // sub-diagonal entry exists only while a dropped column is rotated away)
+  double d[NF];                           // 1 / L[k][k]
+  union { double g[NF]; double dm[NF]; }; // reduced gradient (start-up only) / the current d = J'n
+  union { double npv[NF]; double x[NF]; };// b = L^-1 g (start-up only) / recovered w (exit only)
+  double u[NF], y[YROWS];
   int act[NF];
-  alignas(8) unsigned long long mbar;   // completion barrier of the bulk copy
+  alignas(8) unsigned long long mbar;     // completion barrier of the bulk copy
 };
+static_assert(sizeof(SolveSmem) <= 7312, "28 single-warp CTAs of the solve kernel must fit one SM (228 KB, 1 KB reserved per CTA)");
+// entry (row, col) of R, row <= col + 1
+template <class SM> WBC_DEV double& Rent(SM& s, int col, int row) { return s.Rp[col * (col + 3) / 2 + row]; }
 constexpr int REC_Y = YROWS * YS + 2 * YROWS;   // doubles of [Y | cw | ct]
 constexpr int REC_MISC = 16;                    // status, cmask, nf, nextra, ok, extra_bound, err, Vl, PFl, csum, Vpc
 constexpr int REC_DOUBLES = REC_Y + REC_MISC;   // one record of the reduce -> solve hand-over (4224 B)
@@ -821,7 +827,7 @@ template <int N, class SM> WBC_DEV int gi_solve_ws(SM& s, int lane, const IneqSe
       // r = R^-1 d[:q]  (back substitution; lane k owns r_k; R is kept transposed: R[col][row])
       double rk = dself;
       for (int jj = q - 1; jj >= 0; --jj) {
-        const double rl = s.R[jj][li];
+        const double rl = Rent(s, jj, li);
         const double rj = shfl(rk * rinvl, jj);
         if (lane < jj) rk = fma(-rl, rj, rk);
       }
@@ -857,8 +863,8 @@ template <int N, class SM> WBC_DEV int gi_solve_ws(SM& s, int lane, const IneqSe
           }
           rqq = alpha;
         }
-        if (lane < q) s.R[q][lane] = dself;
-        if (lane == q) { s.R[q][q] = rqq; rinvl = frcp(rqq); ul = up; actl = p; }
+        if (lane < q) Rent(s, q, lane) = dself;
+        if (lane == q) { Rent(s, q, q) = rqq; rinvl = frcp(rqq); ul = up; actl = p; }
         activemask |= 1ull << p;
         ++q;
         __syncwarp();
@@ -868,25 +874,24 @@ template <int N, class SM> WBC_DEV int gi_solve_ws(SM& s, int lane, const IneqSe
       {
         const int dropped = shfl(actl, l);
         activemask &= ~(1ull << dropped);
-        if (row) {
-          for (int jj = l; jj < q - 1; ++jj) s.R[jj][lane] = s.R[jj + 1][lane];
-          s.R[q - 1][lane] = 0.0;
-        }
+        // shift the columns right of l one place left: the triangle becomes upper Hessenberg from column l on
+        for (int jj = l; jj < q - 1; ++jj) { if (lane <= jj + 1) Rent(s, jj, lane) = Rent(s, jj + 1, lane); }
+        if (lane <= q) Rent(s, q - 1, lane) = 0.0;
         const double un = __shfl_down_sync(WBC_FULL, ul, 1);
         const int an = __shfl_down_sync(WBC_FULL, actl, 1);
         if (lane >= l && lane < q - 1) { ul = un; actl = an; }
         __syncwarp();
         // Givens rotations restoring the triangle; same rotations on the columns of W
         for (int k = l; k < q - 1; ++k) {
-          const double a = s.R[k][k], b = s.R[k][k + 1];   // R[k][k], R[k+1][k]
+          const double a = Rent(s, k, k), b = Rent(s, k, k + 1);   // R[k][k], R[k+1][k]
           const double r2 = a * a + b * b;
           __syncwarp();
           if (r2 > 0.0) {
             const double irr = frsqrt(r2);
             const double c = a * irr, sn = b * irr;
-            if (row) {
-              const double r0 = s.R[lane][k], r1 = s.R[lane][k + 1];
-              s.R[lane][k] = c * r0 + sn * r1; s.R[lane][k + 1] = -sn * r0 + c * r1;
+            if (row && lane >= k) {                        // rows k, k+1 are zero left of column k
+              const double r0 = Rent(s, lane, k), r1 = Rent(s, lane, k + 1);
+              Rent(s, lane, k) = c * r0 + sn * r1; Rent(s, lane, k + 1) = -sn * r0 + c * r1;
               if (lane == k) rinvl = frcp(c * r0 + sn * r1);
             }
             const double w0 = Wl[k], w1 = Wl[k + 1];
@@ -902,10 +907,10 @@ template <int N, class SM> WBC_DEV int gi_solve_ws(SM& s, int lane, const IneqSe
   if (lane < q) { s.u[lane] = ul; s.act[lane] = actl; }
   if (Yg) {
     // x = H^-1 Y' C (y - y0)   (exact: y - y0 = Y x and H = Y' C Y); the original Y is read back from the record
-    s.R[0][lane] = s.cw[lane] * (yl - Wl[NF]);            // R is free now: 32 doubles of scratch
+    s.Rp[lane] = s.cw[lane] * (yl - Wl[NF]);              // R is free now: 32 doubles of scratch
     __syncwarp();
     double gk = 0.0;
-    const double* ev = &s.R[0][0];
+    const double* ev = &s.Rp[0];
     for (int r = 0; r < YROWS; ++r) gk = fma(Yg[r * YS + li], ev[r], gk);
     const double bl = tri_fwd_lane<N>(s, lane, gk);
     const double xl = tri_bwd_lane<N>(s, lane, bl);
@@ -1235,6 +1240,9 @@ WBC_DEV void pc_rows(WarpSmem& s, const PcSmem& pc, int lane, int ycol, int m) {
 // ------------------------------------------------------------------------------ the step
 // One control step of instance `inst` (DoSetControlTorques -> ControlLaw,
 // basic_controller.py:286-320). KIND selects the cost / extra rows.
+// One instance's input rows inside the CTA-level staging block of the reduce kernels.
+struct StagedInputs { const double* q; const double* v; const double* traj; const uint8_t* contact; };
+
 // What the solve half needs from the reduce half besides [Y | cw | ct]: registers in the fused kernels, the `misc` words of
 // the hand-over record in the split path.
 struct StepCarry {
@@ -1245,15 +1253,25 @@ struct StepCarry {
 // Phases 0-4 + cost rows: state -> reduced problem [Y | cw | ct] in s (and the joint-acceleration maps in `vdmap`, if given).
 template <int KIND>
 WBC_DEV void reduce_instance(WarpSmem& s, const wbc_model& md, const wbc_params& pr, const Derived& dv, const StepArgs& a,
-                             long long inst, int lane, StepCarry& c, PcSmem* pcs = nullptr, double* vdmap = nullptr) {
+                             long long inst, int lane, StepCarry& c, PcSmem* pcs = nullptr, double* vdmap = nullptr,
+                             const StagedInputs* in = nullptr) {
   int status = 0;
-  // ---- phase 0: coalesced loads into shared memory
-  for (int i = lane; i < WBC_NQ; i += 32) s.q[i] = a.q[inst * WBC_NQ + i];
-  for (int i = lane; i < WBC_NV; i += 32) s.v[i] = a.v[inst * WBC_NV + i];
-  for (int i = lane; i < WBC_NTRAJ; i += 32) async_copy8(&s.traj[i], a.traj + inst * WBC_NTRAJ + i);   // waited for after phase 1
   unsigned cmask = 0;
+  if (in) {
+    // ---- phase 0, staged: the CTA's input rows already sit in shared memory (one bulk copy per array and CTA)
+    for (int i = lane; i < WBC_NQ; i += 32) s.q[i] = in->q[i];
+    for (int i = lane; i < WBC_NV; i += 32) s.v[i] = in->v[i];
+    for (int i = lane; i < WBC_NTRAJ; i += 32) s.traj[i] = in->traj[i];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) cmask |= (a.contact[inst * 4 + k] ? 1u : 0u) << k;
+    for (int k = 0; k < 4; ++k) cmask |= (in->contact[k] ? 1u : 0u) << k;
+  } else {
+    // ---- phase 0: coalesced loads into shared memory
+    for (int i = lane; i < WBC_NQ; i += 32) s.q[i] = a.q[inst * WBC_NQ + i];
+    for (int i = lane; i < WBC_NV; i += 32) s.v[i] = a.v[inst * WBC_NV + i];
+    for (int i = lane; i < WBC_NTRAJ; i += 32) async_copy8(&s.traj[i], a.traj + inst * WBC_NTRAJ + i);   // waited for after phase 1
+#pragma unroll
+    for (int k = 0; k < 4; ++k) cmask |= (a.contact[inst * 4 + k] ? 1u : 0u) << k;
+  }
   const int nc = __popc(cmask);
   __syncwarp();
   // ---- phase 1
