@@ -3,7 +3,8 @@
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
-A "step" is one launch of the hot path (dynamics + ID-QP) over one batch of synthetic states.
+A "step" is one pass of the hot path (dynamics + ID-QP: the reduce kernel and the solve kernel, back to back on one
+stream) over one batch of synthetic states.
 Workload at N = 1: BASELINE.json configs[1] - mini_cheetah ID-QP, 4096 random states per launch, all
 four feet in stance. With N > 1 (torchrun, one rank per GPU) every rank runs the same
 batch size on its own shard of instances: weak scaling, no collective on the data path.
@@ -262,6 +263,12 @@ def run_gpu(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms = float(t.item())
     clocks = sampler.stop() if rank == 0 else None
+    # per-kernel share of the step (events between the two kernels; separate short run, same inputs)
+    ms_r, ms_s = C.c_double(), C.c_double()
+    shares = None
+    if n <= 262144 and ctl.lib.wbc_profile_step(ctl._h, kind, n, C.byref(io), 20, C.c_void_p(stream.cuda_stream), C.byref(ms_r), C.byref(ms_s)) == 0:
+        shares = {"reduce_kernel_ms": ms_r.value, "solve_kernel_ms": ms_s.value,
+                  "solve_share": ms_s.value / max(ms_r.value + ms_s.value, 1e-12)}
 
     # ---- end to end through the host API: pinned host buffers, H2D + kernel + D2H every step
     hq, hv, ht = capi.pinned_empty((n, 19)), capi.pinned_empty((n, 18)), capi.pinned_empty((n, 54))
@@ -311,18 +318,23 @@ def run_gpu(args):
                    "instances_per_step_per_gpu": n, "l2": "flushed between timed launches (256 MB memset outside the event pair)",
                    "mean_active_set_iterations": iters, "tie_break_reg_f": 1e-6},
         "e2e": {"value": world * n * args.steps / e2e_s, "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "path": "wbc_step_host on page-locked host buffers: the kernel reads its inputs from and writes its outputs to host "
-                        "memory over the host link inside the timed region (zero-copy; pageable buffers take the staged two-stream path)"},
+                "path": "wbc_step_host on page-locked host buffers, inputs and outputs cross the host link inside the timed region: the kernels "
+                        "read / write host memory directly (zero-copy, below 131072 instances per call) or the batch goes through the "
+                        "65536-instance two-stream copy / compute pipeline (above; also the path of pageable buffers)"},
         "gpu_launches": int(gpu_launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
                      "traffic": traffic, "peak_source": peak_src,
-                     "note": "860 B/step of algorithmic I/O: this path is FP64-latency bound, not HBM bound (see roofline_fp64)"},
+                     "kernels": shares,
+                     "note": "860 B/step of algorithmic I/O over the whole step (reduce + solve kernel; the dominant one is the solve kernel, "
+                             "share in `kernels`): this path is bound by FP64 dependent-instruction latency and the shared-memory pipe, not by "
+                             "HBM (see roofline_fp64)"},
         "roofline_fp64": {"achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach_tf / fp64_peak,
                           "flops_per_step": exec_flops,
                           "basis": "EXECUTED FP64 work: thread-level DFMA x2 + DMUL + DADD per instance from the committed ncu capture of "
-                                   "the headline workload (profiles/traffic.json) x measured steps/s; the kernel is bound by dependent-"
-                                   "instruction latency at 16 resident warps per SM, not by the FP64 pipe (DESIGN.md 3)",
+                                   "the headline workload (profiles/traffic.json) x measured steps/s; both kernels are bound by dependent-"
+                                   "instruction latency and shared-memory wavefronts at 16 / 28 resident warps per SM, not by the FP64 pipe "
+                                   "(DESIGN.md 3)",
                           "peak_source": "DFMA loop measured in this run (wbc_measure_fp64_peak)",
                           "canonical": {"flops_per_step": canon, "tflops_equivalent": canon * n / (kernel_ms * 1e-3) / 1e12,
                                         "note": "SURVEY 8d F(nc=4): 12 interior-point iterations on the reference-size KKT system. The "

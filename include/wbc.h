@@ -153,7 +153,9 @@ int wbc_coriolis_host(wbc_handle* h, int64_t n, const double* q, const double* v
 
 /* One control step for n instances: DoSetControlTorques -> ControlLaw
  * (basic_controller.py:286-320; inverse_dynamics_controller.py:103-234;
- * clf_controller.py:48-234; pc_controller.py:43-255). Device pointers. */
+ * clf_controller.py:48-234; pc_controller.py:43-255). Device pointers (or page-locked host memory mapped into the
+ * device address space). The step uses per-handle scratch (4.5 KB per instance, at most 262144 instances at a time): calls
+ * on one handle must not overlap on the device, i.e. use one stream per handle or order the streams yourself. */
 int wbc_step(wbc_handle* h, int kind, int64_t n, const wbc_io* io, void* stream);
 int wbc_step_id(wbc_handle* h, int64_t n, const double* q, const double* v, const double* traj,
                 const uint8_t* contact, double* tau, double* metrics, int32_t* status, void* stream);
@@ -166,9 +168,10 @@ int wbc_step_mptc(wbc_handle* h, int64_t n, const double* q, const double* v, co
 /* BasicController.ControlLaw (basic_controller.py:322-352); traj / contact are ignored and may be NULL. */
 int wbc_step_pd(wbc_handle* h, int64_t n, const double* q, const double* v, double* tau, void* stream);
 
-/* Same step with HOST buffers (what the Python LeafSystem shim calls): copies the
- * inputs to the device, runs wbc_step, copies tau/metrics/status (and any optional
- * outputs that are non-NULL) back, and synchronises. */
+/* Same step with HOST buffers (what the Python LeafSystem shim calls); returns after tau / metrics / status (and any
+ * optional outputs that are non-NULL) are in the caller's buffers. Page-locked buffers (wbc_host_alloc /
+ * cudaHostRegister): below 131072 instances the kernels read and write them directly over the host link (zero-copy),
+ * above that - and for pageable buffers - the batch goes through a chunked two-stream copy / compute pipeline. */
 int wbc_step_host(wbc_handle* h, int kind, int64_t n, const wbc_io* host_io);
 
 /* Host-buffer version of wbc_dynamics (allocates device scratch per call; a test/debug entry). */
@@ -184,6 +187,12 @@ void wbc_host_free(void* p);
  * recorded on that same stream). */
 int wbc_time_step(wbc_handle* h, int kind, int64_t n, const wbc_io* io, int reps, void* stream,
                   double* ms_per_launch);
+
+/* Per-kernel share of a control step. A step is two stream-ordered kernels: the reduce kernel (state -> dynamics ->
+ * reduced QP, one hand-over record per instance in library-owned device scratch) and the solve kernel (active-set QP ->
+ * tau / metrics / status). Events are recorded before, between and after them; means over `reps` steps. n <= 262144. */
+int wbc_profile_step(wbc_handle* h, int kind, int64_t n, const wbc_io* io, int reps, void* stream,
+                     double* ms_reduce, double* ms_solve);
 
 /* Measured-peak helper: FP64 FMA throughput of this device in TFLOP/s (a register
  * resident DFMA loop over all SMs), used as the FP64 roofline denominator. */

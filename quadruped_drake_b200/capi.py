@@ -112,6 +112,8 @@ def load_library() -> C.CDLL:
     lib.wbc_step_pd.restype = C.c_int
     lib.wbc_step_host.argtypes = [H, i32, i64, C.POINTER(WbcIO)]
     lib.wbc_time_step.argtypes = [H, i32, i64, C.POINTER(WbcIO), i32, dp, C.POINTER(C.c_double)]
+    lib.wbc_profile_step.argtypes = [H, i32, i64, C.POINTER(WbcIO), i32, dp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    lib.wbc_profile_step.restype = C.c_int
     lib.wbc_measure_fp64_peak.argtypes = [i32, C.POINTER(C.c_double)]
     lib.wbc_dynamics_host.argtypes = [H, i64] + [dp] * 8
     lib.wbc_dynamics_host.restype = C.c_int
@@ -154,7 +156,7 @@ WIRE_SYMBOLS = ["wbc_lcm_decode_trunk_state", "wbc_lcm_encode_trunk_state", "wbc
 ROLLOUT_SYMBOLS = ["wbc_integrate", "wbc_rollout", "wbc_rollout_host"]
 TRAJ_SYMBOLS = ROLLOUT_SYMBOLS + ["wbc_plan_create", "wbc_plan_destroy", "wbc_sample_trajectory", "wbc_sample_trajectory_host"]
 EXPORTED_SYMBOLS = WIRE_SYMBOLS + TRAJ_SYMBOLS + ["wbc_default_params", "wbc_create", "wbc_destroy", "wbc_last_error", "wbc_dynamics", "wbc_coriolis",
-                    "wbc_step", "wbc_step_id", "wbc_step_clf", "wbc_step_pc", "wbc_step_mptc", "wbc_step_pd", "wbc_step_host", "wbc_time_step",
+                    "wbc_step", "wbc_step_id", "wbc_step_clf", "wbc_step_pc", "wbc_step_mptc", "wbc_step_pd", "wbc_step_host", "wbc_time_step", "wbc_profile_step",
                     "wbc_measure_fp64_peak", "wbc_launch_count", "wbc_dynamics_host", "wbc_coriolis_host", "wbc_host_alloc", "wbc_host_free"]
 
 

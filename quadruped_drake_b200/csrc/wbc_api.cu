@@ -285,6 +285,8 @@ struct wbc_handle {
   int32_t* ro_status = nullptr;
   int* ro_counter = nullptr;
   // hand-over records of the split step (reduce -> solve), one slot per internal stream lane
+  cudaEvent_t prof_ev[3] = {nullptr, nullptr, nullptr};   // wbc_profile_step: before reduce / between / after solve
+  bool prof_on = false;
   double* d_rec[2] = {nullptr, nullptr};
   double* d_vdmap[2] = {nullptr, nullptr};
   int64_t rec_cap[2] = {0, 0}, vdmap_cap[2] = {0, 0};
@@ -391,6 +393,7 @@ extern "C" int wbc_destroy(wbc_handle* h) {
   cudaFree(h->ro_traj); cudaFree(h->ro_vd); cudaFree(h->ro_metrics); cudaFree(h->ro_tau); cudaFree(h->ro_t);
   cudaFree(h->ro_contact); cudaFree(h->ro_status); cudaFree(h->ro_counter);
   for (int i = 0; i < 2; ++i) { cudaFree(h->d_rec[i]); cudaFree(h->d_vdmap[i]); }
+  for (int i = 0; i < 3; ++i) if (h->prof_ev[i]) cudaEventDestroy(h->prof_ev[i]);
   if (h->stream) cudaStreamDestroy(h->stream);
   if (h->stream2) cudaStreamDestroy(h->stream2);
   delete h;
@@ -503,9 +506,12 @@ static int launch_split(wbc_handle* h, int kind, int64_t n, const wbc_io* io, cu
     const unsigned grid = (unsigned)((m + WARPS - 1) / WARPS);
     // bulk input staging needs 16-byte aligned rows at the CTA boundaries (chunk offsets are multiples of WARPS)
     const int bulk_ok = bulk_in_mode() && aligned16p(a.q) && aligned16p(a.v) && aligned16p(a.traj) && aligned16p(a.contact);
+    if (h->prof_on) cudaEventRecord(h->prof_ev[0], st);
     if constexpr (KIND == WBC_CTRL_PC) wbc_reduce_pc_kernel<<<grid, WARPS * 32, sizeof(SmemLayoutPC), st>>>(h->d_const, a, h->d_rec[slot], vdmap, bulk_ok);
     else wbc_reduce_kernel<KIND><<<grid, WARPS * 32, sizeof(SmemLayout), st>>>(h->d_const, a, h->d_rec[slot], vdmap, bulk_ok);
+    if (h->prof_on) cudaEventRecord(h->prof_ev[1], st);
     wbc_solve_kernel<KIND><<<(unsigned)((m + SOLVE_WARPS - 1) / SOLVE_WARPS), SOLVE_WARPS * 32, sizeof(SmemLayoutSolve), st>>>(h->d_const, a, h->d_rec[slot], vdmap);
+    if (h->prof_on) cudaEventRecord(h->prof_ev[2], st);
     h->launches += 2;
   }
   return WBC_OK;
@@ -709,6 +715,30 @@ extern "C" int wbc_time_step(wbc_handle* h, int kind, int64_t n, const wbc_io* i
   WBC_CUDA(h, cudaEventElapsedTime(&ms, e0, e1));
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   *ms_per_launch = (double)ms / reps;
+  return WBC_OK;
+}
+
+// Per-kernel share of one control step: CUDA events before the reduce kernel, between the two kernels and after the solve
+// kernel, averaged over `reps` steps (n <= 262144 so that the step is one launch pair). Measurement aid for bench.py.
+extern "C" int wbc_profile_step(wbc_handle* h, int kind, int64_t n, const wbc_io* io, int reps, void* stream, double* ms_reduce,
+                                double* ms_solve) {
+  if (!h) return WBC_ERR_ARG;
+  if (!ms_reduce || !ms_solve || reps <= 0 || n <= 0 || n > SPLIT_CHUNK || kind == WBC_CTRL_PD) return fail_arg(h, "wbc_profile_step: bad arguments");
+  WBC_CUDA(h, cudaSetDevice(h->device));
+  for (int i = 0; i < 3; ++i) if (!h->prof_ev[i]) WBC_CUDA(h, cudaEventCreate(&h->prof_ev[i]));
+  double r = 0.0, s = 0.0;
+  for (int k = 0; k < reps; ++k) {
+    h->prof_on = true;
+    const int rc = wbc_step(h, kind, n, io, stream);
+    h->prof_on = false;
+    if (rc) return rc;
+    WBC_CUDA(h, cudaEventSynchronize(h->prof_ev[2]));
+    float a = 0.f, b = 0.f;
+    WBC_CUDA(h, cudaEventElapsedTime(&a, h->prof_ev[0], h->prof_ev[1]));
+    WBC_CUDA(h, cudaEventElapsedTime(&b, h->prof_ev[1], h->prof_ev[2]));
+    r += a; s += b;
+  }
+  *ms_reduce = r / reps; *ms_solve = s / reps;
   return WBC_OK;
 }
 
