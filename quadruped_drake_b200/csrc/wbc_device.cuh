@@ -304,16 +304,19 @@ WBC_DEV void dynamics_phase(WarpSmem& s, const wbc_model& md, int lane, int& sta
   V3 vw = wb, vv = vb, aw = aw0, av = av0;
   V3 a = mk(0, 0, 0), b = mk(0, 0, 0), org = mk(0, 0, 0);
   V3 wpar = wb, vorg = vb;      // (WITH_JD) angular velocity of the own joint's parent and velocity of its origin
+  // each link lane evaluates sin / cos of its OWN joint once; the chain below fetches joint jj's pair from lane (leg, jj)
+  double sn_own, cs_own;
+  sincos(s.q[md.v_index[3 * leg + jl] + 1], &sn_own, &cs_own);
 #pragma unroll
   for (int jj = 0; jj < 3; ++jj) {
+    const double sn = __shfl_sync(WBC_FULL, sn_own, jj, 8), cs = __shfl_sync(WBC_FULL, cs_own, jj, 8);
     if (jj <= jl) {
       const int k = 3 * leg + jj;
       rho = rho + mul(R, ld3(md.joint_xyz[k]));
       const V3 la = ld3(md.joint_axis[k]);
       a = mul(R, la);
       const int vi = md.v_index[k];
-      const double th = s.q[vi + 1], thd = BIAS_ONLY ? vel_int[6 + k] : s.v[vi];
-      double sn, cs; sincos(th, &sn, &cs);
+      const double thd = BIAS_ONLY ? vel_int[6 + k] : s.v[vi];
       // R <- R * Rot(la, th):  Rot e_m = cs e_m + sn (la x e_m) + (1-cs) la (la . e_m)
       const double oc = 1.0 - cs;
       V3 r0 = mk(cs + oc * la.x * la.x, sn * la.z + oc * la.y * la.x, -sn * la.y + oc * la.z * la.x);
@@ -763,12 +766,28 @@ template <int N, class SM> WBC_DEV int gi_solve_ws(SM& s, int lane, const IneqSe
     s.y[lane] = acc + acc1;
   }
   double yl = s.y[lane];
+  __syncwarp();
+  // |J'n_i|^2 = n_i' H^-1 n_i of the constraint(s) this lane watches: invariant under the orthogonal updates of J, so it is
+  // formed once from the initial W (no warp reduction per pivot); scale of the "no free direction left" test below
+  double ddl0 = 0.0, ddl1 = 0.0;
+  {
+    const double* wa = &s.Y[c0.ra][0];
+    const double* wb = &s.Y[c0.rb][0];
+#pragma unroll
+    for (int k = 0; k < N; ++k) { const double t = fma(c0.ca, wa[k], c0.cb * wb[k]); ddl0 = fma(t, t, ddl0); }
+    if (mi > 32) {
+      const Ineq c1 = get_ineq(S, lane + 32 < mi ? lane + 32 : 0);
+      const double* va = &s.Y[c1.ra][0];
+      const double* vb = &s.Y[c1.rb][0];
+#pragma unroll
+      for (int k = 0; k < N; ++k) { const double t = fma(c1.ca, va[k], c1.cb * vb[k]); ddl1 = fma(t, t, ddl1); }
+    }
+  }
   int q = 0, iters = 0;
   unsigned long long activemask = 0ull;
   double ul = 0.0, rinvl = 0.0;     // lane k < q: multiplier and 1 / R[k][k] of active slot k
   int actl = 0;                     // constraint id in slot `lane`
   minslack = 0.0;
-  __syncwarp();
   for (;;) {
     // most violated inequality (y lives in shared memory: every lane reads the two rows its constraint combines)
     double viol = 0.0; int who = 0;
@@ -797,13 +816,12 @@ template <int N, class SM> WBC_DEV int gi_solve_ws(SM& s, int lane, const IneqSe
     const double nca = -cp.ca, ncb = -cp.cb;
     double up = 0.0;
     bool fail = false;
-    double dd = -1.0;   // |J'n|^2: invariant under the orthogonal column updates
+    const double dd = (p < 32) ? shfl(ddl0, p & 31) : shfl(ddl1, p & 31);   // |J'n_p|^2
     for (;;) {
       if (++iters > max_iter) { status |= WBC_ST_MAXITER; fail = true; break; }
       // ---- d = J'n = -(ca W[ra] + cb W[rb]); lane k owns d_k and publishes it
       const double dself = fma(nca, s.Y[cp.ra][li], ncb * s.Y[cp.rb][li]);
       if (row) s.dm[lane] = dself;
-      if (dd < 0.0) dd = warp_sum(row ? dself * dself : 0.0);
       __syncwarp();
       // free part k >= q: the unrolled chain is entered at k = q
       double zn = 0.0, zn1 = 0.0, wd = 0.0, wd1 = 0.0;    // |d[q:]|^2 and (Y z)_lane = W[lane][q:] . d[q:]
