@@ -647,21 +647,28 @@ template <int N, class SM> WBC_DEV void reduced_hessian(SM& s, int lane, int nf,
 
 // In-place Cholesky (lower) of s.H, then J = L^-T (J J' = H^-1) and the unconstrained minimiser x.
 template <int N, class SM> WBC_DEV void cholesky_factor(SM& s, int lane, int& status, const TriPairs& tp) {
+  // Right-looking elimination on the UNSCALED columns, H[i][k] -= H[i][j] H[k][j] / d_j: one shared-memory round trip per
+  // step (the pivot reciprocal is the only dependent special-function chain); the columns are scaled by 1 / sqrt(d_j)
+  // afterwards, all at once.
   for (int j = 0; j < N; ++j) {
     const double dj = s.H[j][j];
     if (!(dj > 1e-300)) { status |= WBC_ST_NOTPD; }
-    const double inv = frsqrt(dj > 1e-300 ? dj : 1.0);
-    __syncwarp();
-    if (lane < N && lane >= j) s.H[lane][j] *= inv;
-    if (lane == 0) s.d[j] = inv;                    // 1 / L[j][j], reused by the triangular inverse below
-    __syncwarp();
+    const double rd = frcp(dj > 1e-300 ? dj : 1.0);
 #pragma unroll
     for (int h = 0; h < 3; ++h) {
       const int i = tp.i[h], k = tp.k[h];
-      if (i >= 0 && k > j) s.H[i][k] = fma(-s.H[i][j], s.H[k][j], s.H[i][k]);
+      if (i >= 0 && k > j) s.H[i][k] = fma(-s.H[i][j] * rd, s.H[k][j], s.H[i][k]);
     }
     __syncwarp();
   }
+  if (lane < N) { const double dk = s.H[lane][lane]; s.d[lane] = frsqrt(dk > 1e-300 ? dk : 1.0); }   // 1 / L[k][k]
+  __syncwarp();
+#pragma unroll
+  for (int h = 0; h < 3; ++h) {
+    const int i = tp.i[h], k = tp.k[h];
+    if (i >= 0) s.H[i][k] *= s.d[k];
+  }
+  __syncwarp();
 }
 // ------------------------------------------------------------------------------ phase 6
 // Inequality i is  ca*y[ra] + cb*y[rb] <= bound  with y = Y w + y0.
@@ -743,29 +750,30 @@ template <int N, class SM> WBC_DEV int gi_solve_ws(SM& s, int lane, const IneqSe
   const Ineq c0 = get_ineq(S, lane < mi ? lane : 0);
   const bool have0 = lane < mi;
   double* Wl = &s.Y[lane][0];                    // row `lane` of W (after the substitution below)
-  // ---- W = Y L^-T in place: forward substitution along the row, L broadcast from shared memory
+  // ---- W = Y L^-T in place (forward substitution along the row, L broadcast from shared memory), interleaved with the
+  //      forward substitution L b = g (lane k owns b_k; the finished component is broadcast by shuffle and consumed at once
+  //      by the unconstrained minimiser in y:  y = y0 - W b)
+  double yl;
   {
     double w[N];
+    const double dinvl = s.d[li];
+    double accb = row ? s.g[li] : 0.0;
+    double ya = Wl[NF], ya1 = 0.0;
 #pragma unroll
     for (int k = 0; k < N; ++k) {
+      const double bk = shfl(accb * dinvl, k);
+      if (lane > k) accb = fma(-s.H[li][k], bk, accb);
       double acc = Wl[k];
 #pragma unroll
       for (int j = 0; j < k; ++j) acc = fma(-w[j], s.H[k][j], acc);
       w[k] = acc * s.d[k];
+      if (k & 1) ya1 = fma(-w[k], bk, ya1); else ya = fma(-w[k], bk, ya);
     }
-    // ---- unconstrained minimiser in y: b = L^-1 g, y = y0 - W b
-    const double bl = tri_fwd_lane<N>(s, lane, s.g[li]);
-    if (row) s.npv[lane] = bl;
-    __syncwarp();
-    double acc = Wl[NF], acc1 = 0.0;
 #pragma unroll
-    for (int k = 0; k < N; ++k) {
-      Wl[k] = w[k];
-      if (k & 1) acc1 = fma(-w[k], s.npv[k], acc1); else acc = fma(-w[k], s.npv[k], acc);
-    }
-    s.y[lane] = acc + acc1;
+    for (int k = 0; k < N; ++k) Wl[k] = w[k];
+    yl = ya + ya1;
+    s.y[lane] = yl;
   }
-  double yl = s.y[lane];
   __syncwarp();
   // |J'n_i|^2 = n_i' H^-1 n_i of the constraint(s) this lane watches: invariant under the orthogonal updates of J, so it is
   // formed once from the initial W (no warp reduction per pivot); scale of the "no free direction left" test below
@@ -788,13 +796,13 @@ template <int N, class SM> WBC_DEV int gi_solve_ws(SM& s, int lane, const IneqSe
   double ul = 0.0, rinvl = 0.0;     // lane k < q: multiplier and 1 / R[k][k] of active slot k
   int actl = 0;                     // constraint id in slot `lane`
   minslack = 0.0;
-  for (;;) {
-    // most violated inequality (y lives in shared memory: every lane reads the two rows its constraint combines)
-    double viol = 0.0; int who = 0;
+  // most violated inequality (y lives in shared memory: every lane reads the two rows its constraint combines)
+  auto select = [&](double& viol_out, int& p_out) {
+    double viol = 0.0; int who = lane;
     if (have0 && !((activemask >> lane) & 1ull)) {
       const double ta = c0.ca * s.y[c0.ra], tb = c0.cb * s.y[c0.rb];
       const double sl = c0.bound - ta - tb;
-      if (sl < -1e-10 * (1.0 + fabs(c0.bound) + fabs(ta) + fabs(tb))) { viol = -sl; who = lane; }
+      if (sl < -1e-10 * (1.0 + fabs(c0.bound) + fabs(ta) + fabs(tb))) viol = -sl;
     }
     if (mi > 32) {
       const Ineq c1 = get_ineq(S, lane + 32 < mi ? lane + 32 : 0);
@@ -804,12 +812,13 @@ template <int N, class SM> WBC_DEV int gi_solve_ws(SM& s, int lane, const IneqSe
         if (sl < -1e-10 * (1.0 + fabs(c1.bound) + fabs(ta) + fabs(tb)) && -sl > viol) { viol = -sl; who = lane + 32; }
       }
     }
-    int p;
-    {
-      int wl;
-      viol = warp_max_lane(viol, wl);
-      p = shfl(who, wl);
-    }
+    int wl;
+    viol_out = warp_max_lane(viol, wl);
+    p_out = (mi > 32) ? shfl(who, wl) : wl;
+  };
+  double viol; int p;
+  select(viol, p);
+  for (;;) {
     minslack = -viol;
     if (!(viol > 0.0)) break;
     const Ineq cp = get_ineq(S, p);
@@ -862,7 +871,13 @@ template <int N, class SM> WBC_DEV int gi_solve_ws(SM& s, int lane, const IneqSe
       up += t;
       if (!dual_only) { yl = fma(t, wd, yl); s.y[lane] = yl; }
       if (!dual_only && t2 <= t1) {
-        // ---- full step: add p. Householder on d[q:] -> (alpha, 0, ..), W[:, q:] <- W[:, q:] (I - 2 v v'/v'v), v = d[q:] - alpha e_q
+        // ---- full step: add p. The next pivot is selected here, from the y just published: its reductions are independent
+        //      of the Householder update below and overlap it.
+        activemask |= 1ull << p;
+        __syncwarp();
+        double nviol; int np;
+        select(nviol, np);
+        // Householder on d[q:] -> (alpha, 0, ..), W[:, q:] <- W[:, q:] (I - 2 v v'/v'v), v = d[q:] - alpha e_q
         const double nrm = zn * frsqrt(zn);
         const double alpha = dq > 0.0 ? -nrm : nrm;
         double rqq = dq;
@@ -883,8 +898,8 @@ template <int N, class SM> WBC_DEV int gi_solve_ws(SM& s, int lane, const IneqSe
         }
         if (lane < q) Rent(s, q, lane) = dself;
         if (lane == q) { Rent(s, q, q) = rqq; rinvl = frcp(rqq); ul = up; actl = p; }
-        activemask |= 1ull << p;
         ++q;
+        viol = nviol; p = np;
         __syncwarp();
         break;
       }
