@@ -90,6 +90,12 @@ static_assert(offsetof(wbc::SolveSmem, cw) == sizeof(double) * wbc::YROWS * wbc:
               offsetof(wbc::SolveSmem, ct) == offsetof(wbc::SolveSmem, cw) + sizeof(double) * wbc::YROWS, "[Y | cw | ct] must be contiguous");
 constexpr unsigned REC_Y_BYTES = wbc::REC_Y * sizeof(double);
 
+// Programmatic dependent launch: the solve kernel is launched with the programmatic-stream-serialization attribute, so its
+// CTAs become resident while the last reduce CTAs are still running (they have all started by then) and wait here; this
+// hides the launch latency and CTA ramp of the second kernel. Both instructions are no-ops in an ordinary launch.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 // shared -> global bulk copy of `bytes` (multiple of 16), issued by the calling thread; returns once the source may be reused
 __device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, unsigned bytes) {
@@ -164,6 +170,7 @@ __global__ void WBC_STEP_BOUNDS wbc_reduce_kernel(const DevConst* __restrict__ g
                                                   double* __restrict__ vdmap, int bulk_ok) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SmemLayout* sm = reinterpret_cast<SmemLayout*>(smem_raw);
+  pdl_launch_dependents();
   const bool staged = stage_inputs_issue(sm->in, a, bulk_ok != 0);
   const DevConst& dc = stage_consts(sm, gdc);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -191,6 +198,7 @@ __global__ void __launch_bounds__(SOLVE_WARPS * 32, WBC_SOLVE_CTAS) wbc_solve_ke
   wbc::SolveSmem& s = sm->w[warp];
   const double* r = rec + inst * wbc::REC_DOUBLES;
   const double2* m = reinterpret_cast<const double2*>(r + wbc::REC_Y);
+  pdl_wait();                      // the records of the reduce kernel are complete and visible from here on
   const double2 m2 = m[2];
   const bool ok = m2.x != 0.0;
   if (ok && lane == 0) bulk_load(&s.Y[0][0], r, REC_Y_BYTES, &s.mbar);
@@ -209,6 +217,7 @@ __global__ void __launch_bounds__(WARPS * 32, 3) wbc_reduce_pc_kernel(const DevC
                                                                       int bulk_ok) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SmemLayoutPC* sm = reinterpret_cast<SmemLayoutPC*>(smem_raw);
+  pdl_launch_dependents();
   const bool staged = stage_inputs_issue(sm->in, a, bulk_ok != 0);
   const DevConst& dc = stage_consts(sm, gdc);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -488,6 +497,11 @@ static wbc::StepArgs offset_args(const wbc_io* io, int64_t o, int64_t m, int kin
                        io->f ? io->f + o * 12 : nullptr, io->qp_info ? io->qp_info + o * 4 : nullptr, (long long)m, kind};
 }
 
+static int pdl_mode() {   // WBC_PDL=0: ordinary launch of the solve kernel (A/B comparisons)
+  static int mode = -1;
+  if (mode < 0) { const char* e = getenv("WBC_PDL"); mode = e ? atoi(e) : 1; }
+  return mode;
+}
 static bool aligned16p(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 static int bulk_in_mode() {   // WBC_BULK_IN=0: per-lane input loads everywhere (A/B comparisons)
   static int mode = -1;
@@ -510,7 +524,22 @@ static int launch_split(wbc_handle* h, int kind, int64_t n, const wbc_io* io, cu
     if constexpr (KIND == WBC_CTRL_PC) wbc_reduce_pc_kernel<<<grid, WARPS * 32, sizeof(SmemLayoutPC), st>>>(h->d_const, a, h->d_rec[slot], vdmap, bulk_ok);
     else wbc_reduce_kernel<KIND><<<grid, WARPS * 32, sizeof(SmemLayout), st>>>(h->d_const, a, h->d_rec[slot], vdmap, bulk_ok);
     if (h->prof_on) cudaEventRecord(h->prof_ev[1], st);
-    wbc_solve_kernel<KIND><<<(unsigned)((m + SOLVE_WARPS - 1) / SOLVE_WARPS), SOLVE_WARPS * 32, sizeof(SmemLayoutSolve), st>>>(h->d_const, a, h->d_rec[slot], vdmap);
+    const unsigned sgrid = (unsigned)((m + SOLVE_WARPS - 1) / SOLVE_WARPS);
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (pdl_mode()) cudaStreamIsCapturing(st, &cap);
+    if (pdl_mode() && cap == cudaStreamCaptureStatusNone) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(sgrid); cfg.blockDim = dim3(SOLVE_WARPS * 32); cfg.dynamicSmemBytes = sizeof(SmemLayoutSolve); cfg.stream = st;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      at[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      const double* crec = h->d_rec[slot];
+      const double* cvd = vdmap;
+      WBC_CUDA(h, cudaLaunchKernelEx(&cfg, wbc_solve_kernel<KIND>, (const DevConst*)h->d_const, a, crec, cvd));
+    } else {
+      wbc_solve_kernel<KIND><<<sgrid, SOLVE_WARPS * 32, sizeof(SmemLayoutSolve), st>>>(h->d_const, a, h->d_rec[slot], vdmap);
+    }
     if (h->prof_on) cudaEventRecord(h->prof_ev[2], st);
     h->launches += 2;
   }
@@ -592,7 +621,7 @@ extern "C" int wbc_step_host(wbc_handle* h, int kind, int64_t n, const wbc_io* i
     // Measured on B200 (profiles/README.md): zero-copy wins up to ~10^5 instances per call (no staging copies, no extra API
     // calls; the host link delivers ~32 GB/s to the SMs); above that the copy engines (~55 GB/s) in a chunked two-stream
     // pipeline win, so large page-locked batches take the staged path below with 65536-instance chunks.
-    if (mode < 0) mode = n >= 131072 ? 0 : 1;
+    if (mode < 0) { static const long long thr = getenv("WBC_ZC_MAX") ? atoll(getenv("WBC_ZC_MAX")) : 131072; mode = n >= thr ? 0 : 1; }
     bool pinned = mode != 0;
     for (int i = 0; i < 10 && pinned; ++i) {
       if (!ptrs[i]) continue;
@@ -631,7 +660,13 @@ extern "C" int wbc_step_host(wbc_handle* h, int kind, int64_t n, const wbc_io* i
   if (rc) return rc;
   // Chunked two-stream pipeline: the upload of chunk c + 1 overlaps the kernel of chunk c, the download of chunk c the
   // kernel of chunk c + 1 (separate copy engines); small batches go through in one piece.
-  int n_chunks = n >= 131072 ? (int)((n + 65535) / 65536 > 64 ? 64 : (n + 65535) / 65536) : (n >= 2048 ? 2 : 1);
+  // chunk = n / 8 clamped to [8192, 65536] instances: short pipeline fill, copies long enough for the copy engines
+  int n_chunks = n >= 2048 ? 2 : 1;
+  if (n >= 32768) {
+    int64_t per_c = n / 8; per_c = per_c < 8192 ? 8192 : (per_c > 65536 ? 65536 : per_c);
+    const int64_t c = (n + per_c - 1) / per_c;
+    n_chunks = (int)(c > 64 ? 64 : c);
+  }
   if (const char* env = getenv("WBC_HOST_CHUNKS")) { const int v = atoi(env); if (v >= 1 && v <= 64) n_chunks = v; }
   if ((int64_t)n_chunks > n) n_chunks = (int)n;
   const int64_t per = (n + n_chunks - 1) / n_chunks;

@@ -853,10 +853,14 @@ template <int N, class SM> WBC_DEV int gi_solve_ws(SM& s, int lane, const IneqSe
       const double sp = cp.bound - cp.ca * s.y[cp.ra] - cp.cb * s.y[cp.rb];
       // r = R^-1 d[:q]  (back substitution; lane k owns r_k; R is kept transposed: R[col][row])
       double rk = dself;
-      for (int jj = q - 1; jj >= 0; --jj) {
-        const double rl = Rent(s, jj, li);
-        const double rj = shfl(rk * rinvl, jj);
-        if (lane < jj) rk = fma(-rl, rj, rk);
+      {
+        const double* rcol = &s.Rp[(q - 1) * (q + 2) / 2 + li];      // column q-1 of the packed R, this lane's row
+        for (int jj = q - 1; jj >= 0; --jj) {
+          const double rl = *rcol;
+          rcol -= jj + 1;                                            // column jj-1 starts jj+1 entries earlier
+          const double rj = shfl(rk * rinvl, jj);
+          if (lane < jj) rk = fma(-rl, rj, rk);
+        }
       }
       rk *= rinvl;
       int l;

@@ -1,16 +1,18 @@
 #!/bin/bash
-# End-to-end (wbc_step_host, page-locked buffers) and device rate under the input-staging switch; one line per run.
+# End-to-end (wbc_step_host, page-locked buffers): zero-copy against the staged two-stream pipeline over the batch size, and
+# the programmatic-dependent-launch switch on the device-timed step; one line per run.
 out=gpurun_out/sweep_e2e.txt; : > $out
 run() {
   local label=$1; shift
   r=$(env "$@" 2>>gpurun_out/sweep.err | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('dev %.3f M/s  p50 %.4f ms  e2e %.3f M/s' % (d['value']/1e6, d['p50_ms_per_step'], d['e2e']['value']/1e6))")
   echo "$label $r" | tee -a $out
 }
-for batch in 4096 65536 1048576; do
-  steps=100; [ $batch -gt 4096 ] && steps=20
-  for b in 1 0; do
-    run "bulk_in=$b batch=$batch" WBC_BULK_IN=$b python bench.py --no-cpu --steps $steps --warmup 3 --batch $batch
-  done
+for pdl in 1 0; do
+  run "pdl=$pdl batch=4096" WBC_PDL=$pdl python bench.py --no-cpu --steps 200 --warmup 5
+  run "pdl=$pdl batch=1024" WBC_PDL=$pdl python bench.py --no-cpu --steps 200 --warmup 5 --batch 1024
+  run "pdl=$pdl batch=65536" WBC_PDL=$pdl python bench.py --no-cpu --steps 30 --warmup 3 --batch 65536
 done
-run "bulk_in=1 zc=2 batch=4096" WBC_ZC_CHUNKS=2 python bench.py --no-cpu --steps 100 --warmup 3 --batch 4096
-run "bulk_in=1 zc=4 batch=1048576" WBC_ZC_CHUNKS=4 python bench.py --no-cpu --steps 20 --warmup 3 --batch 1048576
+for batch in 16384 32768 65536 131072 262144; do
+  run "zero-copy batch=$batch" WBC_HOST_ZEROCOPY=1 python bench.py --no-cpu --steps 20 --warmup 3 --batch $batch
+  run "staged    batch=$batch" WBC_HOST_ZEROCOPY=0 python bench.py --no-cpu --steps 20 --warmup 3 --batch $batch
+done
