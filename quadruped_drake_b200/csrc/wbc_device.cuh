@@ -91,7 +91,6 @@ struct alignas(16) WarpSmem {
   double AK[4][3][7];    // stance leg k: a_k = AK[k][:, 6] - AK[k][:, 0:6] a_b   (= L_k^-1 (r_k - Jb_k a_b))
   int rowof[AC];         // pivot row of variable c, -1 if free
   int pc[AR];
-  int fcol[NF];          // free (non-pivot) columns of A in increasing order
   // ---- reduced problem ([Y | cw | ct] contiguous and 16-byte aligned: one bulk copy in the split path)
   alignas(16) double Y[YROWS][YS];
   double cw[YROWS], ct[YROWS];   // cost weight / target of each Y row: 1/2 cw (y - ct)^2
@@ -183,21 +182,6 @@ WBC_DEV double warp_sum(double v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(WBC_FULL, v, o);
   return v;
 }
-WBC_DEV double warp_max(double v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(WBC_FULL, v, o));
-  return v;
-}
-// argmin with index; ties -> lowest index
-WBC_DEV void warp_argmin(double& v, int& idx) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    double ov = __shfl_xor_sync(WBC_FULL, v, o);
-    int oi = __shfl_xor_sync(WBC_FULL, idx, o);
-    if (ov < v || (ov == v && oi < idx)) { v = ov; idx = oi; }
-  }
-}
-
 // Arg-max / arg-min of a NON-NEGATIVE double over the warp with two 32-bit redux.sync reductions (IEEE order of
 // non-negative doubles = unsigned order of their bit patterns): high words first, then the low words of the lanes that
 // tie on the high word; the winner is the lowest such lane. Returns the extreme value (exact) and its lane.
@@ -674,7 +658,7 @@ template <int N, class SM> WBC_DEV void cholesky_factor(SM& s, int lane, int& st
 // Inequality i is  ca*y[ra] + cb*y[rb] <= bound  with y = Y w + y0.
 struct Ineq { int ra, rb; double ca, cb, bound; };
 struct IneqSet {
-  unsigned cmask; int nc; double mu; int nfric; int nextra; int ntl; const double* effort; const int* dummy;
+  unsigned cmask; double mu; int nfric; int nextra; int ntl; const double* effort;
   double extra_bound[2];
 };
 WBC_DEV Ineq get_ineq(const IneqSet& S, int i) {
@@ -1341,7 +1325,6 @@ WBC_DEV void reduce_instance(WarpSmem& s, const wbc_model& md, const wbc_params&
   int nextra = 0;
   double extra_bound = 0.0, Vl = 0.0, PFl = 0.0, csum = 0.0;
   if (ok) {
-    if (isfree) s.fcol[widx] = lane;
     // ---- phase 4
     for (int e = lane; e < YROWS * YS; e += 32) (&s.Y[0][0])[e] = 0.0;
     s.cw[lane] = 0.0; s.ct[lane] = 0.0;
@@ -1457,8 +1440,8 @@ WBC_DEV void solve_instance(SM& s, const wbc_model& md, const wbc_params& pr, co
     cholesky_factor<NA>(s, lane, status, tp);
     // ---- phase 6
     IneqSet S;
-    S.cmask = cmask; S.nc = nc; S.mu = pr.mu; S.nfric = 4 * nc; S.nextra = nextra; S.ntl = pr.torque_limits ? 24 : 0;
-    S.effort = md.effort; S.dummy = nullptr; S.extra_bound[0] = extra_bound; S.extra_bound[1] = 0.0;
+    S.cmask = cmask; S.mu = pr.mu; S.nfric = 4 * nc; S.nextra = nextra; S.ntl = pr.torque_limits ? 24 : 0;
+    S.effort = md.effort; S.extra_bound[0] = extra_bound; S.extra_bound[1] = 0.0;
     int qact = 0; double minslack = 0.0;
     int iters = 0;
     if (!(status & WBC_ST_NOTPD)) {

@@ -284,3 +284,64 @@ def test_host_entry_paths_agree(ctl_cache):
                         capi.np_ptr(st), capi.np_ptr(vd), None, None)
         assert ctl.lib.wbc_step_host(ctl._h, capi.WBC_CTRL_ID, n, C.byref(io)) == 0
         assert np.array_equal(tau, a.tau) and np.array_equal(met, a.metrics) and np.array_equal(st, a.status) and np.array_equal(vd, a.vd)
+
+
+@pytest.mark.gpu
+def test_large_batch_chunks_and_staged_pipeline(ctl_cache):
+    """More than one reduce / solve launch pair (262144 instances per pair) and, on page-locked host buffers, the staged
+    two-stream copy pipeline that large batches take: bit-identical to the same instances solved in a small batch."""
+    import ctypes as C
+    from quadruped_drake_b200 import capi
+    from quadruped_drake_b200.synth import generate
+    ctl = ctl_cache("mini_cheetah")
+    base = 4096
+    q0, v0, t0, c0 = generate(ctl.model, base, 91, "mixed", ctl.fk)
+    small = ctl.step("id", q0, v0, t0, c0)
+    n = 262144 + 4096 + 5                                         # two launch pairs, ragged tail
+    idx = np.arange(n) % base
+    hq, hv, ht = capi.pinned_empty((n, 19)), capi.pinned_empty((n, 18)), capi.pinned_empty((n, 54))
+    hc = capi.pinned_empty((n, 4), np.uint8)
+    hq[:], hv[:], ht[:], hc[:] = q0[idx], v0[idx], t0[idx], c0[idx]
+    tau, met, st = capi.pinned_empty((n, 12)), capi.pinned_empty((n, 4)), capi.pinned_empty((n,), np.int32)
+    io = capi.WbcIO(capi.np_ptr(hq), capi.np_ptr(hv), capi.np_ptr(ht), capi.np_ptr(hc), capi.np_ptr(tau), capi.np_ptr(met),
+                    capi.np_ptr(st), None, None, None)
+    launches0 = ctl.launches
+    assert ctl.lib.wbc_step_host(ctl._h, capi.WBC_CTRL_ID, n, C.byref(io)) == 0
+    assert ctl.launches - launches0 >= 4
+    assert np.array_equal(tau, small.tau[idx]) and np.array_equal(st, small.status[idx]) and np.array_equal(met, small.metrics[idx])
+
+
+@pytest.mark.gpu
+def test_unaligned_buffers_and_kernel_profile(ctl_cache):
+    """Rows that do not start on a 16-byte boundary take the per-lane input path of the reduce kernel (no bulk staging):
+    same bits. wbc_profile_step splits a step into its two kernels."""
+    import ctypes as C
+    import torch
+    from quadruped_drake_b200 import capi
+    from quadruped_drake_b200.synth import generate
+    ctl = ctl_cache("mini_cheetah")
+    n = 1024
+    q, v, traj, contact = generate(ctl.model, n, 17, "walk", ctl.fk)
+    ref = ctl.step("id", q, v, traj, contact)
+    dev = torch.device("cuda:0")
+
+    def shifted(a, dtype):                       # device copy whose first element sits 8 bytes past a 16-byte boundary
+        flat = torch.empty(a.size + 16, dtype=dtype, device=dev)
+        off = 1 if dtype == torch.float64 else 8
+        view = flat[off:off + a.size]
+        view.copy_(torch.from_numpy(np.ascontiguousarray(a).reshape(-1)))
+        assert view.data_ptr() % 16 == 8
+        return view
+    tq, tv, tt = shifted(q, torch.float64), shifted(v, torch.float64), shifted(traj, torch.float64)
+    tc = shifted(contact, torch.uint8)
+    tau = torch.empty((n, 12), dtype=torch.float64, device=dev)
+    met = torch.empty((n, 4), dtype=torch.float64, device=dev)
+    st = torch.empty((n,), dtype=torch.int32, device=dev)
+    io = capi.WbcIO(tq.data_ptr(), tv.data_ptr(), tt.data_ptr(), tc.data_ptr(), tau.data_ptr(), met.data_ptr(), st.data_ptr(), None, None, None)
+    stream = torch.cuda.current_stream(dev)
+    assert ctl.lib.wbc_step(ctl._h, capi.WBC_CTRL_ID, n, C.byref(io), C.c_void_p(stream.cuda_stream)) == 0
+    torch.cuda.synchronize()
+    assert np.array_equal(tau.cpu().numpy(), ref.tau) and np.array_equal(st.cpu().numpy(), ref.status)
+    ms_r, ms_s = C.c_double(), C.c_double()
+    assert ctl.lib.wbc_profile_step(ctl._h, capi.WBC_CTRL_ID, n, C.byref(io), 5, C.c_void_p(stream.cuda_stream), C.byref(ms_r), C.byref(ms_s)) == 0
+    assert 0.0 < ms_r.value < 10.0 and 0.0 < ms_s.value < 10.0
