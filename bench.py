@@ -198,8 +198,19 @@ def run_gpu(args):
     if rank == 0:
         g.build()
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
-        dist.barrier()
+        # NCCL announces its version on stdout when the first communicator comes up; stdout carries only the JSON line, so
+        # it is pointed at stderr for the rendezvous
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
     from quadruped_drake_b200 import capi
