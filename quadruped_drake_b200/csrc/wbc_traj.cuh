@@ -61,6 +61,15 @@ __device__ __forceinline__ int segment_of(const double* __restrict__ tend, int n
   return lo;
 }
 
+// One 32-byte coefficient record {A, B, C, D} with a single 256-bit load (sm_100: LDG.256): one sector, one request,
+// instead of two 16-byte halves of the same sector.
+struct Coef4 { double a, b, c, d; };
+__device__ __forceinline__ Coef4 load_coef(const double* __restrict__ rec) {
+  Coef4 r;
+  asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.a), "=d"(r.b), "=d"(r.c), "=d"(r.d) : "l"(rec));
+  return r;
+}
+
 // Two stages per chunk of 32 instances (one warp per chunk):
 //   A  lane = instance: planner time logic (wait / nearest stored sample), the 10 spline segment lookups and the 4 contact
 //      flags, done ONCE per instance; (polynomial index, local time) of every spline go to shared memory;
@@ -156,11 +165,10 @@ __global__ void __launch_bounds__(SAMPLE_WARPS * 32) sample_kernel(PlanTables pt
         p = __ldg(st); v = __ldg(st + stride); a = __ldg(st + 2 * stride);
       } else {
         const double tl = sm.tl[il][s];
-        const double2* c2 = reinterpret_cast<const double2*>(pt.coef + ((size_t)sm.poly[il][s] * 3 + dim) * 4);
-        const double2 ab = __ldg(c2), cd = __ldg(c2 + 1);            // A B | C D
-        p = fma(fma(fma(cd.y, tl, cd.x), tl, ab.y), tl, ab.x);
-        v = fma(fma(3.0 * cd.y, tl, 2.0 * cd.x), tl, ab.y);
-        a = fma(6.0 * cd.y, tl, 2.0 * cd.x);
+        const Coef4 c = load_coef(pt.coef + ((size_t)sm.poly[il][s] * 3 + dim) * 4);
+        p = fma(fma(fma(c.d, tl, c.c), tl, c.b), tl, c.a);
+        v = fma(fma(3.0 * c.d, tl, 2.0 * c.c), tl, c.b);
+        a = fma(6.0 * c.d, tl, 2.0 * c.c);
       }
       double* o = out + il * WBC_NTRAJ + e0;
       o[0] = p; o[stride] = v; o[2 * stride] = a;
@@ -172,9 +180,8 @@ __global__ void __launch_bounds__(SAMPLE_WARPS * 32) sample_kernel(PlanTables pt
         double val = 0.0;
         if (!sm.standing[il]) {
           const double tl = sm.tl[il][s];
-          const double2* c2 = reinterpret_cast<const double2*>(pt.coef + ((size_t)sm.poly[il][s] * 3 + dim) * 4);
-          const double2 ab = __ldg(c2), cd = __ldg(c2 + 1);
-          val = fma(fma(fma(cd.y, tl, cd.x), tl, ab.y), tl, ab.x);
+          const Coef4 c = load_coef(pt.coef + ((size_t)sm.poly[il][s] * 3 + dim) * 4);
+          val = fma(fma(fma(c.d, tl, c.c), tl, c.b), tl, c.a);
         }
         fo[idx] = val;
       }
