@@ -857,6 +857,7 @@ template <int N, class SM> WBC_DEV int gi_solve_ws(SM& s, int lane, const IneqSe
       const bool dual_only = !(t2 < INFINITY);
       if (lane < q) ul -= t * rk;
       up += t;
+      __syncwarp();                                        // every lane has read y[ra], y[rb] of this pivot
       if (!dual_only) { yl = fma(t, wd, yl); s.y[lane] = yl; }
       if (!dual_only && t2 <= t1) {
         // ---- full step: add p. The next pivot is selected here, from the y just published: its reductions are independent
@@ -893,6 +894,7 @@ template <int N, class SM> WBC_DEV int gi_solve_ws(SM& s, int lane, const IneqSe
       }
       // ---- drop the blocking constraint l (position in the active list)
       {
+        __syncwarp();                                      // every lane is done reading R (back substitution above)
         const int dropped = shfl(actl, l);
         activemask &= ~(1ull << dropped);
         // shift the columns right of l one place left: the triangle becomes upper Hessenberg from column l on

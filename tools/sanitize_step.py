@@ -1,0 +1,25 @@
+#!/usr/bin/env python
+"""Small run of every controller kind for compute-sanitizer (memcheck / racecheck / synccheck / initcheck):
+  compute-sanitizer --tool racecheck python tools/sanitize_step.py
+Checks the results against the golden fixtures as well, so a sanitizer-clean run is also a correct one."""
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+from quadruped_drake_b200.controller import BatchedController  # noqa: E402
+
+g = np.load(ROOT / "tests" / "golden" / "mixed_mini_cheetah.npz")
+ctl = BatchedController("mini_cheetah", device=0)
+for kind, tol in (("id", 1e-5), ("clf", 1e-5), ("pc", 1e-5), ("mptc", 1e-5)):
+    out = ctl.step(kind, g["q"], g["v"], g["traj"], g["contact"], debug=True)
+    ok = g[f"{kind}_ok"]
+    err = np.abs(out.tau - g[f"{kind}_tau"])[ok].max()
+    print(kind, "max |tau - golden| = %.3g" % err, "status", np.unique(out.status))
+    assert err < tol
+ctl2 = BatchedController("mini_cheetah", device=0, torque_limits=1)
+out = ctl2.step("id", g["q"], g["v"], g["traj"], g["contact"])
+print("torque limits: status", np.unique(out.status))
+print("sanitize run ok")
