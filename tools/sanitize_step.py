@@ -23,3 +23,18 @@ ctl2 = BatchedController("mini_cheetah", device=0, torque_limits=1)
 out = ctl2.step("id", g["q"], g["v"], g["traj"], g["contact"])
 print("torque limits: status", np.unique(out.status))
 print("sanitize run ok")
+
+# rows next to the step: trajectory sampler + closed-loop rollout (graph replay) + wire codecs
+from quadruped_drake_b200 import planner as pl  # noqa: E402
+from quadruped_drake_b200.rollout import rollout  # noqa: E402
+
+Q0 = np.array([1.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.3] + [0.0, -0.8, 1.6] * 4)
+sampler = pl.TrajectorySampler(ctl, pl.make_gait_plan("mini_cheetah", 0))
+n = 70
+t0 = np.linspace(0.0, 2.5, n)
+r = rollout(ctl, sampler, "id", np.tile(Q0, (n, 1)), np.zeros((n, 18)), t0, 6, 5e-3, log_metrics=True)
+print("rollout: status_or", np.unique(r.status_or), "finite", bool(np.isfinite(r.q).all()))
+assert np.isfinite(r.q).all()
+ref = sampler.sample(t0)
+print("sampler rows", np.asarray(ref["traj"] if isinstance(ref, dict) and "traj" in ref else list(ref.values())[0]).shape)
+print("sanitize aux ok")
