@@ -605,6 +605,7 @@ template <int N> WBC_DEV TriPairs tri_pairs(int lane) {
 
 // H = sum_r cw_r Y_r' Y_r (+ identity on padded dims), g = sum_r cw_r Y_r (y0_r - ct_r) + glin
 template <int N, class SM> WBC_DEV void reduced_hessian(SM& s, int lane, int nf, int nrows, bool extra, const TriPairs& tp) {
+  s.y[lane] = s.cw[lane] * (s.Y[lane][NF] - s.ct[lane]);      // e_r = c_r (y0_r - t_r), once per row (s.y is free until the solve)
 #pragma unroll
   for (int h = 0; h < 3; ++h) {
     const int i = tp.i[h], k = tp.k[h];
@@ -620,10 +621,16 @@ template <int N, class SM> WBC_DEV void reduced_hessian(SM& s, int lane, int nf,
     if (i >= nf) acc = (i == k) ? 1.0 : 0.0;
     s.H[i][k] = acc;
   }
+  __syncwarp();
   if (lane < N) {
-    double acc = 0.0;
-    for (int r = 0; r < nrows; ++r) acc = fma(s.cw[r] * s.Y[r][lane], s.Y[r][NF] - s.ct[r], acc);
-    if (extra) acc = fma(s.cw[30] * s.Y[30][lane], s.Y[30][NF] - s.ct[30], fma(s.cw[31] * s.Y[31][lane], s.Y[31][NF] - s.ct[31], acc));
+    double acc = 0.0, acc1 = 0.0;
+#pragma unroll 3
+    for (int r = 0; r < nrows; r += 2) {
+      acc = fma(s.Y[r][lane], s.y[r], acc);
+      acc1 = fma(s.Y[r + 1][lane], s.y[r + 1], acc1);
+    }
+    acc += acc1;
+    if (extra) acc = fma(s.Y[30][lane], s.y[30], fma(s.Y[31][lane], s.y[31], acc));
     s.g[lane] = (lane < nf) ? acc : 0.0;
   }
   __syncwarp();
@@ -805,7 +812,15 @@ template <int N, class SM> WBC_DEV int gi_solve_ws(SM& s, int lane, const IneqSe
   for (;;) {
     minslack = -viol;
     if (!(viol > 0.0)) break;
-    const Ineq cp = get_ineq(S, p);
+    // descriptor of the pivot: the lane that watches constraint p (< 32) already holds it
+    Ineq cp;
+    if (p < 32) {
+      const int rr = shfl(c0.ra | (c0.rb << 8), p);
+      cp.ra = rr & 0xff; cp.rb = rr >> 8;
+      cp.ca = shfl(c0.ca, p); cp.cb = shfl(c0.cb, p); cp.bound = shfl(c0.bound, p);
+    } else {
+      cp = get_ineq(S, p);
+    }
     const double nca = -cp.ca, ncb = -cp.cb;
     double up = 0.0;
     bool fail = false;
