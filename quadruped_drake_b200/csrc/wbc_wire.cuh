@@ -39,10 +39,35 @@ __device__ __forceinline__ double load_be64(const uint32_t* sm, int off) {
   load8(sm, off, a, b);
   return __hiloint2double((int)bswap32(a), (int)bswap32(b));
 }
+// 8 big-endian bytes of x at byte offset `off` (any alignment) of a 4-byte aligned shared buffer: the widest naturally
+// aligned pieces instead of eight byte stores (2 stores when off is a multiple of 4, 3 when even, 4 when odd); neighbouring
+// doubles share the boundary words, so the pieces never overlap another lane's bytes.
 __device__ __forceinline__ void store_be64(unsigned char* sm, int off, double x) {
   const unsigned long long u = (unsigned long long)__double_as_longlong(x);
-#pragma unroll
-  for (int i = 0; i < 8; ++i) sm[off + i] = (unsigned char)(u >> (56 - 8 * i));
+  const uint32_t first = bswap32((uint32_t)(u >> 32)), second = bswap32((uint32_t)u);   // memory bytes 0-3 / 4-7, little-endian words
+  unsigned char* p = sm + off;
+  switch (off & 3) {
+    case 0:
+      *reinterpret_cast<uint32_t*>(p) = first; *reinterpret_cast<uint32_t*>(p + 4) = second;
+      break;
+    case 2:
+      *reinterpret_cast<uint16_t*>(p) = (uint16_t)first;
+      *reinterpret_cast<uint32_t*>(p + 2) = (first >> 16) | (second << 16);
+      *reinterpret_cast<uint16_t*>(p + 6) = (uint16_t)(second >> 16);
+      break;
+    case 1:
+      p[0] = (unsigned char)first;
+      *reinterpret_cast<uint16_t*>(p + 1) = (uint16_t)(first >> 8);
+      *reinterpret_cast<uint32_t*>(p + 3) = (first >> 24) | (second << 8);
+      p[7] = (unsigned char)(second >> 24);
+      break;
+    default:
+      p[0] = (unsigned char)first;
+      *reinterpret_cast<uint32_t*>(p + 1) = (first >> 8) | (second << 24);
+      *reinterpret_cast<uint16_t*>(p + 5) = (uint16_t)(second >> 8);
+      p[7] = (unsigned char)(second >> 24);
+      break;
+  }
 }
 
 // Coalesced copy of `bytes` bytes between a 16-byte aligned global range and shared memory.
