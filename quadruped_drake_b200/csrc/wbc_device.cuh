@@ -255,14 +255,17 @@ constexpr int DYN_STEP = 0;    // step kernels: gravity folded into the bias (hb
 constexpr int DYN_PARITY = 1;  // wbc_dynamics: hb/hj = Cv only, tau_g (controller sign) to taug_sm[18] (internal order)
 constexpr int DYN_BIAS = 2;    // bias only: b = C(q, vel) vel for the velocity `vel_int` (internal order) -> bias_out[18]
 constexpr int DYN_STEP_JD = 3; // DYN_STEP plus the Jdot leg blocks Ld (PC controller)
+constexpr int DYN_PC = 4;      // DYN_STEP_JD or DYN_BIAS chosen at RUN time (`bias_rt`): one copy of the code for all four
+                               // passes of the PC reduce kernel, which is bound by instruction fetch
 
 // Fills the dynamics block of `s` for the state in s.q / s.v (see the modes above).
 template <int MODE>
 WBC_DEV void dynamics_phase(WarpSmem& s, const wbc_model& md, int lane, int& status, double* taug_sm,
-                            const double* vel_int = nullptr, double* bias_out = nullptr) {
-  constexpr bool GRAV = (MODE == DYN_STEP || MODE == DYN_STEP_JD);
-  constexpr bool BIAS_ONLY = (MODE == DYN_BIAS);
-  constexpr bool WITH_JD = (MODE == DYN_STEP_JD);
+                            const double* vel_int = nullptr, double* bias_out = nullptr, bool bias_rt = false) {
+  // compile-time constants for the templated modes; DYN_PC decides at run time
+  const bool GRAV = (MODE == DYN_STEP || MODE == DYN_STEP_JD) || (MODE == DYN_PC && !bias_rt);
+  const bool BIAS_ONLY = (MODE == DYN_BIAS) || (MODE == DYN_PC && bias_rt);
+  const bool WITH_JD = (MODE == DYN_STEP_JD) || (MODE == DYN_PC && !bias_rt);
   const int leg = lane >> 3, j = lane & 7;
   const bool link = j < 3;
   const int jl = link ? j : 2;
@@ -429,6 +432,17 @@ WBC_DEV void dynamics_phase(WarpSmem& s, const wbc_model& md, int lane, int& sta
     s.task[13] = R0.c2.x; s.task[14] = R0.c2.y; s.task[15] = R0.c2.z;
   }
   __syncwarp();
+}
+
+// The PC / MPTC reduce kernel runs the dynamics four times per instance (state pass + three bias passes of the
+// polarisation); they all go through this one out-of-line copy.
+#ifdef __CUDACC__
+__device__ __noinline__
+#else
+static
+#endif
+void dynamics_pc_pass(WarpSmem& s, const wbc_model& md, int lane, int& status, const double* vel_int, double* bias_out, bool bias) {
+  dynamics_phase<DYN_PC>(s, md, lane, status, nullptr, vel_int, bias_out, bias);
 }
 
 // --------------------------------------------------------------------------- task space
@@ -1233,10 +1247,15 @@ WBC_DEV void pc_precompute(WarpSmem& s, PcSmem& pc, const wbc_model& md, const w
   }
   __syncwarp();
   // ---- C w by polarisation: C w = 1/2 (b(v + w) - b(v) - b(w))          (CalcCoriolisMatrix, basic_controller.py:117-132)
+  //      the three bias passes run through ONE copy of the dynamics code (a rolled loop): the PC reduce kernel is bound by
+  //      instruction fetch, three inlined copies cost more in instruction-cache misses than the loop does in branches
   int st2 = 0;
-  dynamics_phase<DYN_BIAS>(s, md, lane, st2, nullptr, pc.vi, pc.bv);
-  dynamics_phase<DYN_BIAS>(s, md, lane, st2, nullptr, pc.vw, pc.bvw);
-  dynamics_phase<DYN_BIAS>(s, md, lane, st2, nullptr, pc.w, pc.bw);
+#pragma unroll 1
+  for (int pass = 0; pass < 3; ++pass) {
+    const double* vin = pass == 0 ? pc.vi : (pass == 1 ? pc.vw : pc.w);
+    double* bout = pass == 0 ? pc.bv : (pass == 1 ? pc.bvw : pc.bw);
+    dynamics_pc_pass(s, md, lane, st2, vin, bout, true);
+  }
   // ---- g0 = X'(b(v) - C w) - xdd_nom + Jdot w
   if (on) {
     double acc = -t.xddn;
@@ -1264,9 +1283,9 @@ WBC_DEV void pc_rows(WarpSmem& s, const PcSmem& pc, int lane, int ycol, int m) {
 #pragma unroll
   for (int r = 0; r < 15; ++r) if (r < m) row30 = fma(pc.s1[r], yt[r], row30);
   s.Y[30][ycol] = row30;
-#pragma unroll
-  for (int r = 0; r < 15; ++r) {
-    if (r < m) {
+#pragma unroll 1
+  for (int r = 0; r < m; ++r) {
+    {
       double acc = (lane == 31) ? pc.kx[r] : 0.0;
 #pragma unroll
       for (int c = 0; c < 15; ++c) if (c < m) acc = fma(pc.Lam[r][c], yt[c], acc);
@@ -1313,7 +1332,8 @@ WBC_DEV void reduce_instance(WarpSmem& s, const wbc_model& md, const wbc_params&
   const int nc = __popc(cmask);
   __syncwarp();
   // ---- phase 1
-  dynamics_phase<(KIND == WBC_CTRL_PC) ? DYN_STEP_JD : DYN_STEP>(s, md, lane, status, nullptr);
+  if (KIND == WBC_CTRL_PC) dynamics_pc_pass(s, md, lane, status, nullptr, nullptr, false);
+  else dynamics_phase<DYN_STEP>(s, md, lane, status, nullptr);
   async_wait_all();
   __syncwarp();
   BodyTask bt;
