@@ -81,33 +81,33 @@ def run(workload, steps=50, warmup=5, n=1 << 20):
         out.append(_line("trunk-trajectory samples/sec", "samples/s", n, per, 12 + 432 + 4 + 8 + 4, "wbc_sample_trajectory, 4 gait plans, 1Mi (plan, t) pairs", steps, warmup, steps))
     elif workload == "rollout":
         from quadruped_drake_b200.rollout import Q0_MINI_CHEETAH as Q0, rollout
-        nr, k = 4096, 200
-        bh = Q0[6] - ctl.dynamics(Q0[None], np.zeros((1, 18)))["p_feet"][0, :, 2].mean()
-        plans = [pl.make_motion_plan("mini_cheetah", m, 6.0, base_height=bh, phase=ph) for m in ("orientation", "edge", "raise_foot")
-                 for ph in np.linspace(0, 2 * np.pi, 8, endpoint=False)]
-        s = pl.TrajectorySampler(ctl, plans)
-        q0 = np.tile(Q0, (nr, 1)); q0[:, 6] = bh
-        pi = torch.from_numpy(rng.integers(0, len(plans), nr).astype(np.int32)).cuda()
-        res = {}
-        for graph in (True, False):
-            def once():
-                q, v, t = (torch.from_numpy(x).cuda() for x in (q0, np.zeros((nr, 18)), np.zeros(nr)))
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-                r = rollout(ctl, s, "id", q, v, t, k, 5e-3, plan_index=pi, use_graph=graph)
-                e1.record()
-                torch.cuda.synchronize()
-                assert int(r.status_or.max().item()) == 0
-                return e0.elapsed_time(e1)
-            with torch.cuda.stream(torch.cuda.Stream()):
-                for _ in range(2):
-                    once()
-                res[graph] = np.array([once() for _ in range(5)])
-        per = res[True]
-        d = _line("closed-loop robot control steps/sec (sample + ID-QP + integrate)", "robot-steps/s", nr * k, per, 860 + 2 * 444 + 2 * 296 + 144,
-                  "wbc_rollout: 4096 robots x 200 steps, reference test motions, CUDA-graph replay", 5, 2, 3 * k * 5,
-                  {"without_graph_robot_steps_per_s": nr * k / (float(res[False].mean()) * 1e-3)})
-        out.append(d)
+        for nr, k in ((4096, 200), (65536, 50)):
+            bh = Q0[6] - ctl.dynamics(Q0[None], np.zeros((1, 18)))["p_feet"][0, :, 2].mean()
+            plans = [pl.make_motion_plan("mini_cheetah", m, 6.0, base_height=bh, phase=ph) for m in ("orientation", "edge", "raise_foot")
+                     for ph in np.linspace(0, 2 * np.pi, 8, endpoint=False)]
+            s = pl.TrajectorySampler(ctl, plans)
+            q0 = np.tile(Q0, (nr, 1)); q0[:, 6] = bh
+            pi = torch.from_numpy(rng.integers(0, len(plans), nr).astype(np.int32)).cuda()
+            res = {}
+            for graph in (True, False):
+                def once():
+                    q, v, t = (torch.from_numpy(x).cuda() for x in (q0, np.zeros((nr, 18)), np.zeros(nr)))
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    r = rollout(ctl, s, "id", q, v, t, k, 5e-3, plan_index=pi, use_graph=graph)
+                    e1.record()
+                    torch.cuda.synchronize()
+                    assert int(r.status_or.max().item()) == 0
+                    return e0.elapsed_time(e1)
+                with torch.cuda.stream(torch.cuda.Stream()):
+                    for _ in range(2):
+                        once()
+                    res[graph] = np.array([once() for _ in range(5)])
+            per = res[True]
+            d = _line("closed-loop robot control steps/sec (sample + ID-QP + integrate)", "robot-steps/s", nr * k, per, 860 + 2 * 444 + 2 * 296 + 144,
+                      f"wbc_rollout: {nr} robots x {k} steps, reference test motions, CUDA-graph replay", 5, 2, 4 * k * 5,
+                      {"without_graph_robot_steps_per_s": nr * k / (float(res[False].mean()) * 1e-3)})
+            out.append(d)
     else:
         raise SystemExit(f"unknown workload {workload}")
     for d in out:
