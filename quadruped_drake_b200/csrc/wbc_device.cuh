@@ -1314,20 +1314,19 @@ WBC_DEV void reduce_instance(WarpSmem& s, const wbc_model& md, const wbc_params&
                              const StagedInputs* in = nullptr) {
   int status = 0;
   unsigned cmask = 0;
-  if (in) {
-    // ---- phase 0, staged: the CTA's input rows already sit in shared memory (one bulk copy per array and CTA)
-    for (int i = lane; i < WBC_NQ; i += 32) s.q[i] = in->q[i];
-    for (int i = lane; i < WBC_NV; i += 32) s.v[i] = in->v[i];
-    for (int i = lane; i < WBC_NTRAJ; i += 32) s.traj[i] = in->traj[i];
+  // ---- phase 0: input rows into the warp's block - from the CTA-level staging block where the kernel could bulk-copy the
+  //      array (always v and traj, whose rows are multiples of 16 bytes; q and contact only for 4-instance CTAs), with
+  //      coalesced per-lane loads otherwise (the trajectory row by cp.async, awaited after phase 1)
+  if (in && in->q) { for (int i = lane; i < WBC_NQ; i += 32) s.q[i] = in->q[i]; }
+  else { for (int i = lane; i < WBC_NQ; i += 32) s.q[i] = a.q[inst * WBC_NQ + i]; }
+  if (in && in->v) { for (int i = lane; i < WBC_NV; i += 32) s.v[i] = in->v[i]; }
+  else { for (int i = lane; i < WBC_NV; i += 32) s.v[i] = a.v[inst * WBC_NV + i]; }
+  if (in && in->traj) { for (int i = lane; i < WBC_NTRAJ; i += 32) s.traj[i] = in->traj[i]; }
+  else { for (int i = lane; i < WBC_NTRAJ; i += 32) async_copy8(&s.traj[i], a.traj + inst * WBC_NTRAJ + i); }
+  {
+    const uint8_t* cptr = (in && in->contact) ? in->contact : a.contact + inst * 4;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) cmask |= (in->contact[k] ? 1u : 0u) << k;
-  } else {
-    // ---- phase 0: coalesced loads into shared memory
-    for (int i = lane; i < WBC_NQ; i += 32) s.q[i] = a.q[inst * WBC_NQ + i];
-    for (int i = lane; i < WBC_NV; i += 32) s.v[i] = a.v[inst * WBC_NV + i];
-    for (int i = lane; i < WBC_NTRAJ; i += 32) async_copy8(&s.traj[i], a.traj + inst * WBC_NTRAJ + i);   // waited for after phase 1
-#pragma unroll
-    for (int k = 0; k < 4; ++k) cmask |= (a.contact[inst * 4 + k] ? 1u : 0u) << k;
+    for (int k = 0; k < 4; ++k) cmask |= (cptr[k] ? 1u : 0u) << k;
   }
   const int nc = __popc(cmask);
   __syncwarp();
