@@ -89,8 +89,6 @@ struct alignas(16) WarpSmem {
   // ---- reduced base system [B | c0] over u = [a_b(6); per leg f_k (stance) or a_k (swing)] and its reduction
   double A[AR][AC];
   double AK[4][3][7];    // stance leg k: a_k = AK[k][:, 6] - AK[k][:, 0:6] a_b   (= L_k^-1 (r_k - Jb_k a_b))
-  int rowof[AC];         // pivot row of variable c, -1 if free
-  int pc[AR];
   // ---- reduced problem ([Y | cw | ct] contiguous and 16-byte aligned: one bulk copy in the split path)
   alignas(16) double Y[YROWS][YS];
   double cw[YROWS], ct[YROWS];   // cost weight / target of each Y row: 1/2 cw (y - ct)^2
@@ -552,14 +550,16 @@ WBC_DEV void build_base_system(WarpSmem& s, int lane, unsigned cmask, double kd,
   }
 #pragma unroll
   for (int r = 0; r < AR; ++r) s.A[r][c] = col[r];
-  s.rowof[c] = -1;
   __syncwarp();
 }
 
 // Gauss-Jordan, one pivot per row, pivot column = largest remaining entry of that row.
 // Finished pivot columns are left stale (never read again). Returns the bit mask of pivot columns.
-WBC_DEV unsigned gauss_jordan(WarpSmem& s, int lane, int m, int n, int& status) {
+// `rowmap` packs, 3 bits per variable, 1 + the pivot row of the variable (0 = free): warp uniform, so the null-space entries
+// below index it with shifts instead of a shared-memory table.
+WBC_DEV unsigned gauss_jordan(WarpSmem& s, int lane, int m, int n, int& status, unsigned long long& rowmap) {
   unsigned used = 0;
+  rowmap = 0ull;
   for (int r = 0; r < m; ++r) {
     const double arc0 = s.A[r][lane];
     const bool eligible = lane < n && !((used >> lane) & 1);
@@ -567,7 +567,6 @@ WBC_DEV unsigned gauss_jordan(WarpSmem& s, int lane, int m, int n, int& status) 
     const double best = warp_max_lane(eligible ? fabs(arc0) : 0.0, pcol);
     if (!(best > 1e-9)) {            // rows are O(0.01..10) (kg, kg m, lever arms): anything below is round-off
       status |= WBC_ST_RANKDEF;
-      if (lane == 0) s.pc[r] = -1;
       continue;
     }
     const double piv = shfl(arc0, pcol);
@@ -583,9 +582,7 @@ WBC_DEV unsigned gauss_jordan(WarpSmem& s, int lane, int m, int n, int& status) 
       }
       s.A[r][lane] = arc;
     }
-    __syncwarp();
-    if (lane == pcol) s.rowof[lane] = r;
-    if (lane == 0) s.pc[r] = pcol;
+    rowmap |= (unsigned long long)(r + 1) << (3 * pcol);
     used |= 1u << pcol;
     __syncwarp();
   }
@@ -593,10 +590,11 @@ WBC_DEV unsigned gauss_jordan(WarpSmem& s, int lane, int m, int n, int& status) 
 }
 
 // Entry (var, column `lane`) of Z (free lanes) or of z0 (lane 31).
-WBC_DEV double zent(const WarpSmem& s, int lane, int var) {
-  const int r = s.rowof[var];
-  if (lane == 31) return r >= 0 ? s.A[r][31] : 0.0;
-  return r >= 0 ? -s.A[r][lane] : (var == lane ? 1.0 : 0.0);
+// Lane 31 holds the right-hand side in the same column index, with the opposite sign convention.
+WBC_DEV double zent(const WarpSmem& s, int lane, int var, unsigned long long rowmap) {
+  const int r = (int)((rowmap >> (3 * var)) & 7ull) - 1;
+  const double a = s.A[r >= 0 ? r : 0][lane];
+  return r >= 0 ? (lane == 31 ? a : -a) : (var == lane ? 1.0 : 0.0);
 }
 
 // ------------------------------------------------------------------------------ phase 5
@@ -981,11 +979,11 @@ WBC_DEV void put_y(WarpSmem& s, int row, int ycol, double val) { if (ycol >= 0) 
 
 // Rows 0-29 of Y for all controllers: a_b, per-leg rows (contact force of a stance leg, task acceleration J_s vd of a
 // swing leg), joint torques tau = M_j vd + h_j - L' f. Variables: 0-5 a_b, 6+3k+i = f_k,i (stance) or a_k,i (swing).
-WBC_DEV void build_common_rows(WarpSmem& s, int lane, int ycol, unsigned cmask, double* vdmap = nullptr) {
+WBC_DEV void build_common_rows(WarpSmem& s, int lane, int ycol, unsigned cmask, unsigned long long rowmap, double* vdmap = nullptr) {
   double zb[6];
 #pragma unroll
   for (int i = 0; i < 6; ++i) {
-    zb[i] = zent(s, lane, i); put_y(s, i, ycol, zb[i]);
+    zb[i] = zent(s, lane, i, rowmap); put_y(s, i, ycol, zb[i]);
     if (vdmap && ycol >= 0) vdmap[i * YS + ycol] = zb[i];
   }
 #pragma unroll
@@ -993,7 +991,7 @@ WBC_DEV void build_common_rows(WarpSmem& s, int lane, int ycol, unsigned cmask, 
     const bool stance = (cmask >> k) & 1;
     double zl[3], ak[3];
 #pragma unroll
-    for (int i = 0; i < 3; ++i) zl[i] = zent(s, lane, 6 + 3 * k + i);
+    for (int i = 0; i < 3; ++i) zl[i] = zent(s, lane, 6 + 3 * k + i, rowmap);
     const V3 rh = ld3(s.rho[k]);
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
@@ -1349,7 +1347,8 @@ WBC_DEV void reduce_instance(WarpSmem& s, const wbc_model& md, const wbc_params&
   const int ndelta = (KIND == WBC_CTRL_CLF) ? 1 : 0;
   const int n = 18 + ndelta, m = 6;
   build_base_system(s, lane, cmask, pr.contact_damping, status);
-  const unsigned used = gauss_jordan(s, lane, m, n, status);
+  unsigned long long rowmap;
+  const unsigned used = gauss_jordan(s, lane, m, n, status, rowmap);
   const unsigned freemask = ~used & ((n >= 32) ? 0xffffffffu : ((1u << n) - 1u));
   const int nf = __popc(freemask);
   const bool isfree = (freemask >> lane) & 1u;
@@ -1365,7 +1364,7 @@ WBC_DEV void reduce_instance(WarpSmem& s, const wbc_model& md, const wbc_params&
     for (int e = lane; e < YROWS * YS; e += 32) (&s.Y[0][0])[e] = 0.0;
     s.cw[lane] = 0.0; s.ct[lane] = 0.0;
     __syncwarp();
-    build_common_rows(s, lane, ycol, cmask, vdmap);
+    build_common_rows(s, lane, ycol, cmask, rowmap, vdmap);
     // ---- costs
     const double* tr = s.traj;
     if (KIND == WBC_CTRL_ID) {
