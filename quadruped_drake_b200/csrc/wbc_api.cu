@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(W * 32, WBC_MIN_WARPS / W) wbc_reduce_kernel(c
   SmemLayoutT<W>* sm = reinterpret_cast<SmemLayoutT<W>*>(smem_raw);
   pdl_launch_dependents();
   const bool staged = stage_inputs_issue(sm->in, a, bulk_ok != 0);
-  const DevConst& dc = stage_consts(sm, gdc);
+  const DevConst& dc = stage_consts(sm, gdc);   // (reading the tables through L1 instead of staging them measured neutral)
   const int warp = W == 1 ? 0 : (int)(threadIdx.x >> 5), lane = threadIdx.x & 31;
   const long long inst = (long long)blockIdx.x * W + warp;
   if (inst >= a.n) return;

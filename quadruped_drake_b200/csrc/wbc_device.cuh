@@ -1361,7 +1361,11 @@ WBC_DEV void reduce_instance(WarpSmem& s, const wbc_model& md, const wbc_params&
   double extra_bound = 0.0, Vl = 0.0, PFl = 0.0, csum = 0.0;
   if (ok) {
     // ---- phase 4
-    for (int e = lane; e < YROWS * YS; e += 32) (&s.Y[0][0])[e] = 0.0;
+    {
+      double* y0 = &s.Y[0][0];                                       // 16-byte aligned: pairs go out as one 128-bit store
+#pragma unroll
+      for (int e = lane; e < YROWS * YS / 2; e += 32) { y0[2 * e] = 0.0; y0[2 * e + 1] = 0.0; }
+    }
     s.cw[lane] = 0.0; s.ct[lane] = 0.0;
     __syncwarp();
     build_common_rows(s, lane, ycol, cmask, rowmap, vdmap);
