@@ -1105,7 +1105,7 @@ WBC_DEV void pc_precompute(WarpSmem& s, PcSmem& pc, const wbc_model& md, const w
     const double* d = s.Mleg[lane];
     const double a = d[0], b = d[1], c = d[2], e = d[3], f = d[4], g = d[5];     // [[a b c],[b e f],[c f g]]
     const double c00 = e * g - f * f, c01 = c * f - b * g, c02 = b * f - c * e;
-    const double det = a * c00 + b * c01 + c * c02, id = 1.0 / det;
+    const double det = a * c00 + b * c01 + c * c02, id = frcp(det);
     pc.Dinv[lane][0] = c00 * id; pc.Dinv[lane][1] = c01 * id; pc.Dinv[lane][2] = c02 * id;
     pc.Dinv[lane][3] = (a * g - c * c) * id; pc.Dinv[lane][4] = (b * c - a * f) * id; pc.Dinv[lane][5] = (a * e - b * b) * id;
   }
@@ -1126,7 +1126,7 @@ WBC_DEV void pc_precompute(WarpSmem& s, PcSmem& pc, const wbc_model& md, const w
   for (int j = 0; j < 6; ++j) {                     // Cholesky of Sb (lower), lanes = rows
     const double dj = pc.Sb[j][j];
     if (!(dj > 1e-300)) status |= WBC_ST_NOTPD;
-    const double inv = 1.0 / sqrt(dj > 1e-300 ? dj : 1.0);
+    const double inv = frsqrt(dj > 1e-300 ? dj : 1.0);
     __syncwarp();
     if (lane < 6 && lane >= j) pc.Sb[lane][j] *= inv;
     __syncwarp();
@@ -1160,14 +1160,14 @@ WBC_DEV void pc_precompute(WarpSmem& s, PcSmem& pc, const wbc_model& md, const w
       double acc = cb[i];
 #pragma unroll
       for (int k = 0; k < 6; ++k) if (k < i) acc = fma(-pc.Sb[i][k], xb[k], acc);
-      xb[i] = acc / pc.Sb[i][i];
+      xb[i] = acc * frcp(pc.Sb[i][i]);
     }
 #pragma unroll
     for (int i = 5; i >= 0; --i) {                  // L' x = y
       double acc = xb[i];
 #pragma unroll
       for (int k = 0; k < 6; ++k) if (k > i) acc = fma(-pc.Sb[k][i], xb[k], acc);
-      xb[i] = acc / pc.Sb[i][i];
+      xb[i] = acc * frcp(pc.Sb[i][i]);
     }
 #pragma unroll
     for (int i = 0; i < 6; ++i) X[i][lane] = xb[i];
@@ -1208,7 +1208,7 @@ WBC_DEV void pc_precompute(WarpSmem& s, PcSmem& pc, const wbc_model& md, const w
   for (int j = 0; j < m; ++j) {
     const double dj = pc.Lam[j][j];
     if (!(dj > 1e-300)) status |= WBC_ST_RANKDEF;   // J rank deficient (singular swing leg), pc_controller.py:160 would fail too
-    const double inv = 1.0 / sqrt(dj > 1e-300 ? dj : 1.0);
+    const double inv = frsqrt(dj > 1e-300 ? dj : 1.0);
     __syncwarp();
     if (on && lane >= j) pc.Lam[lane][j] *= inv;
     __syncwarp();
@@ -1220,7 +1220,7 @@ WBC_DEV void pc_precompute(WarpSmem& s, PcSmem& pc, const wbc_model& md, const w
     for (int i = 0; i < m; ++i) {
       double acc = (i == lane) ? 1.0 : 0.0;
       for (int k = lane; k < i; ++k) acc = fma(-pc.Lam[i][k], T[k][lane], acc);
-      T[i][lane] = (i >= lane) ? acc / pc.Lam[i][i] : 0.0;
+      T[i][lane] = (i >= lane) ? acc * frcp(pc.Lam[i][i]) : 0.0;
     }
   }
   __syncwarp();
