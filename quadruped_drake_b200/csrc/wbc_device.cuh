@@ -456,15 +456,15 @@ WBC_DEV void body_task(const WarpSmem& s, int lane, int& status, BodyTask& t) {
   double ang = atan2(num, den);
   t.rpy[0] = shfl(ang, 0); t.rpy[1] = shfl(ang, 1); t.rpy[2] = shfl(ang, 2);
   double cy, sy;
+  const double icp = cp < 1e-6 ? 0.0 : frcp(cp);       // one reciprocal serves cos / sin of the yaw and the rate map below
   if (cp < 1e-6) { status |= WBC_ST_GIMBAL; cy = 1.0; sy = 0.0; }
-  else { cy = r00 / cp; sy = r10 / cp; }
+  else { cy = r00 * icp; sy = r10 * icp; }
   const double sp = -r20;
   t.N[0][0] = cy * cp; t.N[0][1] = -sy; t.N[0][2] = 0.0;
   t.N[1][0] = sy * cp; t.N[1][1] = cy;  t.N[1][2] = 0.0;
   t.N[2][0] = -sp;     t.N[2][1] = 0.0; t.N[2][2] = 1.0;
   // rpyd = N^-1 omega
   const double wx = s.v[0], wy = s.v[1], wz = s.v[2];
-  const double icp = cp < 1e-6 ? 0.0 : 1.0 / cp;
   t.rpyd[0] = (cy * wx + sy * wy) * icp;
   t.rpyd[1] = -sy * wx + cy * wy;
   t.rpyd[2] = wz + sp * t.rpyd[0];
