@@ -20,7 +20,11 @@ namespace {
 // the CTA stages all four input arrays of its 4 consecutive instances with one bulk copy each - few large requests, which is
 // what the host link wants (e2e 25.3 vs 22.3 M steps/s at 4096).
 constexpr int WARPS = 1;         // device-resident buffers
-constexpr int WARPS_HOST = 4;    // host-mapped buffers
+#ifndef WBC_WARPS_HOST
+#define WBC_WARPS_HOST 4
+#endif
+constexpr int WARPS_HOST = WBC_WARPS_HOST;    // host-mapped buffers (ID / CLF)
+constexpr int WARPS_PC = 4;                   // PC / MPTC reduce kernel
 #ifndef WBC_MIN_WARPS
 #define WBC_MIN_WARPS 16         // resident warps per SM the reduce kernels are compiled for (128 registers)
 #endif
@@ -349,7 +353,7 @@ static int set_smem_attr(wbc_handle* h) {
   WBC_CUDA(h, cudaFuncSetAttribute(wbc_reduce_kernel<WBC_CTRL_CLF, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   WBC_CUDA(h, cudaFuncSetAttribute(wbc_reduce_kernel<WBC_CTRL_ID, WARPS_HOST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemLayoutT<WARPS_HOST>)));
   WBC_CUDA(h, cudaFuncSetAttribute(wbc_reduce_kernel<WBC_CTRL_CLF, WARPS_HOST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemLayoutT<WARPS_HOST>)));
-  WBC_CUDA(h, cudaFuncSetAttribute(wbc_reduce_pc_kernel<WARPS_HOST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemLayoutPCT<WARPS_HOST>)));
+  WBC_CUDA(h, cudaFuncSetAttribute(wbc_reduce_pc_kernel<WARPS_PC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemLayoutPCT<WARPS_PC>)));
   WBC_CUDA(h, cudaFuncSetAttribute(wbc_solve_kernel<WBC_CTRL_ID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemLayoutSolve)));
   WBC_CUDA(h, cudaFuncSetAttribute(wbc_solve_kernel<WBC_CTRL_CLF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemLayoutSolve)));
   WBC_CUDA(h, cudaFuncSetAttribute(wbc_solve_kernel<WBC_CTRL_PC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemLayoutSolve)));
@@ -536,7 +540,7 @@ static int launch_split(wbc_handle* h, int kind, int64_t n, const wbc_io* io, cu
     if (h->prof_on) cudaEventRecord(h->prof_ev[0], st);
     if (h->host_mapped || KIND == WBC_CTRL_PC) {   // zero-copy call of wbc_step_host: 4-warp CTAs, every array staged per CTA
                                                    // (PC / MPTC too: 20.0 vs 19.7 M steps/s with single-warp CTAs)
-      constexpr int W = WARPS_HOST;
+      constexpr int W = (KIND == WBC_CTRL_PC) ? WARPS_PC : WARPS_HOST;
       const unsigned grid = (unsigned)((m + W - 1) / W);
       const int bulk_ok = bulk_in_mode() && al_vt && al_qc;
       if constexpr (KIND == WBC_CTRL_PC) wbc_reduce_pc_kernel<W><<<grid, W * 32, sizeof(SmemLayoutPCT<W>), st>>>(h->d_const, a, h->d_rec[slot], vdmap, bulk_ok);
