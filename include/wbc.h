@@ -21,7 +21,10 @@
  *     reference writes to its `quad_torques` port (basic_controller.py:320);
  *   - metrics[4] = [V, err, res, Vdot] (basic_controller.py:271-283);
  *   - per-instance failures go to status[i] (bit mask below), never abort the batch
- *     (the reference asserts instead: inverse_dynamics_controller.py:224);
+ *     (the reference asserts instead: inverse_dynamics_controller.py:224). An instance with ANY status bit set
+ *     returns tau = 0 (and f = vd = lam = 0 where requested): an unfinished active-set iterate, a substituted
+ *     orientation (bad quaternion, gimbal lock) or a rank-deficient problem never leaves the library as torques.
+ *     metrics[1] (err) is still the tracking error of the state; callers must mask on status;
  *   - "device" entry points take device pointers and a cudaStream_t passed as void*;
  *     "_host" entry points take host pointers and do the copies themselves.
  *   - one handle per device; calls on one handle must be serialised by the caller.
@@ -43,6 +46,7 @@ extern "C" {
 #define WBC_NBODY 13      /* floating base + 4 x (hip/abduct, thigh, shank) after welding */
 #define WBC_NTRAJ 54
 #define WBC_NMETRIC 4
+#define WBC_NLAM 42       /* inequality multipliers: 16 friction rows + 2 controller rows + 24 torque-box rows */
 
 /* return codes */
 #define WBC_OK 0
@@ -125,6 +129,13 @@ typedef struct wbc_io {
   double* vd;             /* [N][18] QP accelerations, Drake velocity order (optional)  */
   double* f;              /* [N][12] contact forces LF RF LH RH, 0 for swing (optional) */
   double* qp_info;        /* [N][4]  objective, max primal violation, delta, #iters (optional) */
+  double* lam;            /* [N][42] multipliers (>= 0) of the inequality rows at the returned optimum (optional):
+                           *   [4 foot + t]  friction pyramid of foot LF RF LH RH, rows t = +x, -x, +y, -y
+                           *                 (inverse_dynamics_controller.py:66-86, A_i row order)
+                           *   [16], [17]    controller rows: CLF Vdot row (clf_controller.py:27-45) / PC passivity row
+                           *                 (pc_controller.py:14-40, delta eliminated); [17] unused
+                           *   [18 + a], [30 + a]   torque box  +tau_a <= effort_a,  -tau_a <= effort_a  (actuator order a)
+                           * with these, x = [vd; tau; f] satisfies the KKT conditions of the reference QP (+ tie-break) */
 } wbc_io;
 
 /* Fill *p with the reference's constants. */
@@ -154,8 +165,10 @@ int wbc_coriolis_host(wbc_handle* h, int64_t n, const double* q, const double* v
 /* One control step for n instances: DoSetControlTorques -> ControlLaw
  * (basic_controller.py:286-320; inverse_dynamics_controller.py:103-234;
  * clf_controller.py:48-234; pc_controller.py:43-255). Device pointers (or page-locked host memory mapped into the
- * device address space). The step uses per-handle scratch (4.5 KB per instance, at most 262144 instances at a time): calls
- * on one handle must not overlap on the device, i.e. use one stream per handle or order the streams yourself. */
+ * device address space). The step uses per-handle scratch (4.5 KB per instance, at most 262144 instances at a time), so steps
+ * of one handle are serialised on the device: a call on a different stream than the previous call of the handle first makes
+ * its stream wait for the work submitted to the previous one (an event dependency, no host synchronisation). Host threads must
+ * still serialise their calls on one handle; different handles are independent. */
 int wbc_step(wbc_handle* h, int kind, int64_t n, const wbc_io* io, void* stream);
 int wbc_step_id(wbc_handle* h, int64_t n, const double* q, const double* v, const double* traj,
                 const uint8_t* contact, double* tau, double* metrics, int32_t* status, void* stream);

@@ -164,10 +164,10 @@ static int qp_ipm(int n, int me, int mi, const double* P, const double* qv, cons
   const int nk = n + me;
   memset(x, 0, n * sizeof(double)); memset(nu, 0, sizeof(nu));
   for (int i = 0; i < mi; ++i) { s[i] = h[i] > 1.0 ? h[i] : 1.0; lam[i] = 1.0; }
-  double best_score = 1e300;
-  int it;
+  double best_score = 1e300, prev_mu = 1e300;
+  int it, stall = 0, slow = 0;
   memcpy(best, x, n * sizeof(double));
-  for (it = 1; it <= 60; ++it) {
+  for (it = 1; it <= 100; ++it) {
     double score = 0.0, mu = 0.0;
     for (int i = 0; i < n; ++i) {
       double r = qv[i];
@@ -179,6 +179,11 @@ static int qp_ipm(int n, int me, int mi, const double* P, const double* qv, cons
     for (int i = 0; i < me; ++i) { double r = -b[i]; for (int j = 0; j < n; ++j) r += A[i * n + j] * x[j]; re[i] = r; if (fabs(r) > score) score = fabs(r); }
     for (int i = 0; i < mi; ++i) { double r = s[i] - h[i]; for (int j = 0; j < n; ++j) r += G[i * n + j] * x[j]; ri[i] = r; if (fabs(r) > score) score = fabs(r); mu += lam[i] * s[i]; }
     if (mi) mu /= mi;
+    /* jamming guard: when the complementarity gap stops shrinking for two iterations (a badly centred pair caps the step length), the next
+       iterations are pure centring steps (sigma = 0.7, no second-order term) until it moves again */
+    slow = (mi && it > 12 && mu > 0.9 * prev_mu) ? slow + 1 : 0;
+    if (slow >= 2 || it > 40) stall = 1;      /* sticky: rare (a handful of instances per 4096) */
+    prev_mu = mu;
     if (mu > score) score = mu;
     if (!(score == score)) break;
     if (score < best_score) { best_score = score; memcpy(best, x, n * sizeof(double)); }
@@ -194,7 +199,7 @@ static int qp_ipm(int n, int me, int mi, const double* P, const double* qv, cons
     if (lu_factor(K, nk, nk, piv)) break;
     double alpha = 1.0, sigma = 0.0;
     for (int pass = 0; pass < (mi ? 2 : 1); ++pass) {
-      for (int i = 0; i < mi; ++i) rc[i] = (pass == 0) ? lam[i] * s[i] : lam[i] * s[i] + dsa[i] * dla[i] - sigma * mu;
+      for (int i = 0; i < mi; ++i) rc[i] = (pass == 0) ? lam[i] * s[i] : lam[i] * s[i] + (stall ? 0.0 : dsa[i] * dla[i]) - sigma * mu;
       for (int i = 0; i < n; ++i) {
         double r = -rd[i];
         for (int c = 0; c < mi; ++c) r += G[c * n + i] * (rc[c] - lam[c] * ri[c]) / s[c];
@@ -216,6 +221,7 @@ static int qp_ipm(int n, int me, int mi, const double* P, const double* qv, cons
         for (int c = 0; c < mi; ++c) mua += (lam[c] + alpha * dla[c]) * (s[c] + alpha * dsa[c]);
         mua /= mi;
         sigma = mu > 0 ? (mua / mu) * (mua / mu) * (mua / mu) : 0.0;
+        if (stall && sigma < 0.7) sigma = 0.7;
       }
     }
     if (mi) { alpha *= 0.99; if (alpha > 1.0) alpha = 1.0; }

@@ -34,8 +34,8 @@ def id_batch(robot, q, v, traj, contact, threads=None, **params):
     return tau, vd, f, st
 
 
-def time_id_steps(robot, q, v, traj, contact, budget_s=20.0):
-    """Throughput of the C port on all host cores over a bounded sample (bench.py cpu_baseline)."""
+def time_id_steps(robot, q, v, traj, contact, budget_s=20.0, single_thread_s=3.0):
+    """Throughput of the C port over a bounded sample (bench.py cpu_baseline): all host cores, and one thread."""
     cores = os.cpu_count() or 1
     n0 = min(len(q), 8 * cores)
     t0 = time.perf_counter()
@@ -45,9 +45,16 @@ def time_id_steps(robot, q, v, traj, contact, budget_s=20.0):
     t0 = time.perf_counter()
     _, _, _, st = id_batch(robot, q[:n], v[:n], traj[:n], contact[:n], cores)
     wall = time.perf_counter() - t0
+    n1 = int(max(8, min(len(q), single_thread_s / max(per * cores, 1e-9))))
+    t0 = time.perf_counter()
+    id_batch(robot, q[:n1], v[:n1], traj[:n1], contact[:n1], 1)
+    wall1 = time.perf_counter() - t0
     return {"value": n / wall, "unit": "steps/s", "cores": cores, "kind": "port",
+            "single_thread": {"value": n1 / wall1, "unit": "steps/s", "sample": f"{n1} instances on one thread"},
+            "not_converged": int((st != 0).sum()), "build": "gcc -O3 -march=native",
+            "label": "CPU restatement of the reference path (C port of the oracle), NOT Drake + OSQP",
             "sample": f"{n} of the {len(q)} instances of one batch, C restatement of the reference path (oracle/c/oracle_id.c: "
-                      f"18-pass mass matrix + full-size dense IPM QP), one instance stream per host thread; {int((st != 0).sum())} not converged"}
+                      f"18-pass mass matrix + full-size dense IPM QP), one instance stream per host thread"}
 
 
 def fk(robot):

@@ -19,7 +19,14 @@ LIB_PATH = Path(os.environ.get("WBC_LIB") or (Path(__file__).resolve().parent / 
 
 WBC_CTRL_ID, WBC_CTRL_CLF, WBC_CTRL_PC, WBC_CTRL_MPTC, WBC_CTRL_PD = 0, 1, 2, 3, 4
 KINDS = {"id": WBC_CTRL_ID, "clf": WBC_CTRL_CLF, "pc": WBC_CTRL_PC, "mptc": WBC_CTRL_MPTC, "pd": WBC_CTRL_PD}
-ST_MAXITER, ST_INFEASIBLE, ST_RANKDEF, ST_GIMBAL, ST_NOTPD, ST_BADQUAT, ST_UNSUPPORTED = 1, 2, 4, 8, 16, 32, 64
+ST_MAXITER, ST_INFEASIBLE, ST_RANKDEF, ST_GIMBAL, ST_NOTPD, ST_BADQUAT, ST_UNSUPPORTED, ST_DIVERGED = 1, 2, 4, 8, 16, 32, 64, 128
+NLAM = 42
+_ST_NAMES = {ST_MAXITER: "MAXITER", ST_INFEASIBLE: "INFEASIBLE", ST_RANKDEF: "RANKDEF", ST_GIMBAL: "GIMBAL", ST_NOTPD: "NOTPD",
+             ST_BADQUAT: "BADQUAT", ST_UNSUPPORTED: "UNSUPPORTED", ST_DIVERGED: "DIVERGED"}
+
+
+def status_names(status: int) -> str:
+    return "|".join(n for b, n in _ST_NAMES.items() if status & b) or "OK"
 
 _PARAM_DOUBLES = [
     "id_kp_body_p", "id_kd_body_p", "id_kp_body_rpy", "id_kd_body_rpy", "id_kp_foot", "id_kd_foot", "id_w_body", "id_w_foot",
@@ -69,7 +76,7 @@ class WbcIO(C.Structure):
     """ctypes mirror of `wbc_io`; pointers are raw addresses (host or device)."""
     _fields_ = [("q", C.c_void_p), ("v", C.c_void_p), ("traj", C.c_void_p), ("contact", C.c_void_p),
                 ("tau", C.c_void_p), ("metrics", C.c_void_p), ("status", C.c_void_p),
-                ("vd", C.c_void_p), ("f", C.c_void_p), ("qp_info", C.c_void_p)]
+                ("vd", C.c_void_p), ("f", C.c_void_p), ("qp_info", C.c_void_p), ("lam", C.c_void_p)]
 
 
 class WbcRolloutIO(C.Structure):

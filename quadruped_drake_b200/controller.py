@@ -61,10 +61,10 @@ def _is_torch(x):
 
 
 class StepOutput:
-    __slots__ = ("tau", "metrics", "status", "vd", "f", "qp_info")
+    __slots__ = ("tau", "metrics", "status", "vd", "f", "qp_info", "lam")
 
-    def __init__(self, tau, metrics, status, vd=None, f=None, qp_info=None):
-        self.tau, self.metrics, self.status, self.vd, self.f, self.qp_info = tau, metrics, status, vd, f, qp_info
+    def __init__(self, tau, metrics, status, vd=None, f=None, qp_info=None, lam=None):
+        self.tau, self.metrics, self.status, self.vd, self.f, self.qp_info, self.lam = tau, metrics, status, vd, f, qp_info, lam
 
     def __iter__(self):
         return iter((self.tau, self.metrics, self.status))
@@ -121,10 +121,12 @@ class BatchedController:
         vd = np.empty((n, NV)) if debug else None
         f = np.empty((n, 4, 3)) if debug else None
         qi = np.empty((n, 4)) if debug else None
+        lam = np.empty((n, capi.NLAM)) if debug else None
         io = WbcIO(np_ptr(q), np_ptr(v), np_ptr(traj), np_ptr(contact), np_ptr(tau), np_ptr(met), np_ptr(st),
-                   np_ptr(vd) if debug else None, np_ptr(f) if debug else None, np_ptr(qi) if debug else None)
+                   np_ptr(vd) if debug else None, np_ptr(f) if debug else None, np_ptr(qi) if debug else None,
+                   np_ptr(lam) if debug else None)
         self._check(self.lib.wbc_step_host(self._h, k, n, C.byref(io)), "wbc_step_host")
-        return StepOutput(tau, met, st, vd, f, qi)
+        return StepOutput(tau, met, st, vd, f, qi, lam)
 
     def step_pd(self, q, v):
         """BasicController.ControlLaw (basic_controller.py:322-352) for a batch of host states -> tau[N,12]."""
@@ -149,15 +151,16 @@ class BatchedController:
         vd = torch.empty((n, NV), dtype=torch.float64, device=dev) if debug else None
         f = torch.empty((n, 4, 3), dtype=torch.float64, device=dev) if debug else None
         qi = torch.empty((n, 4), dtype=torch.float64, device=dev) if debug else None
-        io = self.make_io(q, v, traj, contact, tau, met, st, vd, f, qi)
+        lam = torch.empty((n, capi.NLAM), dtype=torch.float64, device=dev) if debug else None
+        io = self.make_io(q, v, traj, contact, tau, met, st, vd, f, qi, lam)
         stream = torch.cuda.current_stream(dev).cuda_stream
         self._check(self.lib.wbc_step(self._h, k, n, C.byref(io), C.c_void_p(stream)), "wbc_step")
-        return StepOutput(tau, met, st, vd, f, qi)
+        return StepOutput(tau, met, st, vd, f, qi, lam)
 
     @staticmethod
-    def make_io(q, v, traj, contact, tau, met, st, vd=None, f=None, qi=None) -> WbcIO:
+    def make_io(q, v, traj, contact, tau, met, st, vd=None, f=None, qi=None, lam=None) -> WbcIO:
         p = lambda t: None if t is None else C.c_void_p(t.data_ptr())  # noqa: E731
-        return WbcIO(p(q), p(v), p(traj), p(contact), p(tau), p(met), p(st), p(vd), p(f), p(qi))
+        return WbcIO(p(q), p(v), p(traj), p(contact), p(tau), p(met), p(st), p(vd), p(f), p(qi), p(lam))
 
     def time_step(self, kind, io: WbcIO, n: int, reps: int, stream=0) -> float:
         """Mean device milliseconds per launch over `reps` back-to-back launches (CUDA events on `stream`)."""
@@ -370,8 +373,10 @@ class _QPController(LeafSystem):
         traj, contact = dict_to_traj(trunk)
         out = self.batched.step(self.KIND, q[None], v[None], traj[None], contact[None])
         self.last_status = int(out.status[0])
-        assert self.last_status & (capi.ST_INFEASIBLE | capi.ST_MAXITER | capi.ST_RANKDEF | capi.ST_NOTPD) == 0, \
-            f"QP solve failed (status {self.last_status})"   # reference: assert result.is_success()
+        # reference: `assert result.is_success()` (inverse_dynamics_controller.py:224); a zero / non-finite quaternion, gimbal
+        # lock (CalcRpyDtFromAngularVelocityInParent) and PC in full flight (pc_controller.py:248-249) raise inside Drake /
+        # NumPy there, so every status bit raises here
+        assert self.last_status == 0, f"QP solve failed (status {self.last_status}: {capi.status_names(self.last_status)})"
         m = out.metrics[0]
         self._log(m)
         return out.tau[0].copy()

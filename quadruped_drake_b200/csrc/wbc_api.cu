@@ -299,7 +299,7 @@ struct wbc_handle {
   // device staging for wbc_step_host
   int64_t cap = 0;
   double *d_q = nullptr, *d_v = nullptr, *d_traj = nullptr, *d_tau = nullptr, *d_metrics = nullptr, *d_vd = nullptr,
-         *d_f = nullptr, *d_info = nullptr;
+         *d_f = nullptr, *d_info = nullptr, *d_lam = nullptr;
   uint8_t* d_contact = nullptr;
   int32_t* d_status = nullptr;
   // scratch of wbc_rollout (sized for ro_cap instances)
@@ -312,6 +312,10 @@ struct wbc_handle {
   cudaEvent_t prof_ev[3] = {nullptr, nullptr, nullptr};   // wbc_profile_step: before reduce / between / after solve
   bool prof_on = false;
   bool host_mapped = false;                               // set around the zero-copy launches of wbc_step_host
+  // per-slot ordering of the scratch users: the stream of the last step that used the slot and an event to chain a new one
+  cudaStream_t last_stream[2] = {nullptr, nullptr};
+  bool slot_used[2] = {false, false};
+  cudaEvent_t order_ev = nullptr;
   double* d_rec[2] = {nullptr, nullptr};
   double* d_vdmap[2] = {nullptr, nullptr};
   int64_t rec_cap[2] = {0, 0}, vdmap_cap[2] = {0, 0};
@@ -406,8 +410,8 @@ extern "C" int wbc_create(const wbc_model* model, const wbc_params* params, int 
 
 static void free_staging(wbc_handle* h) {
   cudaFree(h->d_q); cudaFree(h->d_v); cudaFree(h->d_traj); cudaFree(h->d_tau); cudaFree(h->d_metrics);
-  cudaFree(h->d_vd); cudaFree(h->d_f); cudaFree(h->d_info); cudaFree(h->d_contact); cudaFree(h->d_status);
-  h->d_q = h->d_v = h->d_traj = h->d_tau = h->d_metrics = h->d_vd = h->d_f = h->d_info = nullptr;
+  cudaFree(h->d_vd); cudaFree(h->d_f); cudaFree(h->d_info); cudaFree(h->d_lam); cudaFree(h->d_contact); cudaFree(h->d_status);
+  h->d_q = h->d_v = h->d_traj = h->d_tau = h->d_metrics = h->d_vd = h->d_f = h->d_info = h->d_lam = nullptr;
   h->d_contact = nullptr; h->d_status = nullptr; h->cap = 0;
 }
 
@@ -421,6 +425,7 @@ extern "C" int wbc_destroy(wbc_handle* h) {
   cudaFree(h->ro_contact); cudaFree(h->ro_status); cudaFree(h->ro_counter);
   for (int i = 0; i < 2; ++i) { cudaFree(h->d_rec[i]); cudaFree(h->d_vdmap[i]); }
   for (int i = 0; i < 3; ++i) if (h->prof_ev[i]) cudaEventDestroy(h->prof_ev[i]);
+  if (h->order_ev) cudaEventDestroy(h->order_ev);
   if (h->stream) cudaStreamDestroy(h->stream);
   if (h->stream2) cudaStreamDestroy(h->stream2);
   delete h;
@@ -456,25 +461,55 @@ extern "C" int wbc_coriolis(wbc_handle* h, int64_t n, const double* q, const dou
   return WBC_OK;
 }
 
+namespace {
+// Scratch device buffers of the host-buffer debug / codec entries: freed when the scope ends (early error returns included).
+struct DevScratch {
+  void* p[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // at most 8 buffers per scratch
+  int used = 0;
+  cudaError_t err = cudaSuccess;
+  template <typename T> T* in(const T* host, size_t count, cudaStream_t st) {      // NULL stays NULL
+    if (!host || err != cudaSuccess) return nullptr;
+    T* d = out<T>(host, count);
+    if (d) err = cudaMemcpyAsync(d, host, count * sizeof(T), cudaMemcpyHostToDevice, st);
+    return d;
+  }
+  template <typename T> T* out(const T* host, size_t count) {
+    if (!host || err != cudaSuccess) return nullptr;
+    void* d = nullptr;
+    err = cudaMalloc(&d, count * sizeof(T) > 0 ? count * sizeof(T) : 1);
+    if (err != cudaSuccess) return nullptr;
+    p[used++] = d;
+    return static_cast<T*>(d);
+  }
+  template <typename T> void back(T* host, const T* dev, size_t count, cudaStream_t st) {
+    if (host && dev && err == cudaSuccess) err = cudaMemcpyAsync(host, dev, count * sizeof(T), cudaMemcpyDeviceToHost, st);
+  }
+  ~DevScratch() { for (int i = 0; i < used; ++i) cudaFree(p[i]); }
+};
+}  // namespace
+
+#define WBC_SCRATCH_CHECK(h, s)                                                                  \
+  do {                                                                                           \
+    if ((s).err != cudaSuccess) { (h)->err = std::string("host-buffer entry: ") + cudaGetErrorString((s).err); return WBC_ERR_CUDA; } \
+  } while (0)
+
 extern "C" int wbc_coriolis_host(wbc_handle* h, int64_t n, const double* q, const double* v, double* Cm, double* Jd) {
   if (!h) return WBC_ERR_ARG;
   if (n <= 0) return n == 0 ? WBC_OK : fail_arg(h, "wbc_coriolis_host: n < 0");
+  if (!q || !v) return fail_arg(h, "wbc_coriolis_host: null input");
   WBC_CUDA(h, cudaSetDevice(h->device));
   cudaStream_t st = h->stream;
-  double *dq, *dv, *dC = nullptr, *dJ = nullptr;
-  WBC_CUDA(h, cudaMalloc(&dq, n * WBC_NQ * 8)); WBC_CUDA(h, cudaMalloc(&dv, n * WBC_NV * 8));
-  if (Cm) WBC_CUDA(h, cudaMalloc(&dC, n * 324 * 8));
-  if (Jd) WBC_CUDA(h, cudaMalloc(&dJ, n * 216 * 8));
-  WBC_CUDA(h, cudaMemcpyAsync(dq, q, n * WBC_NQ * 8, cudaMemcpyHostToDevice, st));
-  WBC_CUDA(h, cudaMemcpyAsync(dv, v, n * WBC_NV * 8, cudaMemcpyHostToDevice, st));
+  DevScratch s;
+  const size_t N = (size_t)n;
+  const double* dq = s.in(q, N * WBC_NQ, st); const double* dv = s.in(v, N * WBC_NV, st);
+  double* dC = s.out(Cm, N * 324); double* dJ = s.out(Jd, N * 216);
+  WBC_SCRATCH_CHECK(h, s);
   int rc = wbc_coriolis(h, n, dq, dv, dC, dJ, st);
-  if (rc == WBC_OK) {
-    if (Cm) WBC_CUDA(h, cudaMemcpyAsync(Cm, dC, n * 324 * 8, cudaMemcpyDeviceToHost, st));
-    if (Jd) WBC_CUDA(h, cudaMemcpyAsync(Jd, dJ, n * 216 * 8, cudaMemcpyDeviceToHost, st));
-    WBC_CUDA(h, cudaStreamSynchronize(st));
-  }
-  cudaFree(dq); cudaFree(dv); cudaFree(dC); cudaFree(dJ);
-  return rc;
+  if (rc) return rc;
+  s.back(Cm, dC, N * 324, st); s.back(Jd, dJ, N * 216, st);
+  WBC_SCRATCH_CHECK(h, s);
+  WBC_CUDA(h, cudaStreamSynchronize(st));
+  return WBC_OK;
 }
 
 extern "C" int wbc_step_pd(wbc_handle* h, int64_t n, const double* q, const double* v, double* tau, void* stream) {
@@ -512,7 +547,8 @@ static int ensure_split_scratch(wbc_handle* h, int slot, int64_t n, bool with_vd
 static wbc::StepArgs offset_args(const wbc_io* io, int64_t o, int64_t m, int kind) {
   return wbc::StepArgs{io->q + o * WBC_NQ, io->v + o * WBC_NV, io->traj + o * WBC_NTRAJ, io->contact + o * 4, io->tau + o * WBC_NU,
                        io->metrics + o * WBC_NMETRIC, io->status + o, io->vd ? io->vd + o * WBC_NV : nullptr,
-                       io->f ? io->f + o * 12 : nullptr, io->qp_info ? io->qp_info + o * 4 : nullptr, (long long)m, kind};
+                       io->f ? io->f + o * 12 : nullptr, io->qp_info ? io->qp_info + o * 4 : nullptr,
+                       io->lam ? io->lam + o * WBC_NLAM : nullptr, (long long)m, kind};
 }
 
 static int pdl_mode() {   // WBC_PDL=0: ordinary launch of the solve kernel (A/B comparisons)
@@ -527,9 +563,29 @@ static int bulk_in_mode() {   // WBC_BULK_IN=0: per-lane input loads everywhere 
   return mode;
 }
 
+// The hand-over scratch of a slot belongs to one step at a time. A step on another stream than the slot's previous user is
+// ordered behind everything submitted to that stream so far (event dependency; never inside a stream capture, where the
+// caller owns the ordering).
+static int order_slot(wbc_handle* h, int slot, cudaStream_t st) {
+  if (h->slot_used[slot] && h->last_stream[slot] != st) {
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &cap);
+    if (cap == cudaStreamCaptureStatusNone) {
+      if (!h->order_ev) WBC_CUDA(h, cudaEventCreateWithFlags(&h->order_ev, cudaEventDisableTiming));
+      if (cudaEventRecord(h->order_ev, h->last_stream[slot]) == cudaSuccess) WBC_CUDA(h, cudaStreamWaitEvent(st, h->order_ev, 0));
+      else cudaGetLastError();      // the previous stream no longer exists: its work has completed
+    }
+  }
+  h->slot_used[slot] = true;
+  h->last_stream[slot] = st;
+  return WBC_OK;
+}
+
 template <int KIND>
 static int launch_split(wbc_handle* h, int kind, int64_t n, const wbc_io* io, cudaStream_t st, int slot) {
   int rc = ensure_split_scratch(h, slot, n, io->vd != nullptr);
+  if (rc) return rc;
+  rc = order_slot(h, slot, st);
   if (rc) return rc;
   double* vdmap = io->vd ? h->d_vdmap[slot] : nullptr;
   for (int64_t o = 0; o < n; o += SPLIT_CHUNK) {
@@ -628,6 +684,7 @@ static int ensure_staging(wbc_handle* h, int64_t n) {
   WBC_CUDA(h, cudaMalloc(&h->d_vd, n * WBC_NV * sizeof(double)));
   WBC_CUDA(h, cudaMalloc(&h->d_f, n * 12 * sizeof(double)));
   WBC_CUDA(h, cudaMalloc(&h->d_info, n * 4 * sizeof(double)));
+  WBC_CUDA(h, cudaMalloc(&h->d_lam, n * WBC_NLAM * sizeof(double)));
   h->cap = n;
   return WBC_OK;
 }
@@ -647,14 +704,14 @@ extern "C" int wbc_step_host(wbc_handle* h, int kind, int64_t n, const wbc_io* i
   {
     int mode = -1;   // auto; WBC_HOST_ZEROCOPY=0 / 1 forces the staged / zero-copy path (experiments)
     if (const char* env = getenv("WBC_HOST_ZEROCOPY")) mode = atoi(env);
-    const void* ptrs[10] = {io->q, io->v, io->traj, io->contact, io->tau, io->metrics, io->status, io->vd, io->f, io->qp_info};
-    void* dev[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    const void* ptrs[11] = {io->q, io->v, io->traj, io->contact, io->tau, io->metrics, io->status, io->vd, io->f, io->qp_info, io->lam};
+    void* dev[11] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     // Measured on B200 (profiles/README.md): zero-copy wins up to ~10^5 instances per call (no staging copies, no extra API
     // calls; the host link delivers ~32 GB/s to the SMs); above that the copy engines (~55 GB/s) in a chunked two-stream
     // pipeline win, so large page-locked batches take the staged path below with 65536-instance chunks.
     if (mode < 0) { static const long long thr = getenv("WBC_ZC_MAX") ? atoll(getenv("WBC_ZC_MAX")) : 131072; mode = n >= thr ? 0 : 1; }
     bool pinned = mode != 0;
-    for (int i = 0; i < 10 && pinned; ++i) {
+    for (int i = 0; i < 11 && pinned; ++i) {
       if (!ptrs[i]) continue;
       cudaPointerAttributes at;
       if (cudaPointerGetAttributes(&at, ptrs[i]) != cudaSuccess || at.type != cudaMemoryTypeHost || !at.devicePointer) { pinned = false; cudaGetLastError(); }
@@ -662,7 +719,7 @@ extern "C" int wbc_step_host(wbc_handle* h, int kind, int64_t n, const wbc_io* i
     }
     if (pinned) {
       wbc_io dio{(const double*)dev[0], (const double*)dev[1], (const double*)dev[2], (const uint8_t*)dev[3], (double*)dev[4],
-                 (double*)dev[5], (int32_t*)dev[6], (double*)dev[7], (double*)dev[8], (double*)dev[9]};
+                 (double*)dev[5], (int32_t*)dev[6], (double*)dev[7], (double*)dev[8], (double*)dev[9], (double*)dev[10]};
       // The batch goes through in chunks alternating between two streams (each with its own hand-over scratch), so that the
       // input-bound reduce kernel of one chunk overlaps the solve kernel of the previous one and the host link stays busy.
       int zc = 1;
@@ -677,7 +734,8 @@ extern "C" int wbc_step_host(wbc_handle* h, int kind, int64_t n, const wbc_io* i
         const wbc_io cio{dio.q + o * WBC_NQ, dio.v + o * WBC_NV, dio.traj ? dio.traj + o * WBC_NTRAJ : nullptr,
                          dio.contact ? dio.contact + o * 4 : nullptr, dio.tau + o * WBC_NU,
                          dio.metrics ? dio.metrics + o * WBC_NMETRIC : nullptr, dio.status ? dio.status + o : nullptr,
-                         dio.vd ? dio.vd + o * WBC_NV : nullptr, dio.f ? dio.f + o * 12 : nullptr, dio.qp_info ? dio.qp_info + o * 4 : nullptr};
+                         dio.vd ? dio.vd + o * WBC_NV : nullptr, dio.f ? dio.f + o * 12 : nullptr, dio.qp_info ? dio.qp_info + o * 4 : nullptr,
+                         dio.lam ? dio.lam + o * WBC_NLAM : nullptr};
         h->host_mapped = true;
         rc = pd ? wbc_step_pd(h, m, cio.q, cio.v, cio.tau, lanes[c & 1]) : step_launch(h, kind, m, &cio, lanes[c & 1], c & 1);
         h->host_mapped = false;
@@ -716,7 +774,8 @@ extern "C" int wbc_step_host(wbc_handle* h, int kind, int64_t n, const wbc_io* i
     }
     wbc_io dio{h->d_q + o * WBC_NQ, h->d_v + o * WBC_NV, h->d_traj + o * WBC_NTRAJ, h->d_contact + o * 4, h->d_tau + o * WBC_NU,
                h->d_metrics + o * WBC_NMETRIC, h->d_status + o,
-               io->vd ? h->d_vd + o * WBC_NV : nullptr, io->f ? h->d_f + o * 12 : nullptr, io->qp_info ? h->d_info + o * 4 : nullptr};
+               io->vd ? h->d_vd + o * WBC_NV : nullptr, io->f ? h->d_f + o * 12 : nullptr, io->qp_info ? h->d_info + o * 4 : nullptr,
+               io->lam ? h->d_lam + o * WBC_NLAM : nullptr};
     rc = pd ? wbc_step_pd(h, m, dio.q, dio.v, dio.tau, st) : step_launch(h, kind, m, &dio, st, c & 1);
     if (rc) return rc;
     WBC_CUDA(h, cudaMemcpyAsync(io->tau + o * WBC_NU, h->d_tau + o * WBC_NU, m * WBC_NU * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -726,6 +785,7 @@ extern "C" int wbc_step_host(wbc_handle* h, int kind, int64_t n, const wbc_io* i
       if (io->vd) WBC_CUDA(h, cudaMemcpyAsync(io->vd + o * WBC_NV, h->d_vd + o * WBC_NV, m * WBC_NV * sizeof(double), cudaMemcpyDeviceToHost, st));
       if (io->f) WBC_CUDA(h, cudaMemcpyAsync(io->f + o * 12, h->d_f + o * 12, m * 12 * sizeof(double), cudaMemcpyDeviceToHost, st));
       if (io->qp_info) WBC_CUDA(h, cudaMemcpyAsync(io->qp_info + o * 4, h->d_info + o * 4, m * 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
+      if (io->lam) WBC_CUDA(h, cudaMemcpyAsync(io->lam + o * WBC_NLAM, h->d_lam + o * WBC_NLAM, m * WBC_NLAM * sizeof(double), cudaMemcpyDeviceToHost, st));
     }
   }
   WBC_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -737,30 +797,22 @@ extern "C" int wbc_dynamics_host(wbc_handle* h, int64_t n, const double* q, cons
                                  double* taug, double* Jfeet, double* Jdv, double* pfeet) {
   if (!h) return WBC_ERR_ARG;
   if (n <= 0) return n == 0 ? WBC_OK : fail_arg(h, "wbc_dynamics_host: n < 0");
+  if (!q || !v) return fail_arg(h, "wbc_dynamics_host: null input");
   WBC_CUDA(h, cudaSetDevice(h->device));
   cudaStream_t st = h->stream;
-  double *dq, *dv, *dM = nullptr, *dCv = nullptr, *dtg = nullptr, *dJ = nullptr, *dJdv = nullptr, *dp = nullptr;
-  WBC_CUDA(h, cudaMalloc(&dq, n * WBC_NQ * 8)); WBC_CUDA(h, cudaMalloc(&dv, n * WBC_NV * 8));
-  if (M) WBC_CUDA(h, cudaMalloc(&dM, n * 324 * 8));
-  if (Cv) WBC_CUDA(h, cudaMalloc(&dCv, n * 18 * 8));
-  if (taug) WBC_CUDA(h, cudaMalloc(&dtg, n * 18 * 8));
-  if (Jfeet) WBC_CUDA(h, cudaMalloc(&dJ, n * 216 * 8));
-  if (Jdv) WBC_CUDA(h, cudaMalloc(&dJdv, n * 12 * 8));
-  if (pfeet) WBC_CUDA(h, cudaMalloc(&dp, n * 12 * 8));
-  WBC_CUDA(h, cudaMemcpyAsync(dq, q, n * WBC_NQ * 8, cudaMemcpyHostToDevice, st));
-  WBC_CUDA(h, cudaMemcpyAsync(dv, v, n * WBC_NV * 8, cudaMemcpyHostToDevice, st));
+  DevScratch s;
+  const size_t N = (size_t)n;
+  const double* dq = s.in(q, N * WBC_NQ, st); const double* dv = s.in(v, N * WBC_NV, st);
+  double* dM = s.out(M, N * 324); double* dCv = s.out(Cv, N * 18); double* dtg = s.out(taug, N * 18);
+  double* dJ = s.out(Jfeet, N * 216); double* dJdv = s.out(Jdv, N * 12); double* dp = s.out(pfeet, N * 12);
+  WBC_SCRATCH_CHECK(h, s);
   int rc = wbc_dynamics(h, n, dq, dv, dM, dCv, dtg, dJ, dJdv, dp, st);
-  if (rc == WBC_OK) {
-    if (M) WBC_CUDA(h, cudaMemcpyAsync(M, dM, n * 324 * 8, cudaMemcpyDeviceToHost, st));
-    if (Cv) WBC_CUDA(h, cudaMemcpyAsync(Cv, dCv, n * 18 * 8, cudaMemcpyDeviceToHost, st));
-    if (taug) WBC_CUDA(h, cudaMemcpyAsync(taug, dtg, n * 18 * 8, cudaMemcpyDeviceToHost, st));
-    if (Jfeet) WBC_CUDA(h, cudaMemcpyAsync(Jfeet, dJ, n * 216 * 8, cudaMemcpyDeviceToHost, st));
-    if (Jdv) WBC_CUDA(h, cudaMemcpyAsync(Jdv, dJdv, n * 12 * 8, cudaMemcpyDeviceToHost, st));
-    if (pfeet) WBC_CUDA(h, cudaMemcpyAsync(pfeet, dp, n * 12 * 8, cudaMemcpyDeviceToHost, st));
-    WBC_CUDA(h, cudaStreamSynchronize(st));
-  }
-  cudaFree(dq); cudaFree(dv); cudaFree(dM); cudaFree(dCv); cudaFree(dtg); cudaFree(dJ); cudaFree(dJdv); cudaFree(dp);
-  return rc;
+  if (rc) return rc;
+  s.back(M, dM, N * 324, st); s.back(Cv, dCv, N * 18, st); s.back(taug, dtg, N * 18, st);
+  s.back(Jfeet, dJ, N * 216, st); s.back(Jdv, dJdv, N * 12, st); s.back(pfeet, dp, N * 12, st);
+  WBC_SCRATCH_CHECK(h, s);
+  WBC_CUDA(h, cudaStreamSynchronize(st));
+  return WBC_OK;
 }
 
 extern "C" int wbc_time_step(wbc_handle* h, int kind, int64_t n, const wbc_io* io, int reps, void* stream,
@@ -872,38 +924,6 @@ extern "C" int wbc_lcm_encode_robot_state(wbc_handle* h, int64_t n, const double
   WBC_CUDA(h, cudaGetLastError());
   return WBC_OK;
 }
-
-namespace {
-// Scratch device buffers of the host-buffer codec entries: freed when the scope ends.
-struct DevScratch {
-  void* p[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-  int used = 0;
-  cudaError_t err = cudaSuccess;
-  template <typename T> T* in(const T* host, size_t count, cudaStream_t st) {      // NULL stays NULL
-    if (!host || err != cudaSuccess) return nullptr;
-    T* d = out<T>(host, count);
-    if (d) err = cudaMemcpyAsync(d, host, count * sizeof(T), cudaMemcpyHostToDevice, st);
-    return d;
-  }
-  template <typename T> T* out(const T* host, size_t count) {
-    if (!host || err != cudaSuccess) return nullptr;
-    void* d = nullptr;
-    err = cudaMalloc(&d, count * sizeof(T) > 0 ? count * sizeof(T) : 1);
-    if (err != cudaSuccess) return nullptr;
-    p[used++] = d;
-    return static_cast<T*>(d);
-  }
-  template <typename T> void back(T* host, const T* dev, size_t count, cudaStream_t st) {
-    if (host && dev && err == cudaSuccess) err = cudaMemcpyAsync(host, dev, count * sizeof(T), cudaMemcpyDeviceToHost, st);
-  }
-  ~DevScratch() { for (int i = 0; i < used; ++i) cudaFree(p[i]); }
-};
-}  // namespace
-
-#define WBC_SCRATCH_CHECK(h, s)                                                                  \
-  do {                                                                                           \
-    if ((s).err != cudaSuccess) { (h)->err = std::string("wire codec host path: ") + cudaGetErrorString((s).err); return WBC_ERR_CUDA; } \
-  } while (0)
 
 extern "C" int wbc_lcm_decode_trunk_state_host(wbc_handle* h, int64_t n, const uint8_t* msgs, double* timestamp, uint8_t* finished,
                                                double* traj, uint8_t* contact, double* f_plan, int32_t* status) {

@@ -67,7 +67,7 @@ inline void derive_constants(const wbc_params& p, wbc::Derived& d) {
 
 struct StepArgs {
   const double* q; const double* v; const double* traj; const uint8_t* contact;
-  double* tau; double* metrics; int32_t* status; double* vd; double* f; double* qp_info;
+  double* tau; double* metrics; int32_t* status; double* vd; double* f; double* qp_info; double* lam;
   long long n; int kind;
 };
 
@@ -1486,18 +1486,40 @@ WBC_DEV void solve_instance(SM& s, const wbc_model& md, const wbc_params& pr, co
     if (!(status & WBC_ST_NOTPD)) {
       iters = gi_solve_ws<NA>(s, lane, S, pr.max_iter, status, qact, minslack, a.vd != nullptr ? yrec : nullptr);
     }
-    // ---- phase 7: y = Y x + y0 is current in s.y
+    // ---- phase 7: y = Y x + y0 is current in s.y. Any status bit (unfinished active-set iterate, substituted orientation,
+    //      rank-deficient problem) zeroes the torques: nothing that is not the optimum of the reference QP leaves as tau
+    //      (the reference asserts there, inverse_dynamics_controller.py:224); status is warp uniform.
+    const bool failed = status != 0;
     const double res = minslack < 0.0 ? -minslack : 0.0;
     if (lane < 12) {
-      a.tau[inst * WBC_NU + md.act_index[lane]] = s.y[18 + lane];
-      if (a.f) a.f[inst * 12 + lane] = ((cmask >> (lane / 3)) & 1) ? s.y[6 + lane] : 0.0;
+      a.tau[inst * WBC_NU + md.act_index[lane]] = failed ? 0.0 : s.y[18 + lane];
+      if (a.f) a.f[inst * 12 + lane] = (!failed && ((cmask >> (lane / 3)) & 1)) ? s.y[6 + lane] : 0.0;
     }
     if (a.vd && lane < 18) {
       // accelerations as affine maps of w (rows stored by the reduce half: a_b, then the joints in internal order)
       const double* mrow = vdmap + lane * YS;
       double val = mrow[NF];
       for (int w = 0; w < nf; ++w) val = fma(mrow[w], s.x[w], val);
-      a.vd[inst * WBC_NV + (lane < 6 ? lane : md.v_index[lane - 6])] = val;
+      a.vd[inst * WBC_NV + (lane < 6 ? lane : md.v_index[lane - 6])] = failed ? 0.0 : val;
+    }
+    if (a.lam) {
+      // multipliers of the active rows in the fixed layout of wbc.h (R is dead after the solve: scratch for the row)
+      double* lrow = &s.Rp[0];
+      __syncwarp();
+      lrow[lane] = 0.0;
+      if (lane < WBC_NLAM - 32) lrow[32 + lane] = 0.0;
+      __syncwarp();
+      if (!failed && lane < qact) {
+        const int id = s.act[lane];
+        int slot;
+        if (id < S.nfric) slot = 4 * stance_foot(cmask, id >> 2) + (id & 3);
+        else if (id < S.nfric + S.nextra) slot = 16 + (id - S.nfric);
+        else { const int e = id - S.nfric - S.nextra; slot = 18 + md.act_index[e % 12] + (e < 12 ? 0 : 12); }
+        lrow[slot] = s.u[lane];
+      }
+      __syncwarp();
+      a.lam[inst * WBC_NLAM + lane] = lrow[lane];
+      if (lane < WBC_NLAM - 32) a.lam[inst * WBC_NLAM + 32 + lane] = lrow[32 + lane];
     }
     // reference objective 1/2 x'P0x + q0'x (constants dropped, E.5b): rows with a reference cost
     double obj = 0.0;
@@ -1525,6 +1547,7 @@ WBC_DEV void solve_instance(SM& s, const wbc_model& md, const wbc_params& pr, co
     if (c.pc_ok) status |= WBC_ST_RANKDEF;
     if (lane < 12) { a.tau[inst * WBC_NU + lane] = 0.0; if (a.f) a.f[inst * 12 + lane] = 0.0; }
     if (a.vd && lane < 18) a.vd[inst * WBC_NV + lane] = 0.0;
+    if (a.lam) { a.lam[inst * WBC_NLAM + lane] = 0.0; if (lane < WBC_NLAM - 32) a.lam[inst * WBC_NLAM + 32 + lane] = 0.0; }
     if (lane < 4) a.metrics[inst * WBC_NMETRIC + lane] = 0.0;
     if (a.qp_info && lane < 4) a.qp_info[inst * 4 + lane] = 0.0;
   }

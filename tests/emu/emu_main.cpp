@@ -73,7 +73,7 @@ extern "C" int emu_step(const wbc_model* md, const wbc_params* pr, int kind, lon
   j.md = md; j.pr = pr; j.n = n; j.mode = 0;
   j.args.q = io->q; j.args.v = io->v; j.args.traj = io->traj; j.args.contact = io->contact;
   j.args.tau = io->tau; j.args.metrics = io->metrics; j.args.status = io->status;
-  j.args.vd = io->vd; j.args.f = io->f; j.args.qp_info = io->qp_info; j.args.n = n; j.args.kind = kind;
+  j.args.vd = io->vd; j.args.f = io->f; j.args.qp_info = io->qp_info; j.args.lam = io->lam; j.args.n = n; j.args.kind = kind;
   return run(j);
 }
 extern "C" int emu_dynamics(const wbc_model* md, long long n, const double* q, const double* v, double* M, double* Cv,

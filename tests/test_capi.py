@@ -29,7 +29,7 @@ def test_struct_sizes_match_header(built):
     from quadruped_drake_b200.model import WbcModelStruct
     assert C.sizeof(WbcModelStruct) == 8 * (13 + 39 + 78 + 36 + 36 + 12 + 12 + 3) + 4 * 24
     assert C.sizeof(WbcParams) == 8 * 29 + 8 + 8 * 3 + 8 * 12
-    assert C.sizeof(WbcIO) == 80
+    assert C.sizeof(WbcIO) == 88          # 11 pointers (q v traj contact tau metrics status vd f qp_info lam)
 
 
 def test_default_params_match_reference_constants(built):

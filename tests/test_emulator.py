@@ -19,10 +19,18 @@ def emu(built):
     return lib
 
 
-def run_step(emu, robot, kind, g, **params):
+N_EMU = 24     # instances per case through the emulator (one OS thread per lane: ~0.25 s per instance)
+
+
+def first(g, n=N_EMU):
+    """The first n instances of a golden file as a dict."""
+    return {k: (g[k][:n] if g[k].ndim and len(g[k]) >= n and k not in ("dof_order", "params") else g[k]) for k in g.files}
+
+
+def run_step(emu, robot, kind, g, dof_order="depth_first", **params):
     from quadruped_drake_b200 import load_robot
     from quadruped_drake_b200.capi import KINDS, WbcIO, make_params, np_ptr
-    ms, pr = load_robot(robot).as_struct(), make_params(**params)
+    ms, pr = load_robot(robot, dof_order=dof_order).as_struct(), make_params(**params)
     q, v, traj, contact = (np.ascontiguousarray(g[k]) for k in ("q", "v", "traj", "contact"))
     n = len(q)
     tau, met, st = np.zeros((n, 12)), np.zeros((n, 4)), np.zeros(n, np.int32)
@@ -36,7 +44,7 @@ def run_step(emu, robot, kind, g, **params):
 def test_emulated_dynamics_match_golden(emu, case):
     from quadruped_drake_b200 import load_robot
     from quadruped_drake_b200.capi import np_ptr
-    g = np.load(GOLD / f"{case}.npz")
+    g = first(np.load(GOLD / f"{case}.npz"))
     robot = "anymal_b" if "anymal" in case else "mini_cheetah"
     ms = load_robot(robot).as_struct()
     q, v = np.ascontiguousarray(g["q"]), np.ascontiguousarray(g["v"])
@@ -45,14 +53,15 @@ def test_emulated_dynamics_match_golden(emu, case):
     J, Jdv, pf = np.zeros((n, 4, 3, 18)), np.zeros((n, 4, 3)), np.zeros((n, 4, 3))
     emu.emu_dynamics(C.byref(ms), n, np_ptr(q), np_ptr(v), np_ptr(M), np_ptr(Cv), np_ptr(tg), np_ptr(J), np_ptr(Jdv), np_ptr(pf))
     for name, got in (("M", M), ("Cv", Cv), ("tau_g", tg), ("J_feet", J), ("Jdv_feet", Jdv), ("p_feet", pf)):
-        ref = g[name]
-        scale = np.abs(ref).reshape(n, -1).max(axis=1).reshape((n,) + (1,) * (ref.ndim - 1))
-        assert (np.abs(got - ref) / np.maximum(scale, 1e-3)).max() < 1e-9, name     # 1e-9 relative (north star)
+        ref = g[name][:n]
+        m = len(ref)
+        scale = np.abs(ref).reshape(m, -1).max(axis=1).reshape((m,) + (1,) * (ref.ndim - 1))
+        assert (np.abs(got[:m] - ref) / np.maximum(scale, 1e-3)).max() < 1e-9, name     # 1e-9 relative (north star)
 
 
 @pytest.mark.parametrize("case", ["cfg2_mini_cheetah_stand", "cfg3_anymal_trot", "cfg4_mini_cheetah_walk", "mixed_mini_cheetah"])
 def test_emulated_id_step_matches_golden(emu, case):
-    g = np.load(GOLD / f"{case}.npz")
+    g = first(np.load(GOLD / f"{case}.npz"))
     robot = "anymal_b" if "anymal" in case else "mini_cheetah"
     tau, met, st, vd, f, qi = run_step(emu, robot, "id", g)
     assert (st == 0).all()
@@ -66,7 +75,7 @@ def test_emulated_id_step_matches_golden(emu, case):
 @pytest.mark.parametrize("kind", ["clf", "pc", "mptc"])
 @pytest.mark.parametrize("case", ["cfg3_anymal_trot", "cfg4_mini_cheetah_walk"])
 def test_emulated_clf_pc_steps_match_golden(emu, case, kind):
-    g = np.load(GOLD / f"{case}.npz")
+    g = first(np.load(GOLD / f"{case}.npz"), 12)
     robot = "anymal_b" if "anymal" in case else "mini_cheetah"
     tau, met, st, vd, f, qi = run_step(emu, robot, kind, g)
     ok = g[f"{kind}_ok"]
@@ -78,6 +87,23 @@ def test_emulated_clf_pc_steps_match_golden(emu, case, kind):
     assert np.abs(f - g[f"{kind}_f"])[ok].max() < 1e-5
     ref = g[f"{kind}_metrics"][ok]
     assert (np.abs(met[ok] - ref)[:, [0, 1, 3]] / np.maximum(1.0, np.abs(ref[:, [0, 1, 3]]))).max() < 1e-8
+
+
+@pytest.mark.parametrize("case,kind", [("bf_mini_cheetah_mixed", "id"), ("bf_anymal_trot", "clf"), ("bf_mini_cheetah_mixed", "pc"),
+                                       ("tl_mini_cheetah_walk", "id"), ("tl_anymal_trot", "id"), ("fixtures_mini_cheetah", "id"),
+                                       ("fixtures_mini_cheetah", "clf")])
+def test_emulated_other_configs_match_golden(emu, case, kind):
+    """Breadth-first (2021-era Drake) velocity numbering, the torque box and the reference's manual test motions."""
+    g = first(np.load(GOLD / f"{case}.npz"), 12)
+    robot = "anymal_b" if "anymal" in case else "mini_cheetah"
+    extra = {"torque_limits": 1} if case.startswith("tl_") else {}
+    tau, met, st, vd, f, qi = run_step(emu, robot, kind, g, dof_order=str(g["dof_order"]), **extra)
+    ok = g[f"{kind}_ok"]
+    assert ok.sum() >= 9 and (st[ok] == 0).all()
+    assert np.abs(tau - g[f"{kind}_tau"])[ok].max() < 1e-5
+    assert np.abs(vd - g[f"{kind}_vd"])[ok].max() < 1e-6
+    assert np.abs(f - g[f"{kind}_f"])[ok].max() < 1e-5
+    assert (tau[st != 0] == 0).all()
 
 
 def test_emulated_coriolis_matches_oracle(emu):

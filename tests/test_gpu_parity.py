@@ -8,10 +8,23 @@ import pytest
 pytestmark = pytest.mark.gpu
 GOLD = Path(__file__).parent / "golden"
 CASES = ["cfg2_mini_cheetah_stand", "cfg3_anymal_trot", "cfg4_mini_cheetah_walk", "mixed_mini_cheetah"]
+# 2021-era Drake velocity numbering, the optional torque box with ACTIVE limits (BASELINE configs[2]) and the
+# reference's manual test motions (planners/simple.py:87-115); every file holds >= 256 instances (tools/make_golden.py)
+MORE = ["bf_mini_cheetah_mixed", "bf_anymal_trot", "tl_mini_cheetah_walk", "tl_anymal_trot", "fixtures_mini_cheetah"]
 
 
 def robot_of(case):
     return "anymal_b" if "anymal" in case else "mini_cheetah"
+
+
+def ctl_of(ctl_cache, case):
+    """Controller handle built the way the golden file says (dof order, torque box)."""
+    kw = {}
+    if case.startswith("bf_"):
+        kw["dof_order"] = "breadth_first"
+    if case.startswith("tl_"):
+        kw["torque_limits"] = 1
+    return ctl_cache(robot_of(case), **kw)
 
 
 @pytest.fixture(scope="module")
@@ -19,54 +32,68 @@ def ctl_cache(built):
     from quadruped_drake_b200.controller import BatchedController
     cache = {}
 
-    def get(robot, **params):
-        key = (robot, tuple(sorted(params.items())))
+    def get(robot, dof_order="depth_first", **params):
+        key = (robot, dof_order, tuple(sorted(params.items())))
         if key not in cache:
-            cache[key] = BatchedController(robot, device=0, **params)
+            cache[key] = BatchedController(robot, device=0, dof_order=dof_order, **params)
         return cache[key]
     yield get
     for c in cache.values():
         c.close()
 
 
-@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("case", CASES + MORE)
 def test_dynamics_match_golden(ctl_cache, case):
-    """M, Cv, tau_g, J, Jdot v, p within 1e-9 relative (BASELINE.json north star)."""
+    """M, Cv, tau_g, J, Jdot v, p within 1e-9 relative (BASELINE.json north star). The dense terms (M, J) are stored for
+    the first n_dyn instances of a file, the vectors for all of them."""
     g = np.load(GOLD / f"{case}.npz")
-    d = ctl_cache(robot_of(case)).dynamics(g["q"], g["v"])
-    n = len(g["q"])
+    d = ctl_of(ctl_cache, case).dynamics(g["q"], g["v"])
     for name in ("M", "Cv", "tau_g", "J_feet", "Jdv_feet", "p_feet"):
-        ref, got = g[name], d[name]
+        ref = g[name]
+        n = len(ref)
+        got = d[name][:n]
         scale = np.abs(ref).reshape(n, -1).max(axis=1).reshape((n,) + (1,) * (ref.ndim - 1))
         assert (np.abs(got - ref) / np.maximum(scale, 1e-3)).max() < 1e-9, name
 
 
-@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("case", CASES + MORE)
 def test_id_step_matches_golden(ctl_cache, case):
-    """tau within 1e-5 of the exact optimum of the reference QP (+ declared tie-break); vd, f, objective too."""
+    """tau within 1e-5 of the exact optimum of the reference QP (+ declared tie-break); vd, f, objective too.
+    Instances the oracle could not certify (an infeasible torque box) are excluded and must not report success with
+    non-zero torques either."""
     g = np.load(GOLD / f"{case}.npz")
-    out = ctl_cache(robot_of(case)).step("id", g["q"], g["v"], g["traj"], g["contact"], debug=True)
-    assert (out.status == 0).all()
-    assert np.abs(out.tau - g["id_tau"]).max() < 1e-5
-    assert np.abs(out.vd - g["id_vd"]).max() < 1e-6
-    assert np.abs(out.f - g["id_f"]).max() < 1e-5
-    assert np.abs(out.qp_info[:, 0] - g["id_objective"]).max() < 1e-6 * max(1.0, np.abs(g["id_objective"]).max())
-    assert np.abs(out.metrics[:, 1] - g["id_metrics"][:, 1]).max() < 1e-12
+    out = ctl_of(ctl_cache, case).step("id", g["q"], g["v"], g["traj"], g["contact"], debug=True)
+    ok = g["id_ok"]
+    assert ok.mean() > 0.95
+    assert (out.status[ok] == 0).all(), np.unique(out.status[ok], return_counts=True)
+    assert np.abs(out.tau - g["id_tau"])[ok].max() < 1e-5
+    assert np.abs(out.vd - g["id_vd"])[ok].max() < 1e-6
+    assert np.abs(out.f - g["id_f"])[ok].max() < 1e-5
+    assert np.abs(out.qp_info[:, 0] - g["id_objective"])[ok].max() < 1e-6 * max(1.0, np.abs(g["id_objective"][ok]).max())
+    assert np.abs(out.metrics[:, 1] - g["id_metrics"][:, 1])[ok].max() < 1e-12
+    assert (out.tau[out.status != 0] == 0).all()
+    if case.startswith("tl_"):
+        lim = ctl_of(ctl_cache, case).model.effort[np.argsort(ctl_of(ctl_cache, case).model.act_index)]
+        active = (np.abs(g["id_tau"]) > lim - 1e-7).any(axis=1) & ok
+        assert active.sum() >= 25, "the torque-box goldens must exercise ACTIVE limits"
+        assert (out.lam[active, 18:42] > 0).any(axis=1).all()
 
 
-@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("case", CASES + MORE)
 def test_clf_step_matches_golden(ctl_cache, case):
     """CLF-QP (clf_controller.py:48-234): the kernel's closed-form CARE constants against the oracle's numerical CARE."""
     g = np.load(GOLD / f"{case}.npz")
-    out = ctl_cache(robot_of(case)).step("clf", g["q"], g["v"], g["traj"], g["contact"], debug=True)
-    assert (out.status == 0).all()
-    assert np.abs(out.tau - g["clf_tau"]).max() < 1e-5
-    assert np.abs(out.vd - g["clf_vd"]).max() < 1e-6
-    assert np.abs(out.f - g["clf_f"]).max() < 1e-5
-    m, ref = out.metrics, g["clf_metrics"]
+    out = ctl_of(ctl_cache, case).step("clf", g["q"], g["v"], g["traj"], g["contact"], debug=True)
+    ok = g["clf_ok"]
+    assert ok.mean() > 0.95
+    assert (out.status[ok] == 0).all(), np.unique(out.status[ok], return_counts=True)
+    assert np.abs(out.tau - g["clf_tau"])[ok].max() < 1e-5
+    assert np.abs(out.vd - g["clf_vd"])[ok].max() < 1e-6
+    assert np.abs(out.f - g["clf_f"])[ok].max() < 1e-5
+    m, ref = out.metrics[ok], g["clf_metrics"][ok]
     scale = np.maximum(1.0, np.abs(ref))
     assert (np.abs(m[:, [0, 1, 3]] - ref[:, [0, 1, 3]]) / scale[:, [0, 1, 3]]).max() < 1e-8      # V, err, Vdot
-    assert np.abs(out.qp_info[:, 0] - g["clf_objective"]).max() < 1e-6 * max(1.0, np.abs(g["clf_objective"]).max())
+    assert np.abs(out.qp_info[:, 0] - g["clf_objective"])[ok].max() < 1e-6 * max(1.0, np.abs(g["clf_objective"][ok]).max())
 
 
 def test_clf_full_size_config4(ctl_cache):
@@ -79,18 +106,22 @@ def test_clf_full_size_config4(ctl_cache):
     dyn, con, fr = kkt_properties(ctl, q, v, traj, contact, out)
     assert dyn.max() < 1e-7 and con.max() < 1e-7 and fr.max() < 1e-7
     assert (out.qp_info[:, 2] > -1e-9).all()          # delta >= 0 is never optimal to violate: cost w*delta^2, row -delta
+    assert_optimal("clf", ctl, q, v, traj, contact, out, sel=np.arange(0, 65536, 4))
 
 
 @pytest.mark.parametrize("kind", ["pc", "mptc"])
-@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("case", CASES + MORE)
 def test_pc_step_matches_golden(ctl_cache, case, kind):
     """Passivity-constrained QP (pc_controller.py:43-255) and MPTC (mptc_controller.py:125-310): analytic C w / Jdot
     against the oracle's AutoDiff-equivalent."""
     g = np.load(GOLD / f"{case}.npz")
-    out = ctl_cache(robot_of(case)).step(kind, g["q"], g["v"], g["traj"], g["contact"], debug=True)
+    if f"{kind}_tau" not in g.files:
+        pytest.skip("golden file holds no MPTC vectors")
+    out = ctl_of(ctl_cache, case).step(kind, g["q"], g["v"], g["traj"], g["contact"], debug=True)
     g = {k.replace(kind + "_", "pc_") if k.startswith(kind + "_") else k: g[k] for k in g.files if kind == "pc" or not k.startswith("pc_")}
     ok = g["pc_ok"]
-    assert (out.status[ok] == 0).all() and (out.status[~ok] == 64).all()
+    flight = g["contact"].sum(axis=1) == 0
+    assert (out.status[ok] == 0).all() and (out.status[flight] == 64).all() and (ok | flight).mean() > 0.95
     assert np.abs(out.tau - g["pc_tau"])[ok].max() < 1e-5
     assert np.abs(out.vd - g["pc_vd"])[ok].max() < 1e-6
     assert np.abs(out.f - g["pc_f"])[ok].max() < 1e-5
@@ -200,6 +231,60 @@ def test_full_size_properties(ctl_cache, robot, pattern, n, seed):
     assert np.array_equal(again.tau, out.tau)
     # swing feet carry no force, flight instances have tau = M_j vd + h_j only
     assert np.all(out.f[contact == 0] == 0)
+    assert_optimal("id", ctl, q, v, traj, contact, out)
+
+
+def assert_optimal(kind, ctl, q, v, traj, contact, out, params=None, sel=None):
+    """Optimality, not just feasibility: with the exported multipliers the returned [vd; tau; f] satisfies the KKT conditions
+    of the reference QP (tests/kkt.py) - a feasible but sub-optimal torque fails the stationarity row."""
+    import kkt
+    from types import SimpleNamespace
+    if sel is not None:
+        q, v, traj, contact = q[sel], v[sel], traj[sel], contact[sel]
+        out = SimpleNamespace(tau=out.tau[sel], vd=out.vd[sel], f=out.f[sel], qp_info=out.qp_info[sel], lam=out.lam[sel])
+    cert = kkt.certificate(kind, ctl.dynamics(q, v), ctl.model, q, v, traj, contact, out, params)
+    assert cert["stationarity"].max() < 1e-6, cert["stationarity"].max()      # relative to the cost gradient
+    assert cert["dual"].min() >= 0.0
+    assert cert["comp"].max() < 1e-6, cert["comp"].max()
+    assert cert["eq"].max() < 1e-7 and cert["ineq"].max() < 1e-7
+    return cert
+
+
+def test_full_size_config3_torque_limits_optimal(ctl_cache):
+    """BASELINE configs[2] as specified: anymal_b trot, 16384 instances, friction pyramid + torque limits ON. Every instance
+    either solves to a KKT point of the reference QP with the box rows, or reports a status and returns zero torques."""
+    from quadruped_drake_b200.synth import generate
+    ctl = ctl_cache("anymal_b", torque_limits=1)
+    q, v, traj, contact = generate(ctl.model, 16384, 20260120, "trot", ctl.fk)
+    out = ctl.step("id", q, v, traj, contact, debug=True)
+    ok = out.status == 0
+    assert ok.mean() > 0.999, np.unique(out.status, return_counts=True)
+    assert (out.tau[~ok] == 0).all() and (out.lam[~ok] == 0).all()
+    lim = ctl.model.effort[np.argsort(ctl.model.act_index)]
+    assert (np.abs(out.tau) <= lim + 1e-7).all()
+    assert_optimal("id", ctl, q, v, traj, contact, out, {"torque_limits": 1}, sel=ok)
+
+
+def test_failed_instances_return_zero_torques(ctl_cache):
+    """include/wbc.h: any status bit => tau = f = vd = lam = 0 (the reference asserts instead). Failures provoked here: an
+    iteration cap of 2 (MAXITER), a zero quaternion (BADQUAT), gimbal lock (GIMBAL), PC in full flight (UNSUPPORTED)."""
+    from quadruped_drake_b200 import capi
+    from quadruped_drake_b200.synth import generate
+    capped = ctl_cache("mini_cheetah", max_iter=2)
+    q, v, traj, contact = generate(capped.model, 512, 31, "stand", capped.fk)
+    q[1, 0:4] = 0.0
+    q[2, 0:4] = [np.cos(np.pi / 4), 0.0, np.sin(np.pi / 4), 0.0]
+    out = capped.step("id", q, v, traj, contact, debug=True)
+    bad = out.status != 0
+    assert (out.status & capi.ST_MAXITER).astype(bool).sum() > 100 and out.status[1] & capi.ST_BADQUAT and out.status[2] & capi.ST_GIMBAL
+    for arr in (out.tau, out.f, out.vd, out.lam):
+        assert (arr[bad] == 0).all()
+    good = ~bad
+    ref = ctl_cache("mini_cheetah").step("id", q, v, traj, contact)
+    assert good.any() and np.array_equal(out.tau[good], ref.tau[good])          # the cap does not touch instances below it
+    contact[:8] = 0
+    pc = ctl_cache("mini_cheetah").step("pc", q, v, traj, contact, debug=True)
+    assert (pc.status[3:8] == capi.ST_UNSUPPORTED).all() and (pc.tau[:8] == 0).all()
 
 
 def test_instance_independence_and_ragged_sizes(ctl_cache):
@@ -232,18 +317,23 @@ def test_status_flags(ctl_cache):
 
 
 def test_torque_limits_option(ctl_cache):
-    """BASELINE config 3: optional |tau| <= URDF effort box (not in the reference QP)."""
+    """Optional |tau| <= URDF effort box (not in the reference QP): the box holds, an inactive box changes nothing,
+    an active one is a KKT point of the QP with the box rows, and whatever does not solve is flagged and zeroed."""
     from quadruped_drake_b200.synth import generate
     ctl = ctl_cache("mini_cheetah", torque_limits=1)
     free = ctl_cache("mini_cheetah")
     q, v, traj, contact = generate(ctl.model, 2048, 21, "walk", ctl.fk)
     lim = ctl.model.effort[np.argsort(ctl.model.act_index)]
-    a, b = ctl.step("id", q, v, traj, contact), free.step("id", q, v, traj, contact)
+    a, b = ctl.step("id", q, v, traj, contact, debug=True), free.step("id", q, v, traj, contact)
     okay = a.status == 0
-    assert okay.mean() > 0.9
+    assert okay.mean() > 0.995, np.unique(a.status, return_counts=True)
+    assert (a.tau[~okay] == 0).all()
     assert (np.abs(a.tau[okay]) <= lim + 1e-7).all()
     inside = okay & (np.abs(b.tau) < lim - 1e-3).all(axis=1)
     assert inside.any() and np.abs(a.tau[inside] - b.tau[inside]).max() < 1e-6   # inactive box changes nothing
+    active = okay & (a.lam[:, 18:42] > 0).any(axis=1)
+    assert active.sum() > 100
+    assert_optimal("id", ctl, q, v, traj, contact, a, {"torque_limits": 1}, sel=okay)
 
 
 def test_leafsystem_mirror_standing(built):
