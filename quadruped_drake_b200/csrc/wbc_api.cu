@@ -89,8 +89,8 @@ __device__ __forceinline__ const DevConst& stage_consts(L* sm, const DevConst* g
 #define WBC_SOLVE_CTAS (28 / WBC_SOLVE_WARPS)
 #endif
 constexpr int SOLVE_WARPS = WBC_SOLVE_WARPS;
-struct SmemLayoutSolve { wbc::SolveSmem w[SOLVE_WARPS]; };
-static_assert(sizeof(wbc::SolveSmem) % 16 == 0, "SolveSmem must keep 16-byte alignment per warp");
+template <bool VD> struct SmemLayoutSolveT { wbc::SolveSmemT<VD> w[SOLVE_WARPS]; };
+static_assert(sizeof(wbc::SolveSmem) % 16 == 0 && sizeof(wbc::SolveSmemVd) % 16 == 0, "SolveSmem must keep 16-byte alignment per warp");
 static_assert(offsetof(wbc::WarpSmem, Y) % 16 == 0 && sizeof(wbc::WarpSmem) % 16 == 0 && sizeof(DevConst) % 16 == 0, "bulk copy alignment");
 static_assert(offsetof(wbc::WarpSmem, cw) == offsetof(wbc::WarpSmem, Y) + sizeof(double) * wbc::YROWS * wbc::YS &&
               offsetof(wbc::WarpSmem, ct) == offsetof(wbc::WarpSmem, cw) + sizeof(double) * wbc::YROWS, "[Y | cw | ct] must be contiguous");
@@ -105,6 +105,19 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 __device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+// Lane index the compiler cannot re-derive from the special register: under the register caps of the step kernels it
+// otherwise rematerialises every lane-dependent shared-memory address with an S2R (a slow special-register read) + IMAD
+// pair at each use instead of keeping one register live (WBC_OPAQUE_LANE=0 restores the plain form for A/B runs).
+#ifndef WBC_OPAQUE_LANE
+#define WBC_OPAQUE_LANE 1
+#endif
+__device__ __forceinline__ int lane_index() {
+  int lane = (int)(threadIdx.x & 31);
+#if WBC_OPAQUE_LANE
+  asm volatile("" : "+r"(lane));
+#endif
+  return lane;
+}
 // shared -> global bulk copy of `bytes` (multiple of 16), issued by the calling thread; returns once the source may be reused
 __device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, unsigned bytes) {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes of the warp -> visible to the copy engine
@@ -188,7 +201,7 @@ __global__ void __launch_bounds__(W * 32, WBC_MIN_WARPS / W) wbc_reduce_kernel(c
   pdl_launch_dependents();
   const bool staged = stage_inputs_issue(sm->in, a, bulk_ok != 0);
   const DevConst& dc = stage_consts(sm, gdc);   // (reading the tables through L1 instead of staging them measured neutral)
-  const int warp = W == 1 ? 0 : (int)(threadIdx.x >> 5), lane = threadIdx.x & 31;
+  const int warp = W == 1 ? 0 : (int)(threadIdx.x >> 5), lane = lane_index();
   const long long inst = (long long)blockIdx.x * W + warp;
   if (inst >= a.n) return;
   wbc::WarpSmem& s = sm->w[warp];
@@ -201,16 +214,17 @@ __global__ void __launch_bounds__(W * 32, WBC_MIN_WARPS / W) wbc_reduce_kernel(c
   if (lane == 0) store_record(rec + inst * wbc::REC_DOUBLES, c, s);
 }
 
-template <int KIND>
-__global__ void __launch_bounds__(SOLVE_WARPS * 32, WBC_SOLVE_CTAS) wbc_solve_kernel(const DevConst* __restrict__ gdc, wbc::StepArgs a,
-                                                                               const double* __restrict__ rec,
-                                                                               const double* __restrict__ vdmap) {
+// VD: the accelerations are requested (rollout, debug outputs) - the Cholesky factor is kept for the recovery of w, which
+// costs 1.3 KB more shared memory per warp (24 instead of 28 resident warps).
+template <int KIND, bool VD>
+__global__ void __launch_bounds__(SOLVE_WARPS * 32, VD ? (24 / SOLVE_WARPS) : WBC_SOLVE_CTAS) wbc_solve_kernel(
+    const DevConst* __restrict__ gdc, wbc::StepArgs a, const double* __restrict__ rec, const double* __restrict__ vdmap) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  SmemLayoutSolve* sm = reinterpret_cast<SmemLayoutSolve*>(smem_raw);
-  const int warp = SOLVE_WARPS == 1 ? 0 : (int)(threadIdx.x >> 5), lane = threadIdx.x & 31;
+  SmemLayoutSolveT<VD>* sm = reinterpret_cast<SmemLayoutSolveT<VD>*>(smem_raw);
+  const int warp = SOLVE_WARPS == 1 ? 0 : (int)(threadIdx.x >> 5), lane = lane_index();
   const long long inst = (long long)blockIdx.x * SOLVE_WARPS + warp;
   if (inst >= a.n) return;
-  wbc::SolveSmem& s = sm->w[warp];
+  wbc::SolveSmemT<VD>& s = sm->w[warp];
   const double* r = rec + inst * wbc::REC_DOUBLES;
   const double2* m = reinterpret_cast<const double2*>(r + wbc::REC_Y);
   pdl_wait();                      // the records of the reduce kernel are complete and visible from here on
@@ -223,7 +237,7 @@ __global__ void __launch_bounds__(SOLVE_WARPS * 32, WBC_SOLVE_CTAS) wbc_solve_ke
   c.ok = ok; c.pc_ok = m2.y != 0.0; c.extra_bound = m3.x; c.err = m3.y; c.Vl = m4.x; c.PFl = m4.y; c.csum = m5.x; c.Vpc = m5.y;
   __syncwarp();                    // the barrier is initialised before any lane polls it
   if (ok) mbar_wait(&s.mbar, 0);
-  wbc::solve_instance<KIND, wbc::SolveSmem>(s, gdc->md, gdc->pr, a, inst, lane, c, vdmap ? vdmap + inst * wbc::VDMAP_DOUBLES : nullptr, r);
+  wbc::solve_instance<KIND, wbc::SolveSmemT<VD>>(s, gdc->md, gdc->pr, a, inst, lane, c, vdmap ? vdmap + inst * wbc::VDMAP_DOUBLES : nullptr, r);
 }
 
 // PC / MPTC reduce half: same hand-over, extra operational-space workspace per warp (168 registers, 12 warps / SM).
@@ -235,7 +249,7 @@ __global__ void __launch_bounds__(W * 32, 12 / W) wbc_reduce_pc_kernel(const Dev
   pdl_launch_dependents();
   const bool staged = stage_inputs_issue(sm->in, a, bulk_ok != 0);
   const DevConst& dc = stage_consts(sm, gdc);
-  const int warp = W == 1 ? 0 : (int)(threadIdx.x >> 5), lane = threadIdx.x & 31;
+  const int warp = W == 1 ? 0 : (int)(threadIdx.x >> 5), lane = lane_index();
   const long long inst = (long long)blockIdx.x * W + warp;
   if (inst >= a.n) return;
   wbc::WarpSmem& s = sm->w[warp];
@@ -358,9 +372,12 @@ static int set_smem_attr(wbc_handle* h) {
   WBC_CUDA(h, cudaFuncSetAttribute(wbc_reduce_kernel<WBC_CTRL_ID, WARPS_HOST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemLayoutT<WARPS_HOST>)));
   WBC_CUDA(h, cudaFuncSetAttribute(wbc_reduce_kernel<WBC_CTRL_CLF, WARPS_HOST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemLayoutT<WARPS_HOST>)));
   WBC_CUDA(h, cudaFuncSetAttribute(wbc_reduce_pc_kernel<WARPS_PC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemLayoutPCT<WARPS_PC>)));
-  WBC_CUDA(h, cudaFuncSetAttribute(wbc_solve_kernel<WBC_CTRL_ID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemLayoutSolve)));
-  WBC_CUDA(h, cudaFuncSetAttribute(wbc_solve_kernel<WBC_CTRL_CLF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemLayoutSolve)));
-  WBC_CUDA(h, cudaFuncSetAttribute(wbc_solve_kernel<WBC_CTRL_PC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemLayoutSolve)));
+  WBC_CUDA(h, cudaFuncSetAttribute(wbc_solve_kernel<WBC_CTRL_ID, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemLayoutSolveT<false>)));
+  WBC_CUDA(h, cudaFuncSetAttribute(wbc_solve_kernel<WBC_CTRL_CLF, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemLayoutSolveT<false>)));
+  WBC_CUDA(h, cudaFuncSetAttribute(wbc_solve_kernel<WBC_CTRL_PC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemLayoutSolveT<false>)));
+  WBC_CUDA(h, cudaFuncSetAttribute(wbc_solve_kernel<WBC_CTRL_ID, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemLayoutSolveT<true>)));
+  WBC_CUDA(h, cudaFuncSetAttribute(wbc_solve_kernel<WBC_CTRL_CLF, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemLayoutSolveT<true>)));
+  WBC_CUDA(h, cudaFuncSetAttribute(wbc_solve_kernel<WBC_CTRL_PC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemLayoutSolveT<true>)));
   WBC_CUDA(h, cudaFuncSetAttribute(wbc_coriolis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemLayoutPC)));
   WBC_CUDA(h, cudaFuncSetAttribute(wbc_dynamics_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   return WBC_OK;
@@ -614,19 +631,18 @@ static int launch_split(wbc_handle* h, int kind, int64_t n, const wbc_io* io, cu
     // hidden launch latency there), so small launch pairs and stream captures keep the ordinary launch
     const bool pdl = pdl_mode() && m >= 4096;
     if (pdl) cudaStreamIsCapturing(st, &cap);
-    if (pdl && cap == cudaStreamCaptureStatusNone) {
-      cudaLaunchConfig_t cfg = {};
-      cfg.gridDim = dim3(sgrid); cfg.blockDim = dim3(SOLVE_WARPS * 32); cfg.dynamicSmemBytes = sizeof(SmemLayoutSolve); cfg.stream = st;
-      cudaLaunchAttribute at[1];
-      at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-      at[0].val.programmaticStreamSerializationAllowed = 1;
-      cfg.attrs = at; cfg.numAttrs = 1;
-      const double* crec = h->d_rec[slot];
-      const double* cvd = vdmap;
-      WBC_CUDA(h, cudaLaunchKernelEx(&cfg, wbc_solve_kernel<KIND>, (const DevConst*)h->d_const, a, crec, cvd));
-    } else {
-      wbc_solve_kernel<KIND><<<sgrid, SOLVE_WARPS * 32, sizeof(SmemLayoutSolve), st>>>(h->d_const, a, h->d_rec[slot], vdmap);
-    }
+    const bool with_vd = io->vd != nullptr;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(sgrid); cfg.blockDim = dim3(SOLVE_WARPS * 32); cfg.stream = st;
+    cfg.dynamicSmemBytes = with_vd ? sizeof(SmemLayoutSolveT<true>) : sizeof(SmemLayoutSolveT<false>);
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = (pdl && cap == cudaStreamCaptureStatusNone) ? 1 : 0;
+    const double* crec = h->d_rec[slot];
+    const double* cvd = vdmap;
+    if (with_vd) WBC_CUDA(h, cudaLaunchKernelEx(&cfg, wbc_solve_kernel<KIND, true>, (const DevConst*)h->d_const, a, crec, cvd));
+    else WBC_CUDA(h, cudaLaunchKernelEx(&cfg, wbc_solve_kernel<KIND, false>, (const DevConst*)h->d_const, a, crec, cvd));
     if (h->prof_on) cudaEventRecord(h->prof_ev[2], st);
     h->launches += 2;
   }

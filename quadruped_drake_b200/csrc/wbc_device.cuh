@@ -96,19 +96,27 @@ struct alignas(16) WarpSmem {
 
 // Per-warp shared memory of the solve kernel of the split path (phases 5-7 only): the reduced problem (Y, cw, ct - one
 // contiguous 4 KB block, filled by a single bulk copy of the record the reduce kernel wrote) and the Goldfarb-Idnani state.
-struct alignas(16) SolveSmem {
+template <bool VD>
+struct alignas(16) SolveSmemT {
   alignas(16) double Y[YROWS][YS];
   double cw[YROWS], ct[YROWS];
-  double H[NF][NF];                       // reduced Hessian -> its Cholesky factor L (lower triangle, in place)
+  double H[NF][NF];                       // reduced Hessian -> its Cholesky factor L (lower triangle, in place); once W is
+                                          // built L is dead unless the accelerations are requested (x recovery), so without
+                                          // VD the rows of R^-1 (below) live here
   double Rp[NF * (NF + 3) / 2];           // R of the active set, transposed and packed: column c keeps rows 0..c+1 (the
                                           // sub-diagonal entry exists only while a dropped column is rotated away)
   double d[NF];                           // 1 / L[k][k]
-  union { double g[NF]; double dm[NF]; }; // reduced gradient (start-up only) / the current d = J'n
-  union { double npv[NF]; double x[NF]; };// b = L^-1 g (start-up only) / recovered w (exit only)
+  union { double g[NF]; double dm[NF]; }; // start-up: b = W'e / then the current d = J'n
+  union { double npv[NF]; double x[NF]; };// recovered w (exit only)
   double u[NF], y[YROWS];
   int act[NF];
   alignas(8) unsigned long long mbar;     // completion barrier of the bulk copy
+  double Ris[VD ? NF * NF : 1];           // R^-1 of the active set, row k in lane k's row (stride NF: conflict free)
+  static constexpr bool kVd = VD;
 };
+template <class SM> WBC_DEV double* ri_rows(SM& s) { return SM::kVd ? &s.Ris[0] : &s.H[0][0]; }
+using SolveSmem = SolveSmemT<false>;      // step without accelerations (the benchmark path): 28 warps / SM
+using SolveSmemVd = SolveSmemT<true>;     // vd requested (rollout, debug outputs): L is kept for the x recovery, 24 warps / SM
 static_assert(sizeof(SolveSmem) <= 7312, "28 single-warp CTAs of the solve kernel must fit one SM (228 KB, 1 KB reserved per CTA)");
 // entry (row, col) of R, row <= col + 1
 template <class SM> WBC_DEV double& Rent(SM& s, int col, int row) { return s.Rp[col * (col + 3) / 2 + row]; }
@@ -189,6 +197,14 @@ WBC_DEV double warp_max_lane(double v, int& lane_out) {
   const unsigned mlo = __reduce_max_sync(WBC_FULL, hi == mhi ? lo : 0u);
   lane_out = __ffs((int)__ballot_sync(WBC_FULL, hi == mhi && lo == mlo)) - 1;
   return __hiloint2double((int)mhi, (int)mlo);
+}
+// Arg-max of a NON-NEGATIVE double on its high word only (one redux instead of two): the winner is within 2^-20 relative of
+// the maximum, which is all a pivot rule needs. Returns the winning lane, `any` = some lane holds a value >= 2^-1022 * 2^32.
+WBC_DEV int warp_argmax_hi(double v, bool& any) {
+  const unsigned hi = (unsigned)__double2hiint(v);
+  const unsigned mhi = __reduce_max_sync(WBC_FULL, hi);
+  any = mhi != 0u;
+  return __ffs((int)__ballot_sync(WBC_FULL, hi == mhi)) - 1;
 }
 WBC_DEV double warp_min_lane(double v, int& lane_out) {
   const unsigned hi = (unsigned)__double2hiint(v), lo = (unsigned)__double2loint(v);
@@ -615,35 +631,33 @@ template <int N> WBC_DEV TriPairs tri_pairs(int lane) {
   return t;
 }
 
-// H = sum_r cw_r Y_r' Y_r (+ identity on padded dims), g = sum_r cw_r Y_r (y0_r - ct_r) + glin
-template <int N, class SM> WBC_DEV void reduced_hessian(SM& s, int lane, int nf, int nrows, bool extra, const TriPairs& tp) {
-  s.y[lane] = s.cw[lane] * (s.Y[lane][NF] - s.ct[lane]);      // e_r = c_r (y0_r - t_r), once per row (s.y is free until the solve)
+// H = sum_r cw_r Y_r' Y_r (+ identity on padded dims) and e_r = cw_r (y0_r - ct_r) (left in s.y for the solver start-up, which
+// needs b = L^-1 Y'e = W'e). The weight is constant inside a row class - body rows 0-5, the three rows of a leg, the torque
+// rows - so each class is summed unweighted and scaled once.
+template <int N, class SM> WBC_DEV void reduced_hessian(SM& s, int lane, int nf, bool tau_rows, bool extra, const TriPairs& tp) {
+  s.y[lane] = s.cw[lane] * (s.Y[lane][NF] - s.ct[lane]);
+  const double wb = s.cw[0], wl0 = s.cw[6], wl1 = s.cw[9], wl2 = s.cw[12], wl3 = s.cw[15];
 #pragma unroll
   for (int h = 0; h < 3; ++h) {
     const int i = tp.i[h], k = tp.k[h];
     if (i < 0) continue;
-    double acc = 0.0, acc1 = 0.0;
-#pragma unroll 4
-    for (int r = 0; r < nrows; r += 2) {
-      acc = fma(s.cw[r] * s.Y[r][i], s.Y[r][k], acc);
-      acc1 = fma(s.cw[r + 1] * s.Y[r + 1][i], s.Y[r + 1][k], acc1);
+    const double* yi = &s.Y[0][i];
+    const double* yk = &s.Y[0][k];
+    auto term = [&](int r) { return yi[r * YS] * yk[r * YS]; };
+    auto leg = [&](int r) { return fma(yi[(r + 2) * YS], yk[(r + 2) * YS], fma(yi[(r + 1) * YS], yk[(r + 1) * YS], term(r))); };
+    const double b0 = fma(yi[2 * YS], yk[2 * YS], fma(yi[1 * YS], yk[1 * YS], term(0)));
+    const double b1 = fma(yi[5 * YS], yk[5 * YS], fma(yi[4 * YS], yk[4 * YS], term(3)));
+    double acc = wb * (b0 + b1);
+    acc = fma(wl0, leg(6), acc); acc = fma(wl1, leg(9), acc); acc = fma(wl2, leg(12), acc); acc = fma(wl3, leg(15), acc);
+    if (tau_rows) {
+      double t0 = 0.0, t1 = 0.0;
+#pragma unroll
+      for (int r = 18; r < 30; r += 2) { t0 = fma(yi[r * YS], yk[r * YS], t0); t1 = fma(yi[(r + 1) * YS], yk[(r + 1) * YS], t1); }
+      acc = fma(s.cw[18], t0 + t1, acc);
     }
-    acc += acc1;
-    if (extra) acc = fma(s.cw[30] * s.Y[30][i], s.Y[30][k], fma(s.cw[31] * s.Y[31][i], s.Y[31][k], acc));
+    if (extra) acc = fma(s.cw[30] * yi[30 * YS], yk[30 * YS], fma(s.cw[31] * yi[31 * YS], yk[31 * YS], acc));
     if (i >= nf) acc = (i == k) ? 1.0 : 0.0;
     s.H[i][k] = acc;
-  }
-  __syncwarp();
-  if (lane < N) {
-    double acc = 0.0, acc1 = 0.0;
-#pragma unroll 3
-    for (int r = 0; r < nrows; r += 2) {
-      acc = fma(s.Y[r][lane], s.y[r], acc);
-      acc1 = fma(s.Y[r + 1][lane], s.y[r + 1], acc1);
-    }
-    acc += acc1;
-    if (extra) acc = fma(s.Y[30][lane], s.y[30], fma(s.Y[31][lane], s.y[31], acc));
-    s.g[lane] = (lane < nf) ? acc : 0.0;
   }
   __syncwarp();
 }
@@ -742,7 +756,7 @@ template <int N, class SM> WBC_DEV double tri_bwd_lane(const SM& s, int lane, do
 // shared-memory wavefronts per iteration, the limiter measured on that form) reduce to ~85 wavefronts and half the
 // instructions. W is built IN PLACE over Y (W = Y L^-T, forward substitution along each row); the free-part chains enter an
 // unrolled sequence at column q (q is warp uniform) with static shared-memory offsets - no masks, no selects.
-// On entry s.H holds the Cholesky factor L (lower, in place), s.d its inverse diagonal, s.g the reduced gradient.
+// On entry s.H holds the Cholesky factor L (lower, in place), s.d its inverse diagonal, s.y the weighted residuals e.
 // On exit s.y = Y w + y0 and the multipliers are in s.u / s.act; w is recovered (x = H^-1 Y' C (y - y0), Y read back from
 // the hand-over record `Yg`) only when the caller asks for the accelerations.
 template <int N, class SM> WBC_DEV int gi_solve_ws(SM& s, int lane, const IneqSet& S, int max_iter, int& status, int& q_out,
@@ -753,28 +767,40 @@ template <int N, class SM> WBC_DEV int gi_solve_ws(SM& s, int lane, const IneqSe
   const Ineq c0 = get_ineq(S, lane < mi ? lane : 0);
   const bool have0 = lane < mi;
   double* Wl = &s.Y[lane][0];                    // row `lane` of W (after the substitution below)
-  // ---- W = Y L^-T in place (forward substitution along the row, L broadcast from shared memory), interleaved with the
-  //      forward substitution L b = g (lane k owns b_k; the finished component is broadcast by shuffle and consumed at once
-  //      by the unconstrained minimiser in y:  y = y0 - W b)
+  // ---- W = Y L^-T in place (forward substitution along the row, L broadcast from shared memory). The unconstrained minimiser
+  //      needs b = L^-1 g with g = Y'e, i.e. b = W'e: lane k < N sums column k of W against e (left in s.y by
+  //      reduced_hessian) - no triangular solve - and then y = y0 - W b with the row still in registers.
   double yl;
   {
     double w[N];
-    const double dinvl = s.d[li];
-    double accb = row ? s.g[li] : 0.0;
-    double ya = Wl[NF], ya1 = 0.0;
 #pragma unroll
     for (int k = 0; k < N; ++k) {
-      const double bk = shfl(accb * dinvl, k);
-      if (lane > k) accb = fma(-s.H[li][k], bk, accb);
       double acc = Wl[k];
 #pragma unroll
       for (int j = 0; j < k; ++j) acc = fma(-w[j], s.H[k][j], acc);
       w[k] = acc * s.d[k];
-      if (k & 1) ya1 = fma(-w[k], bk, ya1); else ya = fma(-w[k], bk, ya);
     }
 #pragma unroll
     for (int k = 0; k < N; ++k) Wl[k] = w[k];
+    __syncwarp();
+    {
+      const double* wc = &s.Y[0][li];
+      double b0 = 0.0, b1 = 0.0;
+#pragma unroll
+      for (int r = 0; r < 18; r += 2) { b0 = fma(wc[r * YS], s.y[r], b0); b1 = fma(wc[(r + 1) * YS], s.y[r + 1], b1); }
+      if (s.cw[18] != 0.0) {
+#pragma unroll
+        for (int r = 18; r < 30; r += 2) { b0 = fma(wc[r * YS], s.y[r], b0); b1 = fma(wc[(r + 1) * YS], s.y[r + 1], b1); }
+      }
+      b0 = fma(wc[30 * YS], s.y[30], b0); b1 = fma(wc[31 * YS], s.y[31], b1);
+      if (row) s.dm[lane] = b0 + b1;
+    }
+    __syncwarp();
+    double ya = Wl[NF], ya1 = 0.0;
+#pragma unroll
+    for (int k = 0; k < N; ++k) { if (k & 1) ya1 = fma(-w[k], s.dm[k], ya1); else ya = fma(-w[k], s.dm[k], ya); }
     yl = ya + ya1;
+    __syncwarp();                                  // every lane has consumed e (s.y) and b (s.dm)
     s.y[lane] = yl;
   }
   __syncwarp();
@@ -794,13 +820,22 @@ template <int N, class SM> WBC_DEV int gi_solve_ws(SM& s, int lane, const IneqSe
       for (int k = 0; k < N; ++k) { const double t = fma(c1.ca, va[k], c1.cb * vb[k]); ddl1 = fma(t, t, ddl1); }
     }
   }
+  // ---- R^-1 rows start at zero (without VD they overlay L, which is dead from here on: W, b and y are formed)
+  double* const Ril = ri_rows(s) + li * NF;      // row `lane` of R^-1 (entries j < lane stay exactly zero)
+  {
+    double* r0 = ri_rows(s);
+    for (int e = lane; e < NF * NF; e += 32) r0[e] = 0.0;
+  }
+  __syncwarp();
   int q = 0, iters = 0;
   unsigned long long activemask = 0ull;
-  double ul = 0.0, rinvl = 0.0;     // lane k < q: multiplier and 1 / R[k][k] of active slot k
+  double ul = 0.0;                  // lane k < q: multiplier of active slot k
   int actl = 0;                     // constraint id in slot `lane`
   minslack = 0.0;
-  // most violated inequality (y lives in shared memory: every lane reads the two rows its constraint combines)
-  auto select = [&](double& viol_out, int& p_out) {
+  // most violated inequality (y lives in shared memory: every lane reads the two rows its constraint combines); the winner
+  // is chosen on the high word of the violation (one redux)
+  double violl = 0.0;
+  auto select = [&](bool& any, int& p_out, int& wl) {
     double viol = 0.0; int who = lane;
     if (have0 && !((activemask >> lane) & 1ull)) {
       const double ta = c0.ca * s.y[c0.ra], tb = c0.cb * s.y[c0.rb];
@@ -815,15 +850,14 @@ template <int N, class SM> WBC_DEV int gi_solve_ws(SM& s, int lane, const IneqSe
         if (sl < -1e-10 * (1.0 + fabs(c1.bound) + fabs(ta) + fabs(tb)) && -sl > viol) { viol = -sl; who = lane + 32; }
       }
     }
-    int wl;
-    viol_out = warp_max_lane(viol, wl);
+    violl = viol;
+    wl = warp_argmax_hi(viol, any);
     p_out = (mi > 32) ? shfl(who, wl) : wl;
   };
-  double viol; int p;
-  select(viol, p);
+  bool any; int p, wlane;
+  select(any, p, wlane);
   for (;;) {
-    minslack = -viol;
-    if (!(viol > 0.0)) break;
+    if (!any) break;
     // descriptor of the pivot: the lane that watches constraint p (< 32) already holds it
     Ineq cp;
     if (p < 32) {
@@ -858,26 +892,37 @@ template <int N, class SM> WBC_DEV int gi_solve_ws(SM& s, int lane, const IneqSe
 #undef WBC_ACC
         default: break;
       }
-      zn += zn1; wd += wd1;
+      // ---- r = R^-1 d[:q]: lane k owns r_k = R^-1[k][:q] . d[:q] - an FMA chain per lane on its own row of R^-1 (no
+      //      shuffle-serialised back substitution); entered at j = q - 1, entries left of the diagonal are zero
+      double rk = 0.0, rk1 = 0.0;
+      switch (q) {
+#define WBC_RI(K)                                                                                    \
+        case K + 1:                                                                                  \
+          if (K < N) {                                                                               \
+            if (K & 1) rk1 = fma(Ril[K < N ? K : 0], s.dm[K < N ? K : 0], rk1);                      \
+            else rk = fma(Ril[K < N ? K : 0], s.dm[K < N ? K : 0], rk);                              \
+          }
+        WBC_RI(12) WBC_RI(11) WBC_RI(10) WBC_RI(9) WBC_RI(8) WBC_RI(7) WBC_RI(6) WBC_RI(5) WBC_RI(4) WBC_RI(3) WBC_RI(2) WBC_RI(1)
+        WBC_RI(0)
+#undef WBC_RI
+        default: break;
+      }
+      zn += zn1; wd += wd1; rk += rk1;
       const int qc = q < N ? q : N - 1;
       const double dq = s.dm[qc], wq = Wl[qc];
       const double sp = cp.bound - cp.ca * s.y[cp.ra] - cp.cb * s.y[cp.rb];
-      // r = R^-1 d[:q]  (back substitution; lane k owns r_k; R is kept transposed: R[col][row])
-      double rk = dself;
-      {
-        const double* rcol = &s.Rp[(q - 1) * (q + 2) / 2 + li];      // column q-1 of the packed R, this lane's row
-        for (int jj = q - 1; jj >= 0; --jj) {
-          const double rl = *rcol;
-          rcol -= jj + 1;                                            // column jj-1 starts jj+1 entries earlier
-          const double rj = shfl(rk * rinvl, jj);
-          if (lane < jj) rk = fma(-rl, rj, rk);
-        }
-      }
-      rk *= rinvl;
+      // special-function chains of this pivot, issued together so that they overlap the ratio-test reduction:
+      // 1 / |d2|^2 (step length), 1 / |d2| (Householder scale and the new diagonal of R^-1), 1 / (v'v / 2)
+      const bool zok = zn > 1e-14 * fmax(dd, 1e-300);
+      const double zs = zok ? zn : 1.0;
+      const double izn = frcp(zs);
+      const double rs = frsqrt(zs);                        // 1 / |d2|
+      const double nrm = zs * rs;                          // |d2|
+      const double alpha = dq > 0.0 ? -nrm : nrm;
+      const double hv = fma(-dq, alpha, zs);               // |v|^2 / 2 = zn - dq alpha  (> 0: no cancellation by the sign choice)
+      const double ihv = frcp(hv);
       int l;
       const double t1 = warp_min_lane((lane < q && rk > 0.0) ? fmax(ul * frcp(rk), 0.0) + 0.0 : INFINITY, l);
-      const bool zok = zn > 1e-14 * fmax(dd, 1e-300);
-      const double izn = frcp(zok ? zn : 1.0);
       const double t2 = zok ? -sp * izn : INFINITY;
       const double t = fmin(t1, t2);
       if (!(t < INFINITY)) { status |= WBC_ST_INFEASIBLE; fail = true; break; }
@@ -890,48 +935,54 @@ template <int N, class SM> WBC_DEV int gi_solve_ws(SM& s, int lane, const IneqSe
         // ---- full step: add p. The next pivot is selected here, from the y just published: its reductions are independent
         //      of the Householder update below and overlap it.
         activemask |= 1ull << p;
+        if (lane == 0 && q < N - 1) s.dm[qc] = dq - alpha;     // the published d becomes the Householder vector v = d[q:] - alpha e_q
         __syncwarp();
-        double nviol; int np;
-        select(nviol, np);
+        bool nany; int np, nwl;
+        select(nany, np, nwl);
         // Householder on d[q:] -> (alpha, 0, ..), W[:, q:] <- W[:, q:] (I - 2 v v'/v'v), v = d[q:] - alpha e_q
-        const double nrm = zn * frsqrt(zn);
-        const double alpha = dq > 0.0 ? -nrm : nrm;
-        double rqq = dq;
+        double rqq = dq, irq = dq > 0.0 ? rs : -rs;        // one free column left: R[q][q] = d_q = +-|d2|
         if (q < N - 1) {
-          const double vv = 2.0 * (zn - dq * alpha);       // |v|^2
-          if (vv > 0.0) {
-            const double sc = 2.0 * (wd - alpha * wq) * frcp(vv);   // W[lane] . v = wd - alpha W[lane][q]
-            switch (q) {                                   // W[k] -= sc d_k, k >= q
+          const double sc = (wd - alpha * wq) * ihv;       // 2 (W[lane] . v) / v'v,  W[lane] . v = wd - alpha W[lane][q]
+          switch (q) {                                     // W[k] -= sc v_k, k >= q
 #define WBC_UPD(K) case K: if (K < N) Wl[K < N ? K : 0] = fma(-sc, s.dm[K < N ? K : 0], Wl[K < N ? K : 0]);
-              WBC_UPD(0) WBC_UPD(1) WBC_UPD(2) WBC_UPD(3) WBC_UPD(4) WBC_UPD(5) WBC_UPD(6) WBC_UPD(7) WBC_UPD(8) WBC_UPD(9) WBC_UPD(10)
-              WBC_UPD(11) WBC_UPD(12)
+            WBC_UPD(0) WBC_UPD(1) WBC_UPD(2) WBC_UPD(3) WBC_UPD(4) WBC_UPD(5) WBC_UPD(6) WBC_UPD(7) WBC_UPD(8) WBC_UPD(9) WBC_UPD(10)
+            WBC_UPD(11) WBC_UPD(12)
 #undef WBC_UPD
-              default: break;
-            }
-            Wl[qc] = fma(sc, alpha, Wl[qc]);               // column q: v_q = d_q - alpha
+            default: break;
           }
-          rqq = alpha;
+          rqq = alpha; irq = dq > 0.0 ? -rs : rs;          // 1 / alpha
         }
-        if (lane < q) Rent(s, q, lane) = dself;
-        if (lane == q) { Rent(s, q, q) = rqq; rinvl = frcp(rqq); ul = up; actl = p; }
+        // R gains the column (d[:q]; rqq); R^-1 gains the column (-r / rqq; 1 / rqq)
+        if (lane < q) { Rent(s, q, lane) = dself; Ril[qc] = -rk * irq; }
+        if (lane == q) { Rent(s, q, q) = rqq; Ril[qc] = irq; ul = up; actl = p; }
         ++q;
-        viol = nviol; p = np;
+        any = nany; p = np; wlane = nwl;
         __syncwarp();
         break;
       }
       // ---- drop the blocking constraint l (position in the active list)
       {
-        __syncwarp();                                      // every lane is done reading R (back substitution above)
+        __syncwarp();                                      // every lane is done reading R^-1 and d
         const int dropped = shfl(actl, l);
         activemask &= ~(1ull << dropped);
-        // shift the columns right of l one place left: the triangle becomes upper Hessenberg from column l on
+        // shift the columns right of l one place left: the triangle becomes upper Hessenberg from column l on;
+        // R^-1 loses row l (rows below move up one lane)
         for (int jj = l; jj < q - 1; ++jj) { if (lane <= jj + 1) Rent(s, jj, lane) = Rent(s, jj + 1, lane); }
         if (lane <= q) Rent(s, q - 1, lane) = 0.0;
+        {
+          const bool mv = row && lane >= l && lane < q - 1;
+          const double* src = mv ? Ril + NF : Ril;
+          for (int j = 0; j < q; ++j) {
+            const double tv = src[j];
+            __syncwarp();
+            if (mv) Ril[j] = tv;
+          }
+        }
         const double un = __shfl_down_sync(WBC_FULL, ul, 1);
         const int an = __shfl_down_sync(WBC_FULL, actl, 1);
         if (lane >= l && lane < q - 1) { ul = un; actl = an; }
         __syncwarp();
-        // Givens rotations restoring the triangle; same rotations on the columns of W
+        // Givens rotations restoring the triangle; same rotations on the columns of W and of R^-1
         for (int k = l; k < q - 1; ++k) {
           const double a = Rent(s, k, k), b = Rent(s, k, k + 1);   // R[k][k], R[k+1][k]
           const double r2 = a * a + b * b;
@@ -942,17 +993,19 @@ template <int N, class SM> WBC_DEV int gi_solve_ws(SM& s, int lane, const IneqSe
             if (row && lane >= k) {                        // rows k, k+1 are zero left of column k
               const double r0 = Rent(s, lane, k), r1 = Rent(s, lane, k + 1);
               Rent(s, lane, k) = c * r0 + sn * r1; Rent(s, lane, k + 1) = -sn * r0 + c * r1;
-              if (lane == k) rinvl = frcp(c * r0 + sn * r1);
             }
             const double w0 = Wl[k], w1 = Wl[k + 1];
             Wl[k] = c * w0 + sn * w1; Wl[k + 1] = -sn * w0 + c * w1;
+            if (lane < q - 1) {                            // only the rows that stay active: an idle row keeps its zeros left of the diagonal
+              const double i0 = Ril[k], i1 = Ril[k + 1]; Ril[k] = c * i0 + sn * i1; Ril[k + 1] = -sn * i0 + c * i1;
+            }
           }
           __syncwarp();
         }
         --q;
       }
     }
-    if (fail) break;
+    if (fail) { minslack = -shfl(violl, wlane); break; }
   }
   if (lane < q) { s.u[lane] = ul; s.act[lane] = actl; }
   if (Yg) {
@@ -1475,7 +1528,7 @@ WBC_DEV void solve_instance(SM& s, const wbc_model& md, const wbc_params& pr, co
   if (c.ok) {
     // ---- phase 5
     const TriPairs tp = tri_pairs<NA>(lane);
-    reduced_hessian<NA>(s, lane, nf, pr.reg_tau != 0.0 ? 30 : 18, KIND != WBC_CTRL_ID, tp);
+    reduced_hessian<NA>(s, lane, nf, pr.reg_tau != 0.0, KIND != WBC_CTRL_ID, tp);
     cholesky_factor<NA>(s, lane, status, tp);
     // ---- phase 6
     IneqSet S;
@@ -1484,7 +1537,7 @@ WBC_DEV void solve_instance(SM& s, const wbc_model& md, const wbc_params& pr, co
     int qact = 0; double minslack = 0.0;
     int iters = 0;
     if (!(status & WBC_ST_NOTPD)) {
-      iters = gi_solve_ws<NA>(s, lane, S, pr.max_iter, status, qact, minslack, a.vd != nullptr ? yrec : nullptr);
+      iters = gi_solve_ws<NA>(s, lane, S, pr.max_iter, status, qact, minslack, (SM::kVd && a.vd != nullptr) ? yrec : nullptr);
     }
     // ---- phase 7: y = Y x + y0 is current in s.y. Any status bit (unfinished active-set iterate, substituted orientation,
     //      rank-deficient problem) zeroes the torques: nothing that is not the optimum of the reference QP leaves as tau
@@ -1495,7 +1548,7 @@ WBC_DEV void solve_instance(SM& s, const wbc_model& md, const wbc_params& pr, co
       a.tau[inst * WBC_NU + md.act_index[lane]] = failed ? 0.0 : s.y[18 + lane];
       if (a.f) a.f[inst * 12 + lane] = (!failed && ((cmask >> (lane / 3)) & 1)) ? s.y[6 + lane] : 0.0;
     }
-    if (a.vd && lane < 18) {
+    if (SM::kVd && a.vd && lane < 18) {
       // accelerations as affine maps of w (rows stored by the reduce half: a_b, then the joints in internal order)
       const double* mrow = vdmap + lane * YS;
       double val = mrow[NF];

@@ -9,7 +9,7 @@ thread_local EmuWarp* emu_warp;
 
 namespace {
 struct Job {
-  EmuWarp* warp; int lane; wbc::WarpSmem* sm; wbc::SolveSmem* ssm; double* rec; double* vdmap; wbc::PcSmem* pcs; double* Cout; double* Jdout; const wbc_model* md; const wbc_params* pr; wbc::Derived dv;
+  EmuWarp* warp; int lane; wbc::WarpSmem* sm; wbc::SolveSmemVd* ssm; double* rec; double* vdmap; wbc::PcSmem* pcs; double* Cout; double* Jdout; const wbc_model* md; const wbc_params* pr; wbc::Derived dv;
   wbc::StepArgs args; wbc::DynOut dyn; const double* q; const double* v; long long n; int mode;
 };
 template <int KIND> void split_step(Job* j, long long i) {
@@ -21,7 +21,7 @@ template <int KIND> void split_step(Job* j, long long i) {
   __syncwarp();
   if (j->lane == 0) memcpy(&j->ssm->Y[0][0], j->rec, sizeof(double) * wbc::REC_Y);
   __syncwarp();
-  wbc::solve_instance<KIND, wbc::SolveSmem>(*j->ssm, *j->md, *j->pr, j->args, i, j->lane, c, vd, j->rec);
+  wbc::solve_instance<KIND, wbc::SolveSmemVd>(*j->ssm, *j->md, *j->pr, j->args, i, j->lane, c, vd, j->rec);
   __syncwarp();
 }
 void* lane_main(void* p) {
@@ -49,7 +49,7 @@ int run(Job proto) {
   memset(sm, 0, sizeof(*sm));
   wbc::PcSmem* pcs = new wbc::PcSmem();
   memset(pcs, 0, sizeof(*pcs));
-  wbc::SolveSmem* ssm = new wbc::SolveSmem();
+  wbc::SolveSmemVd* ssm = new wbc::SolveSmemVd();
   memset(ssm, 0, sizeof(*ssm));
   std::vector<double> rec(wbc::REC_DOUBLES), vdmap(wbc::VDMAP_DOUBLES);
   std::vector<Job> jobs(32, proto);
