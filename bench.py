@@ -5,22 +5,23 @@
 
 A "step" is one pass of the hot path (dynamics + ID-QP: the reduce kernel and the solve kernel, back to back on one
 stream) over one batch of synthetic states.
-Workload at N = 1: BASELINE.json configs[1] - mini_cheetah ID-QP, 4096 random states per launch, all
-four feet in stance. With N > 1 (torchrun, one rank per GPU) every rank runs the same
-batch size on its own shard of instances: weak scaling, no collective on the data path.
+Workload at N = 1: BASELINE.json configs[1] - mini_cheetah ID-QP, 4096 random states per launch, all four feet in stance
+(SURVEY.md 8d). With N > 1 (torchrun, one rank per GPU) every rank runs the same batch size on its own shard of instances
+(weak scaling, no collective on the data path); `--total T` instead splits T instances over the ranks (strong scaling,
+BASELINE configs[4]).
 
-Printed JSON (rank 0): value = control steps/s with inputs resident in HBM (CUDA events on the launch
-stream, L2 flushed between timed launches, max over ranks); e2e = the same through `wbc_step_host` with
-pinned host buffers (H2D + kernel + D2H inside the timed region); roofline / cpu_baseline as the
-contract asks. `--impl reference` times the CPU restatement of the reference path (oracle/, Python or
-C port) on the host cores instead - pydrake/OSQP themselves are not installable.
+Printed JSON (rank 0): value = control steps/s with inputs resident in HBM (CUDA events on the launch stream, L2 flushed
+between timed launches, max over ranks); e2e = the same through `wbc_step_host` with pinned host buffers (H2D + kernels +
+D2H inside the timed region); roofline / cpu_baseline as the contract asks; latency_n1 = p50 of ONE control step of ONE
+robot through the LeafSystem mirror (the reference's operating point: one step per 5 ms, simulate.py:20-22).
+`--impl reference` times the CPU restatement of the reference path (oracle/, C port) on the host cores instead - pydrake /
+OSQP themselves are not installable; `import pydrake` is probed at start and reported either way.
 """
 from __future__ import annotations
 
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -38,6 +39,19 @@ CANON_FLOPS_PER_STEP = {0: 0.56e6, 1: 0.78e6, 2: 1.05e6, 3: 1.37e6, 4: 1.75e6}  
 WORKLOAD = "mini_cheetah ID-QP controller step, 4096 random synthetic states (BASELINE configs[1])"
 
 
+def shared_config(args, n_per_gpu, world):
+    """The workload description both arms print, key for key (the driver compares them)."""
+    total = n_per_gpu * world
+    experiment = (n_per_gpu != BATCH or args.pattern != PATTERN or args.robot != ROBOT or args.controller != "id" or args.torque_limits
+                  or args.total)
+    wl = WORKLOAD if not experiment else (
+        f"EXPERIMENT (not the BASELINE bench config): {args.robot} {args.controller.upper()}-QP, {n_per_gpu} instances/launch/GPU, "
+        f"pattern {args.pattern}, torque limits {'on' if args.torque_limits else 'off'}")
+    return {"workload": wl, "robot": args.robot, "controller": args.controller.upper(), "contact_pattern": args.pattern,
+            "instances_per_step_per_gpu": int(n_per_gpu), "torque_limits": bool(args.torque_limits), "seed": SEED,
+            "tie_break_reg_f": 1e-6, "total_instances": int(total) if args.total else None}
+
+
 def measured_peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -46,20 +60,29 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def flop_model():
+    """Executed FP64 work per instance as a function of the measured active-set iterations. STATIC: fitted to ncu captures
+    of this kernel build (tools/ncu_flops.py -> profiles/r2_flop_model.json); the file names the captures and the commit."""
+    p = ROOT / "profiles" / "r2_flop_model.json"
+    return json.loads(p.read_text()) if p.exists() else None
+
+
 class ClockSampler:
-    """SM clock and throttle reasons DURING the timed region, polled through NVML every ~2 ms from a thread
-    (the nvidia-smi recipe of B200_PROFILING.md samples too coarsely for a region of tens of milliseconds)."""
+    """SM clock and throttle reasons while the GPU is under this benchmark's load, polled through NVML from a thread.
+    It runs from the first warm-up launch to the last timed launch (the timed region alone lasts ~2 ms at --steps 20, too
+    short for more than one NVML sample); `in_timed` counts the samples that fell inside the timed region."""
 
     def __init__(self, index):
         self.index, self.sm, self.reasons, self.max_mhz, self.err = index, [], set(), None, None
         self._stop = threading.Event()
         self._th = None
+        self.timed = False
+        self.in_timed = 0
 
     def start(self):
         try:
             import pynvml
             pynvml.nvmlInit()
-            # NVML indices follow PCI order like CUDA_VISIBLE_DEVICES-less CUDA; honour the mask if there is one
             vis = os.environ.get("CUDA_VISIBLE_DEVICES")
             idx = int(vis.split(",")[self.index]) if vis and vis.split(",")[self.index].strip().isdigit() else self.index
             self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
@@ -80,6 +103,8 @@ class ClockSampler:
         while not self._stop.is_set():
             try:
                 self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                if self.timed:
+                    self.in_timed += 1
                 get = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
                 mask = int(get(self.h))
                 for k, bit in names.items():
@@ -88,105 +113,137 @@ class ClockSampler:
             except Exception as e:  # noqa: BLE001
                 self.err = repr(e)
                 break
-            time.sleep(0.002)
+            time.sleep(0.001)
 
     def stop(self):
         self._stop.set()
         if self._th is not None:
             self._th.join(timeout=2.0)
         out = {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_mhz,
-               "reasons": sorted(self.reasons), "samples": len(self.sm), "source": "NVML polled every 2 ms during the timed region"}
+               "reasons": sorted(self.reasons), "samples": len(self.sm), "samples_in_timed_region": self.in_timed,
+               "source": "NVML polled every ~1 ms from the first warm-up launch to the last timed launch"}
         if self.err:
             out["error"] = self.err
         return out
 
 
 # ------------------------------------------------------------------------------- CPU arm
-def _cpu_worker(args):
-    robot, q, v, traj, contact = args
-    from oracle.controllers import IDController, traj_to_dict
-    ctl = IDController(robot)
-    t0 = time.perf_counter()
-    for i in range(len(q)):
-        ctl.control_law(q[i], v[i], traj_to_dict(traj[i], contact[i]))
-    return time.perf_counter() - t0
-
-
-def cpu_port_throughput(q, v, traj, contact, budget_s=20.0):
-    """Oracle (CPU restatement of the reference path) on all host cores over a bounded sample."""
-    cport = ROOT / "oracle" / "_build" / "liboracle_c.so"
-    if cport.exists():
-        from oracle.cport import time_id_steps
-        return time_id_steps(ROBOT, q, v, traj, contact, budget_s)
-    import multiprocessing as mp
-    cores = os.cpu_count() or 1
-    t0 = time.perf_counter()
-    _cpu_worker((ROBOT, q[:2], v[:2], traj[:2], contact[:2]))
-    per = (time.perf_counter() - t0) / 2
-    per_core = max(2, min(len(q) // cores, int(budget_s / max(per, 1e-3))))
-    chunks = [(ROBOT, q[c * per_core:(c + 1) * per_core], v[c * per_core:(c + 1) * per_core],
-               traj[c * per_core:(c + 1) * per_core], contact[c * per_core:(c + 1) * per_core]) for c in range(cores)]
-    t0 = time.perf_counter()
-    with mp.get_context("spawn").Pool(cores) as pool:
-        pool.map(_cpu_worker, chunks)
-    wall = time.perf_counter() - t0
-    done = per_core * cores
-    return {"value": done / wall, "unit": "steps/s", "cores": cores, "kind": "port",
-            "sample": f"{done} of the {len(q)} instances of one batch, numpy oracle (oracle/controllers.py), one process per core"}
-
-
-def host_inputs(n, seed):
-    """Synthetic batch on the host. Forward kinematics for the trajectory targets comes from the oracle here
-    only when no GPU is in use (reference arm); the GPU arm uses wbc_dynamics."""
-    from quadruped_drake_b200 import load_robot
-    from quadruped_drake_b200.synth import generate
-    return load_robot(ROBOT), generate
+def cpu_port_throughput(robot, q, v, traj, contact, budget_s=20.0, **params):
+    """C port of the oracle (CPU restatement of the reference path, NOT Drake + OSQP) on all host cores + one thread. It
+    solves the reference QP as the reference builds it: the optional torque box (not in the reference) is not part of it."""
+    from oracle.cport import time_id_steps
+    return time_id_steps(robot, q, v, traj, contact, budget_s)
 
 
 def run_reference(args):
-    """Reference arm: the CPU restatement of the reference path (C twin of the oracle when built, else the numpy
-    oracle) on all host cores, same config / metric / unit; rank 0 only."""
+    """Reference arm: the CPU restatement of the reference path (C twin of the oracle, gcc -O3 -march=native) on all host
+    cores, same config / metric / unit; rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import __graft_entry__ as g
     g.build_oracle()
-    from quadruped_drake_b200 import load_robot
+    from quadruped_drake_b200 import drake_bridge, load_robot
     from quadruped_drake_b200.synth import generate
-    model = load_robot(ROBOT)
-    cport = (ROOT / "oracle" / "_build" / "liboracle_c.so").exists()
-    if cport:
-        from oracle.cport import fk as cfk
-        n, fkc = BATCH, cfk(ROBOT)
-    else:
-        sys.path.insert(0, str(ROOT / "tests"))
-        from conftest import oracle_fk
-        from oracle.dynamics import Plant
-        n, fkc = 64 * (os.cpu_count() or 1), oracle_fk(Plant(ROBOT))
-    q, v, traj, contact = generate(model, n, SEED, PATTERN, fkc)
+    from oracle.cport import fk as cfk
+    if args.controller != "id":
+        raise SystemExit("bench.py --impl reference: the timed C port covers the ID controller (the BASELINE bench config)")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    n = args.total // world if args.total else args.batch
+    model = load_robot(args.robot)
+    ns = min(n, 4096)                                           # bounded sample of the batch (the same first instances)
+    q, v, traj, contact = generate(model, ns, SEED, args.pattern, cfk(args.robot))
     vals = []
     per_step = max(2.0, min(20.0, 120.0 / (args.warmup + args.steps)))
+    extra = {"torque_limits": 1} if args.torque_limits else {}
     for s in range(args.warmup + args.steps):
-        r = cpu_port_throughput(q, v, traj, contact, budget_s=per_step)
+        r = cpu_port_throughput(args.robot, q, v, traj, contact, budget_s=per_step, **extra)
         if s >= args.warmup:
             vals.append(r)
     val = float(np.mean([r["value"] for r in vals]))
     base = dict(vals[-1])
     base["value"] = val
+    base["single_thread"]["value"] = float(np.mean([r["single_thread"]["value"] for r in vals]))
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "steps/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * BATCH / val, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "robot": ROBOT, "controller": "ID", "contact_pattern": PATTERN,
-                       "instances_per_step": BATCH,
-                       "note": "CPU restatement of the reference path on all host cores (pydrake + OSQP are not installable "
-                               "here, DESIGN.md 5); each step is a bounded sample of the 4096-instance batch"},
+            "warmup": args.warmup, "ms_per_step": 1e3 * n / val, "higher_is_better": True,
+            "scaling": "strong" if args.total else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": shared_config(args, n, world),
+            "reference_kind": "CPU restatement of the reference path (C port of the oracle), NOT Drake + OSQP: pydrake is not "
+                              "installable here (DESIGN.md 5); each step is a bounded sample of the batch on all host cores",
+            "pydrake": drake_bridge.probe(),
             "cpu_baseline": base,
             "e2e": {"value": val, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------- GPU arm
+def latency_n1(ctl_kwargs, robot, device):
+    """p50 latency of one control step of one robot: (a) IDController.DoSetControlTorques through the LeafSystem mirror
+    (EvalOutput of "quad_torques", SimpleStanding input: BASELINE configs[0]); (b) wbc_step_host with N = 1 on page-locked
+    buffers; (c) the device-resident step (CUDA events). The reference runs this once per 5 ms (simulate.py:20-22)."""
+    import ctypes as C
+    import torch
+    from quadruped_drake_b200 import capi
+    from quadruped_drake_b200.controller import IDController
+    from quadruped_drake_b200.planner import BasicTrunkPlanner
+    leaf = IDController(robot, 5e-3, device=device, **ctl_kwargs)
+    planner = BasicTrunkPlanner(robot=robot)
+    q0 = leaf.batched.model.nominal_q()
+    ctx = leaf.CreateDefaultContext()
+    ctx.FixValue(0, np.hstack([q0, np.zeros(18)]))
+    ctx.FixValue(1, planner.SetTrunkOutputs(0.0))
+    for _ in range(20):
+        leaf.EvalOutput(ctx, 0)
+    ts = []
+    for _ in range(300):
+        t0 = time.perf_counter()
+        leaf.EvalOutput(ctx, 0)
+        ts.append(time.perf_counter() - t0)
+    out = {"leafsystem_p50_us": 1e6 * float(np.median(ts)), "leafsystem_p99_us": 1e6 * float(np.percentile(ts, 99))}
+    ctl = leaf.batched
+    from quadruped_drake_b200.controller import dict_to_traj
+    traj, contact = dict_to_traj(planner.SetTrunkOutputs(0.0))
+    hq, hv, ht = capi.pinned_empty((1, 19)), capi.pinned_empty((1, 18)), capi.pinned_empty((1, 54))
+    hc = capi.pinned_empty((1, 4), np.uint8)
+    hq[:], hv[:], ht[:], hc[:] = q0, 0.0, traj, contact
+    htau, hmet, hst = capi.pinned_empty((1, 12)), capi.pinned_empty((1, 4)), capi.pinned_empty((1,), np.int32)
+    hio = capi.WbcIO(capi.np_ptr(hq), capi.np_ptr(hv), capi.np_ptr(ht), capi.np_ptr(hc), capi.np_ptr(htau), capi.np_ptr(hmet),
+                     capi.np_ptr(hst))
+    for _ in range(20):
+        ctl.lib.wbc_step_host(ctl._h, capi.WBC_CTRL_ID, 1, C.byref(hio))
+    ts = []
+    for _ in range(300):
+        t0 = time.perf_counter()
+        ctl.lib.wbc_step_host(ctl._h, capi.WBC_CTRL_ID, 1, C.byref(hio))
+        ts.append(time.perf_counter() - t0)
+    out["step_host_p50_us"] = 1e6 * float(np.median(ts))
+    dev = torch.device(f"cuda:{device}")
+    tq, tv, tt = (torch.from_numpy(np.ascontiguousarray(x)).to(dev) for x in (hq, hv, ht))
+    tc = torch.from_numpy(np.ascontiguousarray(hc)).to(dev)
+    tau = torch.empty((1, 12), dtype=torch.float64, device=dev)
+    met = torch.empty((1, 4), dtype=torch.float64, device=dev)
+    st = torch.empty((1,), dtype=torch.int32, device=dev)
+    io = ctl.make_io(tq, tv, tt, tc, tau, met, st)
+    stream = torch.cuda.current_stream(dev)
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(100)]
+    for _ in range(10):
+        ctl.lib.wbc_step(ctl._h, capi.WBC_CTRL_ID, 1, C.byref(io), C.c_void_p(stream.cuda_stream))
+    for e0, e1 in evs:
+        e0.record(stream)
+        ctl.lib.wbc_step(ctl._h, capi.WBC_CTRL_ID, 1, C.byref(io), C.c_void_p(stream.cuda_stream))
+        e1.record(stream)
+    torch.cuda.synchronize()
+    out["device_step_p50_us"] = 1e3 * float(np.median([e0.elapsed_time(e1) for e0, e1 in evs]))
+    out["status"] = int(hst[0])
+    out["reference_period_us"] = 5000.0
+    out["note"] = ("one robot, one control step: launch -> torques in host memory; the reference's own loop ran at ~180-200 "
+                   "steps/s including the plant step (BASELINE.md 1)")
+    leaf.batched.close()
+    return out
+
+
 def run_gpu(args):
+    import ctypes as C
     import torch
     import torch.distributed as dist
     import __graft_entry__ as g
@@ -213,15 +270,24 @@ def run_gpu(args):
             os.close(saved)
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
-    from quadruped_drake_b200 import capi
+    from quadruped_drake_b200 import capi, drake_bridge
     from quadruped_drake_b200.controller import BatchedController, measure_fp64_peak
+    from quadruped_drake_b200.sharding import shard_range
     from quadruped_drake_b200.synth import generate
 
     robot = args.robot
     kind = capi.KINDS[args.controller]
-    ctl = BatchedController(robot, device=local, **({"torque_limits": 1} if args.torque_limits else {}))
-    n = args.batch
-    q, v, traj, contact = generate(ctl.model, n, SEED + 1000 * rank, args.pattern, ctl.fk)   # each rank its own shard
+    ctl_kwargs = {"torque_limits": 1} if args.torque_limits else {}
+    ctl = BatchedController(robot, device=local, **ctl_kwargs)
+    if args.total:                                              # strong scaling: contiguous shard of [0, total)
+        lo, hi = shard_range(args.total, rank, world)
+        n = hi - lo
+    else:
+        n = args.batch
+    # every rank its own shard of instances; generated in pieces so that 10^7 instances do not need 10^7-row FK temporaries
+    parts = [generate(ctl.model, min(1 << 20, n - o), SEED + 1000 * rank + 17 * (o >> 20), args.pattern, ctl.fk) for o in range(0, n, 1 << 20)]
+    q, v, traj, contact = (np.concatenate([p[i] for p in parts]) for i in range(4))
+    del parts
     tq, tv, tt = (torch.from_numpy(x).to(dev) for x in (q, v, traj))
     tc = torch.from_numpy(contact).to(dev)
     tau = torch.empty((n, 12), dtype=torch.float64, device=dev)
@@ -231,48 +297,59 @@ def run_gpu(args):
     io = ctl.make_io(tq, tv, tt, tc, tau, met, st, None, None, qi)
     stream = torch.cuda.current_stream(dev)
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)       # 256 MB > 126 MB L2
-    import ctypes as C
 
     def launch():
         rc = ctl.lib.wbc_step(ctl._h, kind, n, C.byref(io), C.c_void_p(stream.cuda_stream))
         if rc:
             raise RuntimeError(ctl.lib.wbc_last_error(ctl._h).decode())
 
-    for _ in range(max(args.warmup, 3)):
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
         flush.zero_()
         launch()
     torch.cuda.synchronize()
     status = st.cpu().numpy()
     iters = float(qi[:, 3].mean().item())
+    iters_max = float(qi[:, 3].max().item())
     bad = status != 0
     if args.controller in ("pc", "mptc"):
         bad &= status != capi.ST_UNSUPPORTED          # full-flight instances: the reference PC / MPTC raise there too
-    if bad.any():
-        raise SystemExit(f"bench.py: {int(bad.sum())} instances returned a non-zero status")
+    if bad.mean() > (1e-3 if args.torque_limits else 0.0):
+        raise SystemExit(f"bench.py: {int(bad.sum())} of {n} instances returned a non-zero status")
 
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     launches0 = ctl.launches
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    sampler.timed = True
     for e0, e1 in evs:
         flush.zero_()                       # L2 flush between timed launches (not inside the event pair)
         e0.record(stream)
         launch()
         e1.record(stream)
     torch.cuda.synchronize()
+    sampler.timed = False
     if world > 1:
         dist.barrier()
     gpu_launches = ctl.launches - launches0
     per = np.array([e0.elapsed_time(e1) for e0, e1 in evs])     # ms per launch
     total_ms = float(per.sum())
+    my_ms = total_ms
+    per_rank = None
     if world > 1:
         t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms = float(t.item())
+        # per-rank record (to attribute multi-GPU losses): ms per step, p50, mean / max iterations, instances
+        mine = torch.tensor([my_ms / args.steps, float(np.median(per)), iters, iters_max, float(n)], dtype=torch.float64, device=dev)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = [{"rank": r, "ms_per_step": float(a[0]), "p50_ms": float(a[1]), "mean_iterations": float(a[2]),
+                     "max_iterations": float(a[3]), "instances": int(a[4])} for r, a in enumerate(allr)]
     clocks = sampler.stop() if rank == 0 else None
     # per-kernel share of the step (events between the two kernels; separate short run, same inputs)
     ms_r, ms_s = C.c_double(), C.c_double()
@@ -292,8 +369,9 @@ def run_gpu(args):
         ctl.lib.wbc_step_host(ctl._h, kind, n, C.byref(hio))
     if world > 1:
         dist.barrier()
+    e2e_steps = args.steps if n <= (1 << 20) else max(3, args.steps // 4)
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(e2e_steps):
         rc = ctl.lib.wbc_step_host(ctl._h, kind, n, C.byref(hio))
         assert rc == 0
     e2e_s = time.perf_counter() - t0
@@ -304,59 +382,71 @@ def run_gpu(args):
     assert np.array_equal(htau, tau.cpu().numpy()), "host and device entry points disagree"
     h2d = n * (19 + 18 + 54) * 8 + n * 4
     d2h = n * (12 + 4) * 8 + n * 4
+    n_total = n
+    if world > 1:
+        t = torch.tensor([float(n)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        n_total = int(t.item())
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
-    value = world * n * args.steps / (total_ms * 1e-3)
+    value = n_total * args.steps / (total_ms * 1e-3)
     kernel_ms = float(per.mean())
     hbm_peak, peak_src = measured_peaks()
     ach_gbs = ALGO_BYTES_PER_STEP * n / (kernel_ms * 1e-3) / 1e9
-    traffic = None
-    tp = ROOT / "profiles" / "traffic.json"
-    if tp.exists():
-        traffic = json.loads(tp.read_text()).get("dram_bytes_per_launch")
     fp64_peak = measure_fp64_peak(local)
+    fm = flop_model()
+    nc_mean = float(contact.sum(axis=1).mean())
     canon = CANON_FLOPS_PER_STEP[4]
-    exec_flops = json.loads(tp.read_text()).get("fp64_flops_per_instance_executed") if tp.exists() else None
-    ach_tf = (exec_flops or 0.0) * n / (kernel_ms * 1e-3) / 1e12
+    if fm:
+        flops_inst = fm["reduce_flops"] + fm["solve_flops_base"] + fm["solve_flops_per_iteration"] * iters
+        traffic = fm.get("dram_bytes_per_instance_4096", 0.0) * n if fm.get("dram_bytes_per_instance_4096") else None
+    else:
+        flops_inst, traffic = None, None
+    ach_tf = (flops_inst or 0.0) * n / (kernel_ms * 1e-3) / 1e12
+    cfg = shared_config(args, args.batch if not args.total else args.total // world, world)
     line = {
-        "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": total_ms / args.steps, "p50_ms_per_step": float(np.median(per)), "higher_is_better": True, "scaling": "weak",
+        "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
+        "ms_per_step": total_ms / args.steps, "p50_ms_per_step": float(np.median(per)), "higher_is_better": True,
+        "scaling": "strong" if args.total else "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "robot": robot, "controller": args.controller.upper(), "contact_pattern": args.pattern,
-                   "instances_per_step_per_gpu": n, "l2": "flushed between timed launches (256 MB memset outside the event pair)",
-                   "mean_active_set_iterations": iters, "tie_break_reg_f": 1e-6},
-        "e2e": {"value": world * n * args.steps / e2e_s, "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+        "config": cfg,
+        "gpu_details": {"l2": "flushed between timed launches (256 MB memset outside the event pair)",
+                        "mean_active_set_iterations": iters, "max_active_set_iterations": iters_max,
+                        "mean_stance_feet": nc_mean, "kernels": shares, "per_rank": per_rank},
+        "e2e": {"value": n_total * e2e_steps / e2e_s, "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": e2e_steps,
                 "path": "wbc_step_host on page-locked host buffers, inputs and outputs cross the host link inside the timed region: the kernels "
                         "read / write host memory directly (zero-copy, below 131072 instances per call) or the batch goes through the "
                         "65536-instance two-stream copy / compute pipeline (above; also the path of pageable buffers)"},
         "gpu_launches": int(gpu_launches),
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
-                     "traffic": traffic, "peak_source": peak_src,
-                     "kernels": shares,
-                     "note": "860 B/step of algorithmic I/O over the whole step (reduce + solve kernel; the dominant one is the solve kernel, "
-                             "share in `kernels`): this path is bound by FP64 dependent-instruction latency and the shared-memory pipe, not by "
-                             "HBM (see roofline_fp64)"},
-        "roofline_fp64": {"achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach_tf / fp64_peak,
-                          "flops_per_step": exec_flops,
-                          "basis": "EXECUTED FP64 work: thread-level DFMA x2 + DMUL + DADD per instance from the committed ncu capture of "
-                                   "the headline workload (profiles/traffic.json) x measured steps/s; both kernels are bound by dependent-"
-                                   "instruction latency and shared-memory wavefronts at 16 / 28 resident warps per SM, not by the FP64 pipe "
-                                   "(DESIGN.md 3)",
-                          "peak_source": "DFMA loop measured in this run (wbc_measure_fp64_peak)",
-                          "canonical": {"flops_per_step": canon, "tflops_equivalent": canon * n / (kernel_ms * 1e-3) / 1e12,
-                                        "note": "SURVEY 8d F(nc=4): 12 interior-point iterations on the reference-size KKT system. The "
-                                                "null-space + active-set kernel reaches the exact optimum with ~13x fewer flops, so this "
-                                                "equivalent rate can exceed the hardware peak"}},
+        "pydrake": drake_bridge.probe(),
+        "roofline": {"bound": "fp64", "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach_tf / fp64_peak if fp64_peak else None,
+                     "traffic": traffic,
+                     "peak_source": "DFMA loop measured in this run (wbc_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 entry",
+                     "flops_per_step": flops_inst,
+                     "basis": ("EXECUTED FP64 work per instance = reduce + solve_base + solve_per_iteration x the mean active-set iterations "
+                               "MEASURED in this run; the three coefficients are STATIC, fitted to ncu captures of this kernel build: "
+                               + (fm["source"] if fm else "no model file")),
+                     "hbm": {"achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak, "peak_source": peak_src,
+                             "algorithmic_bytes_per_step": ALGO_BYTES_PER_STEP,
+                             "note": "860 B/step of algorithmic I/O: two orders of magnitude below the HBM roof - this path is not HBM bound"},
+                     "binding_resource": (fm or {}).get("binding_resource"),
+                     "canonical": {"flops_per_step": canon, "tflops_equivalent": canon * n / (kernel_ms * 1e-3) / 1e12,
+                                   "note": "SURVEY 8d F(nc=4): 12 interior-point iterations on the reference-size KKT system. The "
+                                           "null-space + active-set kernel reaches the exact optimum with ~14x fewer flops, so this "
+                                           "equivalent rate can exceed the hardware peak"}},
     }
-    if n != BATCH or args.pattern != PATTERN or robot != ROBOT or args.controller != "id" or args.torque_limits:
-        line["config"]["workload"] = (f"EXPERIMENT (not the BASELINE bench config): {robot} {args.controller.upper()}-QP, {n} instances/launch, "
-                                      f"pattern {args.pattern}, torque limits {'on' if args.torque_limits else 'off'}")
     if world == 1 and not args.no_cpu:
-        line["cpu_baseline"] = cpu_port_throughput(q[:4096], v[:4096], traj[:4096], contact[:4096])
+        ns = min(n, 4096)
+        line["cpu_baseline"] = cpu_port_throughput(robot, q[:ns], v[:ns], traj[:ns], contact[:ns], **ctl_kwargs)
+        try:
+            line["latency_n1"] = latency_n1(ctl_kwargs, robot, local)
+        except Exception as e:  # noqa: BLE001
+            line["latency_n1"] = {"error": repr(e)}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -369,8 +459,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH, help="instances per launch per GPU (default: the BASELINE config, 4096)")
+    ap.add_argument("--total", type=int, default=0, help="strong scaling: total instances, split evenly over the ranks (BASELINE configs[4])")
     ap.add_argument("--pattern", default=PATTERN, choices=["stand", "trot", "walk", "mixed"])
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (experiments only)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline and latency legs (experiments only)")
     ap.add_argument("--robot", default=ROBOT, choices=["mini_cheetah", "anymal_b"], help="experiments only")
     ap.add_argument("--controller", default="id", choices=["id", "clf", "pc", "mptc"], help="experiments only")
     ap.add_argument("--torque-limits", action="store_true", help="experiments only: |tau| <= effort rows (BASELINE configs[2])")

@@ -187,6 +187,20 @@ int wbc_step_pd(wbc_handle* h, int64_t n, const double* q, const double* v, doub
  * above that - and for pageable buffers - the batch goes through a chunked two-stream copy / compute pipeline. */
 int wbc_step_host(wbc_handle* h, int kind, int64_t n, const wbc_io* host_io);
 
+/* All GPUs of the box from one call (north star: "instances shard trivially across the 8 GPUs of one box, with no NCCL
+ * beyond an optional host gather"). wbc_multi_create makes one handle per listed device (devices == NULL: 0 ..
+ * n_devices-1; a device may be listed more than once). wbc_multi_step_host splits [0, n) into contiguous shards whose sizes
+ * differ by at most one, runs every shard on its device side by side (one host thread, asynchronous enqueue on all devices,
+ * then one wait per device) and returns when all outputs are in the caller's host arrays - which is the host gather. Same
+ * buffer rules as wbc_step_host; page-locked buffers (wbc_host_alloc) are mapped into every device. */
+typedef struct wbc_multi wbc_multi;
+int wbc_multi_create(const wbc_model* model, const wbc_params* params, int n_devices, const int* devices, wbc_multi** out);
+int wbc_multi_destroy(wbc_multi* m);
+const char* wbc_multi_last_error(const wbc_multi* m);
+int wbc_multi_device_count(const wbc_multi* m);
+int64_t wbc_multi_launch_count(const wbc_multi* m);
+int wbc_multi_step_host(wbc_multi* m, int kind, int64_t n, const wbc_io* host_io);
+
 /* Host-buffer version of wbc_dynamics (allocates device scratch per call; a test/debug entry). */
 int wbc_dynamics_host(wbc_handle* h, int64_t n, const double* q, const double* v,
                       double* M, double* Cv, double* taug, double* Jfeet, double* Jdv, double* pfeet);

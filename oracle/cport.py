@@ -34,7 +34,7 @@ def id_batch(robot, q, v, traj, contact, threads=None, **params):
     return tau, vd, f, st
 
 
-def time_id_steps(robot, q, v, traj, contact, budget_s=20.0, single_thread_s=3.0):
+def time_id_steps(robot, q, v, traj, contact, budget_s=20.0, single_thread_s=3.0, **_ignored):
     """Throughput of the C port over a bounded sample (bench.py cpu_baseline): all host cores, and one thread."""
     cores = os.cpu_count() or 1
     n0 = min(len(q), 8 * cores)

@@ -148,6 +148,15 @@ def load_library() -> C.CDLL:
     lib.wbc_integrate.restype = lib.wbc_rollout.restype = lib.wbc_rollout_host.restype = C.c_int
     for name in WIRE_SYMBOLS:
         getattr(lib, name).restype = C.c_int
+    lib.wbc_multi_create.argtypes = [C.POINTER(WbcModelStruct), C.POINTER(WbcParams), i32, C.POINTER(C.c_int), C.POINTER(H)]
+    lib.wbc_multi_destroy.argtypes = [H]
+    lib.wbc_multi_last_error.argtypes = [H]
+    lib.wbc_multi_last_error.restype = C.c_char_p
+    lib.wbc_multi_device_count.argtypes = [H]
+    lib.wbc_multi_launch_count.argtypes = [H]
+    lib.wbc_multi_launch_count.restype = C.c_int64
+    lib.wbc_multi_step_host.argtypes = [H, i32, i64, C.POINTER(WbcIO)]
+    lib.wbc_multi_create.restype = lib.wbc_multi_destroy.restype = lib.wbc_multi_device_count.restype = lib.wbc_multi_step_host.restype = C.c_int
     lib.wbc_launch_count.argtypes = [H]
     lib.wbc_launch_count.restype = C.c_int64
     for name in ("wbc_default_params", "wbc_create", "wbc_destroy", "wbc_dynamics", "wbc_coriolis", "wbc_step",
@@ -162,7 +171,9 @@ WIRE_SYMBOLS = ["wbc_lcm_decode_trunk_state", "wbc_lcm_encode_trunk_state", "wbc
                 "wbc_lcm_encode_robot_state_host"]
 ROLLOUT_SYMBOLS = ["wbc_integrate", "wbc_rollout", "wbc_rollout_host"]
 TRAJ_SYMBOLS = ROLLOUT_SYMBOLS + ["wbc_plan_create", "wbc_plan_destroy", "wbc_sample_trajectory", "wbc_sample_trajectory_host"]
-EXPORTED_SYMBOLS = WIRE_SYMBOLS + TRAJ_SYMBOLS + ["wbc_default_params", "wbc_create", "wbc_destroy", "wbc_last_error", "wbc_dynamics", "wbc_coriolis",
+MULTI_SYMBOLS = ["wbc_multi_create", "wbc_multi_destroy", "wbc_multi_last_error", "wbc_multi_device_count", "wbc_multi_launch_count",
+                 "wbc_multi_step_host"]
+EXPORTED_SYMBOLS = WIRE_SYMBOLS + TRAJ_SYMBOLS + MULTI_SYMBOLS + ["wbc_default_params", "wbc_create", "wbc_destroy", "wbc_last_error", "wbc_dynamics", "wbc_coriolis",
                     "wbc_step", "wbc_step_id", "wbc_step_clf", "wbc_step_pc", "wbc_step_mptc", "wbc_step_pd", "wbc_step_host", "wbc_time_step", "wbc_profile_step",
                     "wbc_measure_fp64_peak", "wbc_launch_count", "wbc_dynamics_host", "wbc_coriolis_host", "wbc_host_alloc", "wbc_host_free"]
 

@@ -304,24 +304,55 @@ except Exception:  # noqa: BLE001
             return out.get_value().copy()
 
 
+def dict_to_traj_batch(d, n):
+    """Trunk dict of arrays with a leading instance axis (N > 1 under Drake) -> traj[N,54], contact[N,4].
+    A dict without the leading axis (the reference's single-robot dict) is broadcast to all N instances."""
+    traj, contact = np.zeros((n, NTRAJ)), np.zeros((n, 4), np.uint8)
+    for k, key in enumerate(["p_body", "pd_body", "pdd_body", "rpy_body", "rpyd_body", "rpydd_body"]):
+        traj[:, 3 * k:3 * k + 3] = np.asarray(d[key], float).reshape(-1, 3)
+    for i, f in enumerate(FEET):
+        traj[:, 18 + 3 * i:21 + 3 * i] = np.asarray(d["p_" + f], float).reshape(-1, 3)
+        traj[:, 30 + 3 * i:33 + 3 * i] = np.asarray(d["pd_" + f], float).reshape(-1, 3)
+        traj[:, 42 + 3 * i:45 + 3 * i] = np.asarray(d["pdd_" + f], float).reshape(-1, 3)
+    contact[:] = np.asarray(d["contact_states"]).reshape(-1, 4) != 0
+    return traj, contact
+
+
 class _QPController(LeafSystem):
     KIND = "id"
+    HAS_TRUNK_PORT = True
 
-    def __init__(self, plant, dt, use_lcm=False, device=0, dof_order="depth_first", **params):
+    def __init__(self, plant, dt, use_lcm=False, device=0, dof_order="depth_first", n_instances=1, **params):
+        """`(plant, dt, use_lcm)` as in the reference (basic_controller.py:21). `plant`: a pydrake MultibodyPlant (its DOF
+        order is read from the plant itself), a robot name, or a RobotModel. `n_instances` > 1 widens the ports
+        to 37N / 12N / 4N instance-major vectors and the trunk dict to arrays with a leading N axis."""
         LeafSystem.__init__(self)
         self.dt = dt
         self.plant = plant
-        robot = plant if isinstance(plant, (str, RobotModel)) else getattr(plant, "wbc_robot", "mini_cheetah")
+        self.n = int(n_instances)
+        if self.n < 1:
+            raise ValueError("n_instances must be >= 1")
+        from . import drake_bridge
+        if drake_bridge.is_drake_plant(plant):
+            # live plant: velocity / actuator numbering from GetJointByName(j).velocity_start() and MakeActuationMatrix()
+            name = drake_bridge.robot_of_plant(plant)
+            robot = load_robot(name)
+            robot.v_index, robot.act_index = drake_bridge.derive_v_index(plant, name)
+        else:
+            robot = plant if isinstance(plant, (str, RobotModel)) else getattr(plant, "wbc_robot", "mini_cheetah")
         self.batched = BatchedController(robot, device=device, dof_order=dof_order, **params)
-        self.DeclareVectorInputPort("quad_state", BasicVector(NQ + NV))
-        self.DeclareVectorOutputPort("quad_torques", BasicVector(NU), self.DoSetControlTorques)
-        self.V = self.err = self.res = self.Vdot = 0.0
-        self.DeclareVectorOutputPort("output_metrics", BasicVector(4), self.SetLoggingOutputs)
-        self.DeclareAbstractInputPort("trunk_input", AbstractValue.Make({}))
+        self.DeclareVectorInputPort("quad_state", BasicVector((NQ + NV) * self.n))
+        self.DeclareVectorOutputPort("quad_torques", BasicVector(NU * self.n), self.DoSetControlTorques)
+        self.V = self.err = self.res = self.Vdot = 0.0 if self.n == 1 else np.zeros(self.n)
+        self.DeclareVectorOutputPort("output_metrics", BasicVector(4 * self.n), self.SetLoggingOutputs)
+        if self.HAS_TRUNK_PORT:
+            self.DeclareAbstractInputPort("trunk_input", AbstractValue.Make({}))
         self.last_status = 0
         # LCM bridge (basic_controller.py:54-61): messages are decoded / encoded by the device codecs of wire.py. The
         # LCM runtime itself is optional: without it, feed `lcm_callback` yourself and read `published`.
         self.use_lcm = use_lcm
+        if use_lcm and self.n != 1:
+            raise ValueError("the LCM bridge carries one robot (basic_controller.py:79-87)")
         self.q, self.v = np.zeros(NQ), np.zeros(NV)
         self.published = []
         self.lc = None
@@ -346,7 +377,10 @@ class _QPController(LeafSystem):
         self.q, self.v = d["q"][0].copy(), d["v"][0].copy()
 
     def SetLoggingOutputs(self, context, output):
-        output.SetFromVector(np.asarray([self.V, self.err, self.res, self.Vdot]))
+        if self.n == 1:
+            output.SetFromVector(np.asarray([self.V, self.err, self.res, self.Vdot], float))
+        else:   # instance-major [V, err, res, Vdot] per robot
+            output.SetFromVector(np.stack([np.broadcast_to(x, (self.n,)) for x in (self.V, self.err, self.res, self.Vdot)], axis=1).ravel())
 
     def DoSetControlTorques(self, context, output):
         if self.use_lcm:
@@ -365,24 +399,37 @@ class _QPController(LeafSystem):
             output.SetFromVector(np.zeros(NU))
             return
         state = np.asarray(self.EvalVectorInput(context, 0).get_value(), float)
-        q, v = state[:NQ], state[-NV:]
-        output.SetFromVector(self.ControlLaw(context, q, v))
+        if self.n == 1:
+            q, v = state[:NQ], state[-NV:]               # basic_controller.py:299-302
+        else:
+            x = state.reshape(self.n, NQ + NV)
+            q, v = x[:, :NQ], x[:, NQ:]
+        output.SetFromVector(np.asarray(self.ControlLaw(context, q, v)).ravel())
 
     def ControlLaw(self, context, q, v):
         trunk = self.EvalAbstractInput(context, 1).get_value()
-        traj, contact = dict_to_traj(trunk)
-        out = self.batched.step(self.KIND, q[None], v[None], traj[None], contact[None])
-        self.last_status = int(out.status[0])
+        if self.n == 1:
+            traj, contact = dict_to_traj(trunk)
+            traj, contact, q, v = traj[None], contact[None], np.asarray(q)[None], np.asarray(v)[None]
+        else:
+            traj, contact = dict_to_traj_batch(trunk, self.n)
+        out = self.batched.step(self.KIND, q, v, traj, contact)
+        self.last_status = int(out.status[0]) if self.n == 1 else out.status.copy()
         # reference: `assert result.is_success()` (inverse_dynamics_controller.py:224); a zero / non-finite quaternion, gimbal
         # lock (CalcRpyDtFromAngularVelocityInParent) and PC in full flight (pc_controller.py:248-249) raise inside Drake /
         # NumPy there, so every status bit raises here
-        assert self.last_status == 0, f"QP solve failed (status {self.last_status}: {capi.status_names(self.last_status)})"
-        m = out.metrics[0]
-        self._log(m)
-        return out.tau[0].copy()
+        bad = np.nonzero(out.status)[0]
+        assert bad.size == 0, (f"QP solve failed for instance(s) {bad[:8].tolist()} (status "
+                               f"{int(out.status[bad[0]])}: {capi.status_names(int(out.status[bad[0]]))})")
+        self._log(out.metrics[0] if self.n == 1 else out.metrics.T)
+        return out.tau[0].copy() if self.n == 1 else out.tau.copy()
 
     def _log(self, m):
-        self.err, self.res = float(m[1]), float(m[2])
+        self.err, self.res = self._f(m[1]), self._f(m[2])
+
+    @staticmethod
+    def _f(x):
+        return float(x) if np.ndim(x) == 0 else np.array(x, float)
 
 
 class IDController(_QPController):
@@ -395,7 +442,7 @@ class CLFController(_QPController):
     KIND = "clf"
 
     def _log(self, m):
-        self.V, self.err, self.Vdot = float(m[0]), float(m[1]), float(m[3])
+        self.V, self.err, self.Vdot = self._f(m[0]), self._f(m[1]), self._f(m[3])
 
 
 class PCController(_QPController):
@@ -403,7 +450,7 @@ class PCController(_QPController):
     KIND = "pc"
 
     def _log(self, m):
-        self.V, self.err, self.Vdot = float(m[0]), float(m[1]), float(m[3])
+        self.V, self.err, self.Vdot = self._f(m[0]), self._f(m[1]), self._f(m[3])
 
 
 class MPTCController(PCController):
@@ -414,6 +461,9 @@ class MPTCController(PCController):
 class BasicController(_QPController):
     """Drop-in for reference controllers/basic_controller.py:BasicController (joint-space PD, :322-352)."""
     KIND = "pd"
+    HAS_TRUNK_PORT = False            # the reference BasicController declares no trunk input (basic_controller.py:33-50)
 
     def ControlLaw(self, context, q, v):
-        return self.batched.step_pd(q[None], v[None])[0].copy()
+        if self.n == 1:
+            return self.batched.step_pd(np.asarray(q)[None], np.asarray(v)[None])[0].copy()
+        return self.batched.step_pd(q, v)

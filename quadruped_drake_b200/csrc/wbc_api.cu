@@ -86,7 +86,7 @@ __device__ __forceinline__ const DevConst& stage_consts(L* sm, const DevConst* g
 #define WBC_SOLVE_WARPS 1      // one warp per CTA: the shared-memory block sits at a compile-time address, so no per-warp base
 #endif                         // (thread index -> warp -> offset) has to be kept live or re-derived under the 72-register budget
 #ifndef WBC_SOLVE_CTAS
-#define WBC_SOLVE_CTAS (28 / WBC_SOLVE_WARPS)
+#define WBC_SOLVE_CTAS (21 / WBC_SOLVE_WARPS)
 #endif
 constexpr int SOLVE_WARPS = WBC_SOLVE_WARPS;
 template <bool VD> struct SmemLayoutSolveT { wbc::SolveSmemT<VD> w[SOLVE_WARPS]; };
@@ -705,7 +705,17 @@ static int ensure_staging(wbc_handle* h, int64_t n) {
   return WBC_OK;
 }
 
-extern "C" int wbc_step_host(wbc_handle* h, int kind, int64_t n, const wbc_io* io) {
+// Enqueues one host-buffer step on the handle's two internal streams without waiting for it; `wait` must follow before the
+// outputs are read or the next step is enqueued on this handle (wbc_step_host = enqueue + wait; wbc_multi_step_host enqueues on
+// every device first and waits afterwards, so the devices run side by side from one host thread).
+static int step_host_wait(wbc_handle* h) {
+  WBC_CUDA(h, cudaSetDevice(h->device));
+  WBC_CUDA(h, cudaStreamSynchronize(h->stream));
+  WBC_CUDA(h, cudaStreamSynchronize(h->stream2));
+  return WBC_OK;
+}
+
+static int step_host_enqueue(wbc_handle* h, int kind, int64_t n, const wbc_io* io) {
   if (!h) return WBC_ERR_ARG;
   if (!io || n < 0) return fail_arg(h, "wbc_step_host: bad arguments");
   if (n == 0) return WBC_OK;
@@ -758,8 +768,7 @@ extern "C" int wbc_step_host(wbc_handle* h, int kind, int64_t n, const wbc_io* i
         if (rc) return rc;
         used |= 1 << (c & 1);
       }
-      if (used & 1) WBC_CUDA(h, cudaStreamSynchronize(h->stream));
-      if (used & 2) WBC_CUDA(h, cudaStreamSynchronize(h->stream2));
+      (void)used;
       return WBC_OK;
     }
   }
@@ -804,9 +813,85 @@ extern "C" int wbc_step_host(wbc_handle* h, int kind, int64_t n, const wbc_io* i
       if (io->lam) WBC_CUDA(h, cudaMemcpyAsync(io->lam + o * WBC_NLAM, h->d_lam + o * WBC_NLAM, m * WBC_NLAM * sizeof(double), cudaMemcpyDeviceToHost, st));
     }
   }
-  WBC_CUDA(h, cudaStreamSynchronize(h->stream));
-  if (n_chunks > 1) WBC_CUDA(h, cudaStreamSynchronize(h->stream2));
   return WBC_OK;
+}
+
+extern "C" int wbc_step_host(wbc_handle* h, int kind, int64_t n, const wbc_io* io) {
+  const int rc = step_host_enqueue(h, kind, n, io);
+  if (rc || !h || n <= 0) return rc;
+  return step_host_wait(h);
+}
+
+// ------------------------------------------------------------------------------ all GPUs of the box from one call
+// north star: "instances shard trivially across the 8 GPUs of one box, with no NCCL beyond an optional host gather". One
+// handle per device; a call splits [0, n) into contiguous equal shards, enqueues each shard on its device and
+// waits for all of them: the outputs land in the caller's (page-locked or pageable) host arrays, which IS the host gather.
+struct wbc_multi {
+  std::vector<wbc_handle*> h;
+  std::string err;
+};
+
+extern "C" int wbc_multi_destroy(wbc_multi* m) {
+  if (!m) return WBC_OK;
+  for (wbc_handle* h : m->h) wbc_destroy(h);
+  delete m;
+  return WBC_OK;
+}
+
+extern "C" int wbc_multi_create(const wbc_model* model, const wbc_params* params, int n_devices, const int* devices, wbc_multi** out) {
+  if (!model || !out || n_devices <= 0) return WBC_ERR_ARG;
+  *out = nullptr;
+  wbc_multi* m = new (std::nothrow) wbc_multi();
+  if (!m) return WBC_ERR_NOMEM;
+  for (int i = 0; i < n_devices; ++i) {
+    wbc_handle* h = nullptr;
+    const int rc = wbc_create(model, params, devices ? devices[i] : i, &h);
+    if (h) m->h.push_back(h);
+    if (rc) { m->err = h ? h->err : "wbc_create failed"; *out = m; return rc; }
+  }
+  *out = m;
+  return WBC_OK;
+}
+
+extern "C" const char* wbc_multi_last_error(const wbc_multi* m) { return m ? m->err.c_str() : "null handle"; }
+extern "C" int wbc_multi_device_count(const wbc_multi* m) { return m ? (int)m->h.size() : 0; }
+extern "C" int64_t wbc_multi_launch_count(const wbc_multi* m) {
+  int64_t s = 0;
+  if (m) for (const wbc_handle* h : m->h) s += h->launches;
+  return s;
+}
+
+// Shard r of n over w devices: contiguous, sizes differ by at most one (the same rule as quadruped_drake_b200/sharding.py).
+static void shard_of(int64_t n, int r, int w, int64_t* lo, int64_t* hi) {
+  const int64_t base = n / w, rem = n % w;
+  *lo = r * base + (r < rem ? r : rem);
+  *hi = *lo + base + (r < rem ? 1 : 0);
+}
+
+extern "C" int wbc_multi_step_host(wbc_multi* m, int kind, int64_t n, const wbc_io* io) {
+  if (!m) return WBC_ERR_ARG;
+  if (!io || n < 0) { m->err = "wbc_multi_step_host: bad arguments"; return WBC_ERR_ARG; }
+  const int w = (int)m->h.size();
+  int rc = WBC_OK;
+  int enq = 0;
+  for (int r = 0; r < w && rc == WBC_OK; ++r) {
+    int64_t lo, hi;
+    shard_of(n, r, w, &lo, &hi);
+    if (hi <= lo) { ++enq; continue; }
+    const wbc_io sio{io->q + lo * WBC_NQ, io->v + lo * WBC_NV, io->traj ? io->traj + lo * WBC_NTRAJ : nullptr,
+                     io->contact ? io->contact + lo * 4 : nullptr, io->tau + lo * WBC_NU,
+                     io->metrics ? io->metrics + lo * WBC_NMETRIC : nullptr, io->status ? io->status + lo : nullptr,
+                     io->vd ? io->vd + lo * WBC_NV : nullptr, io->f ? io->f + lo * 12 : nullptr,
+                     io->qp_info ? io->qp_info + lo * 4 : nullptr, io->lam ? io->lam + lo * WBC_NLAM : nullptr};
+    rc = step_host_enqueue(m->h[r], kind, hi - lo, &sio);
+    if (rc) m->err = m->h[r]->err;
+    ++enq;
+  }
+  for (int r = 0; r < enq && r < w; ++r) {                 // always drain what was enqueued, even after an error
+    const int rw = step_host_wait(m->h[r]);
+    if (rw && rc == WBC_OK) { rc = rw; m->err = m->h[r]->err; }
+  }
+  return rc;
 }
 
 extern "C" int wbc_dynamics_host(wbc_handle* h, int64_t n, const double* q, const double* v, double* M, double* Cv,

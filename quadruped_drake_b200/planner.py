@@ -228,8 +228,10 @@ def make_gait_plan(robot="mini_cheetah", combo="walk", total_duration=5.0, goal=
 def make_motion_plan(robot="mini_cheetah", motion="standing", total_duration=6.0, base_height=None, phase=0.0):
     """The reference's manual test motions (planners/simple.py:87-115) as a plan for the device sampler: the analytic base
     reference is sampled into Hermite nodes every 0.1 s (position and velocity exact at the nodes, O(h^4) in between).
-    motion: "standing" (SimpleStanding), "orientation" (OrientationTest), "edge" (EdgeTest), "raise_foot" (RaiseFoot: the
-    reference steps the RF target up by 0.1 m at t = 1 s; here it is lifted smoothly over the first half of its swing phase).
+    motion: "standing" (SimpleStanding), "orientation" (OrientationTest), "edge" (EdgeTest: constant trunk target offset
+    (-0.1, 0.63, 0), friction rows active), "raise_foot" (RaiseFoot: the reference steps the RF target up by 0.1 m at t = 1 s;
+    here it is lifted smoothly over the first half of its swing phase), "heave" (not in the reference: p_body z += 0.1 sin t,
+    a vertical exercise used by the rollout tests).
     `phase` shifts the time argument of the sinusoids (different robots of a batch at different phases)."""
     feet, height = SIMPLE_STANDING[robot]
     bh = height if base_height is None else float(base_height)
@@ -241,7 +243,9 @@ def make_motion_plan(robot="mini_cheetah", motion="standing", total_duration=6.0
     lin[:, 2] = bh
     if motion == "orientation":           # rpy = [0, 0.4 sin t, 0.4 cos t]
         ang[:, 1], ang[:, 2], ang[:, 4], ang[:, 5] = 0.4 * np.sin(tn), 0.4 * np.cos(tn), 0.4 * np.cos(tn), -0.4 * np.sin(tn)
-    elif motion == "edge":                # p_body z += 0.1 sin t
+    elif motion == "edge":                # p_body += [-0.1, 0.63, 0]  (planners/simple.py:109-115)
+        lin[:, 0], lin[:, 1] = -0.1, 0.63
+    elif motion == "heave":               # p_body z += 0.1 sin t
         lin[:, 2] += 0.1 * np.sin(tn)
         lin[:, 5] = 0.1 * np.cos(tn)
     elif motion == "raise_foot":          # p_body += [-0.1, 0.05, 0]
@@ -378,11 +382,9 @@ class BasicTrunkPlanner:
             self.output_dict["contact_states"] = [True, False, True, True]
             self.output_dict["p_rf"] += np.array([0.0, 0.0, 0.1])
 
-    def EdgeTest(self, t):                 # planners/simple.py:109-115
+    def EdgeTest(self, t=None):            # planners/simple.py:109-115: trunk moved to the edge of feasibility (friction rows active)
         self.SimpleStanding()
-        self.output_dict["p_body"] += np.array([0.0, 0.0, 0.1 * np.sin(t)])
-        self.output_dict["pd_body"] += np.array([0.0, 0.0, 0.1 * np.cos(t)])
-        self.output_dict["pdd_body"] += np.array([0.0, 0.0, -0.1 * np.sin(t)])
+        self.output_dict["p_body"] += np.array([-0.1, 0.63, 0.0])
 
     def SetTrunkOutputs(self, t):          # planners/simple.py:117-124
         self.SimpleStanding()
@@ -399,11 +401,23 @@ class TowrTrunkPlanner:
         self.sampler = TrajectorySampler(ctl, self.plan)
         self.wait_time = self.plan.wait_time
         self.output_dict = {}
+        self.u2_max = self.ComputeMaxControlInputs()
+
+    def ComputeMaxControlInputs(self):
+        """planners/towr.py:70-90: max over the stored samples of |[foot accelerations; base rpydd; base pdd]|_2."""
+        g = self.plan.grid
+        if g is None or len(g) == 0:
+            return 0.0
+        o = self.sampler.sample(np.asarray(g, float) + self.wait_time)
+        tr = o["traj"]
+        u2 = np.concatenate([tr[:, 42:54], tr[:, 15:18], tr[:, 6:9]], axis=1)
+        return float(np.linalg.norm(u2, axis=1).max())
 
     def sample(self, t, forces=False):
         return self.sampler.sample(t, forces=forces)
 
     def SetTrunkOutputs(self, t):
         o = self.sampler.sample(np.array([float(t)]), forces=True)
-        self.output_dict = traj_to_dict(o["traj"][0], o["contact"][0], f_plan=o["f"][0])
+        # u2_max is only attached once the motion has started (planners/towr.py:148; SimpleStanding leaves it at 0)
+        self.output_dict = traj_to_dict(o["traj"][0], o["contact"][0], f_plan=o["f"][0], u2_max=self.u2_max if t >= self.wait_time else 0.0)
         return self.output_dict

@@ -435,3 +435,77 @@ def test_unaligned_buffers_and_kernel_profile(ctl_cache):
     ms_r, ms_s = C.c_double(), C.c_double()
     assert ctl.lib.wbc_profile_step(ctl._h, capi.WBC_CTRL_ID, n, C.byref(io), 5, C.c_void_p(stream.cuda_stream), C.byref(ms_r), C.byref(ms_s)) == 0
     assert 0.0 < ms_r.value < 10.0 and 0.0 < ms_s.value < 10.0
+
+
+def test_multi_gpu_call_matches_single_handle(ctl_cache):
+    """wbc_multi_step_host (MultiGpuController): one call, contiguous shards on every listed device, host arrays hold all
+    results. On a one-GPU box the two shards run on two handles of the same device; with >= 2 devices on all of them."""
+    import torch
+    from quadruped_drake_b200.sharding import MultiGpuController, shard_range
+    from quadruped_drake_b200.synth import generate
+    ctl = ctl_cache("mini_cheetah")
+    n = 10007                                                    # ragged: shards of different sizes
+    q, v, traj, contact = generate(ctl.model, n, 41, "mixed", ctl.fk)
+    ref = ctl.step("id", q, v, traj, contact)
+    ndev = torch.cuda.device_count()
+    for devices in ([0, 0], list(range(ndev)), [0] * 3 + list(range(ndev))):
+        multi = MultiGpuController("mini_cheetah", devices=devices)
+        buf = multi.pinned(n)
+        buf["q"][:], buf["v"][:], buf["traj"][:], buf["contact"][:] = q, v, traj, contact
+        l0 = multi.launches
+        out = multi.step("id", buf["q"], buf["v"], buf["traj"], buf["contact"], buf["tau"], buf["metrics"], buf["status"])
+        assert np.array_equal(out.tau, ref.tau) and np.array_equal(out.status, ref.status) and np.array_equal(out.metrics, ref.metrics)
+        assert multi.launches - l0 >= 2 * len(devices)
+        pag = multi.step("clf", q, v, traj, contact)             # pageable arrays: staged per shard
+        assert np.array_equal(pag.tau, ctl.step("clf", q, v, traj, contact).tau)
+        assert shard_range(n, len(devices) - 1, len(devices))[1] == n
+        small = multi.step("id", q[:2], v[:2], traj[:2], contact[:2])      # fewer instances than devices: empty shards
+        assert np.array_equal(small.tau, ref.tau[:2])
+        multi.close()
+
+
+def test_leafsystem_batched_ports(built):
+    """for N > 1 the same port names carry instance-major vectors of width 37N / 12N / 4N and the abstract port a
+    dict of arrays with a leading N axis; a failing instance raises like the reference's assert."""
+    from oracle import controllers as oc
+    from quadruped_drake_b200.controller import BasicController, CLFController, IDController
+    n = 5
+    ctl = IDController("mini_cheetah", 5e-3, n_instances=n)
+    assert ctl.get_input_port(0).model_value.size() == 37 * n and ctl.get_output_port(0).model_value.size() == 12 * n
+    assert ctl.get_output_port(1).model_value.size() == 4 * n
+    g = np.load(GOLD / "fixtures_mini_cheetah.npz")
+    q, v, traj, contact = g["q"][:n], g["v"][:n], g["traj"][:n], g["contact"][:n]
+    dicts = [oc.traj_to_dict(traj[i], contact[i]) for i in range(n)]
+    batch = {k: np.stack([np.asarray(d[k]) for d in dicts]) for k in dicts[0] if k not in ("f_cj", "u2_max")}
+    ctx = ctl.CreateDefaultContext()
+    ctx.FixValue(0, np.hstack([q, v]).ravel())
+    ctx.FixValue(1, batch)
+    tau = ctl.EvalOutput(ctx, 0).reshape(n, 12)
+    assert np.abs(tau - g["id_tau"][:n]).max() < 1e-5
+    met = ctl.EvalOutput(ctx, 1).reshape(n, 4)
+    assert np.abs(met[:, 1] - g["id_metrics"][:n, 1]).max() < 1e-12
+    one = CLFController("mini_cheetah", 5e-3)                    # N = 1 keeps the reference's scalar logging attributes
+    c1 = one.CreateDefaultContext()
+    c1.FixValue(0, np.hstack([q[0], v[0]]))
+    c1.FixValue(1, dicts[0])
+    assert np.abs(one.EvalOutput(c1, 0) - g["clf_tau"][0]).max() < 1e-5 and isinstance(one.V, float)
+    bad = np.hstack([q, v])
+    bad[2, 0:4] = 0.0                                            # zero quaternion on instance 2
+    ctx.FixValue(0, bad.ravel())
+    with pytest.raises(AssertionError, match="instance"):
+        ctl.EvalOutput(ctx, 0)
+    pd = BasicController("mini_cheetah", 5e-3)
+    assert [p.get_name() for p in pd._in] == ["quad_state"]      # no trunk input on the PD controller (basic_controller.py:33-50)
+
+
+def test_towr_planner_u2_max(ctl_cache):
+    """TowrTrunkPlanner.ComputeMaxControlInputs (planners/towr.py:70-90): max |[foot pdd; rpydd; pdd]| over the stored samples,
+    attached to the dict once the motion has started."""
+    from quadruped_drake_b200 import planner as pl
+    ctl = ctl_cache("mini_cheetah")
+    p = pl.TowrTrunkPlanner(ctl, robot="mini_cheetah")
+    o = p.sampler.sample(np.asarray(p.plan.grid) + p.wait_time)
+    tr = o["traj"]
+    ref = np.linalg.norm(np.concatenate([tr[:, 42:54], tr[:, 15:18], tr[:, 6:9]], axis=1), axis=1).max()
+    assert p.u2_max == pytest.approx(ref) and p.u2_max > 0.0
+    assert p.SetTrunkOutputs(0.5)["u2_max"] == 0.0 and p.SetTrunkOutputs(2.0)["u2_max"] == pytest.approx(ref)

@@ -97,7 +97,7 @@ def test_full_size_reference_test_motions_six_seconds(ctl):
     from quadruped_drake_b200.rollout import rollout
     bh = Q0[6] - ctl.dynamics(Q0[None], np.zeros((1, 18)))["p_feet"][0, :, 2].mean()      # feet exactly on the ground
     plans = [pl.make_motion_plan("mini_cheetah", m, 6.0, base_height=bh, phase=ph)
-             for m in ("orientation", "edge", "raise_foot") for ph in np.linspace(0, 2 * np.pi, 8, endpoint=False)]
+             for m in ("orientation", "heave", "raise_foot") for ph in np.linspace(0, 2 * np.pi, 8, endpoint=False)]
     s = pl.TrajectorySampler(ctl, plans)
     n, steps, dt = 4096, 1200, 5e-3
     rng = np.random.default_rng(2)

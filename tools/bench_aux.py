@@ -83,7 +83,7 @@ def run(workload, steps=50, warmup=5, n=1 << 20):
         from quadruped_drake_b200.rollout import Q0_MINI_CHEETAH as Q0, rollout
         for nr, k in ((4096, 200), (65536, 50)):
             bh = Q0[6] - ctl.dynamics(Q0[None], np.zeros((1, 18)))["p_feet"][0, :, 2].mean()
-            plans = [pl.make_motion_plan("mini_cheetah", m, 6.0, base_height=bh, phase=ph) for m in ("orientation", "edge", "raise_foot")
+            plans = [pl.make_motion_plan("mini_cheetah", m, 6.0, base_height=bh, phase=ph) for m in ("orientation", "heave", "raise_foot")
                      for ph in np.linspace(0, 2 * np.pi, 8, endpoint=False)]
             s = pl.TrajectorySampler(ctl, plans)
             q0 = np.tile(Q0, (nr, 1)); q0[:, 6] = bh
