@@ -317,6 +317,25 @@ typedef struct wbc_rollout_io {
   double* metrics_log;    /* [n_steps][N][4] every step's output_metrics, what simulate.py:142 logs (optional)   */
 } wbc_rollout_io;
 
+/* One time step of n simulated robots on flat ground (the plant half of simulate.py:36-57,160-182): forward dynamics from
+ * the APPLIED torques, velocity-level ground contact at the four feet (no penetration, Coulomb pyramid with `mu`; projected
+ * Gauss-Seidel, `iters` sweeps from zero; `erp` = fraction of a penetration pushed out per step), semi-implicit Euler. The
+ * scheme is defined in csrc/wbc_plant.cuh - Drake's own contact solver is third party and not restatable - and pinned by
+ * invariants and by oracle/rollout.py. tau [N][12] in actuator order; q, v updated in place; t (optional) advanced by dt;
+ * ctrl_status (optional): robots with a non-zero controller status are frozen; status_or (optional) accumulates;
+ * f_contact (optional) [N][12]: ground forces on LF RF LH RH in world axes (impulse / dt). Device pointers. */
+typedef struct wbc_plant_opts {
+  double mu;        /* ground friction, 1.0 (simulate.py:44-46: static = dynamic = 1.0) */
+  double erp;       /* penetration correction per step, 0.2                            */
+  int32_t iters;    /* Gauss-Seidel sweeps, 30                                         */
+  int32_t reserved;
+} wbc_plant_opts;
+int wbc_default_plant_opts(wbc_plant_opts* o);
+int wbc_plant_step(wbc_handle* h, int64_t n, double dt, const wbc_plant_opts* opts, double* q, double* v, const double* tau,
+                   double* t, const int32_t* ctrl_status, int32_t* status_or, double* f_contact, void* stream);
+int wbc_plant_step_host(wbc_handle* h, int64_t n, double dt, const wbc_plant_opts* opts, double* q, double* v, const double* tau,
+                        double* t, const int32_t* ctrl_status, int32_t* status_or, double* f_contact);
+
 /* n_steps control steps of n robots, entirely on the device: sample the plan at t (wbc_sample_trajectory), run the
  * controller `kind` (wbc_step), integrate (wbc_integrate). No host synchronisation inside; with use_graph != 0 the
  * per-step launches are captured once into a CUDA graph and replayed. Device pointers. */
@@ -324,6 +343,19 @@ int wbc_rollout(wbc_handle* h, int kind, const wbc_plan* plan, int64_t n, int32_
                 const wbc_rollout_io* io, int use_graph, void* stream);
 int wbc_rollout_host(wbc_handle* h, int kind, const wbc_plan* plan, int64_t n, int32_t n_steps, double dt,
                      const wbc_rollout_io* host_io, int use_graph);
+/* The same loop with a choice of plant: plant == 0 integrates the QP's own contact-consistent accelerations ("planned contacts
+ * hold", wbc_rollout); plant == 1 applies the controller's TORQUES to the simulated robot on the ground (wbc_plant_step), so a
+ * controller can fail physically: slip, land, fall. f_contact (optional, device) receives the last step's ground forces. */
+typedef struct wbc_rollout_opts {
+  int32_t use_graph;
+  int32_t plant;
+  wbc_plant_opts plant_opts;
+  double* f_contact;      /* [N][12] or NULL */
+} wbc_rollout_opts;
+int wbc_rollout_ex(wbc_handle* h, int kind, const wbc_plan* plan, int64_t n, int32_t n_steps, double dt,
+                   const wbc_rollout_io* io, const wbc_rollout_opts* opts, void* stream);
+int wbc_rollout_ex_host(wbc_handle* h, int kind, const wbc_plan* plan, int64_t n, int32_t n_steps, double dt,
+                        const wbc_rollout_io* host_io, const wbc_rollout_opts* opts);
 
 /* Number of kernel launches issued through this handle since creation. */
 int64_t wbc_launch_count(const wbc_handle* h);

@@ -84,6 +84,16 @@ class WbcRolloutIO(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("q", "v", "t", "plan_index", "tau", "metrics", "status_or", "err_max", "metrics_log")]
 
 
+class WbcPlantOpts(C.Structure):
+    """ctypes mirror of `wbc_plant_opts` (ground friction, penetration correction, Gauss-Seidel sweeps)."""
+    _fields_ = [("mu", C.c_double), ("erp", C.c_double), ("iters", C.c_int32), ("reserved", C.c_int32)]
+
+
+class WbcRolloutOpts(C.Structure):
+    """ctypes mirror of `wbc_rollout_opts`."""
+    _fields_ = [("use_graph", C.c_int32), ("plant", C.c_int32), ("plant_opts", WbcPlantOpts), ("f_contact", C.c_void_p)]
+
+
 def np_ptr(a: np.ndarray):
     return C.c_void_p(a.ctypes.data)
 
@@ -146,6 +156,13 @@ def load_library() -> C.CDLL:
     lib.wbc_rollout.argtypes = [H, i32, dp, i64, C.c_int32, C.c_double, C.POINTER(WbcRolloutIO), i32, dp]
     lib.wbc_rollout_host.argtypes = [H, i32, dp, i64, C.c_int32, C.c_double, C.POINTER(WbcRolloutIO), i32]
     lib.wbc_integrate.restype = lib.wbc_rollout.restype = lib.wbc_rollout_host.restype = C.c_int
+    lib.wbc_default_plant_opts.argtypes = [C.POINTER(WbcPlantOpts)]
+    lib.wbc_plant_step.argtypes = [H, i64, C.c_double, C.POINTER(WbcPlantOpts), dp, dp, dp, dp, dp, dp, dp, dp]
+    lib.wbc_plant_step_host.argtypes = [H, i64, C.c_double, C.POINTER(WbcPlantOpts), dp, dp, dp, dp, dp, dp, dp]
+    lib.wbc_rollout_ex.argtypes = [H, i32, dp, i64, C.c_int32, C.c_double, C.POINTER(WbcRolloutIO), C.POINTER(WbcRolloutOpts), dp]
+    lib.wbc_rollout_ex_host.argtypes = [H, i32, dp, i64, C.c_int32, C.c_double, C.POINTER(WbcRolloutIO), C.POINTER(WbcRolloutOpts)]
+    lib.wbc_default_plant_opts.restype = lib.wbc_plant_step.restype = lib.wbc_plant_step_host.restype = C.c_int
+    lib.wbc_rollout_ex.restype = lib.wbc_rollout_ex_host.restype = C.c_int
     for name in WIRE_SYMBOLS:
         getattr(lib, name).restype = C.c_int
     lib.wbc_multi_create.argtypes = [C.POINTER(WbcModelStruct), C.POINTER(WbcParams), i32, C.POINTER(C.c_int), C.POINTER(H)]
@@ -169,7 +186,8 @@ def load_library() -> C.CDLL:
 WIRE_SYMBOLS = ["wbc_lcm_decode_trunk_state", "wbc_lcm_encode_trunk_state", "wbc_lcm_decode_robot_state", "wbc_lcm_encode_robot_state",
                 "wbc_lcm_decode_trunk_state_host", "wbc_lcm_encode_trunk_state_host", "wbc_lcm_decode_robot_state_host",
                 "wbc_lcm_encode_robot_state_host"]
-ROLLOUT_SYMBOLS = ["wbc_integrate", "wbc_rollout", "wbc_rollout_host"]
+ROLLOUT_SYMBOLS = ["wbc_integrate", "wbc_rollout", "wbc_rollout_host", "wbc_rollout_ex", "wbc_rollout_ex_host", "wbc_plant_step",
+                   "wbc_plant_step_host", "wbc_default_plant_opts"]
 TRAJ_SYMBOLS = ROLLOUT_SYMBOLS + ["wbc_plan_create", "wbc_plan_destroy", "wbc_sample_trajectory", "wbc_sample_trajectory_host"]
 MULTI_SYMBOLS = ["wbc_multi_create", "wbc_multi_destroy", "wbc_multi_last_error", "wbc_multi_device_count", "wbc_multi_launch_count",
                  "wbc_multi_step_host"]

@@ -10,6 +10,7 @@
 #include "wbc_wire.cuh"
 #include "wbc_traj.cuh"
 #include "wbc_rollout.cuh"
+#include "wbc_plant.cuh"
 #include <vector>
 
 namespace {
@@ -282,6 +283,17 @@ __global__ void __launch_bounds__(WARPS * 32) wbc_dynamics_kernel(const DevConst
   if (inst < n) wbc::dynamics_instance(sm->w[warp], dc.md, q, v, o, inst, lane);
 }
 
+// One time step of the simulated robot on the ground (wbc_plant.cuh), one single-warp CTA per robot.
+struct SmemLayoutPlant { DevConst dc; wbc::WarpSmem w; wbcplant::PlantSmem p; };
+__global__ void __launch_bounds__(32, 8) wbc_plant_kernel(const DevConst* __restrict__ gdc, wbcplant::PlantArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SmemLayoutPlant* sm = reinterpret_cast<SmemLayoutPlant*>(smem_raw);
+  const DevConst& dc = stage_consts(sm, gdc);
+  const int lane = lane_index();
+  const long long inst = blockIdx.x;
+  if (inst < a.n) wbcplant::plant_step_instance(sm->w, sm->p, dc.md, a, inst, lane);
+}
+
 __global__ void wbc_pd_kernel(const DevConst* __restrict__ gdc, const double* q, const double* v, double* tau, long long n) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t < n * WBC_NU) wbc::pd_element(gdc->md, gdc->pr, q, v, tau, t / WBC_NU, (int)(t % WBC_NU));
@@ -380,6 +392,7 @@ static int set_smem_attr(wbc_handle* h) {
   WBC_CUDA(h, cudaFuncSetAttribute(wbc_solve_kernel<WBC_CTRL_PC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemLayoutSolveT<true>)));
   WBC_CUDA(h, cudaFuncSetAttribute(wbc_coriolis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemLayoutPC)));
   WBC_CUDA(h, cudaFuncSetAttribute(wbc_dynamics_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  WBC_CUDA(h, cudaFuncSetAttribute(wbc_plant_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemLayoutPlant)));
   return WBC_OK;
 }
 
@@ -1286,17 +1299,72 @@ static int ensure_rollout_scratch(wbc_handle* h, int64_t n) {
   return WBC_OK;
 }
 
-extern "C" int wbc_rollout(wbc_handle* h, int kind, const wbc_plan* plan, int64_t n, int32_t n_steps, double dt,
-                           const wbc_rollout_io* io, int use_graph, void* stream) {
+extern "C" int wbc_default_plant_opts(wbc_plant_opts* o) {
+  if (!o) return WBC_ERR_ARG;
+  o->mu = 1.0; o->erp = 0.2; o->iters = 30; o->reserved = 0;      // simulate.py:44-46: static = dynamic friction 1.0
+  return WBC_OK;
+}
+
+static int plant_launch(wbc_handle* h, int64_t n, double dt, const wbc_plant_opts* opts, double* q, double* v, const double* tau,
+                        double* t, const int32_t* ctrl_status, int32_t* status_or, double* f_contact, const double* metrics,
+                        double* err_max, double* metrics_log, const int* counter, cudaStream_t st) {
+  wbc_plant_opts o;
+  if (opts) o = *opts; else wbc_default_plant_opts(&o);
+  if (!(o.mu >= 0.0) || !(o.erp >= 0.0 && o.erp <= 1.0) || o.iters < 1 || o.iters > 1000) return fail_arg(h, "wbc_plant_step: bad options");
+  const wbcplant::PlantArgs a{q, v, tau, t, ctrl_status, status_or, f_contact, metrics, err_max, metrics_log, counter, (long long)n, dt,
+                              o.mu, o.erp, o.iters};
+  wbc_plant_kernel<<<(unsigned)n, 32, sizeof(SmemLayoutPlant), st>>>(h->d_const, a);
+  h->launches++;
+  return WBC_OK;
+}
+
+extern "C" int wbc_plant_step(wbc_handle* h, int64_t n, double dt, const wbc_plant_opts* opts, double* q, double* v, const double* tau,
+                              double* t, const int32_t* ctrl_status, int32_t* status_or, double* f_contact, void* stream) {
+  if (!h) return WBC_ERR_ARG;
+  if (n < 0 || !(dt > 0.0) || (n > 0 && (!q || !v || !tau))) return fail_arg(h, "wbc_plant_step: q, v, tau and dt > 0 are required");
+  if (n == 0) return WBC_OK;
+  WBC_CUDA(h, cudaSetDevice(h->device));
+  const int rc = plant_launch(h, n, dt, opts, q, v, tau, t, ctrl_status, status_or, f_contact, nullptr, nullptr, nullptr, nullptr, (cudaStream_t)stream);
+  if (rc) return rc;
+  WBC_CUDA(h, cudaGetLastError());
+  return WBC_OK;
+}
+
+extern "C" int wbc_plant_step_host(wbc_handle* h, int64_t n, double dt, const wbc_plant_opts* opts, double* q, double* v, const double* tau,
+                                   double* t, const int32_t* ctrl_status, int32_t* status_or, double* f_contact) {
+  if (!h) return WBC_ERR_ARG;
+  if (n < 0 || !(dt > 0.0) || (n > 0 && (!q || !v || !tau))) return fail_arg(h, "wbc_plant_step_host: q, v, tau and dt > 0 are required");
+  if (n == 0) return WBC_OK;
+  WBC_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  DevScratch s;
+  const size_t N = (size_t)n;
+  double* dq = s.in(q, N * WBC_NQ, st); double* dv = s.in(v, N * WBC_NV, st); const double* dtau = s.in(tau, N * WBC_NU, st);
+  double* dt_ = s.in(t, N, st); const int32_t* dcs = s.in(ctrl_status, N, st); int32_t* dso = s.in(status_or, N, st);
+  double* df = s.out(f_contact, N * 12);
+  WBC_SCRATCH_CHECK(h, s);
+  const int rc = wbc_plant_step(h, n, dt, opts, dq, dv, dtau, dt_, dcs, dso, df, st);
+  if (rc) return rc;
+  s.back(q, dq, N * WBC_NQ, st); s.back(v, dv, N * WBC_NV, st); s.back(t, dt_, N, st); s.back(status_or, dso, N, st);
+  s.back(f_contact, df, N * 12, st);
+  WBC_SCRATCH_CHECK(h, s);
+  WBC_CUDA(h, cudaStreamSynchronize(st));
+  return WBC_OK;
+}
+
+extern "C" int wbc_rollout_ex(wbc_handle* h, int kind, const wbc_plan* plan, int64_t n, int32_t n_steps, double dt,
+                              const wbc_rollout_io* io, const wbc_rollout_opts* opts, void* stream) {
   if (!h) return WBC_ERR_ARG;
   if (!plan || !io || n < 0 || n_steps < 0 || !(dt > 0.0)) return fail_arg(h, "wbc_rollout: bad arguments");
-  if (kind == WBC_CTRL_PD) return fail_arg(h, "wbc_rollout: the PD law returns no accelerations to integrate");
+  const bool plant = opts && opts->plant != 0;
+  const int use_graph = opts ? opts->use_graph : 1;
+  if (kind == WBC_CTRL_PD && !plant) return fail_arg(h, "wbc_rollout: the PD law returns no accelerations to integrate (use the ground plant)");
   if (n > 0 && (!io->q || !io->v || !io->t)) return fail_arg(h, "wbc_rollout: q, v and t are required");
   if (n == 0 || n_steps == 0) return WBC_OK;
   WBC_CUDA(h, cudaSetDevice(h->device));
   int rc = ensure_rollout_scratch(h, n);
   if (rc) return rc;
-  rc = ensure_split_scratch(h, 0, n, true);
+  rc = ensure_split_scratch(h, 0, n, !plant);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   double* tau = io->tau ? io->tau : h->ro_tau;
@@ -1304,15 +1372,26 @@ extern "C" int wbc_rollout(wbc_handle* h, int kind, const wbc_plan* plan, int64_
   WBC_CUDA(h, cudaMemsetAsync(h->ro_counter, 0, sizeof(int), st));
   if (io->status_or) WBC_CUDA(h, cudaMemsetAsync(io->status_or, 0, n * sizeof(int32_t), st));
   if (io->err_max) WBC_CUDA(h, cudaMemsetAsync(io->err_max, 0, n * sizeof(double), st));
-  wbc_io sio{io->q, io->v, h->ro_traj, h->ro_contact, tau, metrics, h->ro_status, h->ro_vd, nullptr, nullptr};
+  if (kind == WBC_CTRL_PD) {                       // the PD law has no QP: no status / metrics of its own
+    WBC_CUDA(h, cudaMemsetAsync(h->ro_status, 0, n * sizeof(int32_t), st));
+    WBC_CUDA(h, cudaMemsetAsync(metrics, 0, n * WBC_NMETRIC * sizeof(double), st));
+  }
+  // with the ground plant the controller's accelerations are not needed: the step runs without the vd outputs
+  wbc_io sio{io->q, io->v, h->ro_traj, h->ro_contact, tau, metrics, h->ro_status, plant ? nullptr : h->ro_vd, nullptr, nullptr};
   auto one_step = [&]() -> int {
     int r = wbc_sample_trajectory(h, plan, n, io->plan_index, io->t, h->ro_traj, h->ro_contact, nullptr, nullptr, nullptr, st);
     if (r) return r;
     r = wbc_step(h, kind, n, &sio, st);
     if (r) return r;
-    wbcroll::integrate_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, dt, io->q, io->v, h->ro_vd, io->t, h->ro_status, io->status_or,
-                                                                         metrics, io->err_max, io->metrics_log, h->ro_counter);
-    h->launches++;
+    if (plant) {
+      r = plant_launch(h, n, dt, &opts->plant_opts, io->q, io->v, tau, io->t, h->ro_status, io->status_or, opts->f_contact, metrics,
+                       io->err_max, io->metrics_log, h->ro_counter, st);
+      if (r) return r;
+    } else {
+      wbcroll::integrate_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, dt, io->q, io->v, h->ro_vd, io->t, h->ro_status, io->status_or,
+                                                                           metrics, io->err_max, io->metrics_log, h->ro_counter);
+      h->launches++;
+    }
     if (io->metrics_log) { wbcroll::bump_counter_kernel<<<1, 1, 0, st>>>(h->ro_counter); h->launches++; }
     return WBC_OK;
   };
@@ -1346,8 +1425,16 @@ extern "C" int wbc_rollout(wbc_handle* h, int kind, const wbc_plan* plan, int64_
   return WBC_OK;
 }
 
-extern "C" int wbc_rollout_host(wbc_handle* h, int kind, const wbc_plan* plan, int64_t n, int32_t n_steps, double dt,
-                                const wbc_rollout_io* io, int use_graph) {
+extern "C" int wbc_rollout(wbc_handle* h, int kind, const wbc_plan* plan, int64_t n, int32_t n_steps, double dt,
+                           const wbc_rollout_io* io, int use_graph, void* stream) {
+  wbc_rollout_opts o{};
+  o.use_graph = use_graph; o.plant = 0; o.f_contact = nullptr;
+  wbc_default_plant_opts(&o.plant_opts);
+  return wbc_rollout_ex(h, kind, plan, n, n_steps, dt, io, &o, stream);
+}
+
+extern "C" int wbc_rollout_ex_host(wbc_handle* h, int kind, const wbc_plan* plan, int64_t n, int32_t n_steps, double dt,
+                                   const wbc_rollout_io* io, const wbc_rollout_opts* opts) {
   if (!h) return WBC_ERR_ARG;
   if (!plan || !io || n < 0 || n_steps < 0) return fail_arg(h, "wbc_rollout_host: bad arguments");
   if (n > 0 && (!io->q || !io->v || !io->t)) return fail_arg(h, "wbc_rollout_host: q, v and t are required");
@@ -1363,16 +1450,29 @@ extern "C" int wbc_rollout_host(wbc_handle* h, int kind, const wbc_plan* plan, i
   d.tau = s2.out(io->tau, N * WBC_NU); d.metrics = s2.out(io->metrics, N * WBC_NMETRIC);
   d.status_or = s2.out(io->status_or, N); d.err_max = s2.out(io->err_max, N);
   d.metrics_log = s2.out(io->metrics_log, N * WBC_NMETRIC * (size_t)n_steps);
+  wbc_rollout_opts o{};
+  if (opts) o = *opts; else { o.use_graph = 1; wbc_default_plant_opts(&o.plant_opts); }
+  double* host_f = o.f_contact;
+  o.f_contact = s2.out(host_f, N * 12);
   WBC_SCRATCH_CHECK(h, s); WBC_SCRATCH_CHECK(h, s2);
-  int rc = wbc_rollout(h, kind, plan, n, n_steps, dt, &d, use_graph, st);
+  int rc = wbc_rollout_ex(h, kind, plan, n, n_steps, dt, &d, &o, st);
   if (rc) return rc;
   s.back(io->q, d.q, N * WBC_NQ, st); s.back(io->v, d.v, N * WBC_NV, st); s.back(io->t, d.t, N, st);
   s2.back(io->tau, d.tau, N * WBC_NU, st); s2.back(io->metrics, d.metrics, N * WBC_NMETRIC, st);
   s2.back(io->status_or, d.status_or, N, st); s2.back(io->err_max, d.err_max, N, st);
   s2.back(io->metrics_log, d.metrics_log, N * WBC_NMETRIC * (size_t)n_steps, st);
+  s2.back(host_f, o.f_contact, N * 12, st);
   WBC_SCRATCH_CHECK(h, s); WBC_SCRATCH_CHECK(h, s2);
   WBC_CUDA(h, cudaStreamSynchronize(st));
   return WBC_OK;
+}
+
+extern "C" int wbc_rollout_host(wbc_handle* h, int kind, const wbc_plan* plan, int64_t n, int32_t n_steps, double dt,
+                                const wbc_rollout_io* io, int use_graph) {
+  wbc_rollout_opts o{};
+  o.use_graph = use_graph; o.plant = 0; o.f_contact = nullptr;
+  wbc_default_plant_opts(&o.plant_opts);
+  return wbc_rollout_ex_host(h, kind, plan, n, n_steps, dt, io, &o);
 }
 
 extern "C" void* wbc_host_alloc(size_t bytes) {

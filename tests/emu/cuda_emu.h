@@ -51,6 +51,7 @@ static inline int __any_sync(unsigned, int pred) {
   for (int l = 0; l < 32; ++l) acc |= emu_exchange(pred ? 1 : 0, l);
   return acc;
 }
+static inline int __all_sync(unsigned m, int pred) { return !__any_sync(m, !pred); }
 static inline unsigned __reduce_max_sync(unsigned, unsigned v) {
   unsigned acc = 0;
   for (int l = 0; l < 32; ++l) { const unsigned o = emu_exchange(v, l); acc = o > acc ? o : acc; }

@@ -2,6 +2,7 @@
 // tests/test_emulator.py. TEST INFRASTRUCTURE ONLY.
 #include "cuda_emu.h"
 #include "../../quadruped_drake_b200/csrc/wbc_device.cuh"
+#include "../../quadruped_drake_b200/csrc/wbc_plant.cuh"
 #include <vector>
 
 thread_local int emu_lane;
@@ -11,6 +12,7 @@ namespace {
 struct Job {
   EmuWarp* warp; int lane; wbc::WarpSmem* sm; wbc::SolveSmemVd* ssm; double* rec; double* vdmap; wbc::PcSmem* pcs; double* Cout; double* Jdout; const wbc_model* md; const wbc_params* pr; wbc::Derived dv;
   wbc::StepArgs args; wbc::DynOut dyn; const double* q; const double* v; long long n; int mode;
+  wbcplant::PlantSmem* psm; wbcplant::PlantArgs pargs;
 };
 template <int KIND> void split_step(Job* j, long long i) {
   wbc::StepCarry c;
@@ -36,8 +38,10 @@ void* lane_main(void* p) {
       else split_step<WBC_CTRL_PC>(j, i);
     } else if (j->mode == 1) {
       wbc::dynamics_instance(*j->sm, *j->md, j->q, j->v, j->dyn, i, j->lane);
-    } else {
+    } else if (j->mode == 2) {
       wbc::coriolis_instance(*j->sm, *j->pcs, *j->md, j->q, j->v, j->Cout, j->Jdout, i, j->lane);
+    } else {
+      wbcplant::plant_step_instance(*j->sm, *j->psm, *j->md, j->pargs, i, j->lane);
     }
   }
   return nullptr;
@@ -51,11 +55,13 @@ int run(Job proto) {
   memset(pcs, 0, sizeof(*pcs));
   wbc::SolveSmemVd* ssm = new wbc::SolveSmemVd();
   memset(ssm, 0, sizeof(*ssm));
+  wbcplant::PlantSmem* psm = new wbcplant::PlantSmem();
+  memset(psm, 0, sizeof(*psm));
   std::vector<double> rec(wbc::REC_DOUBLES), vdmap(wbc::VDMAP_DOUBLES);
   std::vector<Job> jobs(32, proto);
   std::vector<pthread_t> th(32);
   for (int l = 0; l < 32; ++l) {
-    jobs[l].warp = &warp; jobs[l].lane = l; jobs[l].sm = sm; jobs[l].pcs = pcs; jobs[l].ssm = ssm; jobs[l].rec = rec.data(); jobs[l].vdmap = vdmap.data();
+    jobs[l].warp = &warp; jobs[l].lane = l; jobs[l].sm = sm; jobs[l].pcs = pcs; jobs[l].ssm = ssm; jobs[l].psm = psm; jobs[l].rec = rec.data(); jobs[l].vdmap = vdmap.data();
     pthread_create(&th[l], nullptr, lane_main, &jobs[l]);
   }
   for (int l = 0; l < 32; ++l) pthread_join(th[l], nullptr);
@@ -63,6 +69,7 @@ int run(Job proto) {
   delete sm;
   delete pcs;
   delete ssm;
+  delete psm;
   return 0;
 }
 }  // namespace
@@ -86,6 +93,13 @@ extern "C" int emu_dynamics(const wbc_model* md, long long n, const double* q, c
 extern "C" int emu_coriolis(const wbc_model* md, long long n, const double* q, const double* v, double* Cm, double* Jd) {
   Job j{};
   j.md = md; j.n = n; j.mode = 2; j.q = q; j.v = v; j.Cout = Cm; j.Jdout = Jd;
+  return run(j);
+}
+extern "C" int emu_plant_step(const wbc_model* md, long long n, double dt, double mu, double erp, int iters, double* q, double* v,
+                              const double* tau, double* f_contact, int32_t* status_or) {
+  Job j{};
+  j.md = md; j.n = n; j.mode = 3;
+  j.pargs = wbcplant::PlantArgs{q, v, tau, nullptr, nullptr, status_or, f_contact, nullptr, nullptr, nullptr, nullptr, n, dt, mu, erp, iters};
   return run(j);
 }
 extern "C" int emu_smem_bytes() { return (int)sizeof(wbc::WarpSmem); }

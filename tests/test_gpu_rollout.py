@@ -137,3 +137,111 @@ def test_gait_start_and_frozen_failures(ctl):
     assert np.isfinite(r.q).all() and np.isfinite(r.v).all() and np.abs(r.v).max() < 1e6
     assert (r.status_or != 0).any()                              # straight-line base + 0.5 s diagonal supports: robots tip over
     assert np.allclose(r.t, 2.0)
+
+
+# ------------------------------------------------------------------------------------------ ground-contact plant
+def grounded(ctl, n, rng=None, jitter=0.0, lift=0.0):
+    """n copies of simulate.py's q0 with the feet exactly on the ground (+ optional joint jitter / lift)."""
+    q0 = np.tile(Q0, (n, 1))
+    if rng is not None and jitter > 0:
+        q0[:, 7:] += rng.uniform(-jitter, jitter, (n, 12))
+    pz = ctl.dynamics(q0, np.zeros((n, 18)))["p_feet"][:, :, 2]
+    q0[:, 6] -= pz.min(axis=1)
+    q0[:, 6] += lift
+    return q0
+
+
+def test_plant_step_matches_oracle(ctl):
+    """wbc_plant_step (forward dynamics from tau + projected Gauss-Seidel ground contact + semi-implicit Euler) against the
+    numpy restatement oracle/rollout.py:plant_step: standing, airborne, sliding, penetrating and random states."""
+    from oracle import rollout as ro
+    from oracle.dynamics import Plant
+    from quadruped_drake_b200.rollout import plant_step
+    P = Plant("mini_cheetah")
+    rng = np.random.default_rng(7)
+    n = 24
+    q = grounded(ctl, n, rng, 0.2)
+    v = rng.uniform(-1, 1, (n, 18)); v[:4] = 0.0
+    tau = rng.uniform(-4, 4, (n, 12))
+    q[1, 6] += 0.1; v[2, 3:5] = [0.8, -0.4]; q[3, 6] -= 0.004
+    qn, vn, f, st = plant_step(ctl, q, v, tau, 5e-3)
+    assert (st == 0).all()
+    for i in range(n):
+        qo, vo, fo = ro.plant_step(P, q[i], v[i], tau[i], 5e-3)
+        assert np.abs(qn[i] - qo).max() < 1e-9 and np.abs(vn[i] - vo).max() < 1e-8, i
+        assert np.abs(f[i] - fo).max() < 1e-6 * max(1.0, np.abs(fo).max())
+    assert np.abs(f[1]).max() == 0.0                      # airborne robot: no ground force
+    mu = 1.0
+    assert (np.abs(f[:, :, 0]) <= mu * f[:, :, 2] + 1e-9).all() and (np.abs(f[:, :, 1]) <= mu * f[:, :, 2] + 1e-9).all() and (f[:, :, 2] >= 0).all()
+
+
+def test_closed_loop_on_the_ground_stands_lands_and_lifts_a_foot(ctl):
+    """The controller against the simulated robot on the ground (plant=True: torques in, contact from geometry). 1200 steps =
+    the reference's 6 s: (a) a standing robot stays put and the ground carries its weight; (b) a robot dropped from 3 cm lands
+    without going through the floor and settles on the reference; (c) RaiseFoot: the foot planned in swing really lifts and
+    carries no force while the other three carry the weight."""
+    import torch
+    from quadruped_drake_b200 import planner as pl
+    from quadruped_drake_b200.rollout import rollout
+    rng = np.random.default_rng(11)
+    n = 512
+    q0 = grounded(ctl, n, rng, 0.03)
+    bh = float(grounded(ctl, 1)[0, 6])
+    q0[n // 2:, 6] += 0.03                                      # second half: dropped from 3 cm
+    plans = [pl.make_motion_plan("mini_cheetah", "standing", 6.0, base_height=bh), pl.make_motion_plan("mini_cheetah", "raise_foot", 6.0, base_height=bh)]
+    s = pl.TrajectorySampler(ctl, plans)
+    pi = (np.arange(n) % 2).astype(np.int32)
+    q, v, t, tpi = (torch.from_numpy(x).cuda() for x in (q0.copy(), np.zeros((n, 18)), np.zeros(n), pi))
+    with torch.cuda.stream(torch.cuda.Stream()):
+        r = rollout(ctl, s, "id", q, v, t, 1200, 5e-3, plan_index=tpi, plant=True)
+    torch.cuda.synchronize()
+    st = r.status_or.cpu().numpy()
+    assert (st == 0).all(), np.unique(st, return_counts=True)
+    qf, vf, f = q.cpu().numpy(), v.cpu().numpy(), r.f_contact.cpu().numpy()
+    d = ctl.dynamics(qf, vf)
+    pz = d["p_feet"][:, :, 2]
+    mg = ctl.model.total_mass * 9.81
+    assert pz.min() > -2e-3                                     # no penetration beyond the solver's tolerance
+    assert np.abs(f[:, :, 2].sum(axis=1) - mg).max() < 0.02 * mg and np.abs(vf).max() < 0.05
+    ref = s.sample(np.full(n, 6.0 - 1e-9), pi)["traj"]
+    assert np.abs(qf[:, 4:7] - ref[:, 0:3]).max() < 0.01        # within 1 cm of the reference base position
+    stand, lift = pi == 0, pi == 1
+    assert pz[stand].max() < 2e-3 and (f[stand, :, 2] > 0.05 * mg).all()
+    assert (pz[lift, 1] > 0.05).all() and np.abs(f[lift, 1]).max() == 0.0 and (f[lift][:, [0, 2, 3], 2] > 0.05 * mg).all()
+
+
+def test_plant_rollout_shows_physical_failure_and_graph_equals_plain(ctl):
+    """With the ground plant a dynamically inconsistent plan makes robots fall instead of being frozen at a failed QP: the
+    tracking error grows although the QPs solve. Graph replay and plain launches give the same bits. The PD law of
+    BasicController (basic_controller.py:322-352), which has no accelerations to integrate, runs against the plant too."""
+    import torch
+    from quadruped_drake_b200 import planner as pl
+    from quadruped_drake_b200.rollout import rollout
+    n = 256
+    rng = np.random.default_rng(13)
+    q0 = grounded(ctl, n, rng, 0.02)
+    bh = float(grounded(ctl, 1)[0, 6])
+    s = pl.TrajectorySampler(ctl, pl.make_gait_plan("mini_cheetah", "trot", goal=(1.5, 0.0), base_height=bh))
+    outs = []
+    for graph in (False, True):
+        q, v, t = (torch.from_numpy(x).cuda() for x in (q0.copy(), np.zeros((n, 18)), np.zeros(n)))
+        with torch.cuda.stream(torch.cuda.Stream()):
+            r = rollout(ctl, s, "id", q, v, t, 300, 5e-3, use_graph=graph, plant=True)
+        torch.cuda.synchronize()
+        outs.append([x.cpu().numpy() for x in (q, v, r.tau, r.err_max, r.status_or, r.f_contact)])
+    for a, b in zip(*outs):
+        assert np.array_equal(a, b)
+    qf, vf, _, err_max, st, f = outs[0]
+    assert np.isfinite(qf).all() and np.isfinite(vf).all()
+    assert err_max.max() > 1e-3                                 # the straight-line trot plan is not trackable: errors grow
+    assert (np.abs(f[:, :, 0]) <= f[:, :, 2] + 1e-9).all()
+    # joint-space PD about the standing posture with the reference gains (Kp 30, Kd 1.5). The torque is held over the step
+    # (explicit), so Kd dt / I_joint must stay below 2: with the 1e-3 kg m^2 knee links that needs dt = 1e-3, not 5e-3
+    s2 = pl.TrajectorySampler(ctl, pl.make_motion_plan("mini_cheetah", "standing", 2.0, base_height=bh))
+    r = rollout(ctl, s2, "pd", q0, np.zeros((n, 18)), np.zeros(n), 1000, 1e-3, plant=True)
+    mg = ctl.model.total_mass * 9.81
+    assert np.isfinite(r.q).all() and (r.status_or == 0).all() and r.q[:, 6].min() > 0.2 and np.abs(r.v).max() < 0.2
+    assert np.abs(r.f_contact[:, :, 2].sum(axis=1) - mg).max() < 0.05 * mg        # the soft PD sags a little but stands
+    r = rollout(ctl, s2, "pd", q0, np.zeros((n, 18)), np.zeros(n), 200, 5e-3, plant=True)
+    assert np.isfinite(r.q).all() and np.isfinite(r.v).all()                       # beyond the limit: flagged and frozen, no NaNs
+    assert (r.status_or[r.status_or != 0] == 128).all()
