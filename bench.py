@@ -359,34 +359,78 @@ def run_gpu(args):
                   "solve_share": ms_s.value / max(ms_r.value + ms_s.value, 1e-12)}
 
     # ---- end to end through the host API: pinned host buffers, H2D + kernel + D2H every step
-    hq, hv, ht = capi.pinned_empty((n, 19)), capi.pinned_empty((n, 18)), capi.pinned_empty((n, 54))
-    hc = capi.pinned_empty((n, 4), np.uint8)
-    hq[:], hv[:], ht[:], hc[:] = q, v, traj, contact
-    htau, hmet, hst = capi.pinned_empty((n, 12)), capi.pinned_empty((n, 4)), capi.pinned_empty((n,), np.int32)
-    hio = capi.WbcIO(capi.np_ptr(hq), capi.np_ptr(hv), capi.np_ptr(ht), capi.np_ptr(hc), capi.np_ptr(htau), capi.np_ptr(hmet),
-                     capi.np_ptr(hst), None, None, None)
-    for _ in range(3):
-        ctl.lib.wbc_step_host(ctl._h, kind, n, C.byref(hio))
-    if world > 1:
-        dist.barrier()
-    e2e_steps = args.steps if n <= (1 << 20) else max(3, args.steps // 4)
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        rc = ctl.lib.wbc_step_host(ctl._h, kind, n, C.byref(hio))
-        assert rc == 0
-    e2e_s = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    assert np.array_equal(htau, tau.cpu().numpy()), "host and device entry points disagree"
     h2d = n * (19 + 18 + 54) * 8 + n * 4
     d2h = n * (12 + 4) * 8 + n * 4
+    e2e_s, e2e_steps, e2e_plan = None, 0, None
+    if not args.no_e2e:
+        hq, hv, ht = capi.pinned_empty((n, 19)), capi.pinned_empty((n, 18)), capi.pinned_empty((n, 54))
+        hc = capi.pinned_empty((n, 4), np.uint8)
+        hq[:], hv[:], ht[:], hc[:] = q, v, traj, contact
+        htau, hmet, hst = capi.pinned_empty((n, 12)), capi.pinned_empty((n, 4)), capi.pinned_empty((n,), np.int32)
+        hio = capi.WbcIO(capi.np_ptr(hq), capi.np_ptr(hv), capi.np_ptr(ht), capi.np_ptr(hc), capi.np_ptr(htau), capi.np_ptr(hmet),
+                         capi.np_ptr(hst), None, None, None)
+        for _ in range(3):
+            ctl.lib.wbc_step_host(ctl._h, kind, n, C.byref(hio))
+        if world > 1:
+            dist.barrier()
+        e2e_steps = args.steps if n <= (1 << 20) else max(3, args.steps // 4)
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            rc = ctl.lib.wbc_step_host(ctl._h, kind, n, C.byref(hio))
+            assert rc == 0
+        e2e_s = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_s = float(t.item())
+        assert np.array_equal(htau, tau.cpu().numpy()), "host and device entry points disagree"
+        h2d = n * (19 + 18 + 54) * 8 + n * 4
+        d2h = n * (12 + 4) * 8 + n * 4
+        # ---- second end-to-end figure: trunk targets from a device-resident plan (the host sends q, v, t only: 308 B / instance)
+        e2e_plan = None
+        if world == 1 and not args.no_cpu and kind != capi.WBC_CTRL_PD and n <= (1 << 20):
+            try:
+                from quadruped_drake_b200 import planner as pl
+                bh = float(ctl.model.nominal_q()[6])
+                sampler = pl.TrajectorySampler(ctl, [pl.make_motion_plan(robot, m, 6.0, base_height=bh) for m in ("standing", "orientation", "heave")])
+                rng = np.random.default_rng(SEED)
+                ht_, hpi = capi.pinned_empty((n,)), capi.pinned_empty((n,), np.int32)
+                ht_[:], hpi[:] = rng.uniform(0.0, 6.0, n), rng.integers(0, 3, n)
+                hq2 = capi.pinned_empty((n, 19))
+                hq2[:] = q
+                hq2[:, 4:6] = 0.0                                    # the test motions stay over the origin
+                for _ in range(3):
+                    ctl.step_plan(kind, sampler, hq2, hv, ht_, hpi, htau, hmet, hst)
+                okp = float((hst == 0).mean())
+                t0 = time.perf_counter()
+                for _ in range(e2e_steps):
+                    ctl.step_plan(kind, sampler, hq2, hv, ht_, hpi, htau, hmet, hst)
+                dtp = time.perf_counter() - t0
+                e2e_plan = {"value": n * e2e_steps / dtp, "unit": "steps/s", "h2d_bytes_per_step": n * (19 + 18 + 1) * 8 + n * 4, "d2h_bytes_per_step": d2h,
+                            "solved_fraction": okp,
+                            "path": "wbc_step_plan_host: q, v, t and the plan index cross the host link, the 54-double trajectory row is sampled on the "
+                                    "device from a resident plan (wbc_sample_trajectory -> step kernels); trunk targets = the reference's manual test "
+                                    "motions (planners/simple.py:87-115) at random phases, states = the benchmark's random states"}
+            except Exception as e:  # noqa: BLE001
+                e2e_plan = {"error": repr(e)}
     n_total = n
+    gather = None
     if world > 1:
         t = torch.tensor([float(n)], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         n_total = int(t.item())
+        # the optional gather of the torque shards onto rank 0 over NCCL - outside the timed region, timed on its own
+        from quadruped_drake_b200.sharding import gather_rows
+        if n_total * 96 <= (4 << 30):
+            gather_rows(tau, n_total, dst=0)
+            torch.cuda.synchronize()
+            dist.barrier()
+            g0 = time.perf_counter()
+            full = gather_rows(tau, n_total, dst=0)
+            torch.cuda.synchronize()
+            gather = {"ms": 1e3 * (time.perf_counter() - g0), "bytes": n_total * 96, "backend": "nccl",
+                      "rows_on_rank0": int(full.shape[0]) if full is not None else None}
+            del full
 
     if rank != 0:
         if world > 1:
@@ -416,11 +460,13 @@ def run_gpu(args):
         "gpu_details": {"l2": "flushed between timed launches (256 MB memset outside the event pair)",
                         "mean_active_set_iterations": iters, "max_active_set_iterations": iters_max,
                         "mean_stance_feet": nc_mean, "kernels": shares, "per_rank": per_rank},
-        "e2e": {"value": n_total * e2e_steps / e2e_s, "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+        "e2e": {"value": n_total * e2e_steps / e2e_s if e2e_s else None, "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps,
                 "path": "wbc_step_host on page-locked host buffers, inputs and outputs cross the host link inside the timed region: the kernels "
                         "read / write host memory directly (zero-copy, below 131072 instances per call) or the batch goes through the "
                         "65536-instance two-stream copy / compute pipeline (above; also the path of pageable buffers)"},
+        "e2e_device_plan": e2e_plan,
+        "tau_gather": gather,
         "gpu_launches": int(gpu_launches),
         "clocks": clocks,
         "pydrake": drake_bridge.probe(),
@@ -447,6 +493,14 @@ def run_gpu(args):
             line["latency_n1"] = latency_n1(ctl_kwargs, robot, local)
         except Exception as e:  # noqa: BLE001
             line["latency_n1"] = {"error": repr(e)}
+        if not args.no_aux:
+            # rows next to the step, short runs: LCM wire codecs, trajectory sampler, closed-loop rollouts
+            try:
+                sys.path.insert(0, str(ROOT / "tools"))
+                import bench_aux
+                line["aux"] = bench_aux.summary()
+            except Exception as e:  # noqa: BLE001
+                line["aux"] = {"error": repr(e)}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -462,6 +516,8 @@ def main():
     ap.add_argument("--total", type=int, default=0, help="strong scaling: total instances, split evenly over the ranks (BASELINE configs[4])")
     ap.add_argument("--pattern", default=PATTERN, choices=["stand", "trot", "walk", "mixed"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline and latency legs (experiments only)")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (sweeps at 10^7 instances: 8.6 GB of pinned buffers)")
+    ap.add_argument("--no-aux", action="store_true", help="skip the short wire / sampler / rollout measurements of the `aux` key")
     ap.add_argument("--robot", default=ROBOT, choices=["mini_cheetah", "anymal_b"], help="experiments only")
     ap.add_argument("--controller", default="id", choices=["id", "clf", "pc", "mptc"], help="experiments only")
     ap.add_argument("--torque-limits", action="store_true", help="experiments only: |tau| <= effort rows (BASELINE configs[2])")

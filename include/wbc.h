@@ -300,6 +300,13 @@ int wbc_sample_trajectory(wbc_handle* h, const wbc_plan* plan, int64_t n, const 
 int wbc_sample_trajectory_host(wbc_handle* h, const wbc_plan* plan, int64_t n, const int32_t* plan_index, const double* t,
                                double* traj, uint8_t* contact, double* f_plan, double* t_eval, int32_t* status);
 
+/* Control step with the trunk targets taken from a device-resident plan (TowrTrunkPlanner.SetTrunkOutputs feeding
+ * DoSetControlTorques, planners/towr.py:92-148 -> basic_controller.py:286-320) on HOST state buffers: the host sends q, v
+ * and the plan time t [N] (+ optional plan_index [N]) - 308 B per instance instead of 736 B - the trajectory rows are sampled on
+ * the device into library scratch. Outputs as wbc_step_host. Page-locked buffers below 131072 instances are zero-copy. */
+int wbc_step_plan_host(wbc_handle* h, int kind, const wbc_plan* plan, int64_t n, const double* q, const double* v,
+                       const double* t, const int32_t* plan_index, double* tau, double* metrics, int32_t* status);
+
 /* ---- Closed-loop batched rollout: the caller of the control step, simulate.py:160-182.
  * wbc_integrate: semi-implicit Euler step of n states with the accelerations vd returned by wbc_step
  * (v += dt vd; q += dt N(q) v, quaternion renormalised); t [N] (optional) is advanced by dt. Device pointers. */

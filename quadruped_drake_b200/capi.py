@@ -152,6 +152,8 @@ def load_library() -> C.CDLL:
     lib.wbc_sample_trajectory.argtypes = [H, dp, i64, dp, dp, dp, dp, dp, dp, dp, dp]
     lib.wbc_sample_trajectory_host.argtypes = [H, dp, i64, dp, dp, dp, dp, dp, dp, dp]
     lib.wbc_sample_trajectory.restype = lib.wbc_sample_trajectory_host.restype = lib.wbc_plan_create.restype = C.c_int
+    lib.wbc_step_plan_host.argtypes = [H, i32, dp, i64, dp, dp, dp, dp, dp, dp, dp]
+    lib.wbc_step_plan_host.restype = C.c_int
     lib.wbc_integrate.argtypes = [H, i64, C.c_double, dp, dp, dp, dp, dp]
     lib.wbc_rollout.argtypes = [H, i32, dp, i64, C.c_int32, C.c_double, C.POINTER(WbcRolloutIO), i32, dp]
     lib.wbc_rollout_host.argtypes = [H, i32, dp, i64, C.c_int32, C.c_double, C.POINTER(WbcRolloutIO), i32]
@@ -188,7 +190,7 @@ WIRE_SYMBOLS = ["wbc_lcm_decode_trunk_state", "wbc_lcm_encode_trunk_state", "wbc
                 "wbc_lcm_encode_robot_state_host"]
 ROLLOUT_SYMBOLS = ["wbc_integrate", "wbc_rollout", "wbc_rollout_host", "wbc_rollout_ex", "wbc_rollout_ex_host", "wbc_plant_step",
                    "wbc_plant_step_host", "wbc_default_plant_opts"]
-TRAJ_SYMBOLS = ROLLOUT_SYMBOLS + ["wbc_plan_create", "wbc_plan_destroy", "wbc_sample_trajectory", "wbc_sample_trajectory_host"]
+TRAJ_SYMBOLS = ROLLOUT_SYMBOLS + ["wbc_step_plan_host", "wbc_plan_create", "wbc_plan_destroy", "wbc_sample_trajectory", "wbc_sample_trajectory_host"]
 MULTI_SYMBOLS = ["wbc_multi_create", "wbc_multi_destroy", "wbc_multi_last_error", "wbc_multi_device_count", "wbc_multi_launch_count",
                  "wbc_multi_step_host"]
 EXPORTED_SYMBOLS = WIRE_SYMBOLS + TRAJ_SYMBOLS + MULTI_SYMBOLS + ["wbc_default_params", "wbc_create", "wbc_destroy", "wbc_last_error", "wbc_dynamics", "wbc_coriolis",

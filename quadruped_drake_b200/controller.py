@@ -128,6 +128,22 @@ class BatchedController:
         self._check(self.lib.wbc_step_host(self._h, k, n, C.byref(io)), "wbc_step_host")
         return StepOutput(tau, met, st, vd, f, qi, lam)
 
+    def step_plan(self, kind, sampler, q, v, t, plan_index=None, tau=None, metrics=None, status=None) -> StepOutput:
+        """Control step with the trunk targets sampled from a device-resident plan (`planner.TrajectorySampler`) at the
+        per-instance times t[N]: the host sends q, v, t only (wbc_step_plan_host). Host arrays; outputs may be passed in."""
+        k = KINDS[kind] if isinstance(kind, str) else int(kind)
+        q = np.ascontiguousarray(q, dtype=np.float64).reshape(-1, NQ)
+        n = q.shape[0]
+        v = np.ascontiguousarray(v, dtype=np.float64).reshape(n, NV)
+        t = np.ascontiguousarray(t, dtype=np.float64).reshape(n)
+        pi = None if plan_index is None else np.ascontiguousarray(plan_index, dtype=np.int32).reshape(n)
+        tau = np.empty((n, NU)) if tau is None else tau
+        metrics = np.empty((n, 4)) if metrics is None else metrics
+        status = np.empty(n, dtype=np.int32) if status is None else status
+        self._check(self.lib.wbc_step_plan_host(self._h, k, sampler._p, n, np_ptr(q), np_ptr(v), np_ptr(t), None if pi is None else np_ptr(pi),
+                                                np_ptr(tau), np_ptr(metrics), np_ptr(status)), "wbc_step_plan_host")
+        return StepOutput(tau, metrics, status)
+
     def step_pd(self, q, v):
         """BasicController.ControlLaw (basic_controller.py:322-352) for a batch of host states -> tau[N,12]."""
         q = np.ascontiguousarray(q, dtype=np.float64).reshape(-1, NQ)

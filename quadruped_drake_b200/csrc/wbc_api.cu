@@ -1269,6 +1269,61 @@ extern "C" int wbc_sample_trajectory_host(wbc_handle* h, const wbc_plan* plan, i
   return WBC_OK;
 }
 
+// Control step whose trunk targets come from a device-resident plan: the host sends q, v and the plan time only (300 B + 8 B
+// per instance instead of 732 B - the 54-double trajectory row is 59 % of the step's input bytes), wbc_sample_trajectory fills
+// traj / contact in device scratch and the step kernels read them from there. Page-locked buffers are read / written by the
+// kernels directly (zero-copy), pageable ones are staged.
+static int ensure_rollout_scratch(wbc_handle* h, int64_t n);
+extern "C" int wbc_step_plan_host(wbc_handle* h, int kind, const wbc_plan* plan, int64_t n, const double* q, const double* v,
+                                  const double* t, const int32_t* plan_index, double* tau, double* metrics, int32_t* status) {
+  if (!h) return WBC_ERR_ARG;
+  if (!plan || n < 0 || kind == WBC_CTRL_PD) return fail_arg(h, "wbc_step_plan_host: plan and a QP controller kind are required");
+  if (n > 0 && (!q || !v || !t || !tau || !metrics || !status)) return fail_arg(h, "wbc_step_plan_host: q, v, t, tau, metrics and status are required");
+  if (n == 0) return WBC_OK;
+  WBC_CUDA(h, cudaSetDevice(h->device));
+  int rc = ensure_rollout_scratch(h, n);
+  if (rc) return rc;
+  cudaStream_t st = h->stream;
+  const void* ptrs[7] = {q, v, t, plan_index, tau, metrics, status};
+  void* dev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  bool pinned = n < 131072;
+  for (int i = 0; i < 7 && pinned; ++i) {
+    if (!ptrs[i]) continue;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, ptrs[i]) != cudaSuccess || at.type != cudaMemoryTypeHost || !at.devicePointer) { pinned = false; cudaGetLastError(); }
+    else dev[i] = at.devicePointer;
+  }
+  if (pinned) {
+    rc = wbc_sample_trajectory(h, plan, n, (const int32_t*)dev[3], (const double*)dev[2], h->ro_traj, h->ro_contact, nullptr, nullptr, nullptr, st);
+    if (rc) return rc;
+    const wbc_io io{(const double*)dev[0], (const double*)dev[1], h->ro_traj, h->ro_contact, (double*)dev[4], (double*)dev[5], (int32_t*)dev[6]};
+    h->host_mapped = true;
+    rc = step_launch(h, kind, n, &io, st, 0);
+    h->host_mapped = false;
+    if (rc) return rc;
+    WBC_CUDA(h, cudaStreamSynchronize(st));
+    return WBC_OK;
+  }
+  rc = ensure_staging(h, n);
+  if (rc) return rc;
+  DevScratch s;
+  const int32_t* dpi = s.in(plan_index, (size_t)n, st);
+  WBC_SCRATCH_CHECK(h, s);
+  WBC_CUDA(h, cudaMemcpyAsync(h->d_q, q, n * WBC_NQ * sizeof(double), cudaMemcpyHostToDevice, st));
+  WBC_CUDA(h, cudaMemcpyAsync(h->d_v, v, n * WBC_NV * sizeof(double), cudaMemcpyHostToDevice, st));
+  WBC_CUDA(h, cudaMemcpyAsync(h->ro_t, t, n * sizeof(double), cudaMemcpyHostToDevice, st));
+  rc = wbc_sample_trajectory(h, plan, n, dpi, h->ro_t, h->ro_traj, h->ro_contact, nullptr, nullptr, nullptr, st);
+  if (rc) return rc;
+  const wbc_io io{h->d_q, h->d_v, h->ro_traj, h->ro_contact, h->d_tau, h->d_metrics, h->d_status};
+  rc = step_launch(h, kind, n, &io, st, 0);
+  if (rc) return rc;
+  WBC_CUDA(h, cudaMemcpyAsync(tau, h->d_tau, n * WBC_NU * sizeof(double), cudaMemcpyDeviceToHost, st));
+  WBC_CUDA(h, cudaMemcpyAsync(metrics, h->d_metrics, n * WBC_NMETRIC * sizeof(double), cudaMemcpyDeviceToHost, st));
+  WBC_CUDA(h, cudaMemcpyAsync(status, h->d_status, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  WBC_CUDA(h, cudaStreamSynchronize(st));
+  return WBC_OK;
+}
+
 // ------------------------------------------------------------------------------ closed-loop rollout (wbc_rollout.cuh)
 extern "C" int wbc_integrate(wbc_handle* h, int64_t n, double dt, double* q, double* v, const double* vd, double* t, void* stream) {
   if (!h) return WBC_ERR_ARG;

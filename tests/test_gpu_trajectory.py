@@ -130,3 +130,30 @@ def test_full_size_config3_properties_and_closed_chain(ctl):
     st = out.status.cpu().numpy()
     assert (st == 0).all(), np.unique(st, return_counts=True)
     assert np.isfinite(out.tau.cpu().numpy()).all()
+
+
+def test_step_with_device_plan_equals_sample_then_step(ctl):
+    """wbc_step_plan_host: the host sends q, v, t; the trajectory rows are sampled on the device. Same torques as sampling
+    first and stepping with host trajectory buffers - for pageable arrays (staged) and page-locked ones (zero-copy)."""
+    from quadruped_drake_b200 import capi
+    from quadruped_drake_b200 import planner as pl
+    from quadruped_drake_b200.synth import generate
+    n = 3001
+    q, v, _, _ = generate(ctl.model, n, 5, "stand", ctl.fk)
+    q[:, 4:6] = 0.0
+    bh = float(ctl.model.nominal_q()[6])
+    s = pl.TrajectorySampler(ctl, [pl.make_motion_plan("mini_cheetah", m, 6.0, base_height=bh) for m in ("standing", "raise_foot")])
+    rng = np.random.default_rng(1)
+    t, pi = rng.uniform(0, 6, n), rng.integers(0, 2, n).astype(np.int32)
+    o = s.sample(t, pi)
+    ref = ctl.step("id", q, v, o["traj"], o["contact"])
+    a = ctl.step_plan("id", s, q, v, t, pi)
+    assert np.array_equal(a.tau, ref.tau) and np.array_equal(a.status, ref.status) and np.array_equal(a.metrics, ref.metrics)
+    hq, hv, ht, hpi = capi.pinned_empty((n, 19)), capi.pinned_empty((n, 18)), capi.pinned_empty((n,)), capi.pinned_empty((n,), np.int32)
+    hq[:], hv[:], ht[:], hpi[:] = q, v, t, pi
+    tau, met, st = capi.pinned_empty((n, 12)), capi.pinned_empty((n, 4)), capi.pinned_empty((n,), np.int32)
+    b = ctl.step_plan("id", s, hq, hv, ht, hpi, tau, met, st)
+    assert np.array_equal(b.tau, ref.tau) and np.array_equal(b.status, ref.status)
+    c = ctl.step_plan("clf", s, q, v, t)                       # no plan index: plan 0 for everyone
+    o0 = s.sample(t)
+    assert np.array_equal(c.tau, ctl.step("clf", q, v, o0["traj"], o0["contact"]).tau)

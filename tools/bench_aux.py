@@ -46,6 +46,24 @@ def _line(metric, unit, n, per_ms, bytes_per_unit, workload, steps, warmup, laun
 
 
 def run(workload, steps=50, warmup=5, n=1 << 20):
+    for d in collect(workload, steps, warmup, n):
+        print(json.dumps(d))
+
+
+def summary(steps=10, warmup=3):
+    """Compact record of the rows next to the step for bench.py's main JSON line (`aux` key): value, unit, HBM fraction."""
+    out = {}
+    for w in ("wire", "traj", "rollout"):
+        for d in collect(w, steps, warmup, 1 << 20, rollout_sizes=((4096, 100),)):
+            key = d["config"]["workload"].split(",")[0].split(":")[0]
+            if w == "rollout":
+                key += " plant=" + str(d.get("plant", 0))
+            out[key] = {"value": d["value"], "unit": d["unit"], "ms_per_step": d["ms_per_step"],
+                        "hbm_frac": d["roofline"]["frac"] if w != "rollout" else None, "workload": d["config"]["workload"]}
+    return out
+
+
+def collect(workload, steps=50, warmup=5, n=1 << 20, rollout_sizes=((4096, 200), (65536, 50))):
     import torch
     from quadruped_drake_b200 import planner as pl
     from quadruped_drake_b200.controller import BatchedController
@@ -81,7 +99,7 @@ def run(workload, steps=50, warmup=5, n=1 << 20):
         out.append(_line("trunk-trajectory samples/sec", "samples/s", n, per, 12 + 432 + 4 + 8 + 4, "wbc_sample_trajectory, 4 gait plans, 1Mi (plan, t) pairs", steps, warmup, steps))
     elif workload == "rollout":
         from quadruped_drake_b200.rollout import Q0_MINI_CHEETAH as Q0, rollout
-        for nr, k in ((4096, 200), (65536, 50)):
+        for nr, k, plant in [(a, b, p) for a, b in rollout_sizes for p in (False, True)]:
             bh = Q0[6] - ctl.dynamics(Q0[None], np.zeros((1, 18)))["p_feet"][0, :, 2].mean()
             plans = [pl.make_motion_plan("mini_cheetah", m, 6.0, base_height=bh, phase=ph) for m in ("orientation", "heave", "raise_foot")
                      for ph in np.linspace(0, 2 * np.pi, 8, endpoint=False)]
@@ -94,7 +112,7 @@ def run(workload, steps=50, warmup=5, n=1 << 20):
                     q, v, t = (torch.from_numpy(x).cuda() for x in (q0, np.zeros((nr, 18)), np.zeros(nr)))
                     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     e0.record()
-                    r = rollout(ctl, s, "id", q, v, t, k, 5e-3, plan_index=pi, use_graph=graph)
+                    r = rollout(ctl, s, "id", q, v, t, k, 5e-3, plan_index=pi, use_graph=graph, plant=plant)
                     e1.record()
                     torch.cuda.synchronize()
                     assert int(r.status_or.max().item()) == 0
@@ -104,15 +122,16 @@ def run(workload, steps=50, warmup=5, n=1 << 20):
                         once()
                     res[graph] = np.array([once() for _ in range(5)])
             per = res[True]
-            d = _line("closed-loop robot control steps/sec (sample + ID-QP + integrate)", "robot-steps/s", nr * k, per, 860 + 2 * 444 + 2 * 296 + 144,
-                      f"wbc_rollout: {nr} robots x {k} steps, reference test motions, CUDA-graph replay", 5, 2, 4 * k * 5,
-                      {"without_graph_robot_steps_per_s": nr * k / (float(res[False].mean()) * 1e-3)})
+            what = "sample + ID-QP + ground-contact plant step" if plant else "sample + ID-QP + integrate"
+            d = _line(f"closed-loop robot control steps/sec ({what})", "robot-steps/s", nr * k, per, 860 + 2 * 444 + 2 * 296 + 144,
+                      f"wbc_rollout: {nr} robots x {k} steps, reference test motions, CUDA-graph replay, "
+                      + ("torques applied to the simulated robot on the ground" if plant else "QP accelerations integrated"), 5, 2, 4 * k * 5,
+                      {"without_graph_robot_steps_per_s": nr * k / (float(res[False].mean()) * 1e-3), "plant": int(plant)})
             out.append(d)
     else:
         raise SystemExit(f"unknown workload {workload}")
-    for d in out:
-        print(json.dumps(d))
     ctl.close()
+    return out
 
 
 if __name__ == "__main__":
