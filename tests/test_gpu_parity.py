@@ -509,3 +509,31 @@ def test_towr_planner_u2_max(ctl_cache):
     ref = np.linalg.norm(np.concatenate([tr[:, 42:54], tr[:, 15:18], tr[:, 6:9]], axis=1), axis=1).max()
     assert p.u2_max == pytest.approx(ref) and p.u2_max > 0.0
     assert p.SetTrunkOutputs(0.5)["u2_max"] == 0.0 and p.SetTrunkOutputs(2.0)["u2_max"] == pytest.approx(ref)
+
+
+def test_steps_on_two_streams_of_one_handle_are_ordered(ctl_cache):
+    """include/wbc.h: the hand-over scratch of a handle belongs to one step at a time. A step issued on another stream than
+    the previous one is ordered behind it by the library (event dependency) instead of corrupting the scratch."""
+    import ctypes as C
+    import torch
+    from quadruped_drake_b200 import capi
+    from quadruped_drake_b200.synth import generate
+    ctl = ctl_cache("mini_cheetah")
+    n = 32768
+    dev = torch.device("cuda:0")
+    sets = []
+    for seed in (1, 2):
+        q, v, traj, contact = generate(ctl.model, n, seed, "stand", ctl.fk)
+        ref = ctl.step("id", q, v, traj, contact).tau
+        t = [torch.from_numpy(x).to(dev) for x in (q, v, traj)] + [torch.from_numpy(contact).to(dev)]
+        out = [torch.empty((n, 12), dtype=torch.float64, device=dev), torch.empty((n, 4), dtype=torch.float64, device=dev),
+               torch.empty((n,), dtype=torch.int32, device=dev)]
+        sets.append((ctl.make_io(*t, *out), out, ref, t))
+    sa, sb = torch.cuda.Stream(), torch.cuda.Stream()
+    torch.cuda.synchronize()
+    for rep in range(5):
+        for (io, out, ref, _), st in zip(sets, (sa, sb)):
+            assert ctl.lib.wbc_step(ctl._h, capi.WBC_CTRL_ID, n, C.byref(io), C.c_void_p(st.cuda_stream)) == 0
+    torch.cuda.synchronize()
+    for io, out, ref, _ in sets:
+        assert np.array_equal(out[0].cpu().numpy(), ref)
