@@ -26,6 +26,9 @@ constexpr int WARPS = 1;         // device-resident buffers
 #endif
 constexpr int WARPS_HOST = WBC_WARPS_HOST;    // host-mapped buffers (ID / CLF)
 constexpr int WARPS_PC = 4;                   // PC / MPTC reduce kernel
+#ifndef WBC_PC_MIN_WARPS
+#define WBC_PC_MIN_WARPS 12      // resident warps per SM the PC reduce kernel is compiled for (168 registers)
+#endif
 #ifndef WBC_MIN_WARPS
 #define WBC_MIN_WARPS 16         // resident warps per SM the reduce kernels are compiled for (128 registers)
 #endif
@@ -243,7 +246,7 @@ __global__ void __launch_bounds__(SOLVE_WARPS * 32, VD ? (24 / SOLVE_WARPS) : WB
 
 // PC / MPTC reduce half: same hand-over, extra operational-space workspace per warp (168 registers, 12 warps / SM).
 template <int W>
-__global__ void __launch_bounds__(W * 32, 12 / W) wbc_reduce_pc_kernel(const DevConst* __restrict__ gdc, wbc::StepArgs a,
+__global__ void __launch_bounds__(W * 32, WBC_PC_MIN_WARPS / W) wbc_reduce_pc_kernel(const DevConst* __restrict__ gdc, wbc::StepArgs a,
                                                                     double* __restrict__ rec, double* __restrict__ vdmap, int bulk_ok) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SmemLayoutPCT<W>* sm = reinterpret_cast<SmemLayoutPCT<W>*>(smem_raw);

@@ -367,7 +367,7 @@ WBC_DEV void dynamics_phase(WarpSmem& s, const wbc_model& md, int lane, int& sta
     if (j >= 1) s.Mleg[leg][sym3(j - 1, j)] = dot(a1, Fn) + dot(b1, Ff);
     if (j >= 2) s.Mleg[leg][sym3(j - 2, j)] = dot(a2, Fn) + dot(b2, Ff);
     s.hj[3 * leg + j] = dot(a, fcn) + dot(b, fcf);
-    if (!GRAV && taug_sm) {
+    if (taug_sm && !BIAS_ONLY) {
       // controller-sign gravity term: -S . [h x g ; m g]
       taug_sm[6 + 3 * leg + j] = -(dot(a, cross(Ic.h, grav)) + Ic.m * dot(b, grav));
     }
@@ -414,7 +414,7 @@ WBC_DEV void dynamics_phase(WarpSmem& s, const wbc_model& md, int lane, int& sta
 #pragma unroll
     for (int r = 0; r < 6; ++r) s.Mb[c][r] = col[r];
     s.hb[c] = c < 3 ? comp(ftn, c) : comp(ftf, c - 3);
-    if (!GRAV && taug_sm) {
+    if (taug_sm && !BIAS_ONLY) {
       V3 tg = cross(It.h, grav);
       taug_sm[c] = c < 3 ? -comp(tg, c) : -It.m * comp(grav, c - 3);
     }
@@ -455,8 +455,9 @@ __device__ __noinline__
 #else
 static
 #endif
-void dynamics_pc_pass(WarpSmem& s, const wbc_model& md, int lane, int& status, const double* vel_int, double* bias_out, bool bias) {
-  dynamics_phase<DYN_PC>(s, md, lane, status, nullptr, vel_int, bias_out, bias);
+void dynamics_pc_pass(WarpSmem& s, const wbc_model& md, int lane, int& status, const double* vel_int, double* bias_out, bool bias,
+                      double* taug_out = nullptr) {
+  dynamics_phase<DYN_PC>(s, md, lane, status, taug_out, vel_int, bias_out, bias);
 }
 
 // --------------------------------------------------------------------------- task space
@@ -1090,10 +1091,11 @@ WBC_DEV void build_common_rows(WarpSmem& s, int lane, int ycol, unsigned cmask, 
 //   g0 = X'(b(v) - C w) - xdd_nom + Jdot w,          (C w by polarisation of the bias b)
 //   cost 1/2 |W^1/2 (Lambda (J vd + g0) + Kp x~ + Kd xd~)|^2,   passivity row  s1'(J vd + g0) + xd~'Kp x~ <= 0.
 struct PcSmem {
-  double Lam[16][16];                        // J M^-1 J' -> its Cholesky factor -> Lambda
+  double Lam[16][17];                        // J M^-1 J' -> its Cholesky factor -> Lambda (odd row stride: a row per lane is conflict free)
   double s1[16], g0[16], kx[16], xt[16], xdt[16], wt[16];
-  double vi[18], w[18], vw[18];              // v (internal order), w, v + w
-  double bv[18], bvw[18], bw[18];            // bias at v, v + w, w
+  double vi[18], w[18], vw[18], vmw[18];     // v (internal order), w, v + w, v - w
+  double tg[18];                             // gravity term of the state pass (controller sign): b(v) = h - tg
+  double bvw[18], bw[18];                    // bias at v + w and at v - w
   double Sb[6][6];                           // Schur complement of the leg blocks in M -> its Cholesky factor
   double Dinv[4][6];                         // inverses of the 3x3 leg blocks (symmetric, sym3 indexing)
   int rowidx[16];                            // task row r -> row of Y
@@ -1129,10 +1131,10 @@ WBC_DEV int swing_foot(unsigned cmask, int slot) { return stance_foot(~cmask & 1
 
 WBC_DEV void pc_precompute(WarpSmem& s, PcSmem& pc, const wbc_model& md, const wbc_params& pr, const BodyTask& bt,
                            int lane, unsigned cmask, int m, int& status, double& Vout, double& errout) {
-  double (*X)[16] = reinterpret_cast<double (*)[16]>(&s.Y[0][0]);       // 18 x 16 scratch in the Y region (Y is built later)
-  // 15 x 15 scratch (L^-1) right after the last used entry of X (17*16+14): 287 + 225 = 512 doubles = Y + cw + ct
-  static_assert(offsetof(WarpSmem, ct) + sizeof(double) * YROWS - offsetof(WarpSmem, Y) >= 512 * sizeof(double), "PC scratch");
-  double (*T)[15] = reinterpret_cast<double (*)[15]>(&s.Y[0][0] + 287);
+  double (*X)[17] = reinterpret_cast<double (*)[17]>(&s.Y[0][0]);       // 18 x 16 scratch (row stride 17) in the Y region (Y is built later)
+  // 15 x 15 scratch (L^-1) right after X: 18 * 17 + 225 = 531 of the 544 doubles of Y + cw + ct
+  static_assert(offsetof(WarpSmem, ct) + sizeof(double) * YROWS - offsetof(WarpSmem, Y) >= (18 * 17 + 225) * sizeof(double), "PC scratch");
+  double (*T)[15] = reinterpret_cast<double (*)[15]>(&s.Y[0][0] + 18 * 17);
   const bool on = lane < m;
   const int slot = lane >= 6 ? (lane - 6) / 3 : 0, ri = lane >= 6 ? (lane - 6) % 3 : 0;
   const int rk = (on && lane >= 6) ? swing_foot(cmask, slot) : -1;
@@ -1294,23 +1296,27 @@ WBC_DEV void pc_precompute(WarpSmem& s, PcSmem& pc, const wbc_model& md, const w
   if (lane < 18) {
     double acc = pc.vi[lane];
     for (int c = 0; c < m; ++c) acc = fma(-X[lane][c], pc.s1[c], acc);
-    pc.w[lane] = acc; pc.vw[lane] = pc.vi[lane] + acc;
+    pc.w[lane] = acc; pc.vw[lane] = pc.vi[lane] + acc; pc.vmw[lane] = pc.vi[lane] - acc;
   }
   __syncwarp();
-  // ---- C w by polarisation: C w = 1/2 (b(v + w) - b(v) - b(w))          (CalcCoriolisMatrix, basic_controller.py:117-132)
-  //      the three bias passes run through ONE copy of the dynamics code (a rolled loop): the PC reduce kernel is bound by
-  //      instruction fetch, three inlined copies cost more in instruction-cache misses than the loop does in branches
+  // ---- C w by polarisation of the bias (a homogeneous quadratic form b(v) = B(v, v)): C w = B(v, w) = 1/4 (b(v + w) - b(v - w))
+  //      (CalcCoriolisMatrix, basic_controller.py:117-132) - two bias-only passes; b(v) itself is the state pass' h minus its
+  //      gravity term. The passes run through ONE copy of the dynamics code (a rolled loop): the PC reduce kernel is bound by
+  //      instruction fetch, inlined copies cost more in instruction-cache misses than the loop does in branches.
   int st2 = 0;
 #pragma unroll 1
-  for (int pass = 0; pass < 3; ++pass) {
-    const double* vin = pass == 0 ? pc.vi : (pass == 1 ? pc.vw : pc.w);
-    double* bout = pass == 0 ? pc.bv : (pass == 1 ? pc.bvw : pc.bw);
+  for (int pass = 0; pass < 2; ++pass) {
+    const double* vin = pass == 0 ? pc.vw : pc.vmw;
+    double* bout = pass == 0 ? pc.bvw : pc.bw;
     dynamics_pc_pass(s, md, lane, st2, vin, bout, true);
   }
   // ---- g0 = X'(b(v) - C w) - xdd_nom + Jdot w
   if (on) {
     double acc = -t.xddn;
-    for (int i = 0; i < 18; ++i) acc = fma(X[i][lane], 1.5 * pc.bv[i] - 0.5 * pc.bvw[i] + 0.5 * pc.bw[i], acc);
+    for (int i = 0; i < 18; ++i) {
+      const double bvi = (i < 6 ? s.hb[i] : s.hj[i - 6]) - pc.tg[i];
+      acc = fma(X[i][lane], bvi - 0.25 * (pc.bvw[i] - pc.bw[i]), acc);
+    }
     if (rk >= 0) {
       // Jdot row: [-skew(pdot_f - pdot_b) | 0 | Ld]   (CalcFrameJacobianDot, basic_controller.py:198-220)
       const V3 dv = mk(s.vf[rk][0] - s.v[3], s.vf[rk][1] - s.v[4], s.vf[rk][2] - s.v[5]);
@@ -1382,7 +1388,7 @@ WBC_DEV void reduce_instance(WarpSmem& s, const wbc_model& md, const wbc_params&
   const int nc = __popc(cmask);
   __syncwarp();
   // ---- phase 1
-  if (KIND == WBC_CTRL_PC) dynamics_pc_pass(s, md, lane, status, nullptr, nullptr, false);
+  if (KIND == WBC_CTRL_PC) dynamics_pc_pass(s, md, lane, status, nullptr, nullptr, false, pcs->tg);
   else dynamics_phase<DYN_STEP>(s, md, lane, status, nullptr);
   async_wait_all();
   __syncwarp();
@@ -1670,14 +1676,14 @@ WBC_DEV void coriolis_instance(WarpSmem& s, PcSmem& pc, const wbc_model& md, con
   auto didx = [&](int c) { return c < 6 ? c : md.v_index[c - 6]; };
   if (lane < 18) pc.vi[lane] = lane < 6 ? s.v[lane] : s.v[md.v_index[lane - 6]];
   __syncwarp();
-  dynamics_phase<DYN_BIAS>(s, md, lane, status, nullptr, pc.vi, pc.bv);
+  dynamics_phase<DYN_BIAS>(s, md, lane, status, nullptr, pc.vi, pc.tg);     // (tg doubles as the b(v) scratch of this debug entry)
   if (Cout) {
     for (int j = 0; j < 18; ++j) {
       if (lane < 18) { pc.w[lane] = (lane == j) ? 1.0 : 0.0; pc.vw[lane] = pc.vi[lane] + ((lane == j) ? 1.0 : 0.0); }
       __syncwarp();
       dynamics_phase<DYN_BIAS>(s, md, lane, status, nullptr, pc.vw, pc.bvw);
       dynamics_phase<DYN_BIAS>(s, md, lane, status, nullptr, pc.w, pc.bw);
-      if (lane < 18) Cout[inst * 324 + didx(lane) * 18 + didx(j)] = 0.5 * (pc.bvw[lane] - pc.bv[lane] - pc.bw[lane]);
+      if (lane < 18) Cout[inst * 324 + didx(lane) * 18 + didx(j)] = 0.5 * (pc.bvw[lane] - pc.tg[lane] - pc.bw[lane]);
       __syncwarp();
     }
   }

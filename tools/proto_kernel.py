@@ -1,9 +1,11 @@
 #!/usr/bin/env python
-"""Executable specification of the CUDA step kernel (numpy, one instance at a time).
+"""Numpy sketch of the FIRST step kernel's algorithm (one instance at a time), kept as a second derivation of the dynamics.
 
-Not shipped and not an oracle: it mirrors, step for step, what csrc/wbc_kernels.cuh does per
-warp, so the algorithm can be debugged without a GPU. tests/test_proto.py checks it against
-oracle/ (which uses a different formulation for both the dynamics and the QP).
+Not shipped and not an oracle. Its dynamics part (composite spatial inertias about the base origin, world axes) is the
+formulation `dynamics_phase` in csrc/wbc_device.cuh still implements, and tests/test_oracle_dynamics.py ("two
+derivations, one answer") checks it against oracle/dynamics.py, which uses projected Newton-Euler on the unmerged tree. The
+QP part below describes the round-1 textbook Goldfarb-Idnani iteration on J; the kernel has since moved to the W = Y J form
+with explicit R^-1 rows - the host warp emulator (tests/emu) is what runs the current device code on a CPU.
 
   1. dynamics: composite spatial inertias about the base origin, world axes
   2. equality elimination: Gauss-Jordan with column pivoting on [A | b], z = z0 + Z w
