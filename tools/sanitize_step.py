@@ -38,3 +38,21 @@ assert np.isfinite(r.q).all()
 ref = sampler.sample(t0)
 print("sampler rows", np.asarray(ref["traj"] if isinstance(ref, dict) and "traj" in ref else list(ref.values())[0]).shape)
 print("sanitize aux ok")
+
+# ground-contact plant (one step and a short closed loop), the device-plan host step and the multi-device call
+from quadruped_drake_b200.rollout import plant_step  # noqa: E402
+from quadruped_drake_b200.sharding import MultiGpuController  # noqa: E402
+
+rng = np.random.default_rng(0)
+q = np.tile(Q0, (n, 1)); q[:, 6] = 0.28; q[:, 7:] += rng.uniform(-0.1, 0.1, (n, 12))
+qn, vn, f, st = plant_step(ctl, q, np.zeros((n, 18)), rng.uniform(-3, 3, (n, 12)), 5e-3)
+assert np.isfinite(qn).all() and (st == 0).all()
+r = rollout(ctl, sampler, "id", np.tile(Q0, (n, 1)), np.zeros((n, 18)), t0, 6, 5e-3, plant=True)
+assert np.isfinite(r.q).all()
+a = ctl.step_plan("id", sampler, np.tile(Q0, (n, 1)), np.zeros((n, 18)), t0)
+assert np.isfinite(a.tau).all()
+multi = MultiGpuController("mini_cheetah", devices=[0, 0])
+o = multi.step("id", g["q"], g["v"], g["traj"], g["contact"])
+assert np.abs(o.tau - g["id_tau"]).max() < 1e-5
+multi.close()
+print("sanitize plant / plan / multi ok")
