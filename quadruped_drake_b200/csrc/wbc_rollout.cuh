@@ -39,7 +39,7 @@ __global__ void __launch_bounds__(256) integrate_kernel(long long n, double dt, 
 #pragma unroll
     for (int k = 0; k < WBC_NMETRIC; ++k) dst[k] = metrics[i * WBC_NMETRIC + k];
   }
-  if (st & (WBC_ST_MAXITER | WBC_ST_INFEASIBLE | WBC_ST_RANKDEF | WBC_ST_NOTPD | WBC_ST_BADQUAT | WBC_ST_UNSUPPORTED | WBC_ST_DIVERGED)) {
+  if (st != 0) {      // any status bit (gimbal lock included): the controller returned zero torques / accelerations for this robot
     if (t) t[i] += dt;
     return;
   }
