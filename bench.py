@@ -406,8 +406,20 @@ def run_gpu(args):
                 for _ in range(e2e_steps):
                     ctl.step_plan(kind, sampler, hq2, hv, ht_, hpi, htau, hmet, hst)
                 dtp = time.perf_counter() - t0
+                # the same workload through the raw-buffer entry (trajectory rows sampled once, then sent every step): the A/B
+                o = sampler.sample(np.asarray(ht_), np.asarray(hpi))
+                ht2, hc2 = capi.pinned_empty((n, 54)), capi.pinned_empty((n, 4), np.uint8)
+                ht2[:], hc2[:] = o["traj"], o["contact"]
+                hio2 = capi.WbcIO(capi.np_ptr(hq2), capi.np_ptr(hv), capi.np_ptr(ht2), capi.np_ptr(hc2), capi.np_ptr(htau), capi.np_ptr(hmet),
+                                  capi.np_ptr(hst), None, None, None)
+                for _ in range(3):
+                    ctl.lib.wbc_step_host(ctl._h, kind, n, C.byref(hio2))
+                t0 = time.perf_counter()
+                for _ in range(e2e_steps):
+                    ctl.lib.wbc_step_host(ctl._h, kind, n, C.byref(hio2))
+                dtr = time.perf_counter() - t0
                 e2e_plan = {"value": n * e2e_steps / dtp, "unit": "steps/s", "h2d_bytes_per_step": n * (19 + 18 + 1) * 8 + n * 4, "d2h_bytes_per_step": d2h,
-                            "solved_fraction": okp,
+                            "solved_fraction": okp, "raw_buffers_same_workload": n * e2e_steps / dtr,
                             "path": "wbc_step_plan_host: q, v, t and the plan index cross the host link, the 54-double trajectory row is sampled on the "
                                     "device from a resident plan (wbc_sample_trajectory -> step kernels); trunk targets = the reference's manual test "
                                     "motions (planners/simple.py:87-115) at random phases, states = the benchmark's random states"}
