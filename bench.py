@@ -235,6 +235,18 @@ def latency_n1(ctl_kwargs, robot, device):
     torch.cuda.synchronize()
     out["device_step_p50_us"] = 1e3 * float(np.median([e0.elapsed_time(e1) for e0, e1 in evs]))
     out["status"] = int(hst[0])
+    # BASELINE configs[0]: the reference's whole simulate.py loop for one robot (planner -> controller ports -> plant step)
+    try:
+        sys.path.insert(0, str(ROOT / "examples"))
+        import simulate
+        simulate.run("id", "standing", sim_time=0.25, verbose=False)
+        t0 = time.perf_counter()
+        _, _, lg = simulate.run("id", "standing", sim_time=2.0, verbose=False)
+        out["simulate_loop_steps_per_s"] = len(lg) / (time.perf_counter() - t0)
+        out["simulate_loop_note"] = ("examples/simulate.py: BasicTrunkPlanner -> IDController (LeafSystem mirror) -> wbc_plant_step, one robot, dt 5e-3; "
+                                     "the reference's Drake loop ran at ~180-200 steps/s (BASELINE.md 1)")
+    except Exception as e:  # noqa: BLE001
+        out["simulate_loop_error"] = repr(e)
     out["reference_period_us"] = 5000.0
     out["note"] = ("one robot, one control step: launch -> torques in host memory; the reference's own loop ran at ~180-200 "
                    "steps/s including the plant step (BASELINE.md 1)")

@@ -245,3 +245,19 @@ def test_plant_rollout_shows_physical_failure_and_graph_equals_plain(ctl):
     r = rollout(ctl, s2, "pd", q0, np.zeros((n, 18)), np.zeros(n), 200, 5e-3, plant=True)
     assert np.isfinite(r.q).all() and np.isfinite(r.v).all()                       # beyond the limit: flagged and frozen, no NaNs
     assert (r.status_or[r.status_or != 0] == 128).all()
+
+
+def test_reference_simulation_loop_with_the_dropin_pieces(built):
+    """BASELINE configs[0]: the loop of the reference's simulate.py (planner -> IDController through its LeafSystem ports ->
+    plant) for ONE robot, with the drop-in planner / controller mirrors and the ground-contact plant instead of Drake:
+    2 s of standing and of the OrientationTest motion; the robot stands on the ground and follows the reference."""
+    import sys
+    from pathlib import Path
+    sys.path.insert(0, str(Path(__file__).resolve().parents[1] / "examples"))
+    import simulate
+    q, v, log = simulate.run("id", "standing", sim_time=2.0, verbose=False)
+    assert abs(q[6] - 0.3) < 5e-3 and np.abs(v).max() < 1e-2 and abs(log[-1, 3] - 8.252 * 9.81) < 1.0 and log[-1, 2] < 1e-3   # SimpleStanding: body at 0.3 m
+    q, v, log = simulate.run("clf", "orientation", sim_time=2.0, verbose=False)
+    t = 2.0 - 5e-3
+    rpy = quat_to_rpy(q[None, :4])[0]
+    assert np.abs(rpy - np.array([0.0, 0.4 * np.sin(t), 0.4 * np.cos(t)])).max() < 0.05 and log[-1, 2] < 5e-3
