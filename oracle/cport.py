@@ -45,12 +45,14 @@ def time_id_steps(robot, q, v, traj, contact, budget_s=20.0, single_thread_s=3.0
     t0 = time.perf_counter()
     _, _, _, st = id_batch(robot, q[:n], v[:n], traj[:n], contact[:n], cores)
     wall = time.perf_counter() - t0
-    n1 = int(max(8, min(len(q), single_thread_s / max(per * cores, 1e-9))))
-    t0 = time.perf_counter()
-    id_batch(robot, q[:n1], v[:n1], traj[:n1], contact[:n1], 1)
-    wall1 = time.perf_counter() - t0
+    single = None
+    if single_thread_s > 0:
+        n1 = int(max(8, min(len(q), single_thread_s / max(per * cores, 1e-9))))
+        t0 = time.perf_counter()
+        id_batch(robot, q[:n1], v[:n1], traj[:n1], contact[:n1], 1)
+        single = {"value": n1 / (time.perf_counter() - t0), "unit": "steps/s", "sample": f"{n1} instances on one thread"}
     return {"value": n / wall, "unit": "steps/s", "cores": cores, "kind": "port",
-            "single_thread": {"value": n1 / wall1, "unit": "steps/s", "sample": f"{n1} instances on one thread"},
+            "single_thread": single,
             "not_converged": int((st != 0).sum()), "build": "gcc -O3 -march=native",
             "label": "CPU restatement of the reference path (C port of the oracle), NOT Drake + OSQP",
             "sample": f"{n} of the {len(q)} instances of one batch, C restatement of the reference path (oracle/c/oracle_id.c: "

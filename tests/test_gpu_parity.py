@@ -537,3 +537,17 @@ def test_steps_on_two_streams_of_one_handle_are_ordered(ctl_cache):
     torch.cuda.synchronize()
     for io, out, ref, _ in sets:
         assert np.array_equal(out[0].cpu().numpy(), ref)
+
+
+def test_pc_infeasible_states_agree_with_the_oracle(ctl_cache):
+    """The passivity row (Vdot <= delta, delta <= 0) can make the PC-QP genuinely infeasible (0.14 % of random anymal_b stand
+    states in the soak run, profiles/r2_soak.jsonl); the reference asserts there. For 24 such states the oracle's exact solver finds
+    no feasible point either (primal residual 5-235), the kernel reports WBC_ST_INFEASIBLE with zero torques; the 8 solvable
+    neighbours agree to 1e-5."""
+    from quadruped_drake_b200 import capi
+    g = np.load(GOLD / "pc_infeasible_anymal.npz")
+    out = ctl_cache("anymal_b").step("pc", g["q"], g["v"], g["traj"], g["contact"])
+    ok = g["pc_ok"]
+    assert (~ok).sum() == 24 and (g["oracle_primal_res"][~ok] > 1.0).all()
+    assert (out.status[~ok] == capi.ST_INFEASIBLE).all() and (out.tau[~ok] == 0).all()
+    assert (out.status[ok] == 0).all() and np.abs(out.tau - g["pc_tau"])[ok].max() < 1e-5
