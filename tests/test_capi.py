@@ -30,6 +30,11 @@ def test_struct_sizes_match_header(built):
     assert C.sizeof(WbcModelStruct) == 8 * (13 + 39 + 78 + 36 + 36 + 12 + 12 + 3) + 4 * 24
     assert C.sizeof(WbcParams) == 8 * 29 + 8 + 8 * 3 + 8 * 12
     assert C.sizeof(WbcIO) == 88          # 11 pointers (q v traj contact tau metrics status vd f qp_info lam)
+    from quadruped_drake_b200.capi import WbcPlantOpts, WbcRolloutIO, WbcRolloutOpts
+    assert C.sizeof(WbcPlantOpts) == 24 and C.sizeof(WbcRolloutOpts) == 40 and C.sizeof(WbcRolloutIO) == 72
+    lib = __import__("quadruped_drake_b200.capi", fromlist=["load_library"]).load_library()
+    o = WbcPlantOpts()
+    assert lib.wbc_default_plant_opts(C.byref(o)) == 0 and (o.mu, o.erp, o.iters) == (1.0, 0.2, 30)     # simulate.py:44-46: friction 1.0
 
 
 def test_default_params_match_reference_constants(built):

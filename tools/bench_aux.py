@@ -50,9 +50,37 @@ def run(workload, steps=50, warmup=5, n=1 << 20):
         print(json.dumps(d))
 
 
+def step_configs(steps=10, warmup=3):
+    """Device-timed control-step throughput of the other BASELINE configs (short runs, inputs resident, L2-sized batches):
+    configs[2] anymal_b trot 16384 with the torque box, configs[3] CLF / PC / MPTC at 65536 walk states."""
+    import torch
+    from quadruped_drake_b200.controller import BatchedController
+    from quadruped_drake_b200.synth import generate
+    out = {}
+    for name, robot, kind, pattern, n, params in (("configs[2] anymal_b trot 16384 ID + torque limits", "anymal_b", "id", "trot", 16384, {"torque_limits": 1}),
+                                                  ("configs[3] mini_cheetah CLF walk 65536", "mini_cheetah", "clf", "walk", 65536, {}),
+                                                  ("configs[3] mini_cheetah PC walk 65536", "mini_cheetah", "pc", "walk", 65536, {}),
+                                                  ("configs[3] mini_cheetah MPTC walk 65536", "mini_cheetah", "mptc", "walk", 65536, {})):
+        ctl = BatchedController(robot, device=0, **params)
+        q, v, traj, contact = generate(ctl.model, n, 20260120, pattern, ctl.fk)
+        dev = torch.device("cuda:0")
+        t = [torch.from_numpy(x).to(dev) for x in (q, v, traj)] + [torch.from_numpy(contact).to(dev)]
+        o = [torch.empty((n, 12), dtype=torch.float64, device=dev), torch.empty((n, 4), dtype=torch.float64, device=dev),
+             torch.empty((n,), dtype=torch.int32, device=dev)]
+        io = ctl.make_io(*t, *o)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        ctl.time_step(kind, io, n, warmup, stream)
+        ms = ctl.time_step(kind, io, n, steps, stream)
+        st = o[2].cpu().numpy()
+        out[name] = {"value": n / (ms * 1e-3), "unit": "steps/s", "ms_per_step": ms, "instances": n,
+                     "solved_fraction": float(((st == 0) | (st == 64)).mean())}
+        ctl.close()
+    return out
+
+
 def summary(steps=10, warmup=3):
     """Compact record of the rows next to the step for bench.py's main JSON line (`aux` key): value, unit, HBM fraction."""
-    out = {}
+    out = {"other_configs": step_configs(steps, warmup)}
     for w in ("wire", "traj", "rollout"):
         for d in collect(w, steps, warmup, 1 << 20, rollout_sizes=((4096, 100),)):
             key = d["config"]["workload"].split(",")[0].split(":")[0]
