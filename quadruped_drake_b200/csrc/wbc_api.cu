@@ -347,7 +347,7 @@ struct wbc_handle {
   // per-slot ordering of the scratch users: the stream of the last step that used the slot and an event to chain a new one
   cudaStream_t last_stream[2] = {nullptr, nullptr};
   bool slot_used[2] = {false, false};
-  cudaEvent_t order_ev = nullptr;
+  cudaEvent_t order_ev = nullptr, join_ev = nullptr;
   double* d_rec[2] = {nullptr, nullptr};
   double* d_vdmap[2] = {nullptr, nullptr};
   int64_t rec_cap[2] = {0, 0}, vdmap_cap[2] = {0, 0};
@@ -462,6 +462,7 @@ extern "C" int wbc_destroy(wbc_handle* h) {
   for (int i = 0; i < 2; ++i) { cudaFree(h->d_rec[i]); cudaFree(h->d_vdmap[i]); }
   for (int i = 0; i < 3; ++i) if (h->prof_ev[i]) cudaEventDestroy(h->prof_ev[i]);
   if (h->order_ev) cudaEventDestroy(h->order_ev);
+  if (h->join_ev) cudaEventDestroy(h->join_ev);
   if (h->stream) cudaStreamDestroy(h->stream);
   if (h->stream2) cudaStreamDestroy(h->stream2);
   delete h;
@@ -648,7 +649,8 @@ static int launch_split(wbc_handle* h, int kind, int64_t n, const wbc_io* io, cu
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     // measured: +1.5 % at 4096 instances, neutral above, but -10 % at 1024 (the early-resident solve CTAs cost more than the
     // hidden launch latency there), so small launch pairs and stream captures keep the ordinary launch
-    const bool pdl = pdl_mode() && m >= 4096;
+    static const long long pdl_min = getenv("WBC_PDL_MIN") ? atoll(getenv("WBC_PDL_MIN")) : 4096;
+    const bool pdl = pdl_mode() && m >= pdl_min;
     if (pdl) cudaStreamIsCapturing(st, &cap);
     const bool with_vd = io->vd != nullptr;
     cudaLaunchConfig_t cfg = {};
@@ -684,6 +686,17 @@ static int step_launch(wbc_handle* h, int kind, int64_t n, const wbc_io* io, cud
   return WBC_OK;
 }
 
+static int two_stream_mode() {   // WBC_TWO_STREAMS=0: one reduce -> solve chain per step (A/B comparisons); k >= 2: k chunks
+  static int mode = -1;
+  if (mode < 0) { const char* e = getenv("WBC_TWO_STREAMS"); mode = e ? atoi(e) : 2; }
+  return mode;
+}
+static int64_t two_stream_max() {
+  static int64_t v = -1;
+  if (v < 0) { const char* e = getenv("WBC_TWO_STREAMS_MAX"); v = e ? atoll(e) : 65536; }
+  return v;
+}
+
 extern "C" int wbc_step(wbc_handle* h, int kind, int64_t n, const wbc_io* io, void* stream) {
   if (!h) return WBC_ERR_ARG;
   if (!io || n < 0) return fail_arg(h, "wbc_step: bad arguments");
@@ -692,7 +705,36 @@ extern "C" int wbc_step(wbc_handle* h, int kind, int64_t n, const wbc_io* io, vo
   if (!io->q || !io->v || !io->traj || !io->contact || !io->tau || !io->metrics || !io->status)
     return fail_arg(h, "wbc_step: q, v, traj, contact, tau, metrics and status are required");
   WBC_CUDA(h, cudaSetDevice(h->device));
-  return step_launch(h, kind, n, io, (cudaStream_t)stream, 0);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (two_stream_mode() && !h->prof_on && n >= 4096 && n <= two_stream_max()) {
+    // Small batches go through as two halves, two independent reduce -> solve chains on two streams (the caller's and an
+    // internal one, joined by events): the solve kernel of one half overlaps the reduce kernel and the ramp-down of the other.
+    // Measured +5.9 % at 4096 instances, +4 % at 8192, +2 % at 16384, +1 % at 65536, -2 % at 2048 (profiles/README.md); three
+    // or more chunks lose (launch bound). Never inside a stream capture.
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &cap);
+    if (cap == cudaStreamCaptureStatusNone) {
+      if (!h->order_ev) WBC_CUDA(h, cudaEventCreateWithFlags(&h->order_ev, cudaEventDisableTiming));
+      if (!h->join_ev) WBC_CUDA(h, cudaEventCreateWithFlags(&h->join_ev, cudaEventDisableTiming));
+      const int chunks = two_stream_mode() < 2 ? 2 : two_stream_mode();
+      const int64_t per = (((n + chunks - 1) / chunks) + 3) & ~(int64_t)3;
+      WBC_CUDA(h, cudaEventRecord(h->order_ev, st));
+      WBC_CUDA(h, cudaStreamWaitEvent(h->stream2, h->order_ev, 0));
+      for (int c = 0; c < chunks; ++c) {
+        const int64_t o = c * per, m = (o + per <= n) ? per : n - o;
+        if (m <= 0) break;
+        const wbc_io cio{io->q + o * WBC_NQ, io->v + o * WBC_NV, io->traj + o * WBC_NTRAJ, io->contact + o * 4, io->tau + o * WBC_NU,
+                         io->metrics + o * WBC_NMETRIC, io->status + o, io->vd ? io->vd + o * WBC_NV : nullptr,
+                         io->f ? io->f + o * 12 : nullptr, io->qp_info ? io->qp_info + o * 4 : nullptr, io->lam ? io->lam + o * WBC_NLAM : nullptr};
+        const int rc = step_launch(h, kind, m, &cio, (c & 1) ? h->stream2 : st, c & 1);
+        if (rc) return rc;
+      }
+      WBC_CUDA(h, cudaEventRecord(h->join_ev, h->stream2));
+      WBC_CUDA(h, cudaStreamWaitEvent(st, h->join_ev, 0));
+      return WBC_OK;
+    }
+  }
+  return step_launch(h, kind, n, io, st, 0);
 }
 
 #define WBC_STEP_WRAPPER(name, kind)                                                                               \
