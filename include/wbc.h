@@ -169,8 +169,8 @@ int wbc_coriolis_host(wbc_handle* h, int64_t n, const double* q, const double* v
  * of one handle are serialised on the device: a call on a different stream than the previous call of the handle first makes
  * its stream wait for the work submitted to the previous one (an event dependency, no host synchronisation). Host threads must
  * still serialise their calls on one handle; different handles are independent. Batches of 4096 - 65536 instances are issued as
- * two halves, the second on a library-owned stream that forks from and joins `stream` through events: to the caller the step
- * remains one stream-ordered operation on `stream` (not inside a stream capture, where it stays a single chain). */
+ * two to four chunks, all but the first on library-owned streams that fork from and join `stream` through events: to the caller
+ * the step remains one stream-ordered operation on `stream` (not inside a stream capture, where it stays a single chain). */
 int wbc_step(wbc_handle* h, int kind, int64_t n, const wbc_io* io, void* stream);
 int wbc_step_id(wbc_handle* h, int64_t n, const double* q, const double* v, const double* traj,
                 const uint8_t* contact, double* tau, double* metrics, int32_t* status, void* stream);

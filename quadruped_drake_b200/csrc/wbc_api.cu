@@ -318,6 +318,7 @@ __global__ void fp64_peak_kernel(double* out, int iters) {
 
 }  // namespace
 
+constexpr int WBC_NSLOT = 4;
 struct wbc_handle {
   int device = 0;
   DevConst* d_const = nullptr;
@@ -345,12 +346,13 @@ struct wbc_handle {
   bool prof_on = false;
   bool host_mapped = false;                               // set around the zero-copy launches of wbc_step_host
   // per-slot ordering of the scratch users: the stream of the last step that used the slot and an event to chain a new one
-  cudaStream_t last_stream[2] = {nullptr, nullptr};
-  bool slot_used[2] = {false, false};
+  cudaStream_t last_stream[WBC_NSLOT] = {};
+  bool slot_used[WBC_NSLOT] = {};
   cudaEvent_t order_ev = nullptr, join_ev = nullptr;
-  double* d_rec[2] = {nullptr, nullptr};
-  double* d_vdmap[2] = {nullptr, nullptr};
-  int64_t rec_cap[2] = {0, 0}, vdmap_cap[2] = {0, 0};
+  double* d_rec[WBC_NSLOT] = {};
+  double* d_vdmap[WBC_NSLOT] = {};
+  int64_t rec_cap[WBC_NSLOT] = {}, vdmap_cap[WBC_NSLOT] = {};
+  cudaStream_t xstream[WBC_NSLOT] = {};                  // lanes 2.. of a step issued as more than two chunks (created on demand)
 };
 
 #define WBC_CUDA(h, call)                                                                       \
@@ -459,7 +461,7 @@ extern "C" int wbc_destroy(wbc_handle* h) {
   if (h->d_tau_map) cudaFree(h->d_tau_map);
   cudaFree(h->ro_traj); cudaFree(h->ro_vd); cudaFree(h->ro_metrics); cudaFree(h->ro_tau); cudaFree(h->ro_t);
   cudaFree(h->ro_contact); cudaFree(h->ro_status); cudaFree(h->ro_counter);
-  for (int i = 0; i < 2; ++i) { cudaFree(h->d_rec[i]); cudaFree(h->d_vdmap[i]); }
+  for (int i = 0; i < WBC_NSLOT; ++i) { cudaFree(h->d_rec[i]); cudaFree(h->d_vdmap[i]); if (h->xstream[i]) cudaStreamDestroy(h->xstream[i]); }
   for (int i = 0; i < 3; ++i) if (h->prof_ev[i]) cudaEventDestroy(h->prof_ev[i]);
   if (h->order_ev) cudaEventDestroy(h->order_ev);
   if (h->join_ev) cudaEventDestroy(h->join_ev);
@@ -686,9 +688,9 @@ static int step_launch(wbc_handle* h, int kind, int64_t n, const wbc_io* io, cud
   return WBC_OK;
 }
 
-static int two_stream_mode() {   // WBC_TWO_STREAMS=0: one reduce -> solve chain per step (A/B comparisons); k >= 2: k chunks
-  static int mode = -1;
-  if (mode < 0) { const char* e = getenv("WBC_TWO_STREAMS"); mode = e ? atoi(e) : 2; }
+static int two_stream_mode() {   // WBC_TWO_STREAMS=0: one reduce -> solve chain per step (A/B comparisons); k >= 2: k chunks;
+  static int mode = -1;          // unset (1): chunks of about 2048 instances, 2 to 4 of them
+  if (mode < 0) { const char* e = getenv("WBC_TWO_STREAMS"); mode = e ? atoi(e) : 1; }
   return mode;
 }
 static int64_t two_stream_max() {
@@ -707,30 +709,37 @@ extern "C" int wbc_step(wbc_handle* h, int kind, int64_t n, const wbc_io* io, vo
   WBC_CUDA(h, cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
   if (two_stream_mode() && !h->prof_on && n >= 4096 && n <= two_stream_max()) {
-    // Small batches go through as two halves, two independent reduce -> solve chains on two streams (the caller's and an
-    // internal one, joined by events): the solve kernel of one half overlaps the reduce kernel and the ramp-down of the other.
-    // Measured +5.9 % at 4096 instances, +4 % at 8192, +2 % at 16384, +1 % at 65536, -2 % at 2048 (profiles/README.md); three
-    // or more chunks lose (launch bound). Never inside a stream capture.
+    // Small batches go through as chunks of about 2048 instances, independent reduce -> solve chains on as many streams (the
+    // caller's and internal ones, joined by events): the solve kernel of one chunk overlaps the reduce kernel and the ramp-down
+    // of the others. Measured against one chain: +5.5 % at 4096 instances (2 chunks; 3: +4.5 %, 4: +2.5 %), +7.7 % at 8192
+    // (4 chunks; 2: +4.1 %), +2.6 % at 16384, +1 % at 65536, -2 % at 2048 (profiles/README.md). Never inside a stream capture.
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     cudaStreamIsCapturing(st, &cap);
     if (cap == cudaStreamCaptureStatusNone) {
       if (!h->order_ev) WBC_CUDA(h, cudaEventCreateWithFlags(&h->order_ev, cudaEventDisableTiming));
       if (!h->join_ev) WBC_CUDA(h, cudaEventCreateWithFlags(&h->join_ev, cudaEventDisableTiming));
-      const int chunks = two_stream_mode() < 2 ? 2 : two_stream_mode();
+      int chunks = two_stream_mode() < 2 ? (n >= 8192 ? 4 : 2) : two_stream_mode();
+      if (chunks > WBC_NSLOT) chunks = WBC_NSLOT;
       const int64_t per = (((n + chunks - 1) / chunks) + 3) & ~(int64_t)3;
       WBC_CUDA(h, cudaEventRecord(h->order_ev, st));
-      WBC_CUDA(h, cudaStreamWaitEvent(h->stream2, h->order_ev, 0));
+      for (int c = 1; c < chunks; ++c) {
+        if (c >= 2 && !h->xstream[c]) WBC_CUDA(h, cudaStreamCreateWithFlags(&h->xstream[c], cudaStreamNonBlocking));
+        WBC_CUDA(h, cudaStreamWaitEvent(c == 1 ? h->stream2 : h->xstream[c], h->order_ev, 0));
+      }
       for (int c = 0; c < chunks; ++c) {
         const int64_t o = c * per, m = (o + per <= n) ? per : n - o;
         if (m <= 0) break;
         const wbc_io cio{io->q + o * WBC_NQ, io->v + o * WBC_NV, io->traj + o * WBC_NTRAJ, io->contact + o * 4, io->tau + o * WBC_NU,
                          io->metrics + o * WBC_NMETRIC, io->status + o, io->vd ? io->vd + o * WBC_NV : nullptr,
                          io->f ? io->f + o * 12 : nullptr, io->qp_info ? io->qp_info + o * 4 : nullptr, io->lam ? io->lam + o * WBC_NLAM : nullptr};
-        const int rc = step_launch(h, kind, m, &cio, (c & 1) ? h->stream2 : st, c & 1);
+        cudaStream_t cs = c == 0 ? st : c == 1 ? h->stream2 : h->xstream[c];
+        const int rc = step_launch(h, kind, m, &cio, cs, c);
         if (rc) return rc;
+        if (c) {
+          WBC_CUDA(h, cudaEventRecord(h->join_ev, cs));
+          WBC_CUDA(h, cudaStreamWaitEvent(st, h->join_ev, 0));
+        }
       }
-      WBC_CUDA(h, cudaEventRecord(h->join_ev, h->stream2));
-      WBC_CUDA(h, cudaStreamWaitEvent(st, h->join_ev, 0));
       return WBC_OK;
     }
   }
