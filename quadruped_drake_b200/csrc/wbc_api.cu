@@ -718,7 +718,7 @@ extern "C" int wbc_step(wbc_handle* h, int kind, int64_t n, const wbc_io* io, vo
     if (cap == cudaStreamCaptureStatusNone) {
       if (!h->order_ev) WBC_CUDA(h, cudaEventCreateWithFlags(&h->order_ev, cudaEventDisableTiming));
       if (!h->join_ev) WBC_CUDA(h, cudaEventCreateWithFlags(&h->join_ev, cudaEventDisableTiming));
-      int chunks = two_stream_mode() < 2 ? (n >= 8192 ? 4 : 2) : two_stream_mode();
+      int chunks = two_stream_mode() < 2 ? (n >= 7168 ? 4 : n >= 5120 ? 3 : 2) : two_stream_mode();
       if (chunks > WBC_NSLOT) chunks = WBC_NSLOT;
       const int64_t per = (((n + chunks - 1) / chunks) + 3) & ~(int64_t)3;
       WBC_CUDA(h, cudaEventRecord(h->order_ev, st));
