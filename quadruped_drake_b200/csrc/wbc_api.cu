@@ -802,10 +802,10 @@ static int step_host_enqueue(wbc_handle* h, int kind, int64_t n, const wbc_io* i
     if (const char* env = getenv("WBC_HOST_ZEROCOPY")) mode = atoi(env);
     const void* ptrs[11] = {io->q, io->v, io->traj, io->contact, io->tau, io->metrics, io->status, io->vd, io->f, io->qp_info, io->lam};
     void* dev[11] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    // Measured on B200 (profiles/README.md): zero-copy wins up to ~10^5 instances per call (no staging copies, no extra API
-    // calls; the host link delivers ~32 GB/s to the SMs); above that the copy engines (~55 GB/s) in a chunked two-stream
-    // pipeline win, so large page-locked batches take the staged path below with 65536-instance chunks.
-    if (mode < 0) { static const long long thr = getenv("WBC_ZC_MAX") ? atoll(getenv("WBC_ZC_MAX")) : 131072; mode = n >= thr ? 0 : 1; }
+    // Measured on B200 (profiles/README.md): reading the inputs over the host link from the SMs (zero-copy, ~32 GB/s) wins up
+    // to ~48 k instances per call (no staging copies, no extra API calls); above that the inputs go through the copy engine
+    // (~55 GB/s) in a chunked two-stream pipeline. Page-locked outputs are written straight to host memory in both modes.
+    if (mode < 0) mode = 1;
     bool pinned = mode != 0;
     for (int i = 0; i < 11 && pinned; ++i) {
       if (!ptrs[i]) continue;
@@ -814,27 +814,54 @@ static int step_host_enqueue(wbc_handle* h, int kind, int64_t n, const wbc_io* i
       else dev[i] = at.devicePointer;
     }
     if (pinned) {
-      wbc_io dio{(const double*)dev[0], (const double*)dev[1], (const double*)dev[2], (const uint8_t*)dev[3], (double*)dev[4],
-                 (double*)dev[5], (int32_t*)dev[6], (double*)dev[7], (double*)dev[8], (double*)dev[9], (double*)dev[10]};
+      const wbc_io hio{(const double*)dev[0], (const double*)dev[1], (const double*)dev[2], (const uint8_t*)dev[3], (double*)dev[4],
+                       (double*)dev[5], (int32_t*)dev[6], (double*)dev[7], (double*)dev[8], (double*)dev[9], (double*)dev[10]};
       // The batch goes through in chunks alternating between two streams (each with its own hand-over scratch), so that the
       // input-bound reduce kernel of one chunk overlaps the solve kernel of the previous one and the host link stays busy.
       // two halves on the two internal streams from 4096 instances on: the solve kernel of one half overlaps the link-bound
       // reduce kernel of the other (e2e +4.6 % at 4096, +3.8 % at 16384, +1 % at 65536; three or more chunks lose)
+      static const long long stage_min = getenv("WBC_ZC_MAX") ? atoll(getenv("WBC_ZC_MAX")) : 24576;
+      static const int stage_mask = getenv("WBC_ZC_STAGE_CHUNKS") ? atoi(getenv("WBC_ZC_STAGE_CHUNKS")) : -1;   // experiments
+      // inputs that go through the copy engine into device staging instead of being read over the link by the SMs
+      // (bit 0: traj, bit 1: q, v, contact): +6 % at 65536 instances, +3 % at 131072 - 262144 over the next best mode
+      static const int stage_env = getenv("WBC_ZC_STAGE") ? atoi(getenv("WBC_ZC_STAGE")) : -1;
+      const int stage_in = stage_env >= 0 ? stage_env : (n >= stage_min ? 3 : 0);
       int zc = n >= 4096 ? 2 : 1;
+      if (stage_in) {   // four chunks up to 65536 instances, then chunks of n / 8 clamped to [16384, 32768] instances
+        int64_t per_c = n / 8; per_c = per_c < 16384 ? 16384 : (per_c > 32768 ? 32768 : per_c);
+        if (n < 98304) per_c = ((n + 3) / 4 + 3) & ~(int64_t)3;
+        zc = (int)((n + per_c - 1) / per_c);
+      }
       if (const char* env = getenv("WBC_ZC_CHUNKS")) { const int v = atoi(env); if (v >= 1 && v <= 64) zc = v; }
       if ((int64_t)zc > n) zc = (int)n;
       const int64_t per = ((n + zc - 1) / zc + 3) & ~(int64_t)3;
       cudaStream_t lanes[2] = {h->stream, h->stream2};
       int used = 0;
+      if (stage_in && !pd) { rc = ensure_staging(h, n); if (rc) return rc; }
       for (int c = 0; c < zc; ++c) {
         const int64_t o = c * per, m = (o + per <= n) ? per : n - o;
         if (m <= 0) break;
+        const bool staged = stage_in && !pd && ((stage_mask >> (c & 31)) & 1);
+        wbc_io dio = hio;
+        if (staged) {
+          cudaStream_t cs = lanes[c & 1];
+          if (stage_in & 2) {
+            WBC_CUDA(h, cudaMemcpyAsync(h->d_q + o * WBC_NQ, io->q + o * WBC_NQ, m * WBC_NQ * sizeof(double), cudaMemcpyHostToDevice, cs));
+            WBC_CUDA(h, cudaMemcpyAsync(h->d_v + o * WBC_NV, io->v + o * WBC_NV, m * WBC_NV * sizeof(double), cudaMemcpyHostToDevice, cs));
+            WBC_CUDA(h, cudaMemcpyAsync(h->d_contact + o * 4, io->contact + o * 4, m * 4, cudaMemcpyHostToDevice, cs));
+            dio.q = h->d_q; dio.v = h->d_v; dio.contact = h->d_contact;
+          }
+          if (stage_in & 1) {
+            WBC_CUDA(h, cudaMemcpyAsync(h->d_traj + o * WBC_NTRAJ, io->traj + o * WBC_NTRAJ, m * WBC_NTRAJ * sizeof(double), cudaMemcpyHostToDevice, cs));
+            dio.traj = h->d_traj;
+          }
+        }
         const wbc_io cio{dio.q + o * WBC_NQ, dio.v + o * WBC_NV, dio.traj ? dio.traj + o * WBC_NTRAJ : nullptr,
                          dio.contact ? dio.contact + o * 4 : nullptr, dio.tau + o * WBC_NU,
                          dio.metrics ? dio.metrics + o * WBC_NMETRIC : nullptr, dio.status ? dio.status + o : nullptr,
                          dio.vd ? dio.vd + o * WBC_NV : nullptr, dio.f ? dio.f + o * 12 : nullptr, dio.qp_info ? dio.qp_info + o * 4 : nullptr,
                          dio.lam ? dio.lam + o * WBC_NLAM : nullptr};
-        h->host_mapped = true;
+        h->host_mapped = !staged || (stage_in & 3) != 3;   // the reduce kernel reads host memory (4-warp CTAs, everything staged per CTA)
         rc = pd ? wbc_step_pd(h, m, cio.q, cio.v, cio.tau, lanes[c & 1]) : step_launch(h, kind, m, &cio, lanes[c & 1], c & 1);
         h->host_mapped = false;
         if (rc) return rc;
