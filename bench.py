@@ -400,7 +400,7 @@ def run_gpu(args):
         d2h = n * (12 + 4) * 8 + n * 4
         # ---- second end-to-end figure: trunk targets from a device-resident plan (the host sends q, v, t only: 308 B / instance)
         e2e_plan = None
-        if world == 1 and not args.no_cpu and kind != capi.WBC_CTRL_PD and n <= (1 << 20):
+        if world == 1 and (not args.no_cpu or args.plan) and kind != capi.WBC_CTRL_PD and n <= (1 << 20):
             try:
                 from quadruped_drake_b200 import planner as pl
                 bh = float(ctl.model.nominal_q()[6])
@@ -541,6 +541,7 @@ def main():
     ap.add_argument("--pattern", default=PATTERN, choices=["stand", "trot", "walk", "mixed"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline and latency legs (experiments only)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (sweeps at 10^7 instances: 8.6 GB of pinned buffers)")
+    ap.add_argument("--plan", action="store_true", help="measure `e2e_device_plan` even with --no-cpu")
     ap.add_argument("--no-aux", action="store_true", help="skip the short wire / sampler / rollout measurements of the `aux` key")
     ap.add_argument("--robot", default=ROBOT, choices=["mini_cheetah", "anymal_b"], help="experiments only")
     ap.add_argument("--controller", default="id", choices=["id", "clf", "pc", "mptc"], help="experiments only")

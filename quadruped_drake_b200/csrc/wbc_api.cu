@@ -825,7 +825,10 @@ static int step_host_enqueue(wbc_handle* h, int kind, int64_t n, const wbc_io* i
       // inputs that go through the copy engine into device staging instead of being read over the link by the SMs
       // (bit 0: traj, bit 1: q, v, contact): +6 % at 65536 instances, +3 % at 131072 - 262144 over the next best mode
       static const int stage_env = getenv("WBC_ZC_STAGE") ? atoi(getenv("WBC_ZC_STAGE")) : -1;
-      const int stage_in = stage_env >= 0 ? stage_env : (n >= stage_min ? 3 : 0);
+      // PC / MPTC are compute bound at a third of the rate: the zero-copy reads hide under the reduce kernel up to 131072
+      // instances (e2e 22.3 M steps/s against 20.0 M staged at 65536)
+      const bool pc_kind = kind == WBC_CTRL_PC || kind == WBC_CTRL_MPTC;
+      const int stage_in = stage_env >= 0 ? stage_env : (n >= (pc_kind ? 131072 : stage_min) ? 3 : 0);
       int zc = n >= 4096 ? 2 : 1;
       if (stage_in) {   // four chunks up to 65536 instances, then chunks of n / 8 clamped to [16384, 32768] instances
         int64_t per_c = n / 8; per_c = per_c < 16384 ? 16384 : (per_c > 32768 ? 32768 : per_c);
@@ -1372,7 +1375,7 @@ extern "C" int wbc_step_plan_host(wbc_handle* h, int kind, const wbc_plan* plan,
   cudaStream_t st = h->stream;
   const void* ptrs[7] = {q, v, t, plan_index, tau, metrics, status};
   void* dev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-  bool pinned = n < 131072;
+  bool pinned = true;
   for (int i = 0; i < 7 && pinned; ++i) {
     if (!ptrs[i]) continue;
     cudaPointerAttributes at;
@@ -1382,13 +1385,28 @@ extern "C" int wbc_step_plan_host(wbc_handle* h, int kind, const wbc_plan* plan,
   if (pinned) {
     rc = wbc_sample_trajectory(h, plan, n, (const int32_t*)dev[3], (const double*)dev[2], h->ro_traj, h->ro_contact, nullptr, nullptr, nullptr, st);
     if (rc) return rc;
-    const wbc_io io{(const double*)dev[0], (const double*)dev[1], h->ro_traj, h->ro_contact, (double*)dev[4], (double*)dev[5], (int32_t*)dev[6]};
-    h->host_mapped = true;
-    rc = step_launch(h, kind, n, &io, st, 0);
-    h->host_mapped = false;
-    if (rc) return rc;
-    WBC_CUDA(h, cudaStreamSynchronize(st));
-    return WBC_OK;
+    // the step itself as in the zero-copy mode of wbc_step_host: two halves on the two internal streams. q and v are 304 B per
+    // instance, which the reduce CTAs pull over the link without slowing down at any batch size (57.3 M steps/s at 65536,
+    // 60.8 M at 2^20; copy-engine staging of q and v: 51.5 / 60.6 M)
+    const int zc = n >= 4096 ? 2 : 1;
+    const int64_t per = ((n + zc - 1) / zc + 3) & ~(int64_t)3;
+    cudaStream_t lanes[2] = {st, h->stream2};
+    if (zc > 1) {
+      if (!h->order_ev) WBC_CUDA(h, cudaEventCreateWithFlags(&h->order_ev, cudaEventDisableTiming));
+      WBC_CUDA(h, cudaEventRecord(h->order_ev, st));                 // the sampled rows
+      WBC_CUDA(h, cudaStreamWaitEvent(h->stream2, h->order_ev, 0));
+    }
+    for (int c = 0; c < zc; ++c) {
+      const int64_t o = c * per, m = (o + per <= n) ? per : n - o;
+      if (m <= 0) break;
+      const wbc_io io{(const double*)dev[0] + o * WBC_NQ, (const double*)dev[1] + o * WBC_NV, h->ro_traj + o * WBC_NTRAJ, h->ro_contact + o * 4,
+                      (double*)dev[4] + o * WBC_NU, (double*)dev[5] + o * WBC_NMETRIC, (int32_t*)dev[6] + o};
+      h->host_mapped = true;
+      rc = step_launch(h, kind, m, &io, lanes[c & 1], c & 1);
+      h->host_mapped = false;
+      if (rc) return rc;
+    }
+    return step_host_wait(h);
   }
   rc = ensure_staging(h, n);
   if (rc) return rc;
