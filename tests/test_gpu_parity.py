@@ -357,12 +357,13 @@ def test_leafsystem_mirror_standing(built):
 @pytest.mark.gpu
 def test_host_entry_paths_agree(ctl_cache):
     """wbc_step_host: pageable buffers (staged, two-stream chunked copies) and page-locked buffers (zero-copy: the kernel
-    reads / writes host memory directly) give bit-identical results, for sizes around the chunking threshold."""
+    reads / writes host memory directly; from 24576 instances on the inputs go through the copy engine in four chunks and only
+    the outputs are written zero-copy) give bit-identical results, for sizes around the chunking thresholds."""
     import ctypes as C
     from quadruped_drake_b200 import capi
     from quadruped_drake_b200.synth import generate
     ctl = ctl_cache("mini_cheetah")
-    for n in (1, 5, 2047, 2048, 4099):
+    for n in (1, 5, 2047, 2048, 4099, 24575, 24581):
         q, v, traj, contact = generate(ctl.model, n, 77 + n, "mixed", ctl.fk)
         a = ctl.step("id", q, v, traj, contact, debug=True)                      # numpy arrays: pageable path
         hq, hv, ht = capi.pinned_empty((n, 19)), capi.pinned_empty((n, 18)), capi.pinned_empty((n, 54))
@@ -509,6 +510,29 @@ def test_towr_planner_u2_max(ctl_cache):
     ref = np.linalg.norm(np.concatenate([tr[:, 42:54], tr[:, 15:18], tr[:, 6:9]], axis=1), axis=1).max()
     assert p.u2_max == pytest.approx(ref) and p.u2_max > 0.0
     assert p.SetTrunkOutputs(0.5)["u2_max"] == 0.0 and p.SetTrunkOutputs(2.0)["u2_max"] == pytest.approx(ref)
+
+
+def test_chunked_device_step_matches_single_chain(ctl_cache):
+    """include/wbc.h: a 4096-65536 instance wbc_step is issued as 2-4 chunks on as many streams, joined to the caller's stream.
+    Bit-identical to the same instances solved in pieces below the threshold (one reduce -> solve chain), ragged tails included,
+    with the optional outputs (vd, f, lam) on, and complete when the caller's stream is."""
+    import torch
+    from quadruped_drake_b200.synth import generate
+    ctl = ctl_cache("mini_cheetah")
+    dev = torch.device("cuda:0")
+    for n in (4099, 6145, 8195):
+        q, v, traj, contact = generate(ctl.model, n, 300 + n, "mixed", ctl.fk)
+        pieces = [ctl.step("id", q[o:o + 2000], v[o:o + 2000], traj[o:o + 2000], contact[o:o + 2000], debug=True) for o in range(0, n, 2000)]
+        t = [torch.from_numpy(x).to(dev) for x in (q, v, traj, contact)]
+        st = torch.cuda.Stream()
+        torch.cuda.synchronize()
+        with torch.cuda.stream(st):
+            out = ctl.step("id", *t, debug=True)
+        st.synchronize()                                            # only the caller's stream: the internal ones must have joined it
+        for name in ("tau", "metrics", "status", "vd", "f", "lam"):
+            a = getattr(out, name).cpu().numpy().reshape(n, -1)
+            b = np.concatenate([np.asarray(getattr(p_, name)).reshape(len(p_.status), -1) for p_ in pieces])
+            assert np.array_equal(a, b), (n, name)
 
 
 def test_steps_on_two_streams_of_one_handle_are_ordered(ctl_cache):

@@ -138,7 +138,7 @@ def test_step_with_device_plan_equals_sample_then_step(ctl):
     from quadruped_drake_b200 import capi
     from quadruped_drake_b200 import planner as pl
     from quadruped_drake_b200.synth import generate
-    n = 3001
+    n = 4099                                                    # page-locked buffers: two halves on two streams, ragged tail
     q, v, _, _ = generate(ctl.model, n, 5, "stand", ctl.fk)
     q[:, 4:6] = 0.0
     bh = float(ctl.model.nominal_q()[6])
