@@ -3,8 +3,9 @@
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
-A "step" is one pass of the hot path (dynamics + ID-QP: the reduce kernel and the solve kernel, back to back on one
-stream) over one batch of synthetic states.
+A "step" is one pass of the hot path (dynamics + ID-QP: the reduce kernel and the solve kernel, stream ordered; a 4096-65536
+instance batch goes through as 2-4 chunks of that pair on as many streams, forked from and joined to the launch stream, so
+`gpu_launches` is 4 per step at 4096) over one batch of synthetic states.
 Workload at N = 1: BASELINE.json configs[1] - mini_cheetah ID-QP, 4096 random states per launch, all four feet in stance
 (SURVEY.md 8d). With N > 1 (torchrun, one rank per GPU) every rank runs the same batch size on its own shard of instances
 (weak scaling, no collective on the data path); `--total T` instead splits T instances over the ranks (strong scaling,
