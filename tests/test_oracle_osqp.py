@@ -1,0 +1,90 @@
+"""oracle/osqp_admm.py: the restatement of the solver the reference calls (OSQP through Drake's OsqpSolver).
+
+(1) pinned on the worked example of OSQP's own documentation, (2) run to convergence it lands on the committed golden torques
+(tests/golden/, produced by oracle/qp.py's interior-point + active-set solve): a third, independent algorithm - the reference's own
+solver class - agrees with the optimum the CUDA path is compared with, (3) at OSQP's DEFAULT tolerances (what the reference runs)
+the returned point sits within solver tolerance of the optimum in cost but not in torque, which is why parity is defined against
+the exact optimum. Drake / OSQP binaries are absent: **parity unpinned** against the real library."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import controllers as oc
+from oracle import osqp_admm as oq
+
+GOLD = Path(__file__).parent / "golden"
+
+
+def test_osqp_documentation_example():
+    """minimise 1/2 x'[[4,1],[1,2]]x + [1,1]'x  s.t.  x0 + x1 = 1, 0 <= x <= 0.7  (the "setup and solve" example of the OSQP
+    documentation): x* = (0.3, 0.7), objective 1.88; hand check: on x0 = 1 - x1 the cost is 3 - 3 x1 + 2 x1^2, minimum at 0.75,
+    clipped to 0.7. Multipliers from stationarity: y = (-2.9, 0, 0.2)."""
+    P = np.array([[4.0, 1.0], [1.0, 2.0]])
+    q = np.array([1.0, 1.0])
+    A = np.array([[1.0, 1.0], [1.0, 0.0], [0.0, 1.0]])
+    lo, up = np.array([1.0, 0.0, 0.0]), np.array([1.0, 0.7, 0.7])
+    r = oq.solve(P, q, A, lo, up)
+    assert r.status == "solved" and r.polished and r.iters <= 200
+    assert np.allclose(r.x, [0.3, 0.7], atol=1e-9)
+    assert np.allclose(r.y, [-2.9, 0.0, 0.2], atol=1e-6)
+    assert 0.5 * r.x @ P @ r.x + q @ r.x == pytest.approx(1.88, abs=1e-9)
+    raw = oq.solve(P, q, A, lo, up, oq.Settings(polish=False))          # the plain ADMM iterate: inside the 1e-3 tolerances only
+    assert raw.status == "solved" and 1e-7 < np.abs(raw.x - [0.3, 0.7]).max() < 5e-3
+
+
+def _golden_qps(name, idx, **params):
+    g = np.load(GOLD / name)
+    ctl = oc.IDController("mini_cheetah", **params)
+    for i in idx:
+        o = ctl.control_law(g["q"][i], g["v"][i], oc.traj_to_dict(g["traj"][i], g["contact"][i]))
+        yield i, g, ctl, o
+
+
+def test_admm_run_to_convergence_reaches_the_golden_torques():
+    """The tie-broken QP (reg_f = 1e-6 on the contact forces) is strictly convex: OSQP's ADMM iteration, run far
+    beyond its default tolerances, must converge to the same point as the oracle's exact solve - and to the committed goldens."""
+    tight = oq.Settings(eps_abs=1e-12, eps_rel=1e-12, max_iter=400000, polish=False)
+    worst_vd = worst_tau = 0.0
+    n = 0
+    for i, g, ctl, o in _golden_qps("mixed_mini_cheetah.npz", (0, 1, 2, 5, 9, 17)):
+        if not g["id_ok"][i] or not o.qp[4].shape[0]:
+            continue
+        r = oq.solve_reference_qp(*o.qp, tight)
+        assert r.status == "solved", (i, r.iters)
+        worst_vd = max(worst_vd, np.abs(r.x[:18] - g["id_vd"][i]).max())
+        worst_tau = max(worst_tau, np.abs(r.x[18:30] - g["id_tau"][i]).max())
+        obj = 0.5 * r.x @ o.qp[0] @ r.x + o.qp[1] @ r.x
+        assert obj == pytest.approx(o.objective_reg, rel=1e-9, abs=1e-9)
+        n += 1
+    assert n >= 4
+    assert worst_vd < 1e-7 and worst_tau < 1e-3, (worst_vd, worst_tau)     # tau moves along the 1e-6-convex force directions: slow tail
+
+
+def test_default_osqp_tolerances_against_the_exact_optimum():
+    """What the reference actually runs: eps 1e-3 + polish on the QP WITHOUT the tie-break. Every solve terminates as `solved`, its
+    cost is within 1e-3 (relative) of the exact optimum, a successful polish with the right active set reproduces the exact
+    accelerations - but the torques of a default-tolerance solve differ from the optimum by far more than 1e-5 on part of the
+    instances (un-polished ADMM point, or a different point of the non-unique force set): bit parity with "OSQP's output" is not
+    a well-defined target, the optimum is."""
+    dev_vd, dev_tau, polished = [], [], 0
+    for i, g, ctl, o in _golden_qps("mixed_mini_cheetah.npz", range(12)):
+        if not g["id_ok"][i] or not o.qp[4].shape[0]:
+            continue
+        P, q, A, b, G, h = o.qp
+        P0 = P.copy()
+        P0[30:, 30:] -= ctl.p["reg_f"] * np.eye(P.shape[0] - 30)             # the cost the reference hands the solver
+        r = oq.solve_reference_qp(P0, q, A, b, G, h)
+        assert r.status == "solved" and r.iters <= 1000
+        obj = 0.5 * r.x @ P0 @ r.x + q @ r.x
+        assert abs(obj - o.objective) <= 1e-3 * (1.0 + abs(o.objective))
+        assert np.abs(A @ r.x - b).max() < 5e-2 and (G @ r.x - h).max() < 5e-2
+        polished += int(r.polished)
+        dev_vd.append(np.abs(r.x[:18] - o.vd).max())
+        dev_tau.append(np.abs(r.x[18:30] - o.tau).max())
+    dev_vd, dev_tau = np.array(dev_vd), np.array(dev_tau)
+    assert len(dev_vd) >= 8 and polished >= 1
+    assert dev_vd.min() < 2e-3                       # some solves do land on the optimum (up to the tie-break's footprint)
+    assert dev_tau.max() > 1e-3                      # ... and some are nowhere near 1e-5 in torque
+    print("default OSQP vs exact optimum: |dvd| median %.2e max %.2e, |dtau| median %.2e max %.2e, polished %d of %d"
+          % (np.median(dev_vd), dev_vd.max(), np.median(dev_tau), dev_tau.max(), polished, len(dev_vd)))
