@@ -61,6 +61,21 @@ def test_admm_run_to_convergence_reaches_the_golden_torques():
     assert worst_vd < 1e-7 and worst_tau < 1e-3, (worst_vd, worst_tau)     # tau moves along the 1e-6-convex force directions: slow tail
 
 
+def test_admm_run_to_convergence_clf_and_pc():
+    """The same cross-check on the CLF-QP (extra slack column and CLF row) and on a PC-QP of the golden file."""
+    g = np.load(GOLD / "mixed_mini_cheetah.npz")
+    tight = oq.Settings(eps_abs=1e-12, eps_rel=1e-12, max_iter=400000, polish=False)
+    for kind, cls, idx in (("clf", oc.CLFController, (0, 2, 5, 9, 17)), ("pc", oc.PCController, (2,))):
+        ctl = cls("mini_cheetah")
+        for i in idx:
+            assert g[kind + "_ok"][i]
+            o = ctl.control_law(g["q"][i], g["v"][i], oc.traj_to_dict(g["traj"][i], g["contact"][i]))
+            r = oq.solve_reference_qp(*o.qp, tight)
+            assert r.status == "solved"
+            assert np.abs(r.x[:18] - g[kind + "_vd"][i]).max() < 1e-6, (kind, i)
+            assert np.abs(r.x[18:30] - g[kind + "_tau"][i]).max() < 1e-4, (kind, i)
+
+
 def test_default_osqp_tolerances_against_the_exact_optimum():
     """What the reference actually runs: eps 1e-3 + polish on the QP WITHOUT the tie-break. Every solve terminates as `solved`, its
     cost is within 1e-3 (relative) of the exact optimum, a successful polish with the right active set reproduces the exact
