@@ -1328,9 +1328,16 @@ extern "C" int wbc_sample_trajectory(wbc_handle* h, const wbc_plan* plan, int64_
   if (n == 0) return WBC_OK;
   WBC_CUDA(h, cudaSetDevice(h->device));
   if (reinterpret_cast<uintptr_t>(contact) & 3u) return fail_arg(h, "wbc_sample_trajectory: contact must be 4-byte aligned");
-  const long long chunks = (n + 31) / 32, blocks = (chunks + wbctraj::SAMPLE_WARPS - 1) / wbctraj::SAMPLE_WARPS, cap = (long long)h->sm_count * 16;
-  wbctraj::sample_kernel<<<(unsigned)(blocks < cap ? blocks : cap), wbctraj::SAMPLE_WARPS * 32, 0, (cudaStream_t)stream>>>(
-      plan->t, n, plan_index, t, traj, contact, f_plan, t_eval, status);
+  // instances per warp: 32 (lane = instance) is the throughput shape; small batches are latency bound on the 14 dependent binary
+  // searches per instance, so they spread them over 4 or 16 lanes per instance
+  static const int ipw_env = getenv("WBC_SAMPLE_IPW") ? atoi(getenv("WBC_SAMPLE_IPW")) : 0;
+  const int ipw = ipw_env ? ipw_env : (n >= 32768 ? 32 : n >= 8192 ? 8 : 2);   // rollout of 4096 robots: 45.2 / 48.7 / 49.7 M robot-steps/s with 32 / 8 / 2
+  const long long chunks = (n + ipw - 1) / ipw, blocks = (chunks + wbctraj::SAMPLE_WARPS - 1) / wbctraj::SAMPLE_WARPS, cap = (long long)h->sm_count * 16;
+  const unsigned grid = (unsigned)(blocks < cap ? blocks : cap);
+  cudaStream_t sst = (cudaStream_t)stream;
+  if (ipw == 32) wbctraj::sample_kernel<32><<<grid, wbctraj::SAMPLE_WARPS * 32, 0, sst>>>(plan->t, n, plan_index, t, traj, contact, f_plan, t_eval, status);
+  else if (ipw == 8) wbctraj::sample_kernel<8><<<grid, wbctraj::SAMPLE_WARPS * 32, 0, sst>>>(plan->t, n, plan_index, t, traj, contact, f_plan, t_eval, status);
+  else wbctraj::sample_kernel<2><<<grid, wbctraj::SAMPLE_WARPS * 32, 0, sst>>>(plan->t, n, plan_index, t, traj, contact, f_plan, t_eval, status);
   h->launches++;
   WBC_CUDA(h, cudaGetLastError());
   return WBC_OK;

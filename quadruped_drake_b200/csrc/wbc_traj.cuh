@@ -70,34 +70,42 @@ __device__ __forceinline__ Coef4 load_coef(const double* __restrict__ rec) {
   return r;
 }
 
-// Two stages per chunk of 32 instances (one warp per chunk):
-//   A  lane = instance: planner time logic (wait / nearest stored sample), the 10 spline segment lookups and the 4 contact
-//      flags, done ONCE per instance; (polynomial index, local time) of every spline go to shared memory;
+// Two stages per chunk of IPW instances (one warp per chunk):
+//   A  planner time logic (wait / nearest stored sample) once per instance, then the 10 spline segment lookups and the 4 contact
+//      phase lookups - 14 dependent binary searches - spread over the 32 / IPW lanes that share an instance; (polynomial index,
+//      local time) of every spline go to shared memory;
 //   B  lane = output element: consecutive lanes write consecutive doubles of traj (coalesced), each evaluating one cubic
 //      (or its first / second derivative) from the staged segment info and a 32-byte coefficient record.
+// IPW = 32 (lane = instance, all searches serial) is the throughput shape for large batches; small batches are latency bound on
+// the search chains of a few warps, so they run with IPW = 8 or 2 (4 or 1 searches per lane, 4x / 16x the warps).
 constexpr int SAMPLE_WARPS = 4;
 struct SampleSmem {
   double tl[32][NSPLINE];
+  double t[32];
   int poly[32][NSPLINE];
   int plan[32];
   unsigned char standing[32];
+  unsigned char cb[32][4];
 };
 
+template <int IPW>
 __global__ void __launch_bounds__(SAMPLE_WARPS * 32) sample_kernel(PlanTables pt, long long n, const int* __restrict__ plan_index,
                                                                    const double* __restrict__ tin, double* __restrict__ traj,
                                                                    unsigned char* __restrict__ contact, double* __restrict__ fplan,
                                                                    double* __restrict__ t_eval_out, int* __restrict__ status) {
+  constexpr int G = 32 / IPW;            // lanes per instance in stage A
   __shared__ SampleSmem smem[SAMPLE_WARPS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int il = lane & (IPW - 1), g = lane / IPW;
   SampleSmem& sm = smem[warp];
-  const long long n_chunks = (n + 31) / 32;
+  const long long n_chunks = (n + IPW - 1) / IPW;
   for (long long chunk = (long long)blockIdx.x * SAMPLE_WARPS + warp; chunk < n_chunks; chunk += (long long)gridDim.x * SAMPLE_WARPS) {
-    const long long i0 = chunk * 32;
-    const int cnt = (int)((n - i0) < 32 ? (n - i0) : 32);
+    const long long i0 = chunk * IPW;
+    const int cnt = (int)((n - i0) < IPW ? (n - i0) : IPW);
     __syncwarp();
-    // ---------------------------------------------------------------- stage A
-    if (lane < cnt) {
-      const long long inst = i0 + lane;
+    // ---------------------------------------------------------------- stage A1: time logic, one lane per instance
+    if (g == 0 && il < cnt) {
+      const long long inst = i0 + il;
       int pl = plan_index ? plan_index[inst] : 0;
       int st = 0;
       if (pl < 0 || pl >= pt.n_plans) { pl = 0; st |= WBC_TRAJ_BADPLAN; }
@@ -119,68 +127,74 @@ __global__ void __launch_bounds__(SAMPLE_WARPS * 32) sample_kernel(PlanTables pt
           t = __ldg(ts + best);
         }
       }
-      const int* po = pt.poly_off + pl * (NSPLINE + 1);
       if (!standing) {
+        const int* po = pt.poly_off + pl * (NSPLINE + 1);
         const double t_total = __ldg(pt.tend + __ldg(po + 1) - 1);      // Spline::GetTotalTime of the base spline
         if (!(t >= 0.0)) { t = 0.0; st |= WBC_TRAJ_CLAMPED; }           // the reference asserts t >= 0 (spline.cc:52) ...
         if (t > t_total + 1e-10) { t = t_total; st |= WBC_TRAJ_CLAMPED; }   // ... and runs off the end (spline.cc:65)
       }
       if (status) status[inst] = st;
       if (t_eval_out) t_eval_out[inst] = standing ? -1.0 : t;
-      sm.plan[lane] = pl;
-      sm.standing[lane] = standing ? 1 : 0;
-      unsigned cbits = 0x01010101u;
-      if (!standing) {
-        const int ns = fplan ? NSPLINE : 6;
-        for (int s = 0; s < ns; ++s) {
+      sm.plan[il] = pl;
+      sm.standing[il] = standing ? 1 : 0;
+      sm.t[il] = t;
+    }
+    __syncwarp();
+    // ---------------------------------------------------------------- stage A2: the 14 lookups of an instance over its G lanes
+    if (il < cnt && !sm.standing[il]) {
+      const int pl = sm.plan[il];
+      const double t = sm.t[il];
+      const int* po = pt.poly_off + pl * (NSPLINE + 1);
+      const int ns = fplan ? NSPLINE : 6;
+      for (int s = g; s < NSPLINE + 4; s += G) {
+        if (s < NSPLINE) {
+          if (s >= ns) continue;
           const int p0 = __ldg(po + s), np_ = __ldg(po + s + 1) - p0;
           const int i = segment_of(pt.tend + p0, np_, t);
-          sm.poly[lane][s] = p0 + i;
-          sm.tl[lane][s] = t - (i > 0 ? __ldg(pt.tend + p0 + i - 1) : 0.0);
-        }
-        // contact flags (phase_durations.cc:120-124)
-        const int* fo = pt.phase_off + pl * 5;
-        cbits = 0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
+          sm.poly[il][s] = p0 + i;
+          sm.tl[il][s] = t - (i > 0 ? __ldg(pt.tend + p0 + i - 1) : 0.0);
+        } else {                                                     // contact flags (phase_durations.cc:120-124)
+          const int k = s - NSPLINE;
+          const int* fo = pt.phase_off + pl * 5;
           const int f0 = __ldg(fo + k);
           const int ph = segment_of(pt.phase_tend + f0, __ldg(fo + k + 1) - f0, t);
           const bool c0 = __ldg(pt.contact_start + pl * 4 + k) != 0;
-          cbits |= (unsigned)(((ph & 1) ? !c0 : c0) ? 1 : 0) << (8 * k);
+          sm.cb[il][k] = ((ph & 1) ? !c0 : c0) ? 1 : 0;
         }
       }
-      reinterpret_cast<unsigned*>(contact)[inst] = cbits;              // 4 flags as one aligned 32-bit store
     }
     __syncwarp();
+    if (g == 0 && il < cnt)                                          // 4 flags as one aligned 32-bit store
+      reinterpret_cast<unsigned*>(contact)[i0 + il] = sm.standing[il] ? 0x01010101u : *reinterpret_cast<const unsigned*>(sm.cb[il]);
     // ---------------------------------------------------------------- stage B
     // lane = (instance, spline, dimension): one coefficient record gives position, velocity and acceleration; the three
     // stores of neighbouring lanes fill whole 24-byte groups of the row, which L2 merges into full sectors
     double* out = traj + i0 * WBC_NTRAJ;
     for (int idx = lane; idx < cnt * 18; idx += 32) {
-      const int il = idx / 18, r = idx - il * 18, s = r / 3, dim = r - 3 * s;
+      const int bi = idx / 18, r = idx - bi * 18, s = r / 3, dim = r - 3 * s;
       const int e0 = s < 2 ? 9 * s + dim : 18 + 3 * (s - 2) + dim, stride = s < 2 ? 3 : 12;
       double p, v, a;
-      if (sm.standing[il]) {
-        const double* st = pt.standing + sm.plan[il] * WBC_NTRAJ + e0;
+      if (sm.standing[bi]) {
+        const double* st = pt.standing + sm.plan[bi] * WBC_NTRAJ + e0;
         p = __ldg(st); v = __ldg(st + stride); a = __ldg(st + 2 * stride);
       } else {
-        const double tl = sm.tl[il][s];
-        const Coef4 c = load_coef(pt.coef + ((size_t)sm.poly[il][s] * 3 + dim) * 4);
+        const double tl = sm.tl[bi][s];
+        const Coef4 c = load_coef(pt.coef + ((size_t)sm.poly[bi][s] * 3 + dim) * 4);
         p = fma(fma(fma(c.d, tl, c.c), tl, c.b), tl, c.a);
         v = fma(fma(3.0 * c.d, tl, 2.0 * c.c), tl, c.b);
         a = fma(6.0 * c.d, tl, 2.0 * c.c);
       }
-      double* o = out + il * WBC_NTRAJ + e0;
+      double* o = out + bi * WBC_NTRAJ + e0;
       o[0] = p; o[stride] = v; o[2 * stride] = a;
     }
     if (fplan) {
       double* fo = fplan + i0 * 12;
       for (int idx = lane; idx < cnt * 12; idx += 32) {
-        const int il = idx / 12, r = idx - il * 12, s = 6 + r / 3, dim = r % 3;
+        const int bi = idx / 12, r = idx - bi * 12, s = 6 + r / 3, dim = r % 3;
         double val = 0.0;
-        if (!sm.standing[il]) {
-          const double tl = sm.tl[il][s];
-          const Coef4 c = load_coef(pt.coef + ((size_t)sm.poly[il][s] * 3 + dim) * 4);
+        if (!sm.standing[bi]) {
+          const double tl = sm.tl[bi][s];
+          const Coef4 c = load_coef(pt.coef + ((size_t)sm.poly[bi][s] * 3 + dim) * 4);
           val = fma(fma(fma(c.d, tl, c.c), tl, c.b), tl, c.a);
         }
         fo[idx] = val;
