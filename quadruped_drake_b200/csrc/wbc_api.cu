@@ -6,6 +6,17 @@
 #include <string.h>
 #include <string>
 
+// named barrier `id` over `threads` threads of the CTA (a multiple of 32; skipped when at most one warp takes part)
+#ifndef WBC_PC_MEET
+#define WBC_PC_MEET 1
+#endif
+#if WBC_PC_MEET
+#define WBC_CTA_MEET(id, threads)                                                                    \
+  do {                                                                                               \
+    const int nt_ = (threads);                                                                       \
+    if (nt_ > 32) asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nt_) : "memory");                   \
+  } while (0)
+#endif
 #include "wbc_device.cuh"
 #include "wbc_wire.cuh"
 #include "wbc_traj.cuh"
@@ -25,7 +36,10 @@ constexpr int WARPS = 1;         // device-resident buffers
 #define WBC_WARPS_HOST 4
 #endif
 constexpr int WARPS_HOST = WBC_WARPS_HOST;    // host-mapped buffers (ID / CLF)
-constexpr int WARPS_PC = 4;                   // PC / MPTC reduce kernel
+#ifndef WBC_WARPS_PC
+#define WBC_WARPS_PC 6
+#endif
+constexpr int WARPS_PC = WBC_WARPS_PC;        // PC / MPTC reduce kernel
 #ifndef WBC_PC_MIN_WARPS
 #define WBC_PC_MIN_WARPS 12      // resident warps per SM the PC reduce kernel is compiled for (168 registers)
 #endif
@@ -260,6 +274,19 @@ __global__ void __launch_bounds__(W * 32, WBC_PC_MIN_WARPS / W) wbc_reduce_pc_ke
   wbc::StepCarry c;
   const wbc::StagedInputs in = staged_rows(sm->in, warp);
   if (staged) mbar_wait(&sm->in.mbar, 0);
+  {
+    // meeting points of the CTA's warps ahead of the dynamics passes (wbc_device.cuh: WBC_CTA_MEET): every warp with an instance
+    // takes the state pass, every warp whose instance has a stance foot takes the two polarisation passes
+    const long long first = (long long)blockIdx.x * W;
+    const int n_act = (int)((a.n - first) < W ? (a.n - first) : W);
+    int n_pc = 0;
+    for (int w = 0; w < n_act; ++w) {
+      const uint8_t* cp = (staged && in.contact) ? sm->in.contact + w * 4 : a.contact + (first + w) * 4;
+      n_pc += (cp[0] | cp[1] | cp[2] | cp[3]) ? 1 : 0;
+    }
+    sm->pc[warp].sync_all = 32 * n_act;
+    sm->pc[warp].sync_pc = 32 * n_pc;
+  }
   wbc::reduce_instance<WBC_CTRL_PC>(s, dc.md, dc.pr, dc.dv, a, inst, lane, c, &sm->pc[warp], vdmap ? vdmap + inst * wbc::VDMAP_DOUBLES : nullptr,
                                     staged ? &in : nullptr);
   __syncwarp();

@@ -1090,6 +1090,12 @@ WBC_DEV void build_common_rows(WarpSmem& s, int lane, int ycol, unsigned cmask, 
 //   X = M^-1 J',  Lambda = (J X)^-1,  s1 = Lambda xd~,  w = v - X s1,
 //   g0 = X'(b(v) - C w) - xdd_nom + Jdot w,          (C w by polarisation of the bias b)
 //   cost 1/2 |W^1/2 (Lambda (J vd + g0) + Kp x~ + Kd xd~)|^2,   passivity row  s1'(J vd + g0) + xd~'Kp x~ <= 0.
+// Meeting point of the warps of a CTA ahead of a pass through the (large, out-of-line) dynamics code: warps that enter it
+// together share its instruction fetches. Defined by the kernel translation unit; a no-op elsewhere (host emulator).
+#ifndef WBC_CTA_MEET
+#define WBC_CTA_MEET(id, threads)
+#endif
+
 struct PcSmem {
   double Lam[16][17];                        // J M^-1 J' -> its Cholesky factor -> Lambda (odd row stride: a row per lane is conflict free)
   double s1[16], g0[16], kx[16], xt[16], xdt[16], wt[16];
@@ -1100,6 +1106,7 @@ struct PcSmem {
   double Dinv[4][6];                         // inverses of the 3x3 leg blocks (symmetric, sym3 indexing)
   int rowidx[16];                            // task row r -> row of Y
   double kpxx;                               // xd~' Kp x~
+  int sync_all, sync_pc;                     // threads of this CTA that reach the dynamics passes (0: no CTA-level meeting points)
 };
 
 WBC_DEV double sym3get(const double* d, int i, int j) { return d[sym3(i < j ? i : j, i < j ? j : i)]; }
@@ -1308,6 +1315,7 @@ WBC_DEV void pc_precompute(WarpSmem& s, PcSmem& pc, const wbc_model& md, const w
   for (int pass = 0; pass < 2; ++pass) {
     const double* vin = pass == 0 ? pc.vw : pc.vmw;
     double* bout = pass == 0 ? pc.bvw : pc.bw;
+    WBC_CTA_MEET(2, pc.sync_pc);
     dynamics_pc_pass(s, md, lane, st2, vin, bout, true);
   }
   // ---- g0 = X'(b(v) - C w) - xdd_nom + Jdot w
@@ -1388,8 +1396,10 @@ WBC_DEV void reduce_instance(WarpSmem& s, const wbc_model& md, const wbc_params&
   const int nc = __popc(cmask);
   __syncwarp();
   // ---- phase 1
-  if (KIND == WBC_CTRL_PC) dynamics_pc_pass(s, md, lane, status, nullptr, nullptr, false, pcs->tg);
-  else dynamics_phase<DYN_STEP>(s, md, lane, status, nullptr);
+  if (KIND == WBC_CTRL_PC) {
+    WBC_CTA_MEET(1, pcs->sync_all);
+    dynamics_pc_pass(s, md, lane, status, nullptr, nullptr, false, pcs->tg);
+  } else dynamics_phase<DYN_STEP>(s, md, lane, status, nullptr);
   async_wait_all();
   __syncwarp();
   BodyTask bt;
