@@ -458,6 +458,11 @@ extern "C" int wbc_create(const wbc_model* model, const wbc_params* params, int 
   if (e != cudaSuccess) { h->err = std::string("cudaMemcpy: ") + cudaGetErrorString(e); return bail(WBC_ERR_CUDA); }
   e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking);
+  // lanes 2.. of a chunked step and the fork / join events: created here, not on first use, so that a step never calls a
+  // resource-creating API while some other stream of the process is being captured
+  for (int l = 2; l < WBC_NSLOT && e == cudaSuccess; ++l) e = cudaStreamCreateWithFlags(&h->xstream[l], cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->order_ev, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->join_ev, cudaEventDisableTiming);
   if (e != cudaSuccess) { h->err = std::string("cudaStreamCreate: ") + cudaGetErrorString(e); return bail(WBC_ERR_CUDA); }
   {
     cudaDeviceProp prop;
