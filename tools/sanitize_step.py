@@ -56,3 +56,26 @@ o = multi.step("id", g["q"], g["v"], g["traj"], g["contact"])
 assert np.abs(o.tau - g["id_tau"]).max() < 1e-5
 multi.close()
 print("sanitize plant / plan / multi ok")
+
+# chunked issue of a device step (2-4 reduce -> solve chains on as many streams), the zero-copy host path in two halves and the
+# copy-engine-staged host path (24576+ instances): tiled golden instances, bit-identical to the small batch
+import torch  # noqa: E402
+from quadruped_drake_b200 import capi  # noqa: E402
+
+base = ctl.step("id", g["q"], g["v"], g["traj"], g["contact"])
+for nn in (4100, 8200, 24580):
+    idx = np.arange(nn) % len(g["q"])
+    dev = torch.device("cuda:0")
+    t = [torch.from_numpy(np.ascontiguousarray(g[k][idx])).to(dev) for k in ("q", "v", "traj", "contact")]
+    o = ctl.step("id", *t)
+    torch.cuda.synchronize()
+    assert np.array_equal(o.tau.cpu().numpy(), base.tau[idx]), nn
+    hb = [capi.pinned_empty((nn, w), dt) for w, dt in ((19, np.float64), (18, np.float64), (54, np.float64), (4, np.uint8))]
+    for dst, k in zip(hb, ("q", "v", "traj", "contact")):
+        dst[:] = g[k][idx]
+    tau, met, st = capi.pinned_empty((nn, 12)), capi.pinned_empty((nn, 4)), capi.pinned_empty((nn,), np.int32)
+    import ctypes as C  # noqa: E402
+    io = capi.WbcIO(*(capi.np_ptr(x) for x in hb), capi.np_ptr(tau), capi.np_ptr(met), capi.np_ptr(st), None, None, None)
+    assert ctl.lib.wbc_step_host(ctl._h, capi.WBC_CTRL_ID, nn, C.byref(io)) == 0
+    assert np.array_equal(tau, base.tau[idx]), nn
+print("sanitize chunked / host paths ok")
