@@ -157,3 +157,28 @@ def test_step_with_device_plan_equals_sample_then_step(ctl):
     c = ctl.step_plan("clf", s, q, v, t)                       # no plan index: plan 0 for everyone
     o0 = s.sample(t)
     assert np.array_equal(c.tau, ctl.step("clf", q, v, o0["traj"], o0["contact"]).tau)
+
+
+def test_sampler_kernel_shapes_agree(ctl):
+    """wbc_sample_trajectory picks the instances-per-warp shape by batch size (2 below 8192 samples, 8 below 32768, 32 above;
+    csrc/wbc_traj.cuh): the same (plan, t) pairs through all three give identical bits, ragged tails, bad plan indices, clamped
+    times, grid-mode plans and planned forces included."""
+    from quadruped_drake_b200 import planner as pl
+    plans = [pl.make_gait_plan("mini_cheetah", c) for c in range(4)]
+    s = pl.TrajectorySampler(ctl, plans)
+    rng = np.random.default_rng(11)
+    n = 40003
+    t, pi = rng.uniform(-0.2, 5.3, n), rng.integers(-1, 5, n).astype(np.int32)
+    big = s.sample(t, pi, forces=True)                                   # lane = instance
+    for step in (3001, 10007):                                           # 16 lanes / 4 lanes per instance
+        for o in range(0, n, step):
+            part = s.sample(t[o:o + step], pi[o:o + step], forces=True)
+            for key in ("traj", "contact", "f", "status", "t_eval"):
+                assert np.array_equal(np.asarray(part[key]), np.asarray(big[key])[o:o + step]), (step, o, key)
+    grid = pl.TowrTrunkPlanner(ctl, robot="mini_cheetah", gait="trot")
+    tg = rng.uniform(0.0, 6.0, 33000)
+    bigg = grid.sample(tg, forces=True)
+    for o in (0, 9000, 29000):
+        part = grid.sample(tg[o:o + 4000], forces=True)
+        for key in ("traj", "contact", "f", "t_eval"):
+            assert np.array_equal(np.asarray(part[key]), np.asarray(bigg[key])[o:o + 4000]), (o, key)
