@@ -185,8 +185,9 @@ int wbc_step_pd(wbc_handle* h, int64_t n, const double* q, const double* v, doub
 
 /* Same step with HOST buffers (what the Python LeafSystem shim calls); returns after tau / metrics / status (and any
  * optional outputs that are non-NULL) are in the caller's buffers. Page-locked buffers (wbc_host_alloc /
- * cudaHostRegister): below 131072 instances the kernels read and write them directly over the host link (zero-copy),
- * above that - and for pageable buffers - the batch goes through a chunked two-stream copy / compute pipeline. */
+ * cudaHostRegister): the kernels write the outputs straight into them; the inputs are read over the host link by the kernels
+ * (zero-copy) below 24576 instances (131072 for PC / MPTC) and go through the copy engine into device staging in chunks above.
+ * Pageable buffers go through a chunked two-stream copy / compute pipeline in both directions. */
 int wbc_step_host(wbc_handle* h, int kind, int64_t n, const wbc_io* host_io);
 
 /* All GPUs of the box from one call (north star: "instances shard trivially across the 8 GPUs of one box, with no NCCL
@@ -305,7 +306,7 @@ int wbc_sample_trajectory_host(wbc_handle* h, const wbc_plan* plan, int64_t n, c
 /* Control step with the trunk targets taken from a device-resident plan (TowrTrunkPlanner.SetTrunkOutputs feeding
  * DoSetControlTorques, planners/towr.py:92-148 -> basic_controller.py:286-320) on HOST state buffers: the host sends q, v
  * and the plan time t [N] (+ optional plan_index [N]) - 308 B per instance instead of 736 B - the trajectory rows are sampled on
- * the device into library scratch. Outputs as wbc_step_host. Page-locked buffers below 131072 instances are zero-copy. */
+ * the device into library scratch. Outputs as wbc_step_host. Page-locked buffers are read / written by the kernels directly. */
 int wbc_step_plan_host(wbc_handle* h, int kind, const wbc_plan* plan, int64_t n, const double* q, const double* v,
                        const double* t, const int32_t* plan_index, double* tau, double* metrics, int32_t* status);
 
