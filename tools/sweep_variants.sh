@@ -15,7 +15,7 @@ for spec in "$@"; do
       WBC_LIB=$ROOT/variants/$name.so python $ROOT/bench.py --no-cpu --steps $steps --batch $b ${BENCH_ARGS} 2>/dev/null | python -c "
 import sys,json
 d=json.loads(sys.stdin.read()); k=d['roofline'].get('kernels') or {}
-print('%-28s batch %8d  value %7.2f M/s  e2e %7.2f M/s  p50 %.4f ms  reduce %.1f us  solve %.1f us' % ('$name', $b, d['value']/1e6, d['e2e']['value']/1e6, d['p50_ms_per_step'], 1e3*k.get('reduce_kernel_ms',0), 1e3*k.get('solve_kernel_ms',0)))"
+print('%-28s batch %8d  value %7.2f M/s  e2e %7.2f M/s  p50 %.4f ms  reduce %.1f us  solve %.1f us' % ('$name', $b, d['value']/1e6, (d['e2e']['value'] or 0)/1e6, d['p50_ms_per_step'], 1e3*k.get('reduce_kernel_ms',0), 1e3*k.get('solve_kernel_ms',0)))"
     done
   fi
 done
