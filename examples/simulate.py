@@ -53,6 +53,7 @@ def run(controller="id", planner="standing", sim_time=6.0, dt=5e-3, verbose=True
         q, v = qn[0], vn[0]
         log.append([t, q[6], met[1], f[0, :, 2].sum()])
     wall = time.perf_counter() - t0
+    run.last_wall = wall                                          # the loop alone, without the construction of the controller
     log = np.array(log)
     if verbose:
         print(f"{controller} / {planner}: {len(log)} steps in {wall:.2f} s wall ({len(log) / wall:.0f} control steps/s, real-time factor "

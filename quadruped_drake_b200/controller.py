@@ -364,6 +364,23 @@ class _QPController(LeafSystem):
         if self.HAS_TRUNK_PORT:
             self.DeclareAbstractInputPort("trunk_input", AbstractValue.Make({}))
         self.last_status = 0
+        # page-locked step buffers and the wbc_io over them, made once: a control step writes the state and the trunk targets
+        # into them and calls wbc_step_host, whose kernels read / write them directly (no per-step allocation or staging copy)
+        n = self.n
+        widths = (NQ, NV, NTRAJ, NU, 4)                                # q, v, traj, tau, metrics: doubles; then status, contact
+        slab = capi.pinned_empty((n * (sum(widths) + 1),))             # ONE page-locked allocation (each costs milliseconds)
+        slab[:] = 0.0
+        views, o = [], 0
+        for w in widths:
+            views.append(slab[o:o + n * w].reshape(n, w))
+            o += n * w
+        self._hq, self._hv, self._ht, self._htau, self._hmet = views
+        tail = slab[o:o + n].view(np.uint8)                            # 8 n bytes: n int32 status words, then 4 n contact flags
+        self._hst, self._hc = tail[:4 * n].view(np.int32), tail[4 * n:8 * n].reshape(n, 4)
+        self._slab = slab
+        self._hio = WbcIO(np_ptr(self._hq), np_ptr(self._hv), np_ptr(self._ht), np_ptr(self._hc), np_ptr(self._htau), np_ptr(self._hmet),
+                          np_ptr(self._hst), None, None, None)
+        self._kind = KINDS[self.KIND]
         # LCM bridge (basic_controller.py:54-61): messages are decoded / encoded by the device codecs of wire.py. The
         # LCM runtime itself is optional: without it, feed `lcm_callback` yourself and read `published`.
         self.use_lcm = use_lcm
@@ -422,23 +439,34 @@ class _QPController(LeafSystem):
             q, v = x[:, :NQ], x[:, NQ:]
         output.SetFromVector(np.asarray(self.ControlLaw(context, q, v)).ravel())
 
+    _TRUNK_KEYS = (["p_body", "pd_body", "pdd_body", "rpy_body", "rpyd_body", "rpydd_body"] + ["p_" + f for f in FEET]
+                   + ["pd_" + f for f in FEET] + ["pdd_" + f for f in FEET])      # row order of traj[54] viewed as [18, 3]
+
     def ControlLaw(self, context, q, v):
         trunk = self.EvalAbstractInput(context, 1).get_value()
         if self.n == 1:
-            traj, contact = dict_to_traj(trunk)
-            traj, contact, q, v = traj[None], contact[None], np.asarray(q)[None], np.asarray(v)[None]
+            try:        # one conversion for the 18 three-vectors of the dict (lists, (3,) or (3,1) arrays alike)
+                self._ht[0] = np.array([trunk[k] for k in self._TRUNK_KEYS], dtype=np.float64).reshape(NTRAJ)
+                self._hc[0] = trunk["contact_states"]
+            except ValueError:
+                self._ht[0], self._hc[0] = dict_to_traj(trunk)
+            self._hq[0], self._hv[0] = q, v
         else:
-            traj, contact = dict_to_traj_batch(trunk, self.n)
-        out = self.batched.step(self.KIND, q, v, traj, contact)
-        self.last_status = int(out.status[0]) if self.n == 1 else out.status.copy()
+            self._ht[:], self._hc[:] = dict_to_traj_batch(trunk, self.n)
+            self._hq[:], self._hv[:] = q, v
+        b = self.batched
+        b._check(b.lib.wbc_step_host(b._h, self._kind, self.n, C.byref(self._hio)), "wbc_step_host")
+        st = self._hst
+        self.last_status = int(st[0]) if self.n == 1 else st.copy()
         # reference: `assert result.is_success()` (inverse_dynamics_controller.py:224); a zero / non-finite quaternion, gimbal
         # lock (CalcRpyDtFromAngularVelocityInParent) and PC in full flight (pc_controller.py:248-249) raise inside Drake /
         # NumPy there, so every status bit raises here
-        bad = np.nonzero(out.status)[0]
-        assert bad.size == 0, (f"QP solve failed for instance(s) {bad[:8].tolist()} (status "
-                               f"{int(out.status[bad[0]])}: {capi.status_names(int(out.status[bad[0]]))})")
-        self._log(out.metrics[0] if self.n == 1 else out.metrics.T)
-        return out.tau[0].copy() if self.n == 1 else out.tau.copy()
+        if st.any():
+            bad = np.nonzero(st)[0]
+            raise AssertionError(f"QP solve failed for instance(s) {bad[:8].tolist()} (status "
+                                 f"{int(st[bad[0]])}: {capi.status_names(int(st[bad[0]]))})")
+        self._log(self._hmet[0] if self.n == 1 else self._hmet.T)
+        return self._htau[0].copy() if self.n == 1 else self._htau.copy()
 
     def _log(self, m):
         self.err, self.res = self._f(m[1]), self._f(m[2])
