@@ -371,6 +371,7 @@ struct wbc_handle {
   // hand-over records of the split step (reduce -> solve), one slot per internal stream lane
   cudaEvent_t prof_ev[3] = {nullptr, nullptr, nullptr};   // wbc_profile_step: before reduce / between / after solve
   bool prof_on = false;
+  bool side_by_side = false;                              // set while a step is issued as several concurrent chains
   bool host_mapped = false;                               // set around the zero-copy launches of wbc_step_host
   // per-slot ordering of the scratch users: the stream of the last step that used the slot and an event to chain a new one
   cudaStream_t last_stream[WBC_NSLOT] = {};
@@ -681,10 +682,12 @@ static int launch_split(wbc_handle* h, int kind, int64_t n, const wbc_io* io, cu
     if (h->prof_on) cudaEventRecord(h->prof_ev[1], st);
     const unsigned sgrid = (unsigned)((m + SOLVE_WARPS - 1) / SOLVE_WARPS);
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-    // measured: +1.5 % at 4096 instances, neutral above, but -10 % at 1024 (the early-resident solve CTAs cost more than the
-    // hidden launch latency there), so small launch pairs and stream captures keep the ordinary launch
+    // programmatic dependent launch of the solve kernel (its CTAs become resident while the last reduce CTAs run): +1.5 % at 4096
+    // instances, neutral above; never inside a stream capture ...
     static const long long pdl_min = getenv("WBC_PDL_MIN") ? atoll(getenv("WBC_PDL_MIN")) : 4096;
-    const bool pdl = pdl_mode() && m >= pdl_min;
+    // ... and chains that run beside other chains of the same step (chunked issue): there the early-resident solve CTAs take the
+    // slots the other chunk's reduce CTAs need (-22 % at 2 x 2048). A lone chain gains at every size (+3-4 % at 64 - 1024).
+    const bool pdl = pdl_mode() && (m >= pdl_min || !h->side_by_side);
     if (pdl) cudaStreamIsCapturing(st, &cap);
     const bool with_vd = io->vd != nullptr;
     cudaLaunchConfig_t cfg = {};
@@ -765,7 +768,9 @@ extern "C" int wbc_step(wbc_handle* h, int kind, int64_t n, const wbc_io* io, vo
                          io->metrics + o * WBC_NMETRIC, io->status + o, io->vd ? io->vd + o * WBC_NV : nullptr,
                          io->f ? io->f + o * 12 : nullptr, io->qp_info ? io->qp_info + o * 4 : nullptr, io->lam ? io->lam + o * WBC_NLAM : nullptr};
         cudaStream_t cs = c == 0 ? st : c == 1 ? h->stream2 : h->xstream[c];
+        h->side_by_side = true;
         const int rc = step_launch(h, kind, m, &cio, cs, c);
+        h->side_by_side = false;
         if (rc) return rc;
         if (c) {
           WBC_CUDA(h, cudaEventRecord(h->join_ev, cs));
@@ -897,8 +902,9 @@ static int step_host_enqueue(wbc_handle* h, int kind, int64_t n, const wbc_io* i
                          dio.vd ? dio.vd + o * WBC_NV : nullptr, dio.f ? dio.f + o * 12 : nullptr, dio.qp_info ? dio.qp_info + o * 4 : nullptr,
                          dio.lam ? dio.lam + o * WBC_NLAM : nullptr};
         h->host_mapped = !staged || (stage_in & 3) != 3;   // the reduce kernel reads host memory (4-warp CTAs, everything staged per CTA)
+        h->side_by_side = zc > 1;
         rc = pd ? wbc_step_pd(h, m, cio.q, cio.v, cio.tau, lanes[c & 1]) : step_launch(h, kind, m, &cio, lanes[c & 1], c & 1);
-        h->host_mapped = false;
+        h->host_mapped = false; h->side_by_side = false;
         if (rc) return rc;
         used |= 1 << (c & 1);
       }
@@ -935,7 +941,9 @@ static int step_host_enqueue(wbc_handle* h, int kind, int64_t n, const wbc_io* i
                h->d_metrics + o * WBC_NMETRIC, h->d_status + o,
                io->vd ? h->d_vd + o * WBC_NV : nullptr, io->f ? h->d_f + o * 12 : nullptr, io->qp_info ? h->d_info + o * 4 : nullptr,
                io->lam ? h->d_lam + o * WBC_NLAM : nullptr};
+    h->side_by_side = n_chunks > 1;
     rc = pd ? wbc_step_pd(h, m, dio.q, dio.v, dio.tau, st) : step_launch(h, kind, m, &dio, st, c & 1);
+    h->side_by_side = false;
     if (rc) return rc;
     WBC_CUDA(h, cudaMemcpyAsync(io->tau + o * WBC_NU, h->d_tau + o * WBC_NU, m * WBC_NU * sizeof(double), cudaMemcpyDeviceToHost, st));
     if (!pd) {
@@ -1440,9 +1448,9 @@ extern "C" int wbc_step_plan_host(wbc_handle* h, int kind, const wbc_plan* plan,
       if (m <= 0) break;
       const wbc_io io{(const double*)dev[0] + o * WBC_NQ, (const double*)dev[1] + o * WBC_NV, h->ro_traj + o * WBC_NTRAJ, h->ro_contact + o * 4,
                       (double*)dev[4] + o * WBC_NU, (double*)dev[5] + o * WBC_NMETRIC, (int32_t*)dev[6] + o};
-      h->host_mapped = true;
+      h->host_mapped = true; h->side_by_side = zc > 1;
       rc = step_launch(h, kind, m, &io, lanes[c & 1], c & 1);
-      h->host_mapped = false;
+      h->host_mapped = false; h->side_by_side = false;
       if (rc) return rc;
     }
     return step_host_wait(h);
