@@ -853,14 +853,14 @@ static int step_host_enqueue(wbc_handle* h, int kind, int64_t n, const wbc_io* i
     if (pinned) {
       const wbc_io hio{(const double*)dev[0], (const double*)dev[1], (const double*)dev[2], (const uint8_t*)dev[3], (double*)dev[4],
                        (double*)dev[5], (int32_t*)dev[6], (double*)dev[7], (double*)dev[8], (double*)dev[9], (double*)dev[10]};
-      // The batch goes through in chunks alternating between two streams (each with its own hand-over scratch), so that the
-      // input-bound reduce kernel of one chunk overlaps the solve kernel of the previous one and the host link stays busy.
-      // two halves on the two internal streams from 4096 instances on: the solve kernel of one half overlaps the link-bound
-      // reduce kernel of the other (e2e +4.6 % at 4096, +3.8 % at 16384, +1 % at 65536; three or more chunks lose)
+      // The batch goes through in chunks alternating between the two internal streams (each with its own hand-over scratch); the
+      // outputs are written straight to host memory by the solve kernel in every mode.
+      //  * below 24576 instances the reduce kernel reads its inputs over the host link (zero-copy), two halves from 4096 on:
+      //    the solve kernel of one half overlaps the link-bound reduce kernel of the other (e2e +4.6 % at 4096, +3.8 % at
+      //    16384; three or more chunks lose);
+      //  * above, the inputs go through the copy engine into device staging (WBC_ZC_STAGE bit 0: traj, bit 1: q, v, contact) and
+      //    the single-warp reduce CTAs read resident inputs: e2e +5 % at 32768, +16 % at 65536, +10 % at 2^17 - 2^20.
       static const long long stage_min = getenv("WBC_ZC_MAX") ? atoll(getenv("WBC_ZC_MAX")) : 24576;
-      static const int stage_mask = getenv("WBC_ZC_STAGE_CHUNKS") ? atoi(getenv("WBC_ZC_STAGE_CHUNKS")) : -1;   // experiments
-      // inputs that go through the copy engine into device staging instead of being read over the link by the SMs
-      // (bit 0: traj, bit 1: q, v, contact): +6 % at 65536 instances, +3 % at 131072 - 262144 over the next best mode
       static const int stage_env = getenv("WBC_ZC_STAGE") ? atoi(getenv("WBC_ZC_STAGE")) : -1;
       // PC / MPTC are compute bound at a third of the rate: the zero-copy reads hide under the reduce kernel up to 131072
       // instances (e2e 22.3 M steps/s against 20.0 M staged at 65536)
@@ -881,7 +881,7 @@ static int step_host_enqueue(wbc_handle* h, int kind, int64_t n, const wbc_io* i
       for (int c = 0; c < zc; ++c) {
         const int64_t o = c * per, m = (o + per <= n) ? per : n - o;
         if (m <= 0) break;
-        const bool staged = stage_in && !pd && ((stage_mask >> (c & 31)) & 1);
+        const bool staged = stage_in && !pd;
         wbc_io dio = hio;
         if (staged) {
           cudaStream_t cs = lanes[c & 1];
