@@ -34,11 +34,11 @@ CASES = [
     ("cfg4_mini_cheetah_walk", "mini_cheetah", "walk", 256, 20260121, "depth_first", {}, ALL),
     ("mixed_mini_cheetah", "mini_cheetah", "mixed", 256, 20260122, "depth_first", {}, ALL),
     # 2021-era Drake velocity numbering: all abductions, all hips, all knees
-    ("bf_mini_cheetah_mixed", "mini_cheetah", "mixed", 256, 20260123, "breadth_first", {}, QP3),
-    ("bf_anymal_trot", "anymal_b", "trot", 256, 20260124, "breadth_first", {}, QP3),
+    ("bf_mini_cheetah_mixed", "mini_cheetah", "mixed", 256, 20260123, "breadth_first", {}, ALL),
+    ("bf_anymal_trot", "anymal_b", "trot", 256, 20260124, "breadth_first", {}, ALL),
     # optional |tau| <= effort box (BASELINE configs[2]); states chosen so that the box is active for many instances
-    ("tl_mini_cheetah_walk", "mini_cheetah", "walk", 256, 20260125, "depth_first", {"torque_limits": 1}, QP3),
-    ("tl_anymal_trot", "anymal_b", "trot+", 256, 20260126, "depth_first", {"torque_limits": 1}, QP3),
+    ("tl_mini_cheetah_walk", "mini_cheetah", "walk", 256, 20260125, "depth_first", {"torque_limits": 1}, ALL),
+    ("tl_anymal_trot", "anymal_b", "trot+", 256, 20260126, "depth_first", {"torque_limits": 1}, ALL),
     # the reference's manual test motions (planners/simple.py:87-115) as direct step cases
     ("fixtures_mini_cheetah", "mini_cheetah", "fixtures", 288, 20260127, "depth_first", {}, ALL),
 ]
