@@ -76,6 +76,39 @@ def test_admm_run_to_convergence_clf_and_pc():
             assert np.abs(r.x[18:30] - g[kind + "_tau"][i]).max() < 1e-4, (kind, i)
 
 
+@pytest.mark.parametrize("name,robot,dof_order,params", [
+    ("tl_mini_cheetah_walk.npz", "mini_cheetah", "depth_first", {"torque_limits": 1}),
+    ("cfg3_anymal_trot.npz", "anymal_b", "depth_first", {}),
+    ("bf_anymal_trot.npz", "anymal_b", "breadth_first", {}),
+])
+def test_admm_run_to_convergence_other_robots_orders_and_the_torque_box(name, robot, dof_order, params):
+    """Same cross-check on anymal_b, on the 2021-era breadth-first velocity numbering and with the torque box - including
+    instances whose golden torques sit ON the box (the box rows then belong to the active set OSQP has to find)."""
+    from oracle.dynamics import Plant
+    g = np.load(GOLD / name)
+    plant = Plant(robot, dof_order)
+    ctl = oc.IDController(plant, **params)
+    idx = list(range(0, 40, 5))
+    if params.get("torque_limits"):
+        at_box = np.nonzero((np.abs(np.abs(g["id_tau"]) - plant.effort) < 1e-9).any(axis=1) & g["id_ok"])[0]
+        assert len(at_box) >= 4
+        idx += [int(i) for i in at_box[:4]]
+    tight = oq.Settings(eps_abs=1e-12, eps_rel=1e-12, max_iter=400000, polish=False)
+    n = 0
+    for i in idx:
+        if not g["id_ok"][i]:
+            continue
+        o = ctl.control_law(g["q"][i], g["v"][i], oc.traj_to_dict(g["traj"][i], g["contact"][i]))
+        if not o.qp[4].shape[0]:
+            continue
+        r = oq.solve_reference_qp(*o.qp, tight)
+        assert r.status == "solved", (i, r.iters)
+        assert np.abs(r.x[:18] - g["id_vd"][i]).max() < 1e-6, i
+        assert np.abs(r.x[18:30] - g["id_tau"][i]).max() < 1e-3, i
+        n += 1
+    assert n >= 6
+
+
 def test_default_osqp_tolerances_against_the_exact_optimum():
     """What the reference actually runs: eps 1e-3 + polish on the QP WITHOUT the tie-break. Every solve terminates as `solved`, its
     cost is within 1e-3 (relative) of the exact optimum, a successful polish with the right active set reproduces the exact
