@@ -5,7 +5,9 @@ Stands in for `OsqpSolver().Solve(mp)` (reference inverse_dynamics_controller.py
 method run at eps_abs = eps_rel = 1e-3, far looser than the 1e-5
 parity target, so parity is defined against the exact optimum of the same QP
 (SURVEY.md 7 "Hard parts"). **parity unpinned**: the reference has no golden QP
-solutions; this solver is pinned by its own KKT certificate, which every test checks.
+solutions; this solver is pinned by its own KKT certificate, which every test checks, and
+cross-checked by `oracle/osqp_admm.py`: OSQP's published ADMM iteration, run to convergence,
+reaches the same point (tests/test_oracle_osqp.py).
 
     minimise 1/2 x'Px + q'x   s.t.  A x = b,  G x <= h
 
