@@ -130,7 +130,8 @@ def test_pc_step_matches_golden(ctl_cache, case, kind):
 
 
 def test_pc_full_size_config4(ctl_cache):
-    """BASELINE config 4 (PC variant, 65536 instances, walk patterns): solves; constraints and passivity row hold."""
+    """BASELINE config 4 (PC variant, 65536 instances, walk patterns): solves; constraints and passivity row hold; a random
+    sample of the batch (PC and MPTC) is the optimum of the oracle's full-size QP."""
     from quadruped_drake_b200.synth import generate
     ctl = ctl_cache("mini_cheetah")
     q, v, traj, contact = generate(ctl.model, 65536, 20260121, "walk", ctl.fk)
@@ -139,6 +140,15 @@ def test_pc_full_size_config4(ctl_cache):
     dyn, con, fr = kkt_properties(ctl, q, v, traj, contact, out)
     assert dyn.max() < 1e-7 and con.max() < 1e-7 and fr.max() < 1e-7
     assert (out.metrics[:, 3] < 1e-7 * np.maximum(1.0, np.abs(out.metrics[:, 0]))).all()      # Vdot <= delta <= 0
+    # optimality on a random sample of the full-size batch: the oracle's PC-QP (AutoDiff-equivalent C and Jdot, full-size QP)
+    from oracle import controllers as oc
+    mptc = ctl.step("mptc", q, v, traj, contact, debug=True)
+    assert (mptc.status == 0).all()
+    for got, octl, cnt in ((out, oc.PCController("mini_cheetah"), 24), (mptc, oc.MPTCController("mini_cheetah"), 12)):
+        for i in np.random.default_rng(5).choice(65536, cnt, replace=False):
+            o = octl.control_law(q[i], v[i], oc.traj_to_dict(traj[i], contact[i]))
+            assert o.status in ("optimal", "ipm")
+            assert np.abs(got.tau[i] - o.tau).max() < 1e-5 and np.abs(got.vd[i] - o.vd).max() < 1e-6, i
 
 
 def test_coriolis_entry_matches_oracle(ctl_cache):
